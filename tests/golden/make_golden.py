@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports naver/deep-image-retrieval from /root/reference (read-only, nothing is copied),
+feeds it the seeded synthetic inputs of ``deep-image-retrieval_b200/synth.py`` and stores the
+reference's outputs as small ``.npz`` files.  Inputs are NOT stored when they can be
+regenerated from a seed; the seeds/shapes are recorded in each file.
+"""
+import importlib.util
+import os
+import pickle
+import sys
+import tempfile
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+
+os.environ.setdefault("DB_ROOT", tempfile.mkdtemp(prefix="dbroot_"))
+os.environ.setdefault("TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD", "1")
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+
+spec = importlib.util.spec_from_file_location("synth", os.path.join(REPO, "deep-image-retrieval_b200", "synth.py"))
+synth = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(synth)
+
+import dirtorch.nets as nets  # noqa: E402  (the reference)
+from dirtorch.utils import common  # noqa: E402
+from dirtorch.nets.layers.pooling import GeneralizedMeanPooling  # noqa: E402
+import dirtorch.test_dir as ref_test_dir  # noqa: E402
+from dirtorch.datasets.generic import ImageListRelevants  # noqa: E402
+
+assert nets.__file__.startswith(REF), nets.__file__
+
+
+def ref_model(arch, seed, **kw):
+    net = nets.create_model(arch, pretrained="", **kw)
+    sd = synth.make_state_dict(arch, seed=seed, out_dim=kw.get("out_dim", 2048), gemp=kw.get("gemp", 3))
+    if not kw.get("pooling", "gem").startswith("gem"):
+        sd.pop("adpool.p")                      # max/avg pooling has no learnable p (rmac_resnet.py:24-31)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    return net
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: getattr(v, "shape", v) for k, v in arrays.items()})
+
+
+@torch.no_grad()
+def gold_extract():
+    # config 1: Resnet50-GeM, 4 x 224 x 224
+    net = ref_model("resnet50_rmac", seed=0)
+    x = synth.make_images(4, 224, 224, seed=1234)
+    d4 = net(x).numpy()
+    d1 = net(x[:1]).numpy()                       # B=1 -> squeezed (2048,)
+    xr = synth.make_images(2, 160, 224, seed=99)  # non-square
+    dr = net(xr).numpy()
+    # intermediate statistics for debugging a mismatching kernel
+    feats = {}
+    hooks = []
+    for lname in ["maxpool", "layer1", "layer2", "layer3", "layer4"]:
+        hooks.append(getattr(net, lname).register_forward_hook(
+            lambda m, i, o, lname=lname: feats.__setitem__(lname, o.detach())))
+    net(x)
+    for h in hooks:
+        h.remove()
+    stats = {("stat_" + k): np.array([v.mean().item(), v.abs().mean().item(), v.abs().max().item()]) for k, v in feats.items()}
+    # one exact activation slice per stage: image 0, all channels, one pixel
+    slices = {("slice_" + k): v[0, :, v.shape[2] // 2, v.shape[3] // 3].numpy() for k, v in feats.items()}
+    save("extract_r50.npz", arch="resnet50_rmac", seed=0, img_seed=1234, img_shape=np.array([4, 224, 224]),
+         desc=d4, desc_b1=d1, img_seed_rect=99, img_shape_rect=np.array([2, 160, 224]), desc_rect=dr, **stats, **slices)
+
+    # head options (rmac_resnet.py:24-31,61-66)
+    xs = synth.make_images(2, 128, 128, seed=5)
+    out = {}
+    for tag, kw in [("max", dict(pooling="max")), ("avg", dict(pooling="avg")),
+                    ("normfeat", dict(norm_features=True)), ("nofc", dict(without_fc=True)),
+                    ("gemp2", dict(gemp=2))]:
+        out["desc_" + tag] = ref_model("resnet50_rmac", seed=3, **kw)(xs).numpy()
+    save("extract_r50_options.npz", arch="resnet50_rmac", seed=3, img_seed=5, img_shape=np.array([2, 128, 128]), **out)
+
+    net = ref_model("resnet101_rmac", seed=1)
+    x = synth.make_images(2, 224, 224, seed=77)
+    save("extract_r101.npz", arch="resnet101_rmac", seed=1, img_seed=77, img_shape=np.array([2, 224, 224]),
+         desc=net(x).numpy())
+
+
+@torch.no_grad()
+def gold_gem():
+    r = np.random.RandomState(3)
+    x = torch.from_numpy(r.standard_normal((2, 8, 5, 7)).astype(np.float32))
+    out = {"x": x.numpy()}
+    for p in (3.0, 2.5, 1.0):
+        out["p%g" % p] = GeneralizedMeanPooling(p)(x).numpy().reshape(2, 8)
+    save("gem.npz", **out)
+
+
+def gold_pool():
+    r = np.random.RandomState(4)
+    xs = [torch.from_numpy(r.standard_normal((5, 16)).astype(np.float32)) for _ in range(3)]
+    save("pool.npz", x0=xs[0].numpy(), x1=xs[1].numpy(), x2=xs[2].numpy(),
+         mean=common.pool(xs, "mean").numpy(), gem3=common.pool(xs, "gem", 3).numpy(),
+         gem2=common.pool(xs[:2], "gem", 2).numpy(), single=common.pool(xs[:1], "gem", 3).numpy())
+
+
+def gold_whiten():
+    out = {}
+    for tag, dt in (("f32", np.float32), ("f64", np.float64)):
+        pca = synth.make_pca(64, seed=11, dtype=dt)
+        X = synth._unit_rows(np.random.RandomState(12).standard_normal((10, 64))).astype(np.float32)
+        out["X"] = X
+        out["mean_" + tag], out["comp_" + tag], out["var_" + tag] = pca.mean_, pca.components_, pca.explained_variance_
+        out["w_p025_" + tag] = common.whiten_features(X, pca, whitenp=0.25)
+        out["w_p05_v32_m2_" + tag] = common.whiten_features(X, pca, whitenp=0.5, whitenv=32, whitenm=2.0)
+        out["w_nol2_" + tag] = common.whiten_features(X, pca, l2norm=False, whitenp=0.25)
+    save("whiten.npz", **out)
+
+
+def gold_rank_ap():
+    db, q, pos = synth.make_descriptor_db(400, 6, dim=32, n_pos=5, db_seed=21, q_seed=22)
+    scores = common.matmul(q, db)
+    gnd = synth.oxford_gt(pos, n_junk=3, n_db=400, seed=5)
+    tmp = tempfile.mkdtemp()
+    imlist = ["im%04d" % i for i in range(400)]
+    with open(os.path.join(tmp, "gnd.pkl"), "wb") as f:
+        pickle.dump({"imlist": imlist, "qimlist": imlist[:6], "gnd": gnd}, f)
+    ds = ImageListRelevants(os.path.join(tmp, "gnd.pkl"), root=tmp)
+    aps = np.array([ds.eval_query_AP(i, scores[i]) for i in range(6)])
+    order = np.stack([np.argsort(scores[i])[::-1] for i in range(6)])
+    # revisited (easy/hard) protocol, generic.py:210-224
+    gnd2 = [{"bbx": g["bbx"], "easy": g["ok"][:2], "hard": g["ok"][2:], "junk": g["junk"]} for g in gnd]
+    with open(os.path.join(tmp, "gnd2.pkl"), "wb") as f:
+        pickle.dump({"imlist": imlist, "qimlist": imlist[:6], "gnd": gnd2}, f)
+    ds2 = ImageListRelevants(os.path.join(tmp, "gnd2.pkl"), root=tmp)
+    aps2 = [ds2.eval_query_AP(i, scores[i]) for i in range(6)]
+    save("rank_ap.npz", n_db=400, n_q=6, dim=32, n_pos=5, db_seed=21, q_seed=22, n_junk=3, gt_seed=5,
+         scores=scores, order=order, aps=aps,
+         aps_easy=np.array([a["easy"] for a in aps2]), aps_medium=np.array([a["medium"] for a in aps2]),
+         aps_hard=np.array([a["hard"] for a in aps2]))
+
+
+def gold_aqe():
+    db, q, pos = synth.make_descriptor_db(300, 5, dim=48, n_pos=4, db_seed=31, q_seed=32)
+    out = {"n_db": 300, "n_q": 5, "dim": 48, "n_pos": 4, "db_seed": 31, "q_seed": 32}
+    out["aqe_k2_a05"] = ref_test_dir.expand_descriptors(q, db=db, k=2, alpha=0.5)
+    out["aqe_k3_a1"] = ref_test_dir.expand_descriptors(q, db=db, k=3, alpha=1)
+    out["aqe_k0"] = ref_test_dir.expand_descriptors(q, db=db, k=0, alpha=1)
+    small = db[:40].copy()
+    small[1] = synth._unit_rows((small[0] + 0.3 * small[1])[None])[0]   # make sure each row has a positive neighbour
+    sim = small @ small.T
+    np.fill_diagonal(sim, 0)
+    if (np.sort(sim, axis=1)[:, -2:] > 0).all():
+        out["dba_in"] = small
+        out["dba_k2_a1"] = ref_test_dir.expand_descriptors(small, db=None, k=2, alpha=1)
+    save("aqe.npz", **out)
+
+
+if __name__ == "__main__":
+    gold_gem()
+    gold_pool()
+    gold_whiten()
+    gold_rank_ap()
+    gold_aqe()
+    gold_extract()

@@ -1,0 +1,115 @@
+"""Pin the CPU oracle (oracle/dir_oracle.py) against the golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+import dirb200.synth as synth
+from oracle import dir_oracle as O
+from conftest import rel_l2
+
+
+def test_gem(golden):
+    g = golden("gem.npz")
+    x = torch.from_numpy(g["x"])
+    for p in (3.0, 2.5, 1.0):
+        np.testing.assert_allclose(O.gem(x, p).numpy(), g["p%g" % p], rtol=1e-6, atol=1e-7)
+
+
+def test_pool(golden):
+    g = golden("pool.npz")
+    xs = [g["x0"], g["x1"], g["x2"]]
+    np.testing.assert_allclose(O.pool_scales(xs, "mean"), g["mean"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(O.pool_scales(xs, "gem", 3), g["gem3"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(O.pool_scales(xs[:2], "gem", 2), g["gem2"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_array_equal(O.pool_scales(xs[:1], "gem", 3), g["single"])
+
+
+def test_whiten(golden):
+    g = golden("whiten.npz")
+    from types import SimpleNamespace
+    for tag, tol in (("f32", 2e-6), ("f64", 1e-12)):
+        pca = SimpleNamespace(mean_=g["mean_" + tag], components_=g["comp_" + tag],
+                              explained_variance_=g["var_" + tag], whiten=True)
+        # the generator is deterministic: same arrays as synth.make_pca
+        ref = synth.make_pca(64, seed=11, dtype=pca.mean_.dtype)
+        np.testing.assert_array_equal(ref.components_, pca.components_)
+        assert rel_l2(O.whiten_features(g["X"], pca, whitenp=0.25), g["w_p025_" + tag]) < tol
+        assert rel_l2(O.whiten_features(g["X"], pca, whitenp=0.5, whitenv=32, whitenm=2.0), g["w_p05_v32_m2_" + tag]) < tol
+        assert rel_l2(O.whiten_features(g["X"], pca, l2norm=False, whitenp=0.25), g["w_nol2_" + tag]) < tol
+
+
+def test_rank_and_ap(golden):
+    g = golden("rank_ap.npz")
+    db, q, pos = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                          db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    gnd = synth.oxford_gt(pos, n_junk=int(g["n_junk"]), n_db=int(g["n_db"]), seed=int(g["gt_seed"]))
+    sc = O.scores_exact(q, db)
+    np.testing.assert_allclose(sc, g["scores"], rtol=0, atol=2e-6)       # reference is fp32 np.dot
+    for i in range(sc.shape[0]):
+        order = O.rank_desc(sc[i])
+        ref = g["order"][i]
+        # identical wherever adjacent reference scores are separated by more than fp32 noise
+        gaps = np.abs(np.diff(g["scores"][i][ref]))
+        assert (order == ref)[:-1][gaps > 1e-5].all() and (order == ref)[1:][gaps > 1e-5].all()
+        assert (order[:50] == ref[:50]).all()
+        ap = O.eval_query_ap(sc[i], gnd[i]["ok"], gnd[i]["junk"])
+        assert abs(ap - g["aps"][i]) < 1e-12
+        # revisited protocol (generic.py:150-170,210-224): easy=ok[:2], hard=ok[2:]
+        ok, junk = gnd[i]["ok"], gnd[i]["junk"]
+        assert abs(O.eval_query_ap(sc[i], ok[:2], junk + ok[2:]) - g["aps_easy"][i]) < 1e-12
+        assert abs(O.eval_query_ap(sc[i], ok, junk) - g["aps_medium"][i]) < 1e-12
+        assert abs(O.eval_query_ap(sc[i], ok[2:], junk + ok[:2]) - g["aps_hard"][i]) < 1e-12
+    # top-k agrees with the full ranking
+    s, idx = O.topk(q, db, 20)
+    np.testing.assert_array_equal(idx, g["order"][:, :20])
+
+
+def test_aqe(golden):
+    g = golden("aqe.npz")
+    db, q, pos = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                          db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    assert rel_l2(O.expand_descriptors(q, db=db, k=2, alpha=0.5), g["aqe_k2_a05"]) < 1e-6
+    assert rel_l2(O.expand_descriptors(q, db=db, k=3, alpha=1), g["aqe_k3_a1"]) < 1e-6
+    np.testing.assert_array_equal(O.expand_descriptors(q, db=db, k=0, alpha=1), g["aqe_k0"])
+    if "dba_in" in g.files:
+        assert rel_l2(O.expand_descriptors(g["dba_in"], db=None, k=2, alpha=1), g["dba_k2_a1"]) < 1e-6
+
+
+def _check_extract(g, arch, tol=2e-5):
+    sd = synth.make_state_dict(arch, seed=int(g["seed"]))
+    b, h, w = [int(v) for v in g["img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["img_seed"]))
+    d = O.extract(x, sd, arch).numpy()
+    assert d.shape == g["desc"].shape
+    assert rel_l2(d, g["desc"]) < tol
+    return sd, x
+
+
+def test_extract_r50(golden):
+    g = golden("extract_r50.npz")
+    sd, x = _check_extract(g, "resnet50_rmac")
+    d1 = O.extract(x[:1], sd, "resnet50_rmac").numpy()
+    assert d1.shape == (2048,) and rel_l2(d1, g["desc_b1"]) < 2e-5     # squeeze_ at B=1, rmac_resnet.py:64
+    b, h, w = [int(v) for v in g["img_shape_rect"]]
+    xr = synth.make_images(b, h, w, seed=int(g["img_seed_rect"]))
+    assert rel_l2(O.extract(xr, sd, "resnet50_rmac").numpy(), g["desc_rect"]) < 2e-5
+    _, stages = O.trunk(x, sd, "resnet50", return_stages=True)
+    for name, key in (("stem", "maxpool"), ("layer1", "layer1"), ("layer2", "layer2"), ("layer3", "layer3"), ("layer4", "layer4")):
+        v = stages[name]
+        sl = v[0, :, v.shape[2] // 2, v.shape[3] // 3].numpy()
+        assert rel_l2(sl, g["slice_" + key]) < 2e-5
+
+
+def test_extract_r50_options(golden):
+    g = golden("extract_r50_options.npz")
+    b, h, w = [int(v) for v in g["img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["img_seed"]))
+    for tag, kw, gemp in [("max", dict(pooling="max"), 3), ("avg", dict(pooling="avg"), 3),
+                          ("normfeat", dict(norm_features=True), 3), ("nofc", dict(without_fc=True), 3),
+                          ("gemp2", dict(), 2)]:
+        sd = synth.make_state_dict("resnet50_rmac", seed=int(g["seed"]), gemp=gemp)
+        assert rel_l2(O.extract(x, sd, "resnet50_rmac", **kw).numpy(), g["desc_" + tag]) < 2e-5, tag
+
+
+def test_extract_r101(golden):
+    _check_extract(golden("extract_r101.npz"), "resnet101_rmac")
