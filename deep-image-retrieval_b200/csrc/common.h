@@ -1,0 +1,51 @@
+// Host-side plumbing shared by all translation units: error reporting, status codes, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dirb200.h"
+
+namespace dirb {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define DIRB_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      ::dirb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return static_cast<int>(_e);                                                              \
+    }                                                                                           \
+  } while (0)
+
+#define DIRB_REQUIRE(cond, code, ...)   \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::dirb::set_error(__VA_ARGS__);   \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+#define DIRB_TRY(expr)         \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != 0) return _s;    \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// fp16 row-major [outer][inner] matrix, box = box_inner x box_outer elements, 128-byte swizzle.
+int encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                   uint32_t box_inner, uint32_t box_outer);
+// fp16 NHWC activation viewed as (C, W, H, B); box (64, tw*es, th*es, nb) traversed with element stride es
+// on W and H (es = conv stride), 128-byte swizzle, out-of-bounds elements read as zero.
+int encode_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tw, int th, int nb, int es);
+
+// Launch counter (the "gpu_launches" the benchmark reports): every kernel launch of this library bumps it.
+void count_launch(int n = 1);
+int64_t launches_total();
+
+}  // namespace dirb

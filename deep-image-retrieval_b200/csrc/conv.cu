@@ -1,0 +1,255 @@
+// Convolution + folded BatchNorm (+ residual) (+ ReLU) on NHWC fp16 activations.
+//   impl 0: tcgen05 implicit GEMM (gemm_tc.cuh) - every Bottleneck conv (Cin % 64 == 0)
+//   impl 1: mma.sync implicit GEMM            - the 7x7 stem (Cin padded 3 -> 8) and the validation path
+// Reference semantics: dirtorch/nets/backbones/resnet.py:56-63 (convs, bias=False), :70-85 (BN, ReLU, residual add),
+// :115-118 (stem).  BatchNorm (eval) is folded by the caller into scale = gamma/sqrt(var+eps), shift = beta-mean*scale.
+#include "conv.h"
+
+#include "gemm_tc.cuh"
+
+namespace dirb {
+
+// ------------------------------------------------------------------------------------------------ tcgen05 path
+// Pick the (tw,th,nb) output patch (tw*th*nb == 128) that minimises the number of tiles (= wasted MMA rows),
+// preferring square-ish patches (halo reuse in L2) on ties.
+static void pick_patch(int B, int Ho, int Wo, int* tw, int* th, int* nb) {
+  int64_t best = -1;
+  int bt = 16, bh = 8, bb = 1, bscore = 1 << 30;
+  for (int w = 1; w <= 128; w *= 2)
+    for (int h = 1; w * h <= 128; h *= 2) {
+      const int b = 128 / (w * h);
+      if (w > 64 || h > 64) continue;  // keeps the TMA box (w*stride, h*stride) <= 256 for stride 2
+      const int64_t tiles = ceil_div(Wo, w) * ceil_div(Ho, h) * ceil_div(B, b);
+      const int shape_penalty = (w > h ? w / h : h / w) + (b > 1 ? 1 : 0) + (w < 8 ? 4 : 0);
+      if (best < 0 || tiles < best || (tiles == best && shape_penalty < bscore)) {
+        best = tiles;
+        bscore = shape_penalty;
+        bt = w;
+        bh = h;
+        bb = b;
+      }
+    }
+  *tw = bt;
+  *th = bh;
+  *nb = bb;
+}
+
+template <int BN>
+static int conv_tc_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+                      const __half* res, int relu, __half* out, cudaStream_t stream) {
+  const int Ho = s.Ho(), Wo = s.Wo();
+  const int Ktot = s.KH * s.KW * s.Cin;
+  GemmTcParams p{};
+  p.taps = s.KH * s.KW;
+  p.kw_taps = s.KW;
+  p.cin_blocks = s.Cin / 64;
+  p.stride = s.stride;
+  p.pad = s.pad;
+  p.B = s.B;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.N = s.Cout;
+  p.n_tiles = s.Cout / BN;
+  p.scale = scale;
+  p.shift = shift;
+  p.res = res;
+  p.out = out;
+  p.relu = relu;
+  CUtensorMap tmA, tmB;
+  int64_t m_tiles;
+  const bool flat = (s.KH == 1 && s.KW == 1 && s.stride == 1 && s.pad == 0);
+  if (flat) {
+    p.a_spatial = 0;
+    p.M = s.B * s.H * s.W;
+    p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
+    m_tiles = ceil_div(p.M, 128);
+    DIRB_TRY(encode_tmap_2d(&tmA, in, s.Cin, p.M, (uint64_t)s.Cin * 2, 64, 128));
+  } else {
+    p.a_spatial = 1;
+    pick_patch(s.B, Ho, Wo, &p.tw, &p.th, &p.nb);
+    p.tiles_w = (int)ceil_div(Wo, p.tw);
+    p.tiles_h = (int)ceil_div(Ho, p.th);
+    p.M = s.B * Ho * Wo;
+    m_tiles = (int64_t)p.tiles_w * p.tiles_h * ceil_div(s.B, p.nb);
+    DIRB_TRY(encode_tmap_nhwc(&tmA, in, s.B, s.H, s.W, s.Cin, p.tw, p.th, p.nb, s.stride));
+  }
+  DIRB_TRY(encode_tmap_2d(&tmB, w, Ktot, s.Cout, (uint64_t)Ktot * 2, 64, BN));
+  // 3 ring slots of (16 + BN/8) KB -> two CTAs per SM: one CTA's epilogue overlaps the other's main loop.
+  return gemm_tc_launch<BN, 3, EPI_CONV, 2>(tmA, tmB, p, m_tiles, stream);
+}
+
+int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+            const __half* res, int relu, __half* out, cudaStream_t stream) {
+  DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
+               "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
+  DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
+  if (s.Cout % 128 == 0) return conv_tc_bn<128>(s, in, w, scale, shift, res, relu, out, stream);
+  return conv_tc_bn<64>(s, in, w, scale, shift, res, relu, out, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ mma.sync path
+// CTA tile 128 pixels x 64 channels, K chunks of 32, 3-stage cp.async ring, 8 warps (4 x 2), warp tile 32 x 32.
+namespace {
+
+constexpr int MM_BM = 128, MM_BN = 64, MM_BK = 32, MM_LD = 40 /* padded row, halfs */, MM_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool pred) {
+  const uint32_t d = smem_u32(dst);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+struct MmaConvParams {
+  const __half* in;
+  const __half* w;      // [Cout][Kpad]
+  const float* scale;
+  const float* shift;
+  const __half* res;
+  __half* out;
+  int B, H, W, Cin, Cout, KH, KW, stride, pad, Ho, Wo;
+  int Ktot, Kpad, M, relu;
+};
+
+__global__ void __launch_bounds__(256) conv_mma_kernel(const MmaConvParams p) {
+  __shared__ __align__(16) __half sA[MM_STAGES][MM_BM][MM_LD];
+  __shared__ __align__(16) __half sB[MM_STAGES][MM_BN][MM_LD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;          // 4 x 2 warps
+  const int m0 = blockIdx.x * MM_BM, n0 = blockIdx.y * MM_BN;
+  const int kchunks = p.Kpad / MM_BK;
+
+  // A gather bookkeeping: this thread loads vector `av` (8 halfs) of rows ar0 and ar0+64.
+  const int av = tid & 3, ar0 = tid >> 2;
+  int a_n[2], a_h[2], a_w[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int m = m0 + ar0 + 64 * j;
+    a_ok[j] = m < p.M;
+    const int mm = a_ok[j] ? m : 0;
+    a_w[j] = (mm % p.Wo) * p.stride - p.pad;
+    a_h[j] = ((mm / p.Wo) % p.Ho) * p.stride - p.pad;
+    a_n[j] = mm / (p.Wo * p.Ho);
+  }
+  const int bv = tid & 3, br = tid >> 2;  // B: one vector of row br
+
+  auto load_stage = [&](int kc, int st) {
+    const int k = kc * MM_BK + av * 8;
+    const int tap = k / p.Cin, c = k - tap * p.Cin;
+    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int hi = a_h[j] + kh, wi = a_w[j] + kw;
+      const bool ok = a_ok[j] && k < p.Ktot && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+      const __half* src = ok ? p.in + ((static_cast<int64_t>(a_n[j]) * p.H + hi) * p.W + wi) * p.Cin + c : p.in;
+      cp_async16(&sA[st][ar0 + 64 * j][av * 8], src, ok);
+    }
+    cp_async16(&sB[st][br][bv * 8], p.w + static_cast<int64_t>(n0 + br) * p.Kpad + kc * MM_BK + bv * 8, true);
+  };
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < MM_STAGES - 1; ++s) {
+    if (s < kchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kc = 0; kc < kchunks; ++kc) {
+    cp_async_wait<MM_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kc + MM_STAGES - 1;
+      if (nk < kchunks) load_stage(nk, nk % MM_STAGES);
+      cp_async_commit();
+    }
+    const int st = kc % MM_STAGES;
+#pragma unroll
+    for (int ks = 0; ks < MM_BK; ks += 16) {
+      uint32_t af[2][4], bf[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        ldmatrix_x4(af[i], &sA[st][wm * 32 + i * 16 + (lane & 15)][ks + (lane >> 4) * 8]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        ldmatrix_x4(bf[j], &sB[st][wn * 32 + j * 16 + ((lane >> 4) << 3) + (lane & 7)][ks + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma16816(acc[i][j], af[i], &bf[j >> 1][(j & 1) * 2]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> (row g+8)
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int m = m0 + wm * 32 + i * 16 + g + hrow * 8;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = n0 + wn * 32 + j * 8 + t * 2;
+        float v0 = fmaf(acc[i][j][hrow * 2 + 0], p.scale[c], p.shift[c]);
+        float v1 = fmaf(acc[i][j][hrow * 2 + 1], p.scale[c + 1], p.shift[c + 1]);
+        const int64_t off = static_cast<int64_t>(m) * p.Cout + c;
+        if (p.res != nullptr) {
+          const float2 r = __half22float2(*reinterpret_cast<const __half2*>(p.res + off));
+          v0 += r.x;
+          v1 += r.y;
+        }
+        if (p.relu) {
+          v0 = fmaxf(v0, 0.f);
+          v1 = fmaxf(v1, 0.f);
+        }
+        *reinterpret_cast<__half2*>(p.out + off) = __floats2half2_rn(v0, v1);
+      }
+    }
+}
+
+}  // namespace
+
+int conv_mma(const ConvShape& s, const __half* in, const __half* w, int Kpad, const float* scale, const float* shift,
+             const __half* res, int relu, __half* out, cudaStream_t stream) {
+  DIRB_REQUIRE(s.Cin % 8 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
+               "mma.sync conv needs Cin %% 8 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
+  MmaConvParams p{};
+  p.in = in; p.w = w; p.scale = scale; p.shift = shift; p.res = res; p.out = out;
+  p.B = s.B; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.KH = s.KH; p.KW = s.KW;
+  p.stride = s.stride; p.pad = s.pad; p.Ho = s.Ho(); p.Wo = s.Wo();
+  p.Ktot = s.KH * s.KW * s.Cin;
+  p.Kpad = Kpad;
+  DIRB_REQUIRE(Kpad % MM_BK == 0 && Kpad >= p.Ktot, DIRB200_EINVAL, "bad Kpad %d for K %d", Kpad, p.Ktot);
+  p.M = s.B * p.Ho * p.Wo;
+  p.relu = relu;
+  dim3 grid((unsigned)ceil_div(p.M, MM_BM), (unsigned)(s.Cout / MM_BN));
+  conv_mma_kernel<<<grid, 256, 0, stream>>>(p);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dirb

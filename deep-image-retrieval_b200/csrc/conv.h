@@ -1,0 +1,36 @@
+// Internal C++ interface of the convolution kernels (conv.cu) and the small fused operators (ops.cu).
+#pragma once
+#include "common.h"
+
+namespace dirb {
+
+struct ConvShape {
+  int B, H, W, Cin, Cout, KH, KW, stride, pad;
+  int Ho() const { return (H + 2 * pad - KH) / stride + 1; }
+  int Wo() const { return (W + 2 * pad - KW) / stride + 1; }
+  double flops() const { return 2.0 * B * Ho() * Wo() * (double)Cout * KH * KW * Cin; }
+};
+
+// w: [Cout][KH*KW*Cin] fp16 (K index = (kh*KW + kw)*Cin + c).
+int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+            const __half* res, int relu, __half* out, cudaStream_t stream);
+// w: [Cout][Kpad] fp16, Kpad = KH*KW*Cin rounded up to 32, zero padded.
+int conv_mma(const ConvShape& s, const __half* in, const __half* w, int Kpad, const float* scale, const float* shift,
+             const __half* res, int relu, __half* out, cudaStream_t stream);
+
+int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_t stream);
+int maxpool_3x3s2(const __half* in, int B, int H, int W, int C, __half* out, cudaStream_t stream);
+
+size_t head_workspace_floats(int B, int HW, int C, int out_dim);
+int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features,
+                    const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
+                    cudaStream_t stream);
+
+int pool_scales(const float* xs, int S, int64_t N, int D, int mode, float gemp, int l2, float* out,
+                cudaStream_t stream);
+int l2_normalize(const float* x, int64_t N, int D, float eps, float* out, __half* out16, cudaStream_t stream);
+int f32_to_f16(const float* x, int64_t n, __half* out, cudaStream_t stream);
+int whiten(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale, int Dout,
+           int l2norm, float* y, __half* y16, cudaStream_t stream);
+
+}  // namespace dirb

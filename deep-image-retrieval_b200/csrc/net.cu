@@ -1,0 +1,398 @@
+// ResNet-50/101 + GeM + FC + L2 descriptor network on one GPU: weight packing and the launch schedule.
+//
+// Reference: dirtorch/nets/backbones/resnet.py:46-87 (Bottleneck), :102-168 (ResNet.__init__/forward),
+//            dirtorch/nets/rmac_resnet.py:12-69 (head), dirtorch/nets/layers/pooling.py:38-54 (GeM).
+// Data layout in HBM: activations NHWC fp16; conv weights [Cout][KH][KW][Cin] fp16 (K-major rows, the B operand
+// of the implicit GEMM); BatchNorm folded to per-channel fp32 (scale, shift) applied in the conv epilogue together
+// with the residual add and ReLU; head weights fp32.  A batch is processed in chunks of `chunk` images so that
+// the activations of consecutive layers stay L2-resident.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv.h"
+
+using namespace dirb;
+
+namespace {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+struct ConvLayer {
+  std::string conv, bn;          // state-dict prefixes
+  int Cin, Cout, K, stride, pad;
+  int CinPad, Kpad;              // packed layout
+  __half* w = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+
+struct Block {
+  ConvLayer c1, c2, c3, down;
+  bool has_down = false;
+};
+
+}  // namespace
+
+struct dirb200_net {
+  int device = 0;
+  std::string arch;
+  std::vector<int> nblocks;
+  // options
+  int pooling = 0, norm_features = 0, without_fc = 0, out_dim = 2048, chunk = 0, conv_impl = 0;
+  float gem_p = 3.0f, gem_eps = 1e-6f;
+  // host state dict
+  std::map<std::string, HostTensor> sd;
+  bool finalized = false;
+  // device weights
+  ConvLayer stem;
+  std::vector<Block> blocks;      // flattened over layer1..4
+  std::vector<int> layer_end;     // index (exclusive) of the last block of each layer
+  float* fc_w = nullptr;
+  float* fc_b = nullptr;
+  std::vector<void*> owned;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // staging for forward_host
+  float* h2d = nullptr;
+  size_t h2d_bytes = 0;
+  float* d_desc = nullptr;
+  size_t d_desc_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  // debug taps of the last chunk
+  struct Tap { const __half* ptr; int n, h, w, c; };
+  std::map<std::string, Tap> taps;
+  int64_t last_launches = 0;
+  double last_flops = 0;
+};
+
+static int dev_alloc(dirb200_net* n, void** p, size_t bytes) {
+  DIRB_CUDA(cudaMalloc(p, bytes));
+  n->owned.push_back(*p);
+  return 0;
+}
+
+static int get_tensor(dirb200_net* n, const std::string& name, const HostTensor** out, size_t expect) {
+  auto it = n->sd.find(name);
+  DIRB_REQUIRE(it != n->sd.end(), DIRB200_EKEY, "missing state-dict tensor '%s'", name.c_str());
+  DIRB_REQUIRE(it->second.data.size() == expect, DIRB200_EINVAL, "tensor '%s' has %zu elements, expected %zu",
+               name.c_str(), it->second.data.size(), expect);
+  *out = &it->second;
+  return 0;
+}
+
+// OIHW fp32 -> [Cout][KH][KW][CinPad] fp16 rows padded to Kpad; BN -> (scale, shift).
+static int pack_conv(dirb200_net* n, ConvLayer& L) {
+  const HostTensor *w, *g, *b, *m, *v;
+  const size_t kk = static_cast<size_t>(L.K) * L.K;
+  DIRB_TRY(get_tensor(n, L.conv + ".weight", &w, static_cast<size_t>(L.Cout) * L.Cin * kk));
+  DIRB_TRY(get_tensor(n, L.bn + ".weight", &g, L.Cout));
+  DIRB_TRY(get_tensor(n, L.bn + ".bias", &b, L.Cout));
+  DIRB_TRY(get_tensor(n, L.bn + ".running_mean", &m, L.Cout));
+  DIRB_TRY(get_tensor(n, L.bn + ".running_var", &v, L.Cout));
+  L.CinPad = (L.Cin % 8 == 0) ? L.Cin : ((L.Cin + 7) / 8 * 8);
+  const int Ktot = L.K * L.K * L.CinPad;
+  L.Kpad = (Ktot + 31) / 32 * 32;
+  std::vector<__half> hw(static_cast<size_t>(L.Cout) * L.Kpad, __float2half(0.f));
+  for (int o = 0; o < L.Cout; ++o)
+    for (int c = 0; c < L.Cin; ++c)
+      for (int kh = 0; kh < L.K; ++kh)
+        for (int kw = 0; kw < L.K; ++kw)
+          hw[static_cast<size_t>(o) * L.Kpad + (static_cast<size_t>(kh) * L.K + kw) * L.CinPad + c] =
+              __float2half_rn(w->data[((static_cast<size_t>(o) * L.Cin + c) * L.K + kh) * L.K + kw]);
+  std::vector<float> sc(L.Cout), sh(L.Cout);
+  for (int o = 0; o < L.Cout; ++o) {
+    // BatchNorm2d eval: y = (x - mean) / sqrt(var + 1e-5) * gamma + beta   (eps: torch default, resnet.py:57)
+    const float s = g->data[o] / sqrtf(v->data[o] + 1e-5f);
+    sc[o] = s;
+    sh[o] = b->data[o] - m->data[o] * s;
+  }
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&L.w), hw.size() * sizeof(__half)));
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&L.scale), L.Cout * sizeof(float)));
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&L.shift), L.Cout * sizeof(float)));
+  DIRB_CUDA(cudaMemcpy(L.w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  DIRB_CUDA(cudaMemcpy(L.scale, sc.data(), L.Cout * sizeof(float), cudaMemcpyHostToDevice));
+  DIRB_CUDA(cudaMemcpy(L.shift, sh.data(), L.Cout * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static ConvLayer make_layer(const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride,
+                            int pad) {
+  ConvLayer L;
+  L.conv = conv; L.bn = bn; L.Cin = cin; L.Cout = cout; L.K = k; L.stride = stride; L.pad = pad;
+  L.CinPad = cin; L.Kpad = 0;
+  return L;
+}
+
+static int run_conv(dirb200_net* n, const ConvLayer& L, const __half* in, int B, int H, int W, const __half* res,
+                    int relu, __half* out, cudaStream_t stream, int force_mma = 0) {
+  ConvShape s{B, H, W, L.CinPad, L.Cout, L.K, L.K, L.stride, L.pad};
+  n->last_flops += 2.0 * B * s.Ho() * s.Wo() * static_cast<double>(L.Cout) * L.K * L.K * L.Cin;
+  if (force_mma || n->conv_impl == 1 || L.CinPad % 64 != 0)
+    return conv_mma(s, in, L.w, L.Kpad, L.scale, L.shift, res, relu, out, stream);
+  return conv_tc(s, in, L.w, L.scale, L.shift, res, relu, out, stream);
+}
+
+extern "C" {
+
+int dirb200_net_create(const char* arch, int device, dirb200_net** out) {
+  DIRB_REQUIRE(arch && out, DIRB200_EINVAL, "null argument");
+  DIRB_TRY(dirb200_device_check(device));
+  auto* n = new dirb200_net();
+  n->device = device;
+  n->arch = arch;
+  if (n->arch == "resnet50_rmac") n->nblocks = {3, 4, 6, 3};          // rmac_resnet.py:80
+  else if (n->arch == "resnet101_rmac") n->nblocks = {3, 4, 23, 3};   // rmac_resnet.py:84
+  else {
+    delete n;
+    DIRB_REQUIRE(false, DIRB200_ENOTSUP, "unknown model architecture '%s' (supported: resnet50_rmac, resnet101_rmac)", arch);
+  }
+  *out = n;
+  return 0;
+}
+
+int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
+  DIRB_REQUIRE(n && key, DIRB200_EINVAL, "null argument");
+  const std::string k(key);
+  if (k == "pooling") n->pooling = static_cast<int>(value);
+  else if (k == "norm_features") n->norm_features = value != 0;
+  else if (k == "without_fc") n->without_fc = value != 0;
+  else if (k == "out_dim") n->out_dim = static_cast<int>(value);
+  else if (k == "chunk") n->chunk = static_cast<int>(value);
+  else if (k == "conv_impl") n->conv_impl = static_cast<int>(value);
+  else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
+  else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown net option '%s'", key);
+  return 0;
+}
+
+int dirb200_net_set_tensor(dirb200_net* n, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+  DIRB_REQUIRE(n && name && (host_data || ndim == 0) && ndim >= 0 && ndim <= 4, DIRB200_EINVAL, "bad tensor argument");
+  DIRB_REQUIRE(!n->finalized, DIRB200_ESTATE, "network already finalized");
+  std::string key(name);
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DataParallel prefix, common.py:128-133
+  const char* nbt = "num_batches_tracked";
+  if (key.size() >= strlen(nbt) && key.compare(key.size() - strlen(nbt), strlen(nbt), nbt) == 0) return 0;
+  HostTensor t;
+  size_t numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    numel *= static_cast<size_t>(shape[i]);
+  }
+  t.data.assign(host_data, host_data + numel);
+  n->sd[key] = std::move(t);
+  return 0;
+}
+
+int dirb200_net_finalize(dirb200_net* n) {
+  DIRB_REQUIRE(n, DIRB200_EINVAL, "null");
+  DIRB_REQUIRE(!n->finalized, DIRB200_ESTATE, "network already finalized");
+  DIRB_CUDA(cudaSetDevice(n->device));
+  n->stem = make_layer("conv1", "bn1", 3, 64, 7, 2, 3);          // resnet.py:115-117
+  DIRB_TRY(pack_conv(n, n->stem));
+  int inplanes = 64;
+  const int planes_per_layer[4] = {64, 128, 256, 512};           // resnet.py:120-123
+  for (int li = 0; li < 4; ++li) {
+    const int planes = planes_per_layer[li];
+    for (int b = 0; b < n->nblocks[li]; ++b) {
+      const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
+      const int stride = (li > 0 && b == 0) ? 2 : 1;
+      Block blk;
+      blk.c1 = make_layer(p + "conv1", p + "bn1", inplanes, planes, 1, 1, 0);
+      blk.c2 = make_layer(p + "conv2", p + "bn2", planes, planes, 3, stride, 1);     // stride on conv2, resnet.py:58
+      blk.c3 = make_layer(p + "conv3", p + "bn3", planes, planes * 4, 1, 1, 0);
+      blk.has_down = (b == 0);                                                     // resnet.py:136-141
+      DIRB_TRY(pack_conv(n, blk.c1));
+      DIRB_TRY(pack_conv(n, blk.c2));
+      DIRB_TRY(pack_conv(n, blk.c3));
+      if (blk.has_down) {
+        blk.down = make_layer(p + "downsample.0", p + "downsample.1", inplanes, planes * 4, 1, stride, 0);
+        DIRB_TRY(pack_conv(n, blk.down));
+      }
+      n->blocks.push_back(blk);
+      inplanes = planes * 4;
+    }
+    n->layer_end.push_back(static_cast<int>(n->blocks.size()));
+  }
+  if (n->pooling == 0) {
+    const HostTensor* p;
+    DIRB_TRY(get_tensor(n, "adpool.p", &p, 1));                  // pooling.py:54
+    n->gem_p = p->data[0];
+    DIRB_REQUIRE(n->gem_p > 0, DIRB200_EINVAL, "GeM p must be positive");
+  }
+  if (!n->without_fc) {
+    const HostTensor *w, *b;
+    DIRB_TRY(get_tensor(n, "fc.weight", &w, static_cast<size_t>(n->out_dim) * 2048));   // rmac_resnet.py:34
+    DIRB_TRY(get_tensor(n, "fc.bias", &b, n->out_dim));
+    DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&n->fc_w), w->data.size() * 4));
+    DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&n->fc_b), b->data.size() * 4));
+    DIRB_CUDA(cudaMemcpy(n->fc_w, w->data.data(), w->data.size() * 4, cudaMemcpyHostToDevice));
+    DIRB_CUDA(cudaMemcpy(n->fc_b, b->data.data(), b->data.size() * 4, cudaMemcpyHostToDevice));
+  }
+  n->sd.clear();
+  n->finalized = true;
+  return 0;
+}
+
+static int auto_chunk(int B, int H, int W) {
+  // keep (chunk x largest activation = layer1 output, 256 ch at H/4 x W/4 fp16) around 1/2 of the 126 MB L2,
+  // but give every launch at least ~2 waves of tiles.
+  const double per_img = 256.0 * (H / 4.0) * (W / 4.0) * 2.0;
+  int c = static_cast<int>(64e6 / per_img);
+  const double px_per_img = (H / 32.0) * (W / 32.0);  // layer4 pixels: the smallest GEMM M
+  const int min_for_fill = static_cast<int>(ceil(148.0 * 128.0 / (px_per_img * 4.0)));
+  if (c < min_for_fill) c = min_for_fill;
+  if (c < 1) c = 1;
+  if (c > B) c = B;
+  return c;
+}
+
+int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int W, float* desc_dev, void* desc16_dev,
+                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(n && imgs_dev && desc_dev, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(n->finalized, DIRB200_ESTATE, "dirb200_net_finalize has not been called");
+  DIRB_REQUIRE(B >= 1 && H >= 32 && W >= 32, DIRB200_ENOTSUP, "need B >= 1 and H, W >= 32 (got %d, %d, %d)", B, H, W);
+  DIRB_CUDA(cudaSetDevice(n->device));
+  const int64_t launches0 = launches_total();
+  n->last_flops = 0;
+  const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
+  const int D = n->without_fc ? 2048 : n->out_dim;
+
+  // ---- spatial sizes
+  const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;     // stem conv
+  const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1;   // maxpool
+  // ---- workspace: in8, stem, and five rotating activation buffers sized for the largest tensor of the trunk
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  const size_t o_in8 = carve(static_cast<size_t>(chunk) * H * W * 8 * 2);
+  const size_t o_stem = carve(static_cast<size_t>(chunk) * H1 * W1 * 64 * 2);
+  const size_t act_max = static_cast<size_t>(chunk) * H2 * W2 * 256 * 2;   // layer1 output is the largest
+  size_t o_act[5];
+  for (int i = 0; i < 5; ++i) o_act[i] = carve(act_max);
+  int Hf = H2, Wf = W2;
+  for (int li = 1; li < 4; ++li) { Hf = (Hf + 2 - 3) / 2 + 1; Wf = (Wf + 2 - 3) / 2 + 1; }
+  const size_t o_head = carve(head_workspace_floats(chunk, Hf * Wf, 2048, n->out_dim) * 4);
+  if (off > n->ws_bytes) {
+    if (n->ws) DIRB_CUDA(cudaFree(n->ws));
+    n->ws = nullptr;
+    DIRB_CUDA(cudaMalloc(&n->ws, off));
+    n->ws_bytes = off;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(n->ws);
+  __half* in8 = reinterpret_cast<__half*>(ws + o_in8);
+  __half* stem_out = reinterpret_cast<__half*>(ws + o_stem);
+  __half* act[5];
+  for (int i = 0; i < 5; ++i) act[i] = reinterpret_cast<__half*>(ws + o_act[i]);
+  float* head_ws = reinterpret_cast<float*>(ws + o_head);
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int cb = std::min(chunk, B - b0);
+    DIRB_TRY(nchw_to_nhwc8(imgs_dev + static_cast<size_t>(b0) * 3 * H * W, cb, H, W, in8, stream));
+    DIRB_TRY(run_conv(n, n->stem, in8, cb, H, W, nullptr, 1, stem_out, stream, /*force_mma=*/1));
+    __half* x = act[0];
+    DIRB_TRY(maxpool_3x3s2(stem_out, cb, H1, W1, 64, x, stream));
+    n->taps["stem"] = {x, cb, H2, W2, 64};
+    int h = H2, w = W2, cur = 0, layer = 0;
+    for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
+      const Block& blk = n->blocks[bi];
+      __half* t1 = act[(cur + 1) % 5];
+      __half* t2 = act[(cur + 2) % 5];
+      __half* rs = act[(cur + 3) % 5];
+      __half* y = act[(cur + 4) % 5];
+      const int s = blk.c2.stride;
+      const int ho = (h + 2 - 3) / s + 1, wo = (w + 2 - 3) / s + 1;
+      DIRB_TRY(run_conv(n, blk.c1, x, cb, h, w, nullptr, 1, t1, stream));
+      DIRB_TRY(run_conv(n, blk.c2, t1, cb, h, w, nullptr, 1, t2, stream));
+      const __half* res = x;
+      if (blk.has_down) {
+        DIRB_TRY(run_conv(n, blk.down, x, cb, h, w, nullptr, 0, rs, stream));
+        res = rs;
+      }
+      DIRB_TRY(run_conv(n, blk.c3, t2, cb, ho, wo, res, 1, y, stream));
+      x = y;
+      cur = (cur + 4) % 5;
+      h = ho;
+      w = wo;
+      if (static_cast<int>(bi) + 1 == n->layer_end[layer]) {
+        n->taps["layer" + std::to_string(layer + 1)] = {x, cb, h, w, blk.c3.Cout};
+        ++layer;
+      }
+    }
+    DIRB_TRY(head_pool_fc_l2(x, cb, h * w, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
+                             n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, head_ws,
+                             desc_dev + static_cast<size_t>(b0) * D,
+                             desc16_dev ? static_cast<__half*>(desc16_dev) + static_cast<size_t>(b0) * D : nullptr,
+                             stream));
+    if (!n->without_fc) n->last_flops += 2.0 * cb * 2048.0 * n->out_dim;
+  }
+  n->last_launches = launches_total() - launches0;
+  return 0;
+}
+
+int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int H, int W, float* desc_host) {
+  DIRB_REQUIRE(n && imgs_host && desc_host, DIRB200_EINVAL, "null argument");
+  DIRB_CUDA(cudaSetDevice(n->device));
+  if (!n->own_stream) DIRB_CUDA(cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking));
+  const size_t in_bytes = static_cast<size_t>(B) * 3 * H * W * 4;
+  const int D = n->without_fc ? 2048 : n->out_dim;
+  const size_t out_bytes = static_cast<size_t>(B) * D * 4;
+  if (in_bytes > n->h2d_bytes) {
+    if (n->h2d) DIRB_CUDA(cudaFree(n->h2d));
+    n->h2d = nullptr;
+    DIRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&n->h2d), in_bytes));
+    n->h2d_bytes = in_bytes;
+  }
+  if (out_bytes > n->d_desc_bytes) {
+    if (n->d_desc) DIRB_CUDA(cudaFree(n->d_desc));
+    n->d_desc = nullptr;
+    DIRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&n->d_desc), out_bytes));
+    n->d_desc_bytes = out_bytes;
+  }
+  DIRB_CUDA(cudaMemcpyAsync(n->h2d, imgs_host, in_bytes, cudaMemcpyHostToDevice, n->own_stream));
+  DIRB_TRY(dirb200_net_forward(n, n->h2d, B, H, W, n->d_desc, nullptr, n->own_stream));
+  DIRB_CUDA(cudaMemcpyAsync(desc_host, n->d_desc, out_bytes, cudaMemcpyDeviceToHost, n->own_stream));
+  DIRB_CUDA(cudaStreamSynchronize(n->own_stream));
+  return 0;
+}
+
+int dirb200_net_debug_stage(dirb200_net* n, const char* what, void* dst_dev, size_t capacity, int dims[4],
+                            void* stream_) {
+  DIRB_REQUIRE(n && what && dst_dev && dims, DIRB200_EINVAL, "null argument");
+  auto it = n->taps.find(what);
+  DIRB_REQUIRE(it != n->taps.end(), DIRB200_EKEY, "no stage '%s' recorded (run a forward first)", what);
+  const auto& t = it->second;
+  const size_t bytes = static_cast<size_t>(t.n) * t.h * t.w * t.c * 2;
+  DIRB_REQUIRE(bytes <= capacity, DIRB200_EINVAL, "stage '%s' needs %zu bytes", what, bytes);
+  dims[0] = t.n; dims[1] = t.h; dims[2] = t.w; dims[3] = t.c;
+  DIRB_CUDA(cudaMemcpyAsync(dst_dev, t.ptr, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream_)));
+  return 0;
+}
+
+int dirb200_net_last_launches(dirb200_net* n, int64_t* launches, double* flops) {
+  DIRB_REQUIRE(n, DIRB200_EINVAL, "null");
+  if (launches) *launches = n->last_launches;
+  if (flops) *flops = n->last_flops;
+  return 0;
+}
+
+int dirb200_net_destroy(dirb200_net* n) {
+  if (!n) return 0;
+  cudaSetDevice(n->device);
+  for (void* p : n->owned) cudaFree(p);
+  if (n->ws) cudaFree(n->ws);
+  if (n->h2d) cudaFree(n->h2d);
+  if (n->d_desc) cudaFree(n->d_desc);
+  if (n->own_stream) cudaStreamDestroy(n->own_stream);
+  delete n;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+// Small memory-bound operators around the convolution stack and the descriptor post-processing.
+// All of them are HBM-bound: one coalesced 16-byte access per thread per element group, fp32 arithmetic.
+#include "conv.h"
+#include "ptx.cuh"
+
+namespace dirb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCHW fp32 (B,3,H,W) -> NHWC fp16 (B,H,W,8), channels 3..7 = 0.   (input staging for the stem, resnet.py:158)
+__global__ void nchw_to_nhwc8_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t hw, int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;  // pixel index over B*H*W
+  if (i >= total) return;
+  const int64_t b = i / hw, px = i - b * hw;
+  const float* src = in + b * 3 * hw + px;
+  uint4 o;
+  o.x = pack_h2(src[0], src[hw]);
+  o.y = pack_h2(src[2 * hw], 0.f);
+  o.z = 0u;
+  o.w = 0u;
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_t stream) {
+  const int64_t hw = static_cast<int64_t>(H) * W, total = hw * B;
+  nchw_to_nhwc8_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(in, out, hw, total);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MaxPool2d(kernel 3, stride 2, padding 1), NHWC fp16, 8 channels per thread.   (resnet.py:119,161)
+__global__ void maxpool_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C,
+                               int Ho, int Wo) {
+  const int cv = C / 8;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * cv;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % cv);
+  int64_t r = i / cv;
+  const int wo = static_cast<int>(r % Wo);
+  r /= Wo;
+  const int ho = static_cast<int>(r % Ho);
+  const int b = static_cast<int>(r / Ho);
+  __half2 m[4];
+  const __half2 ninf = __floats2half2_rn(-65504.f, -65504.f);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) m[e] = ninf;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int hi = ho * 2 - 1 + dy;
+    if (hi < 0 || hi >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int wi = wo * 2 - 1 + dx;
+      if (wi < 0 || wi >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<int64_t>(b) * H + hi) * W + wi) * C) + c8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h[e]);
+    }
+  }
+  reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<uint4*>(m);
+}
+
+int maxpool_3x3s2(const __half* in, int B, int H, int W, int C, __half* out, cudaStream_t stream) {
+  DIRB_REQUIRE(C % 8 == 0, DIRB200_ENOTSUP, "maxpool needs C %% 8 == 0");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * (C / 8);
+  maxpool_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(in, out, B, H, W, C, Ho, Wo);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Head: global pooling (GeM / max / avg) -> (L2 over C) -> FC + bias -> L2.      (rmac_resnet.py:59-68, pooling.py:38-40)
+// Stage 1 streams the NHWC feature map once (the only large read), stage 2..4 are tiny.
+namespace {
+
+constexpr int HEAD_PX_LANES = 8;
+
+__device__ __forceinline__ float gem_pow(float x, float p, int p_is3) { return p_is3 ? x * x * x : powf(x, p); }
+
+// grid (C/256, S, B), block 256: thread = (pixel lane 0..7, channel group 0..31 of 8 channels)
+__global__ void head_pool_partial_kernel(const __half* __restrict__ feat, float* __restrict__ partial, int HW, int C,
+                                         int S, int pooling, float p, float eps) {
+  __shared__ float red[HEAD_PX_LANES][256 + 8];
+  const int cg = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cg * 8;
+  const int s = blockIdx.y, b = blockIdx.z;
+  const int per = (HW + S - 1) / S;
+  const int beg = s * per, end = min(HW, beg + per);
+  const int p_is3 = (p == 3.0f);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = (pooling == 1) ? -INFINITY : 0.f;
+  if (c0 < C) {
+    for (int px = beg + pl; px < end; px += HEAD_PX_LANES) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(feat + (static_cast<int64_t>(b) * HW + px) * C + c0));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_h2(u[e]);
+        if (pooling == 0) {
+          acc[2 * e] += gem_pow(fmaxf(f.x, eps), p, p_is3);
+          acc[2 * e + 1] += gem_pow(fmaxf(f.y, eps), p, p_is3);
+        } else if (pooling == 1) {
+          acc[2 * e] = fmaxf(acc[2 * e], f.x);
+          acc[2 * e + 1] = fmaxf(acc[2 * e + 1], f.y);
+        } else {
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][cg * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < C) {
+    float r = red[0][c];
+#pragma unroll
+    for (int l = 1; l < HEAD_PX_LANES; ++l) r = (pooling == 1) ? fmaxf(r, red[l][c]) : r + red[l][c];
+    partial[(static_cast<int64_t>(b) * S + s) * C + blockIdx.x * 256 + c] = r;
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < nw) ? sh[l] : 0.f;
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+// one block per image: finish the pooling, optional L2 over channels.
+__global__ void head_pool_final_kernel(const float* __restrict__ partial, float* __restrict__ g, int HW, int C, int S,
+                                       int pooling, float p, int norm_features) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float r = partial[(static_cast<int64_t>(b) * S) * C + c];
+    for (int s = 1; s < S; ++s) {
+      const float q = partial[(static_cast<int64_t>(b) * S + s) * C + c];
+      r = (pooling == 1) ? fmaxf(r, q) : r + q;
+    }
+    if (pooling == 0) r = powf(r / static_cast<float>(HW), 1.0f / p);
+    else if (pooling == 2) r = r / static_cast<float>(HW);
+    g[static_cast<int64_t>(b) * C + c] = r;
+    ss += r * r;
+  }
+  if (norm_features) {
+    const float tot = block_sum(ss, sh);
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) g[static_cast<int64_t>(b) * C + c] *= inv;
+  }
+}
+
+// y[b][o] = sum_c W[o][c] g[b][c] + bias[o]; grid (ceil(out/8), ceil(B/8)), block 256 = 8 warps, warp = one output row
+__global__ void head_fc_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ y, int B, int C, int out_dim) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + warp;
+  const int b0 = blockIdx.y * 8;
+  if (o >= out_dim) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const float4* wr = reinterpret_cast<const float4*>(w + static_cast<int64_t>(o) * C);
+  for (int c4 = lane; c4 < C / 4; c4 += 32) {
+    const float4 wv = __ldg(wr + c4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (b0 + i < B) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(b0 + i) * C) + c4);
+        acc[i] = fmaf(wv.x, gv.x, acc[i]);
+        acc[i] = fmaf(wv.y, gv.y, acc[i]);
+        acc[i] = fmaf(wv.z, gv.z, acc[i]);
+        acc[i] = fmaf(wv.w, gv.w, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = acc[i];
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0 && b0 + i < B) y[static_cast<int64_t>(b0 + i) * out_dim + o] = v + (bias ? bias[o] : 0.f);
+  }
+}
+
+// one block per row: out = x / max(||x||, eps)
+__global__ void l2_rows_kernel(const float* __restrict__ x, float* __restrict__ out, __half* __restrict__ out16, int D,
+                               float eps) {
+  __shared__ float sh[32];
+  const int64_t r = blockIdx.x;
+  const float* xr = x + r * D;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) ss += xr[c] * xr[c];
+  const float tot = block_sum(ss, sh);
+  const float nrm = sqrtf(tot);
+  const float inv = 1.0f / (eps > 0.f ? fmaxf(nrm, eps) : nrm);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = xr[c] * inv;
+    if (out) out[r * D + c] = v;
+    if (out16) out16[r * D + c] = __float2half_rn(v);
+  }
+}
+
+}  // namespace
+
+static int head_splits(int B, int HW, int C) {
+  // enough blocks for ~4 waves of 148 SMs, at least 16 pixels per split
+  const int64_t base = static_cast<int64_t>(B) * ceil_div(C, 256);
+  int S = static_cast<int>(ceil_div(148 * 8, base));
+  S = max(1, min(S, max(1, HW / 16)));
+  return min(S, 64);
+}
+
+size_t head_workspace_floats(int B, int HW, int C, int out_dim) {
+  return static_cast<size_t>(B) * head_splits(B, HW, C) * C + static_cast<size_t>(B) * C +
+         static_cast<size_t>(B) * (out_dim > C ? out_dim : C);
+}
+
+int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features,
+                    const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
+                    cudaStream_t stream) {
+  DIRB_REQUIRE(C % 8 == 0 && C % 4 == 0, DIRB200_ENOTSUP, "head needs C %% 8 == 0");
+  DIRB_REQUIRE(pooling >= 0 && pooling <= 2, DIRB200_EINVAL, "pooling mode %d", pooling);
+  const int S = head_splits(B, HW, C);
+  float* partial = ws;
+  float* g = partial + static_cast<size_t>(B) * S * C;
+  float* y = g + static_cast<size_t>(B) * C;
+  dim3 g1((unsigned)ceil_div(C, 256), (unsigned)S, (unsigned)B);
+  head_pool_partial_kernel<<<g1, 256, 0, stream>>>(feat, partial, HW, C, S, pooling, p, eps);
+  head_pool_final_kernel<<<B, 256, 0, stream>>>(partial, g, HW, C, S, pooling, p, norm_features);
+  const float* pre = g;
+  int D = C;
+  if (fc_w != nullptr) {
+    dim3 g3((unsigned)ceil_div(out_dim, 8), (unsigned)ceil_div(B, 8));
+    head_fc_kernel<<<g3, 256, 0, stream>>>(g, fc_w, fc_b, y, B, C, out_dim);
+    count_launch();
+    pre = y;
+    D = out_dim;
+  }
+  l2_rows_kernel<<<B, 256, 0, stream>>>(pre, desc, desc16, D, 1e-12f);
+  count_launch(3);
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int l2_normalize(const float* x, int64_t N, int D, float eps, float* out, __half* out16, cudaStream_t stream) {
+  if (N == 0) return 0;
+  l2_rows_kernel<<<static_cast<unsigned>(N), 256, 0, stream>>>(x, out, out16, D, eps);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// common.pool over S transform chains (+ F.normalize): common.py:41-55, test_dir.py:121-122.
+__global__ void pool_scales_kernel(const float* __restrict__ xs, float* __restrict__ out, int S, int64_t N, int D,
+                                   int mode, float gemp, int l2) {
+  __shared__ float sh[32];
+  const int64_t r = blockIdx.x;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float v = xs[(static_cast<int64_t>(s) * N + r) * D + c];
+      if (mode == 0) {
+        acc += v;
+      } else {  // signed power: sign(v) * max(|v|, 1e-6)^p
+        const float sg = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
+        acc += sg * powf(fmaxf(v * sg, 1e-6f), gemp);
+      }
+    }
+    acc /= static_cast<float>(S);
+    if (mode == 1) {
+      const float sg = (acc > 0.f) ? 1.f : ((acc < 0.f) ? -1.f : 0.f);
+      acc = sg * powf(fmaxf(acc * sg, 1e-6f), 1.0f / gemp);
+    }
+    out[r * D + c] = acc;
+    ss += acc * acc;
+  }
+  if (l2) {
+    const float tot = block_sum(ss, sh);
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) out[r * D + c] *= inv;
+  }
+}
+
+int pool_scales(const float* xs, int S, int64_t N, int D, int mode, float gemp, int l2, float* out,
+                cudaStream_t stream) {
+  DIRB_REQUIRE(S >= 1 && (mode == 0 || mode == 1), DIRB200_EINVAL, "pool_scales: S=%d mode=%d", S, mode);
+  if (N == 0) return 0;
+  if (S == 1) mode = 0;  // common.py:42-43: a single chain is returned unchanged
+  pool_scales_kernel<<<static_cast<unsigned>(N), 256, 0, stream>>>(xs, out, S, N, D, mode, gemp, l2);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ out, int64_t n) {
+  const int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    uint2 o;
+    o.x = pack_h2(v.x, v.y);
+    o.y = pack_h2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) out[j] = __float2half_rn(x[j]);
+  }
+}
+
+int f32_to_f16(const float* x, int64_t n, __half* out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  f32_to_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(n, 4), 256)), 256, 0, stream>>>(x, out, n);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PCA whitening: Y = ((X - mean) . comp^T) * colscale, optional row L2.                     (common.py:221-239)
+// fp32 SIMT GEMM, 64x64 tile, 4x4 per thread: exact fp32 products (the reference runs this in NumPy fp32/fp64).
+namespace {
+constexpr int WT = 64, WK = 16;
+
+__global__ void __launch_bounds__(256) whiten_gemm_kernel(const float* __restrict__ x, const float* __restrict__ comp,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ colscale, float* __restrict__ y,
+                                                          int64_t N, int D, int Dout) {
+  __shared__ float As[WK][WT + 4];
+  __shared__ float Bs[WK][WT + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * WT;
+  const int n0 = blockIdx.y * WT;
+  const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;  // loader: row 0..63, k offset 0,4,8,12
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < D; k0 += WK) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (m0 + lr < N) {
+      a = *reinterpret_cast<const float4*>(x + (m0 + lr) * D + k0 + lk);
+      if (mean) {
+        const float4 mu = *reinterpret_cast<const float4*>(mean + k0 + lk);
+        a.x -= mu.x; a.y -= mu.y; a.z -= mu.z; a.w -= mu.w;
+      }
+    }
+    if (n0 + lr < Dout) b = *reinterpret_cast<const float4*>(comp + static_cast<int64_t>(n0 + lr) * D + k0 + lk);
+    __syncthreads();
+    As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+    Bs[lk + 0][lr] = b.x; Bs[lk + 1][lr] = b.y; Bs[lk + 2][lr] = b.z; Bs[lk + 3][lr] = b.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < WK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < Dout) y[m * Dout + n] = acc[i][j] * (colscale ? colscale[n] : 1.0f);
+    }
+  }
+}
+}  // namespace
+
+int whiten(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale, int Dout,
+           int l2norm, float* y, __half* y16, cudaStream_t stream) {
+  DIRB_REQUIRE(D % WK == 0, DIRB200_ENOTSUP, "whiten needs D %% 16 == 0 (got %d)", D);
+  if (N == 0) return 0;
+  dim3 grid((unsigned)ceil_div(N, WT), (unsigned)ceil_div(Dout, WT));
+  DIRB_REQUIRE(ceil_div(N, WT) < (int64_t(1) << 31) && grid.y < 65536u, DIRB200_ENOTSUP, "whiten: shape too large");
+  whiten_gemm_kernel<<<grid, 256, 0, stream>>>(x, comp, mean, colscale, y, N, D, Dout);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  if (l2norm) return l2_normalize(y, N, Dout, 0.f, y, y16, stream);
+  if (y16) return f32_to_f16(y, N * Dout, y16, stream);
+  return 0;
+}
+
+}  // namespace dirb

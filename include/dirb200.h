@@ -1,0 +1,153 @@
+/* dirb200 - C ABI of the B200-native descriptor-extraction + retrieval hot path.
+ *
+ * The reference (naver/deep-image-retrieval, "dirtorch") has no FFI: its boundary is a Python
+ * duck-type.  This header is the boundary a binding for that path would target:
+ * plain C types, raw device/host pointers + sizes, a CUDA stream as void*, no torch types.
+ * Each entry point names the reference call it replaces (file:line relative to the reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DIRB200_E* code for library errors, or a
+ *     positive cudaError_t; dirb200_last_error() returns a thread-local message;
+ *   - "dev" pointers are device memory owned by the caller; the library allocates only inside
+ *     opaque handles (packed weights, workspaces) freed by the matching *_destroy;
+ *   - all launches are asynchronous on the given stream unless the name ends in _host;
+ *   - a handle is bound to one device and is not re-entrant (one handle per GPU / stream);
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry
+ *     point fails with DIRB200_ENODEVICE.
+ */
+#ifndef DIRB200_H_
+#define DIRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIRB200_OK 0
+#define DIRB200_EINVAL (-1)    /* bad argument                                            */
+#define DIRB200_ENOTSUP (-2)   /* shape / option outside what the kernels support          */
+#define DIRB200_EDRIVER (-3)   /* driver entry point (cuTensorMapEncodeTiled) unavailable  */
+#define DIRB200_EOVERFLOW (-4) /* candidate buffer overflow that could not be resolved     */
+#define DIRB200_ESTATE (-5)    /* handle used in the wrong state                           */
+#define DIRB200_ENODEVICE (-6) /* no sm_100 CUDA device                                    */
+#define DIRB200_EKEY (-7)      /* unknown tensor / option name                             */
+
+typedef struct dirb200_net dirb200_net;     /* one ResNet-GeM network on one GPU            */
+typedef struct dirb200_index dirb200_index; /* one row-shard of a descriptor database       */
+
+int dirb200_version(void);
+const char* dirb200_last_error(void);
+/* 0 if `device` exists and is compute capability 10.x. */
+int dirb200_device_check(int device);
+
+/* ------------------------------------------------------------------ network (extraction)
+ * Replaces nets.create_model(arch, **model_options) + net.load_state_dict(sd) + net(imgs):
+ * dirtorch/nets/__init__.py:24-64, dirtorch/nets/rmac_resnet.py:12-69,
+ * dirtorch/nets/backbones/resnet.py:46-87,102-174, dirtorch/nets/layers/pooling.py:38-54.   */
+
+/* arch: "resnet50_rmac" | "resnet101_rmac" (Bottleneck trunks, rmac_resnet.py:78-84). */
+int dirb200_net_create(const char* arch, int device, dirb200_net** out);
+/* Options (rmac_resnet.py:15-37): "pooling" 0=gem 1=max 2=avg; "norm_features" 0/1;
+ * "without_fc" 0/1; "out_dim"; "chunk" images processed per pass (0 = auto);
+ * "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path). */
+int dirb200_net_set_option(dirb200_net* net, const char* key, double value);
+/* One state_dict tensor by its reference key ("layer3.5.bn2.running_var", "adpool.p", "fc.weight" ...),
+ * fp32 host memory, reference shape (conv OIHW).  "num_batches_tracked" keys are ignored. */
+int dirb200_net_set_tensor(dirb200_net* net, const char* name, const float* host_data, const int64_t* shape,
+                           int ndim);
+/* Fold BN into per-channel scale/shift, repack conv weights to [Cout][KH][KW][Cin] fp16, upload. */
+int dirb200_net_finalize(dirb200_net* net);
+/* net(imgs): imgs_dev = NCHW fp32 normalised images (B,3,H,W); desc_dev = (B,out_dim) fp32 L2-normalised
+ * descriptors; desc16_dev (optional, may be NULL) = the same in fp16.  test_dir.py:74. */
+int dirb200_net_forward(dirb200_net* net, const float* imgs_dev, int B, int H, int W, float* desc_dev,
+                        void* desc16_dev, void* stream);
+/* Same through HOST buffers: H2D copy of the images, forward, D2H copy of the descriptors, stream sync
+ * (the common.variables() -> net() -> tonumpy() sequence, common.py:205-218,23-27). */
+int dirb200_net_forward_host(dirb200_net* net, const float* imgs_host, int B, int H, int W, float* desc_host);
+/* Debug tap: copy the NHWC fp16 activation after stage `what` ("stem","layer1".."layer4") of the LAST chunk of
+ * the last forward into dst_dev (capacity in bytes); returns its dims as {n,h,w,c}. */
+int dirb200_net_debug_stage(dirb200_net* net, const char* what, void* dst_dev, size_t capacity, int dims[4],
+                            void* stream);
+/* Number of kernels the last forward launched / algorithmic conv+fc FLOPs of the last forward. */
+int dirb200_net_last_launches(dirb200_net* net, int64_t* launches, double* flops);
+int dirb200_net_destroy(dirb200_net* net);
+
+/* ------------------------------------------------------------------ single operators
+ * (the building blocks of the network, exported for parity tests and reuse)                 */
+
+/* NCHW fp32 (B,3,H,W) -> NHWC fp16 (B,H,W,8), channels 3..7 zero.  Input staging of resnet.py:158. */
+int dirb200_nchw_to_nhwc8(const float* in_dev, int B, int H, int W, void* out_dev, void* stream);
+/* Conv2d(bias=False) + folded BatchNorm (+ residual add) (+ ReLU), NHWC fp16 in/out.
+ * w_dev: [Cout][KH][KW][Cin] fp16; scale/shift: [Cout] fp32; res_dev may be NULL.
+ * impl: 0 tcgen05 (needs Cin%64==0, Cout%64==0), 1 mma.sync (needs Cin%8==0, Cout%64==0).
+ * resnet.py:56-63,70-85,115-118. */
+int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const void* w_dev, int Cout, int KH,
+                        int KW, int stride, int pad, const float* scale_dev, const float* shift_dev,
+                        const void* res_dev, int relu, int impl, void* out_dev, void* stream);
+/* MaxPool2d(3, stride 2, pad 1) on NHWC fp16.  resnet.py:119,161. */
+int dirb200_maxpool_3x3s2(const void* in_dev, int B, int H, int W, int C, void* out_dev, void* stream);
+/* Global pooling + (L2 over C) + FC + L2: rmac_resnet.py:59-68, pooling.py:38-40.
+ * feat_dev NHWC fp16 (B,h,w,C); pooling 0 gem(p, eps) / 1 max / 2 avg; fc_w_dev [out_dim][C] fp32 (NULL = without_fc);
+ * ws_dev: fp32 scratch of dirb200_head_workspace_floats(B,h*w,C,out_dim) floats. */
+size_t dirb200_head_workspace_floats(int B, int HW, int C, int out_dim);
+int dirb200_head_pool_fc_l2(const void* feat_dev, int B, int HW, int C, int pooling, float p, float eps,
+                            int norm_features, const float* fc_w_dev, const float* fc_b_dev, int out_dim,
+                            float* ws_dev, float* desc_dev, void* desc16_dev, void* stream);
+
+/* ------------------------------------------------------------------ descriptor post-processing */
+
+/* common.pool + F.normalize: common.py:41-55, test_dir.py:121-122.  xs_dev: (S,N,D) fp32 stacked;
+ * mode 0 mean, 1 gem (signed power gemp); l2 != 0 appends the row L2 normalisation. */
+int dirb200_pool_scales(const float* xs_dev, int S, int64_t N, int D, int mode, float gemp, int l2, float* out_dev,
+                        void* stream);
+/* Row L2 normalisation, eps as F.normalize (1e-12). */
+int dirb200_l2_normalize(const float* x_dev, int64_t N, int D, float eps, float* out_dev, void* out16_dev,
+                         void* stream);
+/* common.whiten_features: common.py:221-239.  Y = ((X - mean) . comp^T) * colscale, optional row L2.
+ * comp_dev [Dout][D] fp32 (pca.components_[:whitenv]); mean_dev [D] or NULL; colscale_dev [Dout] =
+ * 1 / (whitenm * explained_variance_^whitenp) or NULL; y16_dev optional fp16 copy. */
+int dirb200_whiten(const float* x_dev, int64_t N, int D, const float* comp_dev, const float* mean_dev,
+                   const float* colscale_dev, int Dout, int l2norm, float* y_dev, void* y16_dev, void* stream);
+int dirb200_f32_to_f16(const float* x_dev, int64_t n, void* out16_dev, void* stream);
+
+/* ------------------------------------------------------------------ similarity + top-k
+ * Replaces scores = common.matmul(q, db) (common.py:30-38, test_dir.py:145) followed by the per-query
+ * ranking (generic.py:207,221; dataset.py:100; test_dir.py:36) for the first k ranks.  Ordering: exact
+ * (fp64-accumulated) dot product of the fp32 rows, descending; ties -> lower index first.               */
+
+int dirb200_index_create(int device, int dim, dirb200_index** out);
+/* Attach one row shard: db32_dev [N][dim] fp32 (exact re-scoring), db16_dev [N][dim] fp16 (tensor-core pass);
+ * both caller-owned and must outlive the index.  index_offset is added to every returned index
+ * (row-wise sharding across GPUs). */
+int dirb200_index_set_db(dirb200_index* idx, const float* db32_dev, const void* db16_dev, int64_t N,
+                         int64_t index_offset);
+/* "eps16": bound on |fp16-path score - exact score| used for the candidate band (default 1.2e-3, valid for
+ * unit-norm rows); "sample_rows": rows scored densely to seed the threshold (0 = auto). */
+int dirb200_index_set_option(dirb200_index* idx, const char* key, double value);
+/* q32_dev [Q][dim] fp32.  Outputs (device): scores_dev [Q][k] fp64 exact scores, idx_dev [Q][k] int64.
+ * If N < k the tail is filled with score -inf / index -1.  Synchronises the stream (overflow check). */
+int dirb200_index_search(dirb200_index* idx, const float* q32_dev, int Q, int k, double* scores_dev,
+                         int64_t* idx_dev, void* stream);
+/* Statistics of the last search: {dense_rows, candidates_total, survivors_total, retries, launches}. */
+int dirb200_index_last_stats(dirb200_index* idx, int64_t stats[5]);
+int dirb200_index_destroy(dirb200_index* idx);
+
+/* Merge G per-shard top-k lists ([G][Q][k] scores fp64 + global indices int64, as produced by an
+ * all-gather of dirb200_index_search outputs) into the global top-k with the same ordering rule. */
+int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, double* out_scores_dev,
+                       int64_t* out_idx_dev, void* stream);
+/* Full exact score matrix (fp64 accumulate, fp32 out): the literal common.matmul for small evaluation sets. */
+int dirb200_scores_exact(const float* q_dev, int Q, const float* db_dev, int64_t N, int D, float* out_dev,
+                         void* stream);
+/* Alpha query expansion, test_dir.py:24-44:  out_i = normalize(mean([q_i] + [db_j * s_ij^alpha, j in topk(i)])).
+ * nn_idx_dev/nn_scores_dev: [Q][k] neighbours (LOCAL row numbers into db32_dev, -1 = none) and their scores.
+ * partial != 0 writes the un-normalised SUM over the local neighbours only (for a cross-GPU all-reduce). */
+int dirb200_aqe_expand(const float* q_dev, int Q, int D, const float* db32_dev, const int64_t* nn_idx_dev,
+                       const double* nn_scores_dev, int k, double alpha, int partial, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIRB200_H_ */
