@@ -215,11 +215,10 @@ __global__ void l2_rows_kernel(const float* __restrict__ x, float* __restrict__ 
 }  // namespace
 
 static int head_splits(int B, int HW, int C) {
-  // enough blocks for ~4 waves of 148 SMs, at least 16 pixels per split
-  const int64_t base = static_cast<int64_t>(B) * ceil_div(C, 256);
-  int S = static_cast<int>(ceil_div(148 * 8, base));
-  S = max(1, min(S, max(1, HW / 16)));
-  return min(S, 64);
+  // Depends on the spatial size only, so that a descriptor does not depend on the batch it was computed in
+  // (the partial sums of one image are always combined in the same order).
+  (void)B; (void)C;
+  return max(1, min(16, HW / 64));
 }
 
 size_t head_workspace_floats(int B, int HW, int C, int out_dim) {

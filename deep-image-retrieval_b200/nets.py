@@ -1,0 +1,271 @@
+"""Model API of the extraction path: the duck-type the reference's callers use, backed by libdirb200.
+
+Mirrors ``dirtorch/nets/__init__.py:18-95`` (``model_names``, ``create_model``, ``load_pretrained_weights``)
+and the module surface of ``dirtorch/nets/rmac_resnet.py:12-69`` that ``test_dir.py:57-74,185-190`` and
+``common.py:150-175`` touch: ``net(imgs) -> (B,D)`` L2-normalised descriptors (``(D,)`` at B=1),
+``preprocess``, ``rgb_means/rgb_stds/input_size``, ``iscuda``, ``pca``, ``fc_name``, ``feat_dim``,
+``eval()``, ``state_dict()``, ``load_state_dict()``.
+
+The forward pass is NOT torch: the state dict is handed to the C library, which folds BatchNorm, repacks the
+convolutions for the tcgen05 implicit-GEMM kernels and runs the whole network on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import lib, synth
+
+_ARCH_BLOCKS = {"resnet50_rmac": [3, 4, 6, 3], "resnet101_rmac": [3, 4, 23, 3]}
+model_names = set(_ARCH_BLOCKS)
+
+
+def _reference_style_init(arch, out_dim, seed_gen=None):
+    """Fresh weights with the statistics of the reference's constructor: conv ~ N(0, sqrt(2/(k*k*Cout)))
+    and BN weight 1 / bias 0 (resnet.py:92-99), identity running stats, Linear default init."""
+    g = seed_gen or torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+    sd = OrderedDict()
+
+    def conv(name, cout, cin, k):
+        sd[name] = torch.randn((cout, cin, k, k), generator=g) * math.sqrt(2.0 / (k * k * cout))
+
+    def bn(name, c):
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    conv("conv1.weight", 64, 3, 7)
+    bn("bn1", 64)
+    inplanes = 64
+    for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], _ARCH_BLOCKS[arch]), start=1):
+        for b in range(nblk):
+            p = "layer%d.%d." % (li, b)
+            conv(p + "conv1.weight", planes, inplanes, 1)
+            bn(p + "bn1", planes)
+            conv(p + "conv2.weight", planes, planes, 3)
+            bn(p + "bn2", planes)
+            conv(p + "conv3.weight", planes * 4, planes, 1)
+            bn(p + "bn3", planes * 4)
+            if b == 0:
+                conv(p + "downsample.0.weight", planes * 4, inplanes, 1)
+                bn(p + "downsample.1", planes * 4)
+            inplanes = planes * 4
+    bound = 1.0 / math.sqrt(2048)
+    sd["fc.weight"] = (torch.rand((out_dim, 2048), generator=g) * 2 - 1) * bound
+    sd["fc.bias"] = (torch.rand(out_dim, generator=g) * 2 - 1) * bound
+    return sd
+
+
+class ResNetRMAC:
+    """ResNet-50/101 trunk + global pooling + FC + L2 (``ResNet_RMAC``, rmac_resnet.py:12-69)."""
+
+    def __init__(self, arch, out_dim=2048, norm_features=False, pooling="gem", gemp=3, center_bias=0,
+                 dropout_p=None, without_fc=False, **kwargs):
+        kwargs.pop("scales", None)                              # rmac_resnet.py:75,79,83
+        if kwargs:
+            raise TypeError("unexpected model options: %s" % sorted(kwargs))
+        if arch not in _ARCH_BLOCKS:
+            raise NameError("unknown model architecture '%s'\nSelect one in %s" % (arch, ",".join(sorted(model_names))))
+        if not (pooling in ("max", "avg") or pooling.startswith("gem")):
+            raise ValueError(pooling)                            # rmac_resnet.py:30-31
+        if center_bias:
+            raise NotImplementedError("center_bias > 0 (rmac_resnet.py:52-56) is not supported by the B200 path")
+        self.arch = arch
+        self.model_name = arch.split("_")[0]
+        self.rgb_means = list(synth.RGB_MEANS)                   # resnet.py:110-112
+        self.rgb_stds = list(synth.RGB_STDS)
+        self.input_size = (3, 224, 224)
+        self.norm_features = bool(norm_features)
+        self.without_fc = bool(without_fc)
+        self.pooling = pooling
+        self.center_bias = center_bias
+        self.dropout = None                                      # identity in eval mode (rmac_resnet.py:44-45)
+        self.fc_name = "fc"
+        self.feat_dim = out_dim
+        self.out_dim = out_dim
+        self.detach = False
+        self.iscuda = False
+        self.training = False
+        self.preprocess = dict(mean=self.rgb_means, std=self.rgb_stds, input_size=max(self.input_size))
+        self._sd = _reference_style_init(arch, out_dim)
+        if pooling.startswith("gem"):
+            self._sd["adpool.p"] = torch.ones(1) * float(gemp)   # pooling.py:54
+        self._handle = None
+        self._handle_device = None
+        self._opts = {}
+
+    # ------------------------------------------------------------------ nn.Module-like surface
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("the B200 path is inference-only (the reference ships no trainer either)")
+        return self
+
+    def cuda(self, device=None):
+        self.iscuda = True
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def state_dict(self):
+        return OrderedDict((k, v.clone()) for k, v in self._sd.items())
+
+    def load_state_dict(self, state_dict, strict=True):
+        new = OrderedDict()
+        for k, v in state_dict.items():
+            if k.startswith("module."):
+                k = k[7:]
+            new[k] = v.detach().to("cpu")
+        missing = [k for k in self._sd if k not in new]
+        unexpected = [k for k in new if k not in self._sd]
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict: missing keys %s, unexpected keys %s" % (missing, unexpected))
+        for k, v in new.items():
+            if k in self._sd:
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    raise RuntimeError("size mismatch for %s: %s vs %s" % (k, tuple(v.shape), tuple(self._sd[k].shape)))
+                self._sd[k] = v.to(self._sd[k].dtype).clone()
+        self._release()
+        return self
+
+    def set_backend_option(self, key, value):
+        """Library tuning knobs ('chunk', 'conv_impl'); see include/dirb200.h."""
+        self._opts[key] = float(value)
+        self._release()
+
+    # ------------------------------------------------------------------ native handle
+    def _release(self):
+        if self._handle is not None:
+            lib.raw("dirb200_net_destroy")(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure(self, device_index):
+        if self._handle is not None and self._handle_device == device_index:
+            return self._handle
+        self._release()
+        h = C.c_void_p()
+        lib.call("dirb200_net_create", self.arch.encode(), int(device_index), C.byref(h))
+        try:
+            mode = 0 if self.pooling.startswith("gem") else (1 if self.pooling == "max" else 2)
+            for k, v in [("pooling", mode), ("norm_features", self.norm_features), ("without_fc", self.without_fc),
+                         ("out_dim", self.out_dim)] + list(self._opts.items()):
+                lib.call("dirb200_net_set_option", h, k.encode(), float(v))
+            for name, t in self._sd.items():
+                if name.endswith("num_batches_tracked"):
+                    continue
+                a = np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32))
+                shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+                lib.call("dirb200_net_set_tensor", h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim)
+            lib.call("dirb200_net_finalize", h)
+        except Exception:
+            lib.raw("dirb200_net_destroy")(h)
+            raise
+        self._handle, self._handle_device = h, device_index
+        return h
+
+    # ------------------------------------------------------------------ forward
+    @property
+    def descriptor_dim(self):
+        return 2048 if self.without_fc else self.out_dim
+
+    def forward(self, x, want_f16=False):
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
+            raise TypeError("expected a (B,3,H,W) tensor")
+        if not x.is_cuda:
+            x = x.cuda(non_blocking=True)                        # common.variables, common.py:213-215
+        x = x.contiguous().float()
+        b, _, hgt, wid = x.shape
+        h = self._ensure(x.device.index or 0)
+        with torch.cuda.device(x.device):
+            desc = torch.empty((b, self.descriptor_dim), dtype=torch.float32, device=x.device)
+            d16 = torch.empty((b, self.descriptor_dim), dtype=torch.float16, device=x.device) if want_f16 else None
+            lib.call("dirb200_net_forward", h, C.c_void_p(x.data_ptr()), b, hgt, wid, C.c_void_p(desc.data_ptr()),
+                     C.c_void_p(d16.data_ptr()) if want_f16 else C.c_void_p(0),
+                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if want_f16:
+            return desc, d16
+        if b == 1:
+            desc = desc[0]                                       # x.squeeze_() at B=1, rmac_resnet.py:64
+        return desc
+
+    __call__ = forward
+
+    def forward_host(self, imgs: np.ndarray, device=0) -> np.ndarray:
+        """Host NCHW fp32 array in, host descriptors out; H2D + forward + D2H inside one C call."""
+        a = np.ascontiguousarray(imgs, dtype=np.float32)
+        b, _, hgt, wid = a.shape
+        h = self._ensure(device)
+        out = np.empty((b, self.descriptor_dim), dtype=np.float32)
+        lib.call("dirb200_net_forward_host", h, a.ctypes.data_as(C.c_void_p), b, hgt, wid, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def debug_stage(self, what):
+        """NHWC fp16 activation after 'stem' / 'layer1'..'layer4' of the last chunk of the last forward."""
+        dims = (C.c_int * 4)()
+        dev = torch.device("cuda", self._handle_device)
+        buf = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+        lib.call("dirb200_net_debug_stage", self._handle, what.encode(), C.c_void_p(buf.data_ptr()), buf.numel(), dims,
+                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        n, hh, ww, c = [int(v) for v in dims]
+        return buf[: n * hh * ww * c * 2].view(torch.float16).view(n, hh, ww, c).clone()
+
+    def last_launch_stats(self):
+        n, f = C.c_int64(), C.c_double()
+        lib.call("dirb200_net_last_launches", self._handle, C.byref(n), C.byref(f))
+        return int(n.value), float(f.value)
+
+
+def resnet50_rmac(**kwargs):
+    return ResNetRMAC("resnet50_rmac", **kwargs)
+
+
+def resnet101_rmac(**kwargs):
+    return ResNetRMAC("resnet101_rmac", **kwargs)
+
+
+def create_model(arch, pretrained="", delete_fc=False, *args, **kwargs):
+    """nets.create_model, dirtorch/nets/__init__.py:24-64."""
+    if arch not in model_names:
+        raise NameError("unknown model architecture '%s'\nSelect one in %s" % (arch, ",".join(sorted(model_names))))
+    model = ResNetRMAC(arch, *args, **kwargs)
+    if os.path.isfile(pretrained or ""):
+        weights = torch.load(pretrained, map_location="cpu", weights_only=False)["state_dict"]
+        load_pretrained_weights(model, weights, delete_fc=delete_fc)
+    elif pretrained:
+        raise AssertionError("Model %s must be initialized with a valid model file (not %s)" % (arch, pretrained))
+    return model
+
+
+def load_pretrained_weights(net, state_dict, delete_fc=False):
+    """Tolerant load: strips 'module.', keeps the net's own tensor when a layer is missing or mis-shaped
+    (dirtorch/nets/__init__.py:67-95)."""
+    new = OrderedDict()
+    for k, v in state_dict.items():
+        new[k[7:] if k.startswith("module.") else k] = v
+    own = net.state_dict()
+    for k, v in own.items():
+        if k not in new:
+            if not k.endswith("num_batches_tracked"):
+                print("Loading weights for %s: Missing layer %s" % (type(net).__name__, k))
+            new[k] = v
+        elif tuple(v.shape) != tuple(new[k].shape):
+            print("Loading weights for %s: Bad shape for layer %s, skipping" % (type(net).__name__, k))
+            new[k] = v
+    net.load_state_dict({k: v for k, v in new.items() if k in own})

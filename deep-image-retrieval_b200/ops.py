@@ -1,0 +1,215 @@
+"""Torch-tensor front-end of the single operators of the C ABI (device memory + streams come from torch).
+
+Every function takes CUDA tensors, hands raw pointers to libdirb200.so and launches on torch's
+current stream.  Nothing here computes with torch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t
+
+
+def require_gpu(device=0):
+    lib.call("dirb200_device_check", int(device))
+
+
+def nchw_to_nhwc8(x):
+    _chk(x, torch.float32, "x")
+    b, c, h, w = x.shape
+    assert c == 3
+    out = torch.empty((b, h, w, 8), dtype=torch.float16, device=x.device)
+    lib.call("dirb200_nchw_to_nhwc8", _ptr(x), b, h, w, _ptr(out), _stream())
+    return out
+
+
+def pack_conv_weight(w_oihw: torch.Tensor, cin_pad=None) -> torch.Tensor:
+    """OIHW fp32 -> [Cout][KH][KW][CinPad] fp16, rows zero-padded to a multiple of 32 (the layout
+    dirb200_conv_bn_act expects).  Host-side repack (weights are packed once)."""
+    o, i, kh, kw = w_oihw.shape
+    cp = cin_pad or i
+    w = torch.zeros((o, kh, kw, cp), dtype=torch.float32)
+    w[..., :i] = w_oihw.detach().float().cpu().permute(0, 2, 3, 1)
+    k = kh * kw * cp
+    kpad = (k + 31) // 32 * 32
+    out = torch.zeros((o, kpad), dtype=torch.float16)
+    out[:, :k] = w.reshape(o, k).half()
+    return out
+
+
+def conv_bn_act(x, w_packed, cout, kh, kw, stride, pad, scale, shift, res=None, relu=True, impl=0):
+    """x NHWC fp16 (B,H,W,Cin) -> NHWC fp16 (B,Ho,Wo,Cout)."""
+    _chk(x, torch.float16, "x")
+    _chk(w_packed, torch.float16, "w_packed")
+    _chk(scale, torch.float32, "scale")
+    _chk(shift, torch.float32, "shift")
+    b, h, w, cin = x.shape
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    out = torch.empty((b, ho, wo, cout), dtype=torch.float16, device=x.device)
+    if res is not None:
+        _chk(res, torch.float16, "res")
+        assert res.shape == out.shape
+    lib.call("dirb200_conv_bn_act", _ptr(x), b, h, w, cin, _ptr(w_packed), cout, kh, kw, stride, pad, _ptr(scale),
+             _ptr(shift), _ptr(res), int(bool(relu)), int(impl), _ptr(out), _stream())
+    return out
+
+
+def maxpool_3x3s2(x):
+    _chk(x, torch.float16, "x")
+    b, h, w, c = x.shape
+    out = torch.empty((b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.float16, device=x.device)
+    lib.call("dirb200_maxpool_3x3s2", _ptr(x), b, h, w, c, _ptr(out), _stream())
+    return out
+
+
+POOLING = {"gem": 0, "max": 1, "avg": 2}
+
+
+def head_pool_fc_l2(feat, pooling="gem", p=3.0, eps=1e-6, norm_features=False, fc_w=None, fc_b=None, want_f16=False):
+    """feat NHWC fp16 (B,h,w,C) -> (B,D) fp32 L2-normalised (rmac_resnet.py:59-68)."""
+    _chk(feat, torch.float16, "feat")
+    b, h, w, c = feat.shape
+    out_dim = fc_w.shape[0] if fc_w is not None else c
+    if fc_w is not None:
+        _chk(fc_w, torch.float32, "fc_w")
+        _chk(fc_b, torch.float32, "fc_b")
+    nws = lib.raw("dirb200_head_workspace_floats")(b, h * w, c, out_dim)
+    ws = torch.empty(nws, dtype=torch.float32, device=feat.device)
+    desc = torch.empty((b, out_dim), dtype=torch.float32, device=feat.device)
+    d16 = torch.empty((b, out_dim), dtype=torch.float16, device=feat.device) if want_f16 else None
+    mode = POOLING["gem" if pooling.startswith("gem") else pooling]
+    lib.call("dirb200_head_pool_fc_l2", _ptr(feat), b, h * w, c, mode, float(p), float(eps), int(bool(norm_features)),
+             _ptr(fc_w), _ptr(fc_b), out_dim, _ptr(ws), _ptr(desc), _ptr(d16), _stream())
+    return (desc, d16) if want_f16 else desc
+
+
+def pool_scales(xs, pooling="mean", gemp=3, l2=True):
+    """common.pool (+ F.normalize when l2): list of (N,D) fp32 CUDA tensors -> (N,D)."""
+    if pooling not in ("mean", "gem"):
+        raise ValueError("Bad pooling mode: " + str(pooling))
+    stacked = torch.stack([_chk(x, torch.float32, "xs[i]") for x in xs], dim=0).contiguous()
+    s, n, d = stacked.shape
+    out = torch.empty((n, d), dtype=torch.float32, device=stacked.device)
+    lib.call("dirb200_pool_scales", _ptr(stacked), s, n, d, 0 if pooling == "mean" else 1, float(gemp), int(bool(l2)),
+             _ptr(out), _stream())
+    return out
+
+
+def l2_normalize(x, eps=1e-12, want_f16=False):
+    _chk(x, torch.float32, "x")
+    n, d = x.shape
+    out = torch.empty_like(x)
+    o16 = torch.empty((n, d), dtype=torch.float16, device=x.device) if want_f16 else None
+    lib.call("dirb200_l2_normalize", _ptr(x), n, d, float(eps), _ptr(out), _ptr(o16), _stream())
+    return (out, o16) if want_f16 else out
+
+
+def f32_to_f16(x):
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lib.call("dirb200_f32_to_f16", _ptr(x), x.numel(), _ptr(out), _stream())
+    return out
+
+
+def whiten(x, comp, mean=None, colscale=None, l2norm=True, want_f16=False):
+    """((x - mean) . comp^T) * colscale, row L2 (common.py:221-239).  x (N,D), comp (Dout,D) fp32 CUDA."""
+    _chk(x, torch.float32, "x")
+    _chk(comp, torch.float32, "comp")
+    n, d = x.shape
+    dout = comp.shape[0]
+    y = torch.empty((n, dout), dtype=torch.float32, device=x.device)
+    y16 = torch.empty((n, dout), dtype=torch.float16, device=x.device) if want_f16 else None
+    lib.call("dirb200_whiten", _ptr(x), n, d, _ptr(comp), _ptr(mean), _ptr(colscale), dout, int(bool(l2norm)), _ptr(y),
+             _ptr(y16), _stream())
+    return (y, y16) if want_f16 else y
+
+
+def scores_exact(q, db):
+    _chk(q, torch.float32, "q")
+    _chk(db, torch.float32, "db")
+    out = torch.empty((q.shape[0], db.shape[0]), dtype=torch.float32, device=q.device)
+    lib.call("dirb200_scores_exact", _ptr(q), q.shape[0], _ptr(db), db.shape[0], q.shape[1], _ptr(out), _stream())
+    return out
+
+
+def topk_merge(scores, idx, k):
+    """scores/idx: (G,Q,k) fp64 / int64 per-shard lists with global indices -> merged (Q,k)."""
+    _chk(scores, torch.float64, "scores")
+    _chk(idx, torch.int64, "idx")
+    g, q, kk = scores.shape
+    assert kk == k
+    os_ = torch.empty((q, k), dtype=torch.float64, device=scores.device)
+    oi = torch.empty((q, k), dtype=torch.int64, device=scores.device)
+    lib.call("dirb200_topk_merge", _ptr(scores), _ptr(idx), g, q, k, _ptr(os_), _ptr(oi), _stream())
+    return os_, oi
+
+
+def aqe_expand(q, db32, nn_idx, nn_scores, alpha, partial=False):
+    _chk(q, torch.float32, "q")
+    _chk(db32, torch.float32, "db32")
+    _chk(nn_idx, torch.int64, "nn_idx")
+    _chk(nn_scores, torch.float64, "nn_scores")
+    out = torch.empty_like(q)
+    lib.call("dirb200_aqe_expand", _ptr(q), q.shape[0], q.shape[1], _ptr(db32), _ptr(nn_idx), _ptr(nn_scores),
+             nn_idx.shape[1], float(alpha), int(bool(partial)), _ptr(out), _stream())
+    return out
+
+
+class Index:
+    """One row shard of a descriptor database on one GPU (dirb200_index)."""
+
+    def __init__(self, db32: torch.Tensor, index_offset: int = 0, db16: torch.Tensor = None):
+        _chk(db32, torch.float32, "db32")
+        self.db32 = db32
+        self.db16 = db16 if db16 is not None else f32_to_f16(db32)
+        self.n, self.dim = db32.shape
+        self.offset = int(index_offset)
+        self._h = C.c_void_p()
+        lib.call("dirb200_index_create", db32.device.index or 0, self.dim, C.byref(self._h))
+        lib.call("dirb200_index_set_db", self._h, _ptr(self.db32), _ptr(self.db16), self.n, self.offset)
+
+    def set_option(self, key, value):
+        lib.call("dirb200_index_set_option", self._h, key.encode(), float(value))
+
+    def search(self, q32: torch.Tensor, k: int):
+        """-> (scores fp64 (Q,k), idx int64 (Q,k)), exact order: score desc, index asc."""
+        _chk(q32, torch.float32, "q32")
+        nq = q32.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
+        idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
+        lib.call("dirb200_index_search", self._h, _ptr(q32), nq, int(k), _ptr(scores), _ptr(idx), _stream())
+        return scores, idx
+
+    def stats(self):
+        arr = (C.c_int64 * 5)()
+        lib.call("dirb200_index_last_stats", self._h, arr)
+        return dict(zip(["dense_rows", "candidates", "survivors", "retries", "launches"], [int(v) for v in arr]))
+
+    def close(self):
+        if self._h:
+            lib.raw("dirb200_index_destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

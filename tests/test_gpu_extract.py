@@ -1,0 +1,80 @@
+"""End-to-end descriptor extraction on the GPU vs the golden vectors of the unmodified reference and the
+CPU oracle.  Tolerance: 1e-3 relative L2 on the unit-norm descriptor (BASELINE.json north_star).  -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import dirb200.synth as synth
+from oracle import dir_oracle as O
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _net(arch, seed, **kw):
+    from dirb200 import nets, ops
+    ops.require_gpu(0)
+    net = nets.create_model(arch, **kw)
+    sd = synth.make_state_dict(arch, seed=seed, gemp=kw.get("gemp", 3))
+    if not kw.get("pooling", "gem").startswith("gem"):
+        sd.pop("adpool.p")
+    net.load_state_dict(sd)
+    net.eval()
+    return net, sd
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma"])
+def test_extract_r50_golden(golden, impl):
+    g = golden("extract_r50.npz")
+    net, sd = _net("resnet50_rmac", int(g["seed"]))
+    net.set_backend_option("conv_impl", impl)
+    x = synth.make_images(4, 224, 224, seed=int(g["img_seed"]))
+    d = net(x.cuda()).cpu().numpy()
+    # stage-by-stage diagnostics against the reference's activations (one pixel, all channels)
+    for stage, key in (("stem", "maxpool"), ("layer1", "layer1"), ("layer2", "layer2"), ("layer3", "layer3"), ("layer4", "layer4")):
+        a = net.debug_stage(stage).float().cpu()
+        sl = a[0, a.shape[1] // 2, a.shape[2] // 3, :].numpy()
+        assert rel_l2(sl, g["slice_" + key]) < 5e-3, stage
+    assert d.shape == (4, 2048)
+    assert rel_l2(d, g["desc"]) < TOL
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    d1 = net(x[:1].cuda())
+    assert tuple(d1.shape) == (2048,)                     # squeeze at B=1, rmac_resnet.py:64
+    assert rel_l2(d1.cpu().numpy(), g["desc_b1"]) < TOL
+    xr = synth.make_images(2, 160, 224, seed=int(g["img_seed_rect"]))
+    assert rel_l2(net(xr.cuda()).cpu().numpy(), g["desc_rect"]) < TOL
+    # chunking must not change anything: same descriptors with 1 image per pass
+    net.set_backend_option("chunk", 1)
+    net.set_backend_option("conv_impl", impl)
+    assert np.array_equal(net(x.cuda()).cpu().numpy(), d)
+    # host-buffer entry point (H2D + forward + D2H inside the C call)
+    assert np.array_equal(net.forward_host(x.numpy()), d)
+
+
+def test_extract_r50_options(golden):
+    g = golden("extract_r50_options.npz")
+    b, h, w = [int(v) for v in g["img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["img_seed"])).cuda()
+    for tag, kw in [("max", dict(pooling="max")), ("avg", dict(pooling="avg")), ("normfeat", dict(norm_features=True)),
+                    ("nofc", dict(without_fc=True)), ("gemp2", dict(gemp=2))]:
+        net, _ = _net("resnet50_rmac", int(g["seed"]), **kw)
+        assert rel_l2(net(x).cpu().numpy(), g["desc_" + tag]) < TOL, tag
+
+
+def test_extract_r101_golden(golden):
+    g = golden("extract_r101.npz")
+    net, _ = _net("resnet101_rmac", int(g["seed"]))
+    x = synth.make_images(2, 224, 224, seed=int(g["img_seed"]))
+    assert rel_l2(net(x.cuda()).cpu().numpy(), g["desc"]) < TOL
+
+
+def test_extract_r101_large_image_vs_oracle():
+    # one 512x384 image against the CPU oracle, plus batch-composition invariance at that size
+    net, sd = _net("resnet101_rmac", 2)
+    x = synth.make_images(3, 384, 512, seed=9)
+    d = net(x.cuda()).cpu().numpy()
+    ref = O.extract(x[:1], sd, "resnet101_rmac", squeeze=False).numpy()
+    assert rel_l2(d[:1], ref) < TOL
+    d_alone = net(x[1:2].cuda()).cpu().numpy()
+    assert np.array_equal(d_alone, d[1])

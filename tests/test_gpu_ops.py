@@ -1,0 +1,150 @@
+"""Parity of the CUDA operators (through the C ABI) against the CPU oracle.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dirb200.synth as synth
+from oracle import dir_oracle as O
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from dirb200 import ops
+    ops.require_gpu(0)
+    return ops
+
+
+def _conv_case(ops, B, H, W, Cin, Cout, k, stride, pad, use_res, relu, impl, seed=0):
+    r = np.random.RandomState(seed)
+    x = torch.from_numpy(r.standard_normal((B, H, W, Cin)).astype(np.float32)).half()
+    w = torch.from_numpy((r.standard_normal((Cout, Cin, k, k)) * np.sqrt(2.0 / (Cin * k * k))).astype(np.float32))
+    scale = torch.from_numpy(r.uniform(0.5, 1.5, Cout).astype(np.float32))
+    shift = torch.from_numpy((0.2 * r.standard_normal(Cout)).astype(np.float32))
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.from_numpy(r.standard_normal((B, Ho, Wo, Cout)).astype(np.float32)).half() if use_res else None
+    # oracle: fp32 conv of the SAME fp16-rounded operands (resnet.py:56-63,70-85)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), None, stride=stride, padding=pad)
+    y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if use_res:
+        y = y + res.float().permute(0, 3, 1, 2)
+    if relu:
+        y = F.relu(y)
+    y = y.permute(0, 2, 3, 1).contiguous()
+    wp = ops.pack_conv_weight(w).to(DEV)
+    out = ops.conv_bn_act(x.to(DEV), wp, Cout, k, k, stride, pad, scale.to(DEV), shift.to(DEV),
+                          res.to(DEV) if use_res else None, relu, impl)
+    torch.cuda.synchronize()
+    out = out.float().cpu()
+    assert out.shape == y.shape
+    err = (out - y).abs().max().item()
+    tol = 2e-3 * max(1.0, y.abs().max().item())       # fp16 output rounding (2^-11 relative) + fp32 sum order
+    return err, tol
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad, res, relu
+    (2, 16, 16, 64, 64, 1, 1, 0, False, True),
+    (2, 14, 14, 256, 64, 1, 1, 0, False, True),      # M = 392: ragged last tile
+    (1, 56, 56, 64, 256, 1, 1, 0, True, True),       # conv3 + residual
+    (1, 16, 16, 64, 128, 3, 1, 1, False, True),
+    (2, 14, 14, 128, 128, 3, 1, 1, False, True),     # patch 7x7-ish, zero padding at the borders
+    (3, 7, 7, 512, 512, 3, 1, 1, False, True),       # several images per patch
+    (2, 15, 17, 64, 64, 3, 2, 1, False, True),       # odd sizes, stride 2
+    (2, 28, 28, 128, 128, 3, 2, 1, False, True),
+    (2, 14, 14, 256, 512, 1, 2, 0, False, False),    # downsample branch (no ReLU)
+    (1, 32, 32, 1024, 256, 1, 1, 0, False, True),    # long K
+    (1, 64, 64, 256, 256, 3, 1, 1, False, True),     # layer3-like at 1024^2 input
+]
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(str(v) for v in c[:8]))
+def test_conv_bn_act(case, impl):
+    err, tol = _conv_case(_ops(), *case, impl=impl)
+    assert err <= tol, (err, tol)
+
+
+def test_stem_and_maxpool():
+    ops = _ops()
+    x = synth.make_images(2, 64, 96, seed=3)
+    sd = synth.make_state_dict("resnet50_rmac", seed=0)
+    x8 = ops.nchw_to_nhwc8(x.to(DEV))
+    torch.cuda.synchronize()
+    ref8 = torch.zeros(2, 64, 96, 8)
+    ref8[..., :3] = x.permute(0, 2, 3, 1)
+    assert torch.equal(x8.cpu(), ref8.half())
+    w = sd["conv1.weight"]
+    s = sd["bn1.weight"] / torch.sqrt(sd["bn1.running_var"] + 1e-5)
+    b = sd["bn1.bias"] - sd["bn1.running_mean"] * s
+    wp = ops.pack_conv_weight(w, cin_pad=8).to(DEV)
+    y = ops.conv_bn_act(x8, wp, 64, 7, 7, 2, 3, s.to(DEV), b.to(DEV), None, True, impl=1)
+    yp = ops.maxpool_3x3s2(y)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.half().float(), w.half().float(), None, stride=2, padding=3) * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1))
+    assert (y.float().cpu() - ref.permute(0, 2, 3, 1)).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    refp = F.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(yp.float().cpu(), refp)            # max of fp16 values is exact
+
+
+@pytest.mark.parametrize("kw", [dict(pooling="gem", p=3.0), dict(pooling="gem", p=2.5), dict(pooling="max"),
+                                dict(pooling="avg"), dict(pooling="gem", p=3.0, norm_features=True),
+                                dict(pooling="gem", p=3.0, without_fc=True)],
+                         ids=["gem3", "gem2.5", "max", "avg", "normfeat", "nofc"])
+@pytest.mark.parametrize("shape", [(4, 7, 7), (1, 5, 9), (3, 32, 32)], ids=["4x7x7", "1x5x9", "3x32x32"])
+def test_head(shape, kw):
+    ops = _ops()
+    b, h, w = shape
+    r = np.random.RandomState(1)
+    feat = torch.from_numpy(np.abs(r.standard_normal((b, h, w, 2048))).astype(np.float32)).half()
+    feat[0, 0, 0, :7] = 0.0                                # exercises clamp(min=eps)
+    sd = {"adpool.p": torch.tensor([kw.get("p", 3.0)]),
+          "fc.weight": torch.from_numpy((r.standard_normal((2048, 2048)) / 45.0).astype(np.float32)),
+          "fc.bias": torch.from_numpy((0.01 * r.standard_normal(2048)).astype(np.float32))}
+    without_fc = kw.get("without_fc", False)
+    ref = O.head(feat.float().permute(0, 3, 1, 2), sd, pooling=kw["pooling"], norm_features=kw.get("norm_features", False),
+                 without_fc=without_fc, squeeze=False).numpy()
+    out = ops.head_pool_fc_l2(feat.to(DEV), pooling=kw["pooling"], p=kw.get("p", 3.0), eps=1e-6,
+                              norm_features=kw.get("norm_features", False),
+                              fc_w=None if without_fc else sd["fc.weight"].to(DEV),
+                              fc_b=None if without_fc else sd["fc.bias"].to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu().numpy(), ref) < 2e-5
+
+
+def test_pool_scales_l2_whiten(golden):
+    ops = _ops()
+    g = golden("pool.npz")
+    xs = [torch.from_numpy(g[k]).to(DEV) for k in ("x0", "x1", "x2")]
+    np.testing.assert_allclose(ops.pool_scales(xs, "mean", 3, l2=False).cpu().numpy(), g["mean"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(ops.pool_scales(xs, "gem", 3, l2=False).cpu().numpy(), g["gem3"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(ops.pool_scales(xs[:2], "gem", 2, l2=False).cpu().numpy(), g["gem2"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_array_equal(ops.pool_scales(xs[:1], "gem", 3, l2=False).cpu().numpy(), g["single"])
+    with pytest.raises(ValueError):
+        ops.pool_scales(xs, "bogus")
+    pooled = ops.pool_scales(xs, "gem", 3, l2=True).cpu().numpy()
+    assert rel_l2(pooled, O.l2n(g["gem3"])) < 1e-5
+    # whitening against the golden (D=64) and against the oracle at D=2048
+    w = golden("whiten.npz")
+    X = torch.from_numpy(w["X"]).to(DEV)
+    comp, mean, var = w["comp_f32"], w["mean_f32"], w["var_f32"]
+    cs = (1.0 / (1.0 * np.power(var, 0.25))).astype(np.float32)
+    y = ops.whiten(X, torch.from_numpy(comp).to(DEV), torch.from_numpy(mean).to(DEV), torch.from_numpy(cs).to(DEV))
+    assert rel_l2(y.cpu().numpy(), w["w_p025_f64"]) < 1e-5
+    cs2 = (1.0 / (2.0 * np.power(var[:32], 0.5))).astype(np.float32)
+    y2 = ops.whiten(X, torch.from_numpy(comp[:32].copy()).to(DEV), torch.from_numpy(mean).to(DEV), torch.from_numpy(cs2).to(DEV))
+    assert rel_l2(y2.cpu().numpy(), w["w_p05_v32_m2_f64"]) < 1e-5
+    y3 = ops.whiten(X, torch.from_numpy(comp).to(DEV), torch.from_numpy(mean).to(DEV), torch.from_numpy(cs).to(DEV), l2norm=False)
+    assert rel_l2(y3.cpu().numpy(), w["w_nol2_f64"]) < 1e-5
+    pca = synth.make_pca(2048, seed=11, dtype=np.float32)
+    Xb = synth._unit_rows(np.random.RandomState(5).standard_normal((300, 2048))).astype(np.float32)
+    ref = O.whiten_features(Xb.astype(np.float64), synth.make_pca(2048, seed=11, dtype=np.float64), whitenp=0.25)
+    csb = (1.0 / np.power(pca.explained_variance_.astype(np.float64), 0.25)).astype(np.float32)
+    yb, yb16 = ops.whiten(torch.from_numpy(Xb).to(DEV), torch.from_numpy(pca.components_).to(DEV),
+                          torch.from_numpy(pca.mean_).to(DEV), torch.from_numpy(csb).to(DEV), want_f16=True)
+    assert rel_l2(yb.cpu().numpy(), ref) < 1e-3            # north-star tolerance; fp32 SIMT gives ~1e-6
+    assert rel_l2(yb.cpu().numpy(), ref) < 2e-5
+    assert rel_l2(yb16.float().cpu().numpy(), ref) < 1e-3

@@ -1,0 +1,110 @@
+"""Parity of similarity + top-k, merge, exact scores and alpha-QE against the CPU oracle.  -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import dirb200.synth as synth
+from oracle import dir_oracle as O
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from dirb200 import ops
+    ops.require_gpu(0)
+    return ops
+
+
+def _check_topk(ops, n_db, n_q, dim, k, n_pos=10, sample_rows=0, seed=0):
+    db, q, pos = synth.make_descriptor_db(n_db, n_q, dim=dim, n_pos=n_pos, db_seed=100 + seed, q_seed=200 + seed)
+    index = ops.Index(torch.from_numpy(db).to(DEV), index_offset=0)
+    if sample_rows:
+        index.set_option("sample_rows", sample_rows)
+    s, i = index.search(torch.from_numpy(q).to(DEV), k)
+    torch.cuda.synchronize()
+    rs, ri = O.topk(q, db, k)
+    kk = min(k, n_db)
+    np.testing.assert_array_equal(i.cpu().numpy()[:, :kk], ri)           # indices bit-exact
+    np.testing.assert_allclose(s.cpu().numpy()[:, :kk], rs, rtol=0, atol=1e-12)
+    if k > n_db:
+        assert (i.cpu().numpy()[:, n_db:] == -1).all()
+    return index.stats(), pos, i.cpu().numpy()
+
+
+@pytest.mark.parametrize("n_db,n_q,dim,k", [(100, 4, 2048, 10), (100, 4, 2048, 100), (50, 3, 128, 100),
+                                             (1000, 70, 2048, 100), (5000, 130, 256, 20), (20000, 7, 2048, 1)])
+def test_topk_small_db(n_db, n_q, dim, k):
+    _check_topk(_ops(), n_db, n_q, dim, k)
+
+
+def test_topk_filtered_pass():
+    # N > sample rows -> seed pass + filtered tensor-core pass + exact rescoring
+    st, pos, idx = _check_topk(_ops(), 30000, 70, 2048, 100, sample_rows=4096)
+    assert st["dense_rows"] == 4096 and st["candidates"] > 0 and st["retries"] == 0
+    for qi in range(pos.shape[0]):                                        # every planted positive is retrieved
+        assert set(pos[qi]) <= set(idx[qi])
+
+
+def test_topk_overflow_retry():
+    # a tiny seed sample makes a loose threshold -> candidate overflow -> tightened re-run must stay exact
+    st, _, _ = _check_topk(_ops(), 60000, 5, 256, 50, sample_rows=256, seed=3)
+    assert st["retries"] >= 1
+
+
+def test_topk_ties_lowest_index_first():
+    ops = _ops()
+    db, q, _ = synth.make_descriptor_db(2000, 3, dim=128, n_pos=0)
+    db[100] = db[7]
+    db[1500] = db[7]                                                      # three identical rows
+    q[0] = db[7]
+    s, i = ops.Index(torch.from_numpy(db).to(DEV)).search(torch.from_numpy(q).to(DEV), 5)
+    assert i[0, :3].cpu().tolist() == [7, 100, 1500]
+    rs, ri = O.topk(q, db, 5)
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+
+
+def test_shard_merge_matches_single_index():
+    ops = _ops()
+    db, q, _ = synth.make_descriptor_db(12000, 33, dim=512, n_pos=6)
+    k, G = 50, 4
+    qd = torch.from_numpy(q).to(DEV)
+    parts = np.array_split(np.arange(12000), G)
+    ss, ii = [], []
+    for part in parts:
+        idx = ops.Index(torch.from_numpy(db[part[0]:part[-1] + 1]).to(DEV), index_offset=int(part[0]))
+        s, i = idx.search(qd, k)
+        ss.append(s)
+        ii.append(i)
+    ms, mi = ops.topk_merge(torch.stack(ss).contiguous(), torch.stack(ii).contiguous(), k)
+    rs, ri = O.topk(q, db, k)
+    np.testing.assert_array_equal(mi.cpu().numpy(), ri)
+    np.testing.assert_allclose(ms.cpu().numpy(), rs, rtol=0, atol=1e-12)
+    os_, oi = O.merge_topk([s.cpu().numpy() for s in ss], [i.cpu().numpy() for i in ii], k)
+    np.testing.assert_array_equal(mi.cpu().numpy(), oi)
+
+
+def test_scores_exact_and_map(golden):
+    ops = _ops()
+    g = golden("rank_ap.npz")
+    db, q, pos = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                          db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    sc = ops.scores_exact(torch.from_numpy(q).to(DEV), torch.from_numpy(db).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(sc, g["scores"], rtol=0, atol=2e-6)
+    gnd = synth.oxford_gt(pos, n_junk=int(g["n_junk"]), n_db=int(g["n_db"]), seed=int(g["gt_seed"]))
+    for i in range(sc.shape[0]):
+        assert abs(O.eval_query_ap(sc[i], gnd[i]["ok"], gnd[i]["junk"]) - g["aps"][i]) < 1e-12
+
+
+def test_aqe(golden):
+    ops = _ops()
+    g = golden("aqe.npz")
+    db, q, pos = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                          db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    dbd, qd = torch.from_numpy(db).to(DEV), torch.from_numpy(q).to(DEV)
+    for k, alpha, key in ((2, 0.5, "aqe_k2_a05"), (3, 1.0, "aqe_k3_a1")):
+        rs, ri = O.topk(q, db, k)
+        out = ops.aqe_expand(qd, dbd, torch.from_numpy(ri).to(DEV), torch.from_numpy(rs).to(DEV), alpha)
+        assert rel_l2(out.cpu().numpy(), g[key]) < 1e-5
+        assert rel_l2(out.cpu().numpy(), O.expand_descriptors(q, db=db, k=k, alpha=alpha)) < 1e-5
