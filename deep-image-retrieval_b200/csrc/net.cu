@@ -67,9 +67,10 @@ struct dirb200_net {
   float* d_desc = nullptr;
   size_t d_desc_bytes = 0;
   cudaStream_t own_stream = nullptr;
-  // debug taps of the last chunk
-  struct Tap { const __half* ptr; int n, h, w, c; };
+  // debug taps of the last chunk (copies, only when the "debug_taps" option is set)
+  struct Tap { __half* ptr; size_t cap; int n, h, w, c; };
   std::map<std::string, Tap> taps;
+  int debug_taps = 0;
   int64_t last_launches = 0;
   double last_flops = 0;
 };
@@ -77,6 +78,23 @@ struct dirb200_net {
 static int dev_alloc(dirb200_net* n, void** p, size_t bytes) {
   DIRB_CUDA(cudaMalloc(p, bytes));
   n->owned.push_back(*p);
+  return 0;
+}
+
+// keep a copy of an intermediate activation (the rotating buffers are overwritten by later layers)
+static int record_tap(dirb200_net* n, const std::string& name, const __half* src, int nb, int h, int w, int c,
+                      cudaStream_t stream) {
+  if (!n->debug_taps) return 0;
+  const size_t bytes = static_cast<size_t>(nb) * h * w * c * 2;
+  auto& t = n->taps[name];
+  if (t.cap < bytes) {
+    if (t.ptr) DIRB_CUDA(cudaFree(t.ptr));
+    t.ptr = nullptr;
+    DIRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&t.ptr), bytes));
+    t.cap = bytes;
+  }
+  t.n = nb; t.h = h; t.w = w; t.c = c;
+  DIRB_CUDA(cudaMemcpyAsync(t.ptr, src, bytes, cudaMemcpyDeviceToDevice, stream));
   return 0;
 }
 
@@ -169,6 +187,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "chunk") n->chunk = static_cast<int>(value);
   else if (k == "conv_impl") n->conv_impl = static_cast<int>(value);
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
+  else if (k == "debug_taps") n->debug_taps = value != 0;
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown net option '%s'", key);
   return 0;
 }
@@ -299,7 +318,7 @@ int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int
     DIRB_TRY(run_conv(n, n->stem, in8, cb, H, W, nullptr, 1, stem_out, stream, /*force_mma=*/1));
     __half* x = act[0];
     DIRB_TRY(maxpool_3x3s2(stem_out, cb, H1, W1, 64, x, stream));
-    n->taps["stem"] = {x, cb, H2, W2, 64};
+    DIRB_TRY(record_tap(n, "stem", x, cb, H2, W2, 64, stream));
     int h = H2, w = W2, cur = 0, layer = 0;
     for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
       const Block& blk = n->blocks[bi];
@@ -322,7 +341,7 @@ int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int
       h = ho;
       w = wo;
       if (static_cast<int>(bi) + 1 == n->layer_end[layer]) {
-        n->taps["layer" + std::to_string(layer + 1)] = {x, cb, h, w, blk.c3.Cout};
+        DIRB_TRY(record_tap(n, "layer" + std::to_string(layer + 1), x, cb, h, w, blk.c3.Cout, stream));
         ++layer;
       }
     }
@@ -367,7 +386,8 @@ int dirb200_net_debug_stage(dirb200_net* n, const char* what, void* dst_dev, siz
                             void* stream_) {
   DIRB_REQUIRE(n && what && dst_dev && dims, DIRB200_EINVAL, "null argument");
   auto it = n->taps.find(what);
-  DIRB_REQUIRE(it != n->taps.end(), DIRB200_EKEY, "no stage '%s' recorded (run a forward first)", what);
+  DIRB_REQUIRE(it != n->taps.end() && it->second.ptr, DIRB200_EKEY,
+               "no stage '%s' recorded (set option debug_taps=1 and run a forward first)", what);
   const auto& t = it->second;
   const size_t bytes = static_cast<size_t>(t.n) * t.h * t.w * t.c * 2;
   DIRB_REQUIRE(bytes <= capacity, DIRB200_EINVAL, "stage '%s' needs %zu bytes", what, bytes);
@@ -387,6 +407,7 @@ int dirb200_net_destroy(dirb200_net* n) {
   if (!n) return 0;
   cudaSetDevice(n->device);
   for (void* p : n->owned) cudaFree(p);
+  for (auto& kv : n->taps) if (kv.second.ptr) cudaFree(kv.second.ptr);
   if (n->ws) cudaFree(n->ws);
   if (n->h2d) cudaFree(n->h2d);
   if (n->d_desc) cudaFree(n->d_desc);

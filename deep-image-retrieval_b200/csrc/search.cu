@@ -293,6 +293,7 @@ struct dirb200_index {
   int64_t N = 0, offset = 0;
   double eps16 = 1.2e-3;
   int64_t sample_rows = 0;
+  int cand_cap = 0;          // 0 = auto
   // workspaces (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -347,6 +348,7 @@ int dirb200_index_set_option(dirb200_index* h, const char* key, double value) {
   const std::string k(key);
   if (k == "eps16") h->eps16 = value;
   else if (k == "sample_rows") h->sample_rows = static_cast<int64_t>(value);
+  else if (k == "cand_cap") h->cand_cap = static_cast<int>(value);
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown index option '%s'", key);
   return 0;
 }
@@ -393,6 +395,7 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   const int64_t S_ld = ceil_div(S, 128) * 128;   // dense row stride (16-byte aligned rows)
   const double expect = small ? (2.0 * k + 64) : (1.5 * k * static_cast<double>(N) / S);
   int cap = static_cast<int>(std::min<double>(std::max<double>(4096, 4 * expect), 1 << 18));
+  if (h->cand_cap > 0) cap = std::max(h->cand_cap, 2 * k);
   cap = (cap + 255) / 256 * 256;
   const float band = static_cast<float>(2.0 * h->eps16);
 

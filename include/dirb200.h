@@ -51,7 +51,8 @@ int dirb200_device_check(int device);
 int dirb200_net_create(const char* arch, int device, dirb200_net** out);
 /* Options (rmac_resnet.py:15-37): "pooling" 0=gem 1=max 2=avg; "norm_features" 0/1;
  * "without_fc" 0/1; "out_dim"; "chunk" images processed per pass (0 = auto);
- * "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path). */
+ * "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path);
+ * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage. */
 int dirb200_net_set_option(dirb200_net* net, const char* key, double value);
 /* One state_dict tensor by its reference key ("layer3.5.bn2.running_var", "adpool.p", "fc.weight" ...),
  * fp32 host memory, reference shape (conv OIHW).  "num_batches_tracked" keys are ignored. */
@@ -66,8 +67,8 @@ int dirb200_net_forward(dirb200_net* net, const float* imgs_dev, int B, int H, i
 /* Same through HOST buffers: H2D copy of the images, forward, D2H copy of the descriptors, stream sync
  * (the common.variables() -> net() -> tonumpy() sequence, common.py:205-218,23-27). */
 int dirb200_net_forward_host(dirb200_net* net, const float* imgs_host, int B, int H, int W, float* desc_host);
-/* Debug tap: copy the NHWC fp16 activation after stage `what` ("stem","layer1".."layer4") of the LAST chunk of
- * the last forward into dst_dev (capacity in bytes); returns its dims as {n,h,w,c}. */
+/* Debug tap (needs option "debug_taps"): copy the NHWC fp16 activation after stage `what` ("stem","layer1".."layer4")
+ * of the LAST chunk of the last forward into dst_dev (capacity in bytes); returns its dims as {n,h,w,c}. */
 int dirb200_net_debug_stage(dirb200_net* net, const char* what, void* dst_dev, size_t capacity, int dims[4],
                             void* stream);
 /* Number of kernels the last forward launched / algorithmic conv+fc FLOPs of the last forward. */
@@ -124,7 +125,8 @@ int dirb200_index_create(int device, int dim, dirb200_index** out);
 int dirb200_index_set_db(dirb200_index* idx, const float* db32_dev, const void* db16_dev, int64_t N,
                          int64_t index_offset);
 /* "eps16": bound on |fp16-path score - exact score| used for the candidate band (default 1.2e-3, valid for
- * unit-norm rows); "sample_rows": rows scored densely to seed the threshold (0 = auto). */
+ * unit-norm rows); "sample_rows": rows scored densely to seed the threshold (0 = auto); "cand_cap": per-query
+ * candidate-list capacity (0 = auto; a small value forces the overflow -> tightened re-run path). */
 int dirb200_index_set_option(dirb200_index* idx, const char* key, double value);
 /* q32_dev [Q][dim] fp32.  Outputs (device): scores_dev [Q][k] fp64 exact scores, idx_dev [Q][k] int64.
  * If N < k the tail is filled with score -inf / index -1.  Synchronises the stream (overflow check). */

@@ -29,6 +29,7 @@ def test_extract_r50_golden(golden, impl):
     g = golden("extract_r50.npz")
     net, sd = _net("resnet50_rmac", int(g["seed"]))
     net.set_backend_option("conv_impl", impl)
+    net.set_backend_option("debug_taps", 1)
     x = synth.make_images(4, 224, 224, seed=int(g["img_seed"]))
     d = net(x.cuda()).cpu().numpy()
     # stage-by-stage diagnostics against the reference's activations (one pixel, all channels)

@@ -17,11 +17,13 @@ def _ops():
     return ops
 
 
-def _check_topk(ops, n_db, n_q, dim, k, n_pos=10, sample_rows=0, seed=0):
+def _check_topk(ops, n_db, n_q, dim, k, n_pos=10, sample_rows=0, seed=0, cand_cap=0):
     db, q, pos = synth.make_descriptor_db(n_db, n_q, dim=dim, n_pos=n_pos, db_seed=100 + seed, q_seed=200 + seed)
     index = ops.Index(torch.from_numpy(db).to(DEV), index_offset=0)
     if sample_rows:
         index.set_option("sample_rows", sample_rows)
+    if cand_cap:
+        index.set_option("cand_cap", cand_cap)
     s, i = index.search(torch.from_numpy(q).to(DEV), k)
     torch.cuda.synchronize()
     rs, ri = O.topk(q, db, k)
@@ -49,7 +51,7 @@ def test_topk_filtered_pass():
 
 def test_topk_overflow_retry():
     # a tiny seed sample makes a loose threshold -> candidate overflow -> tightened re-run must stay exact
-    st, _, _ = _check_topk(_ops(), 60000, 5, 256, 50, sample_rows=256, seed=3)
+    st, _, _ = _check_topk(_ops(), 60000, 5, 256, 50, sample_rows=256, seed=3, cand_cap=512)
     assert st["retries"] >= 1
 
 
