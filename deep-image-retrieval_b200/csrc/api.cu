@@ -23,6 +23,7 @@ int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const 
   ConvShape s{B, H, W, Cin, Cout, KH, KW, stride, pad};
   DIRB_REQUIRE(s.Ho() > 0 && s.Wo() > 0, DIRB200_EINVAL, "empty output");
   if (impl == 0) return conv_tc(s, CH16(in_dev), CH16(w_dev), scale_dev, shift_dev, CH16(res_dev), relu, H16(out_dev), ST(stream));
+  if (impl == 2) return conv_tc_np(s, CH16(in_dev), CH16(w_dev), scale_dev, shift_dev, CH16(res_dev), relu, H16(out_dev), ST(stream));
   const int K = KH * KW * Cin;
   return conv_mma(s, CH16(in_dev), CH16(w_dev), (K + 31) / 32 * 32, scale_dev, shift_dev, CH16(res_dev), relu,
                   H16(out_dev), ST(stream));

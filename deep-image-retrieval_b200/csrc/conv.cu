@@ -5,6 +5,7 @@
 // :115-118 (stem).  BatchNorm (eval) is folded by the caller into scale = gamma/sqrt(var+eps), shift = beta-mean*scale.
 #include "conv.h"
 
+#include "conv_pers.cuh"
 #include "gemm_tc.cuh"
 
 namespace dirb {
@@ -78,13 +79,80 @@ static int conv_tc_bn(const ConvShape& s, const __half* in, const __half* w, con
   return gemm_tc_launch<BN, 3, EPI_CONV, 2>(tmA, tmB, p, m_tiles, stream);
 }
 
-int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
-            const __half* res, int relu, __half* out, cudaStream_t stream) {
+int conv_tc_np(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+               const __half* res, int relu, __half* out, cudaStream_t stream) {
   DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
                "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
   DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
   if (s.Cout % 128 == 0) return conv_tc_bn<128>(s, in, w, scale, shift, res, relu, out, stream);
   return conv_tc_bn<64>(s, in, w, scale, shift, res, relu, out, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ persistent tcgen05 path
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+                        const __half* res, int relu, __half* out, cudaStream_t stream) {
+  const int Ho = s.Ho(), Wo = s.Wo();
+  const int Ktot = s.KH * s.KW * s.Cin;
+  ConvPersParams p{};
+  p.taps = s.KH * s.KW;
+  p.kw_taps = s.KW;
+  p.cin_blocks = s.Cin / 64;
+  p.stride = s.stride;
+  p.pad = s.pad;
+  p.n_tiles = s.Cout / BN;
+  p.has_res = res != nullptr;
+  p.relu = relu;
+  p.scale = scale;
+  p.shift = shift;
+  CUtensorMap tmA, tmB, tmR, tmO;
+  int64_t m_tiles;
+  const bool flat = (s.KH == 1 && s.KW == 1 && s.stride == 1 && s.pad == 0);
+  if (flat) {
+    const int64_t M = static_cast<int64_t>(s.B) * s.H * s.W;
+    p.a_spatial = 0;
+    p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
+    m_tiles = ceil_div(M, 128);
+    DIRB_TRY(encode_tmap_2d(&tmA, in, s.Cin, M, (uint64_t)s.Cin * 2, 64, 128));
+    DIRB_TRY(encode_tmap_2d(&tmO, out, s.Cout, M, (uint64_t)s.Cout * 2, 64, 128));
+    if (res) DIRB_TRY(encode_tmap_2d(&tmR, res, s.Cout, M, (uint64_t)s.Cout * 2, 64, 128));
+  } else {
+    p.a_spatial = 1;
+    pick_patch(s.B, Ho, Wo, &p.tw, &p.th, &p.nb);
+    p.tiles_w = (int)ceil_div(Wo, p.tw);
+    p.tiles_h = (int)ceil_div(Ho, p.th);
+    m_tiles = (int64_t)p.tiles_w * p.tiles_h * ceil_div(s.B, p.nb);
+    DIRB_TRY(encode_tmap_nhwc(&tmA, in, s.B, s.H, s.W, s.Cin, p.tw, p.th, p.nb, s.stride));
+    DIRB_TRY(encode_tmap_nhwc(&tmO, out, s.B, Ho, Wo, s.Cout, p.tw, p.th, p.nb, 1));
+    if (res) DIRB_TRY(encode_tmap_nhwc(&tmR, res, s.B, Ho, Wo, s.Cout, p.tw, p.th, p.nb, 1));
+  }
+  if (!res) tmR = tmO;
+  DIRB_TRY(encode_tmap_2d(&tmB, w, Ktot, s.Cout, (uint64_t)Ktot * 2, 64, BN));
+  const int64_t total = m_tiles * p.n_tiles;
+  DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
+  p.total_tiles = static_cast<int>(total);
+  return conv_pers_launch<BN, STAGES>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
+}
+
+int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+            const __half* res, int relu, __half* out, cudaStream_t stream) {
+  DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
+               "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
+  DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
+  if (s.Cout % 256 == 0) return conv_pers_bn<256, 3>(s, in, w, scale, shift, res, relu, out, stream);
+  if (s.Cout % 128 == 0) return conv_pers_bn<128, 4>(s, in, w, scale, shift, res, relu, out, stream);
+  return conv_pers_bn<64, 4>(s, in, w, scale, shift, res, relu, out, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ mma.sync path

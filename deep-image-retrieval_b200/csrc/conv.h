@@ -14,6 +14,9 @@ struct ConvShape {
 // w: [Cout][KH*KW*Cin] fp16 (K index = (kh*KW + kw)*Cin + c).
 int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
             const __half* res, int relu, __half* out, cudaStream_t stream);
+// The earlier one-tile-per-CTA tcgen05 kernel (gemm_tc.cuh), kept as an A/B baseline (impl 2).
+int conv_tc_np(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+               const __half* res, int relu, __half* out, cudaStream_t stream);
 // w: [Cout][Kpad] fp16, Kpad = KH*KW*Cin rounded up to 32, zero padded.
 int conv_mma(const ConvShape& s, const __half* in, const __half* w, int Kpad, const float* scale, const float* shift,
              const __half* res, int relu, __half* out, cudaStream_t stream);

@@ -1,0 +1,288 @@
+// Persistent tcgen05 implicit-GEMM convolution + BN + residual + ReLU for sm_100a.
+//
+// One CTA per SM loops over output tiles (128 pixels x BN channels, BN up to 256); 8 warps, each with one job:
+//
+//   warp 0  TMA producer   A (128x64 activation patch) and B (BNx64 weights) into a STAGES-deep smem ring
+//   warp 1  MMA issuer     tcgen05.mma (M=128, N=BN, K=16) x 4 per ring slot into one of TWO TMEM accumulators,
+//                          so the tensor core starts tile i+1 while tile i is still being drained
+//   warp 2  residual TMA   prefetches the residual tile (same box as the output tile) 64 channels at a time into
+//                          the staging buffers, up to NBUF chunks ahead of the epilogue
+//   warp 3  TMEM allocator
+//   warps 4-7 epilogue     tcgen05.ld (one accumulator row per thread) -> scale/shift (+ residual read from the
+//                          staging buffer) (+ ReLU) -> fp16, written back IN PLACE into the 128-byte-swizzled
+//                          staging buffer -> one TMA store per 64-channel chunk (clips ragged edges by itself)
+//
+// All global traffic is bulk/asynchronous (TMA); no thread ever issues a strided global load or store.  The A
+// operand addressing (flat rows or NHWC patches with taps, padding and stride through the tensor map) is the same
+// as in gemm_tc.cuh.
+#pragma once
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dirb {
+
+struct ConvPersParams {
+  int a_spatial, taps, kw_taps, cin_blocks, stride, pad;
+  int tw, th, nb, tiles_w, tiles_h;
+  int n_tiles, total_tiles;
+  int has_res, relu;
+  const float* scale;
+  const float* shift;
+};
+
+template <int BN, int STAGES>
+struct ConvPersSmem {
+  static constexpr int NBUF = 4;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = 128 * 128;                      // 128 rows x 64 channels fp16
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + NBUF * STG_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF;
+  static constexpr int TOTAL = BAR_OFF + 8 * NUM_BARS + 16 + 1024;  // + tmem slot + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;                          // two accumulators
+};
+
+struct TileCoord {
+  int m_tile, n_tile, wo0, ho0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvPersParams& p, int t) {
+  TileCoord c;
+  c.n_tile = t % p.n_tiles;
+  c.m_tile = t / p.n_tiles;
+  c.wo0 = c.ho0 = c.n0 = 0;
+  if (p.a_spatial) {
+    const int tx = c.m_tile % p.tiles_w;
+    const int ty = (c.m_tile / p.tiles_w) % p.tiles_h;
+    const int tb = c.m_tile / (p.tiles_w * p.tiles_h);
+    c.wo0 = tx * p.tw;
+    c.ho0 = ty * p.th;
+    c.n0 = tb * p.nb;
+  }
+  return c;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                 const ConvPersParams p) {
+  using L = ConvPersSmem<BN, STAGES>;
+  constexpr int NBUF = L::NBUF;
+  constexpr int CHUNKS = BN / 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + L::STG_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* res_full = acc_empty + 2;
+  uint64_t* res_empty = res_full + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + NBUF);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int k_iters = p.taps * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    if (p.has_res) tma_prefetch_desc(&tmR);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);      // one arrival per epilogue warp
+    }
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&res_full[b], 1);
+      mbar_init(&res_empty[b], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 3) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ A/B producer
+      uint32_t g = 0;  // ring slot counter, runs across tiles
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        for (int it = 0; it < k_iters; ++it, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          const int tap = it / p.cin_blocks;
+          const int kc = it - tap * p.cin_blocks;
+          if (p.a_spatial) {
+            const int kh = tap / p.kw_taps;
+            const int kw = tap - kh * p.kw_taps;
+            tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, c.wo0 * p.stride + kw - p.pad,
+                        c.ho0 * p.stride + kh - p.pad, c.n0);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[s], it * 64, c.m_tile * 128);
+          }
+          tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[s], it * 64, c.n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      uint32_t g = 0, i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        const uint32_t a = i & 1;
+        mbar_wait(&acc_empty[a], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int it = 0; it < k_iters; ++it, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&full_bar[s], (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[a]);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0 && p.has_res) {
+      // ------------------------------------------------------------ residual producer
+      uint32_t cc = 0;  // staging chunk counter, runs across tiles
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
+          const int b = cc % NBUF;
+          mbar_wait(&res_empty[b], ((cc / NBUF) & 1) ^ 1);
+          mbar_expect_tx(&res_full[b], L::STG_BYTES);
+          if (p.a_spatial)
+            tma_load_4d(stg + b * L::STG_BYTES, &tmR, &res_full[b], c.n_tile * BN + ch * 64, c.wo0, c.ho0, c.n0);
+          else
+            tma_load_2d(stg + b * L::STG_BYTES, &tmR, &res_full[b], c.n_tile * BN + ch * 64, c.m_tile * 128);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------- epilogue (128 threads)
+    const int quarter = warp - 4;
+    const int row = quarter * 32 + lane;
+    const bool leader = (threadIdx.x == 128);
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    uint32_t cc = 0, i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const TileCoord c = decode_tile(p, t);
+      const uint32_t a = i & 1;
+      mbar_wait(&acc_full[a], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + a * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
+        const int b = cc % NBUF;
+        uint8_t* buf = stg + b * L::STG_BYTES;
+        if (p.has_res) {
+          mbar_wait(&res_full[b], (cc / NBUF) & 1);       // residual chunk has landed in `buf`
+        } else {
+          if (leader) bulk_wait_read<NBUF - 1>();           // the store issued NBUF chunks ago has left `buf`
+          named_bar_sync(1, 128);
+        }
+        const int col0 = c.n_tile * BN + ch * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(taddr + ch * 64 + half * 32, v);
+          tmem_ld_wait();
+          if (ch == CHUNKS - 1 && half == 1) {             // last TMEM read of this tile: release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+          }
+          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
+            v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                    // 4 x 16-byte chunks (8 channels each) of this half
+            const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+            uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
+            if (p.has_res) {
+              const uint4 r = *sp;
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_h2(rr[e]);
+                v[j * 8 + e * 2] += f.x;
+                v[j * 8 + e * 2 + 1] += f.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
+            }
+            uint4 o;
+            o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
+            o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
+            o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
+            o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
+            *sp = o;
+          }
+        }
+        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(2, 128);
+        if (leader) {
+          if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
+          else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
+          bulk_commit();
+          if (p.has_res && cc >= 1) {                       // the previous chunk's store has finished reading its
+            bulk_wait_read<1>();                            // buffer -> hand that buffer back to the residual producer
+            mbar_arrive(&res_empty[(cc - 1) % NBUF]);
+          }
+        }
+      }
+    }
+    if (leader) bulk_wait<0>();                             // all output bytes written before the CTA retires
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int BN, int STAGES>
+int conv_pers_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
+                     const ConvPersParams& p, int num_sms, cudaStream_t stream) {
+  using L = ConvPersSmem<BN, STAGES>;
+  auto kern = conv_pers_kernel<BN, STAGES>;
+  DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  kern<<<grid, 256, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dirb

@@ -156,6 +156,7 @@ static int run_conv(dirb200_net* n, const ConvLayer& L, const __half* in, int B,
   n->last_flops += 2.0 * B * s.Ho() * s.Wo() * static_cast<double>(L.Cout) * L.K * L.K * L.Cin;
   if (force_mma || n->conv_impl == 1 || L.CinPad % 64 != 0)
     return conv_mma(s, in, L.w, L.Kpad, L.scale, L.shift, res, relu, out, stream);
+  if (n->conv_impl == 2) return conv_tc_np(s, in, L.w, L.scale, L.shift, res, relu, out, stream);
   return conv_tc(s, in, L.w, L.scale, L.shift, res, relu, out, stream);
 }
 

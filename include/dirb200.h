@@ -51,7 +51,8 @@ int dirb200_device_check(int device);
 int dirb200_net_create(const char* arch, int device, dirb200_net** out);
 /* Options (rmac_resnet.py:15-37): "pooling" 0=gem 1=max 2=avg; "norm_features" 0/1;
  * "without_fc" 0/1; "out_dim"; "chunk" images processed per pass (0 = auto);
- * "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path);
+ * "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path),
+ * 2 = one-tile-per-CTA tcgen05 kernel (A/B baseline);
  * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage. */
 int dirb200_net_set_option(dirb200_net* net, const char* key, double value);
 /* One state_dict tensor by its reference key ("layer3.5.bn2.running_var", "adpool.p", "fc.weight" ...),
@@ -82,7 +83,7 @@ int dirb200_net_destroy(dirb200_net* net);
 int dirb200_nchw_to_nhwc8(const float* in_dev, int B, int H, int W, void* out_dev, void* stream);
 /* Conv2d(bias=False) + folded BatchNorm (+ residual add) (+ ReLU), NHWC fp16 in/out.
  * w_dev: [Cout][KH][KW][Cin] fp16; scale/shift: [Cout] fp32; res_dev may be NULL.
- * impl: 0 tcgen05 (needs Cin%64==0, Cout%64==0), 1 mma.sync (needs Cin%8==0, Cout%64==0).
+ * impl: 0 persistent tcgen05 (needs Cin%64==0, Cout%64==0), 1 mma.sync (needs Cin%8==0, Cout%64==0), 2 one-tile-per-CTA tcgen05.
  * resnet.py:56-63,70-85,115-118. */
 int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const void* w_dev, int Cout, int KH,
                         int KW, int stride, int pad, const float* scale_dev, const float* shift_dev,

@@ -11,6 +11,8 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 
 def pytest_configure(config):
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))   # oracle convs: many-core boxes oversubscribe badly
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 

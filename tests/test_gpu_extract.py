@@ -24,7 +24,7 @@ def _net(arch, seed, **kw):
     return net, sd
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma", "tcgen05np"])
 def test_extract_r50_golden(golden, impl):
     g = golden("extract_r50.npz")
     net, sd = _net("resnet50_rmac", int(g["seed"]))

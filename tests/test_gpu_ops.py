@@ -58,10 +58,16 @@ CONV_CASES = [
     (2, 14, 14, 256, 512, 1, 2, 0, False, False),    # downsample branch (no ReLU)
     (1, 32, 32, 1024, 256, 1, 1, 0, False, True),    # long K
     (1, 64, 64, 256, 256, 3, 1, 1, False, True),     # layer3-like at 1024^2 input
+    # more tiles than SMs: the persistent kernel wraps its accumulator / staging / ring state across tiles
+    (8, 64, 64, 64, 256, 1, 1, 0, True, True),       # 256 tiles x 4 chunks, residual prefetch ring
+    (6, 64, 64, 128, 128, 3, 1, 1, False, True),     # 192 tiles, 18 k-iterations each
+    (3, 96, 96, 64, 64, 3, 1, 1, False, True),       # BN = 64
+    (4, 64, 64, 512, 512, 1, 1, 0, True, True),      # 2 n-tiles per m-tile, residual
+    (5, 30, 30, 256, 512, 1, 2, 0, False, False),    # stride-2 projection, ragged patches
 ]
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["tcgen05", "mma"])
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["tcgen05", "mma", "tcgen05np"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(str(v) for v in c[:8]))
 def test_conv_bn_act(case, impl):
     err, tol = _conv_case(_ops(), *case, impl=impl)
