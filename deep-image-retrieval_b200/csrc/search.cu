@@ -252,18 +252,27 @@ __global__ void scores_exact_kernel(const float* __restrict__ q, int Q, const fl
 // alpha query expansion: out_i = normalize(q_i + sum_j db[idx_ij] * s_ij^alpha)   (test_dir.py:38-42; the mean's
 // 1/(k+1) cancels in the normalisation).  partial: un-normalised neighbour sum only.
 __global__ void aqe_kernel(const float* __restrict__ q, int D, const float* __restrict__ db, const int64_t* __restrict__ nn,
-                           const double* __restrict__ ns, int k, double alpha, int partial, float* __restrict__ out) {
-  extern __shared__ float wts[];  // [k]
+                           const double* __restrict__ ns, int k, double alpha, int partial, int64_t row_offset,
+                           int64_t n_rows, float* __restrict__ out) {
+  extern __shared__ float wts[];  // [k] weights, then [k] local rows (as int64 pairs of floats)
   __shared__ float sh[32];
+  int64_t* rows = reinterpret_cast<int64_t*>(wts + ((k + 1) & ~1));
   const int i = blockIdx.x;
-  for (int j = threadIdx.x; j < k; j += blockDim.x)
-    wts[j] = (nn[static_cast<int64_t>(i) * k + j] >= 0) ? static_cast<float>(pow(ns[static_cast<int64_t>(i) * k + j], alpha)) : 0.f;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    int64_t r = nn[static_cast<int64_t>(i) * k + j];
+    if (r >= 0 && n_rows > 0) {                      // global index -> local row of this shard, or "not mine"
+      r -= row_offset;
+      if (r < 0 || r >= n_rows) r = -1;
+    }
+    rows[j] = r;
+    wts[j] = (r >= 0) ? static_cast<float>(pow(ns[static_cast<int64_t>(i) * k + j], alpha)) : 0.f;
+  }
   __syncthreads();
   float ss = 0.f;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float acc = partial ? 0.f : q[static_cast<int64_t>(i) * D + c];
     for (int j = 0; j < k; ++j) {
-      const int64_t r = nn[static_cast<int64_t>(i) * k + j];
+      const int64_t r = rows[j];
       if (r >= 0) acc += db[r * D + c] * wts[j];
     }
     out[static_cast<int64_t>(i) * D + c] = acc;
@@ -514,13 +523,14 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   return 0;
 }
 
-int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, double* out_scores_dev,
-                       int64_t* out_idx_dev, void* stream_) {
+int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, int64_t shard_stride,
+                       double* out_scores_dev, int64_t* out_idx_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DIRB_REQUIRE(scores_dev && idx_dev && out_scores_dev && out_idx_dev, DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(G >= 1 && Q >= 1 && k >= 1 && static_cast<int64_t>(G) * k <= 4096, DIRB200_ENOTSUP,
                "merge supports G*k <= 4096 (got G=%d k=%d)", G, k);
-  // inputs are [G][Q][k]; the kernel wants the G lists of one query contiguous -> gather with a strided copy
+  // shard g holds [Q][k] at element offset g*shard_stride; the kernel wants the G lists of one query contiguous
+  if (shard_stride <= 0) shard_stride = static_cast<int64_t>(Q) * k;
   const int n = G * k;
   double* tmp_s = nullptr;
   int64_t* tmp_i = nullptr;
@@ -528,10 +538,10 @@ int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, 
   DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp_i), static_cast<size_t>(Q) * n * 8, stream));
   for (int g = 0; g < G; ++g) {
     DIRB_CUDA(cudaMemcpy2DAsync(tmp_s + static_cast<size_t>(g) * k, static_cast<size_t>(n) * 8,
-                                scores_dev + static_cast<size_t>(g) * Q * k, static_cast<size_t>(k) * 8,
+                                scores_dev + static_cast<size_t>(g) * shard_stride, static_cast<size_t>(k) * 8,
                                 static_cast<size_t>(k) * 8, Q, cudaMemcpyDeviceToDevice, stream));
     DIRB_CUDA(cudaMemcpy2DAsync(tmp_i + static_cast<size_t>(g) * k, static_cast<size_t>(n) * 8,
-                                idx_dev + static_cast<size_t>(g) * Q * k, static_cast<size_t>(k) * 8,
+                                idx_dev + static_cast<size_t>(g) * shard_stride, static_cast<size_t>(k) * 8,
                                 static_cast<size_t>(k) * 8, Q, cudaMemcpyDeviceToDevice, stream));
   }
   int P = 2;
@@ -559,13 +569,15 @@ int dirb200_scores_exact(const float* q_dev, int Q, const float* db_dev, int64_t
 }
 
 int dirb200_aqe_expand(const float* q_dev, int Q, int D, const float* db32_dev, const int64_t* nn_idx_dev,
-                       const double* nn_scores_dev, int k, double alpha, int partial, float* out_dev, void* stream_) {
+                       const double* nn_scores_dev, int k, double alpha, int partial, int64_t row_offset, int64_t n_rows,
+                       float* out_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DIRB_REQUIRE(q_dev && db32_dev && nn_idx_dev && nn_scores_dev && out_dev, DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(k >= 1 && k <= 4096 && alpha >= 0, DIRB200_EINVAL, "k and alpha must be non-negative (test_dir.py:25)");
   if (Q == 0) return 0;
-  aqe_kernel<<<Q, 256, static_cast<size_t>(k) * 4, stream>>>(q_dev, D, db32_dev, nn_idx_dev, nn_scores_dev, k, alpha,
-                                                              partial, out_dev);
+  const size_t smem = static_cast<size_t>((k + 1) & ~1) * 4 + static_cast<size_t>(k) * 8;
+  aqe_kernel<<<Q, 256, smem, stream>>>(q_dev, D, db32_dev, nn_idx_dev, nn_scores_dev, k, alpha, partial, row_offset,
+                                       n_rows, out_dev);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   return 0;

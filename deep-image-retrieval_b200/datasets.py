@@ -1,0 +1,186 @@
+"""Minimal dataset layer behind the CLIs: image lists and Oxford-style retrieval ground truth.
+
+Mirrors the parts of ``dirtorch/datasets`` the evaluation path touches: ``ImageList`` (generic.py:13-30),
+``ImageListRelevants`` + ``eval_query_AP`` (generic.py:120-224), ``ImageListROIs`` (generic.py:226-250),
+the Oxford/Paris wrappers (oxford.py, paris.py) and ``create`` (create.py:19-24).  AP arithmetic follows
+``utils/evaluation.py:46-82``.  File bookkeeping only - nothing here is on the GPU hot path.
+"""
+from __future__ import annotations
+
+import os
+import os.path as osp
+import pickle
+
+import numpy as np
+
+
+def compute_average_precision(positive_ranks):
+    """Trapezoidal AP over sorted zero-based ranks of the positives (Revisited Oxford/Paris convention)."""
+    n = len(positive_ranks)
+    if not n:
+        return 0.0
+    ap = 0.0
+    for i, rank in enumerate(positive_ranks):
+        left = 1.0 if not rank else i / rank
+        right = (i + 1) / (rank + 1)
+        ap += (left + right) / (2.0 * n)
+    return ap
+
+
+class Dataset:
+    root = ""
+    img_dir = ""
+    nimg = 0
+    nquery = 0
+
+    def __len__(self):
+        return self.nimg
+
+    def get_key(self, i):
+        raise NotImplementedError()
+
+    def get_filename(self, i, root=None):
+        return os.path.join(root or self.root, self.img_dir, self.get_key(i))
+
+    def get_image(self, i, resize=None):
+        from PIL import Image
+        img = Image.open(self.get_filename(i)).convert("RGB")
+        if resize:
+            img = img.resize(resize, Image.LANCZOS if np.prod(resize) < np.prod(img.size) else Image.BICUBIC)
+        return img
+
+    def get_label(self, i, toint=False):
+        raise NotImplementedError()
+
+    def get_query_db(self):
+        raise NotImplementedError()
+
+    def eval_query_AP(self, query_idx, scores):
+        raise NotImplementedError()
+
+    def eval_query_top(self, query_idx, scores, k=(1, 5, 10, 20, 50, 100)):
+        raise NotImplementedError()
+
+    def __repr__(self):
+        return "Dataset: %s\n  %d images, %d queries" % (type(self).__name__, self.nimg, self.nquery)
+
+
+class ImageList(Dataset):
+    """A list of images (text file, one path per row, or an explicit list)."""
+
+    def __init__(self, img_list_path=None, root="", imgs=None):
+        self.root = root
+        self.imgs = list(imgs) if imgs is not None else [e.strip() for e in open(img_list_path) if e.strip()]
+        self.nimg = len(self.imgs)
+
+    def get_key(self, i):
+        return self.imgs[i]
+
+
+class ImageListROIs(Dataset):
+    def __init__(self, root, img_dir, imgs, rois):
+        self.root, self.img_dir, self.imgs, self.rois = root, img_dir, imgs, rois
+        self.nimg = len(imgs)
+
+    def get_key(self, i):
+        return self.imgs[i]
+
+    def get_image(self, i, resize=None):
+        from PIL import Image
+        img = Image.open(self.get_filename(i)).convert("RGB").crop(self.rois[i])
+        if resize:
+            img = img.resize(resize, Image.LANCZOS if np.prod(resize) < np.prod(img.size) else Image.BICUBIC)
+        return img
+
+
+class ImageListRelevants(Dataset):
+    """Images + query list + per-query relevant / junk indices from an Oxford-format pickle."""
+
+    def __init__(self, gt_file, root=None, img_dir="jpg", ext=".jpg"):
+        self.root, self.img_dir = root, img_dir
+        with open(gt_file, "rb") as f:
+            gt = pickle.load(f)
+        fix = lambda e: osp.splitext(e)[0] + (osp.splitext(e)[1] or ext)
+        self.imgs = [fix(e) for e in gt["imlist"]]
+        self.qimgs = [fix(e) for e in gt["qimlist"]]
+        self.qroi = [tuple(e["bbx"]) for e in gt["gnd"]]
+        if "ok" in gt["gnd"][0]:
+            self.relevants = [e["ok"] for e in gt["gnd"]]
+        else:
+            self.relevants = None
+            self.easy = [e["easy"] for e in gt["gnd"]]
+            self.hard = [e["hard"] for e in gt["gnd"]]
+        self.junk = [e["junk"] for e in gt["gnd"]]
+        self.nimg, self.nquery = len(self.imgs), len(self.qimgs)
+
+    def get_key(self, i):
+        return self.imgs[i]
+
+    def get_query_key(self, i):
+        return self.qimgs[i]
+
+    def get_query_db(self):
+        return ImageListROIs(self.root, self.img_dir, self.qimgs, self.qroi)
+
+    def get_relevants(self, q, mode="classic"):
+        return {"classic": lambda: self.relevants[q], "easy": lambda: self.easy[q],
+                "medium": lambda: self.easy[q] + self.hard[q], "hard": lambda: self.hard[q]}[mode]()
+
+    def get_junk(self, q, mode="classic"):
+        return {"classic": lambda: self.junk[q], "easy": lambda: self.junk[q] + self.hard[q],
+                "medium": lambda: self.junk[q], "hard": lambda: self.junk[q] + self.easy[q]}[mode]()
+
+    def get_query_groundtruth(self, q, what="AP", mode="classic"):
+        res = -np.ones(self.nimg, dtype=np.int8)
+        res[self.get_relevants(q, mode)] = 1
+        res[self.get_junk(q, mode)] = 0
+        return res
+
+    def _ap(self, q, scores, mode):
+        gt = self.get_query_groundtruth(q, "AP", mode)
+        assert gt.shape == scores.shape, "scores should have shape %s" % str(gt.shape)
+        keep = gt != 0
+        if mode != "classic" and (gt[keep] > 0).sum() == 0:
+            return -1
+        gt, sc = gt[keep], scores[keep]
+        order = np.lexsort((np.arange(sc.shape[0]), -sc))          # descending, ties -> lower index
+        return compute_average_precision(np.where(gt[order] == 1)[0])
+
+    def eval_query_AP(self, query_idx, scores):
+        scores = np.asarray(scores)
+        if self.relevants:
+            return self._ap(query_idx, scores, "classic")
+        return {m: self._ap(query_idx, scores, m) for m in ("easy", "medium", "hard")}
+
+
+def _db_root():
+    return os.environ["DB_ROOT"]
+
+
+def _oxford_like(name, gnd):
+    class _DS(ImageListRelevants):
+        def __init__(self):
+            ImageListRelevants.__init__(self, os.path.join(_db_root(), name, gnd), root=os.path.join(_db_root(), name))
+    return _DS
+
+
+Oxford5K = _oxford_like("oxford5k", "gnd_oxford5k.pkl")
+ROxford5K = _oxford_like("oxford5k", "gnd_roxford5k.pkl")
+Paris6K = _oxford_like("paris6k", "gnd_paris6k.pkl")
+RParis6K = _oxford_like("paris6k", "gnd_rparis6k.pkl")
+for _n, _c in (("Oxford5K", Oxford5K), ("ROxford5K", ROxford5K), ("Paris6K", Paris6K), ("RParis6K", RParis6K)):
+    _c.__name__ = _n
+
+
+def create(dataset_cmd):
+    """datasets.create: evaluate a dataset expression such as ``ImageList("list.txt", "imgs")`` (create.py:19-24)."""
+    if "(" not in dataset_cmd:
+        dataset_cmd += "()"
+    names = {k: v for k, v in globals().items() if isinstance(v, type) and issubclass(v, Dataset)}
+    try:
+        return eval(dataset_cmd, {"__builtins__": {}}, names)
+    except NameError:
+        import sys
+        print("Error: unknown dataset %s\nAvailable datasets: %s" % (dataset_cmd.replace("()", ""), ", ".join(sorted(names))),
+              file=sys.stderr)
+        sys.exit(1)

@@ -1,0 +1,62 @@
+"""Multi-GPU retrieval: the database is sharded row-wise, one process per GPU.
+
+Rank g owns the contiguous rows [g*N/G, (g+1)*N/G) - the descriptors it extracted - and searches them with
+dirb200_index_search (global indices = local row + offset).  The only data-path exchange is ONE all-gather of
+the per-shard top-k lists ((fp64 score, int64 index)[Q][k] per rank, 16*Q*k bytes) followed by the same k-way
+merge on every rank; alpha query expansion adds ONE all-reduce of the Q x D partial neighbour sums.  The
+reference's analogue is nn.DataParallel (dirtorch/utils/common.py:155); extraction needs no communication.
+
+torch.distributed is plumbing only (NCCL over NVLink on GPUs, gloo on CPU for the unit tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_rows: int, world: int, rank: int):
+    """Contiguous row range of `rank`: [start, end)."""
+    return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
+
+
+def all_gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """packed (2,Q,k) int64 per rank -> (G,2,Q,k); a single collective."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return packed.unsqueeze(0)
+    flat = torch.empty(world * packed.numel(), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(flat, packed.contiguous().view(-1), group=group)
+    return flat.view((world,) + tuple(packed.shape))
+
+
+class ShardedIndex:
+    """Row shard of the database on this rank + the cross-rank top-k exchange."""
+
+    def __init__(self, db32_local: torch.Tensor, row_offset: int, group=None, db16_local=None):
+        from . import ops
+        self.ops = ops
+        self.group = group
+        self.row_offset = int(row_offset)
+        self.local = ops.Index(db32_local, index_offset=row_offset, db16=db16_local)
+
+    def search_local(self, q32: torch.Tensor, k: int):
+        packed = torch.empty((2, q32.shape[0], k), dtype=torch.int64, device=q32.device)
+        self.local.search(q32, k, out=packed)
+        return packed
+
+    def search(self, q32: torch.Tensor, k: int):
+        """Global exact top-k: local search -> one all-gather -> merge.  Returns (scores fp64, idx int64), (Q,k)."""
+        packed = self.search_local(q32, k)
+        gathered = all_gather_packed(packed, self.group)
+        return self.ops.topk_merge_packed(gathered, k)
+
+    def expand_queries(self, q32: torch.Tensor, k: int, alpha: float):
+        """alpha-QE (test_dir.py:24-44) over the sharded database: global top-k, each rank sums the neighbours it
+        owns, one all-reduce, add the query, normalise."""
+        scores, idx = self.search(q32, k)
+        partial = self.ops.aqe_expand(q32, self.local.db32, idx, scores, alpha, partial=True,
+                                      row_offset=self.row_offset, n_rows=self.local.n)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
+        # normalize(q + sum) == normalize(mean([q, sum])): reuse the scale-pooling kernel
+        return self.ops.pool_scales([partial, q32], "mean", l2=True)

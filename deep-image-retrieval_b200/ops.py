@@ -158,18 +158,31 @@ def topk_merge(scores, idx, k):
     assert kk == k
     os_ = torch.empty((q, k), dtype=torch.float64, device=scores.device)
     oi = torch.empty((q, k), dtype=torch.int64, device=scores.device)
-    lib.call("dirb200_topk_merge", _ptr(scores), _ptr(idx), g, q, k, _ptr(os_), _ptr(oi), _stream())
+    lib.call("dirb200_topk_merge", _ptr(scores), _ptr(idx), g, q, k, 0, _ptr(os_), _ptr(oi), _stream())
     return os_, oi
 
 
-def aqe_expand(q, db32, nn_idx, nn_scores, alpha, partial=False):
+def topk_merge_packed(packed, k):
+    """packed: (G,2,Q,k) int64 all-gather buffer, [:,0] = fp64 score bits, [:,1] = global indices -> merged (Q,k)."""
+    _chk(packed, torch.int64, "packed")
+    g, two, q, kk = packed.shape
+    assert two == 2 and kk == k
+    os_ = torch.empty((q, k), dtype=torch.float64, device=packed.device)
+    oi = torch.empty((q, k), dtype=torch.int64, device=packed.device)
+    base = packed.data_ptr()
+    lib.call("dirb200_topk_merge", C.c_void_p(base), C.c_void_p(base + q * k * 8), g, q, k, 2 * q * k, _ptr(os_),
+             _ptr(oi), _stream())
+    return os_, oi
+
+
+def aqe_expand(q, db32, nn_idx, nn_scores, alpha, partial=False, row_offset=0, n_rows=0):
     _chk(q, torch.float32, "q")
     _chk(db32, torch.float32, "db32")
     _chk(nn_idx, torch.int64, "nn_idx")
     _chk(nn_scores, torch.float64, "nn_scores")
     out = torch.empty_like(q)
     lib.call("dirb200_aqe_expand", _ptr(q), q.shape[0], q.shape[1], _ptr(db32), _ptr(nn_idx), _ptr(nn_scores),
-             nn_idx.shape[1], float(alpha), int(bool(partial)), _ptr(out), _stream())
+             nn_idx.shape[1], float(alpha), int(bool(partial)), int(row_offset), int(n_rows), _ptr(out), _stream())
     return out
 
 
@@ -189,12 +202,18 @@ class Index:
     def set_option(self, key, value):
         lib.call("dirb200_index_set_option", self._h, key.encode(), float(value))
 
-    def search(self, q32: torch.Tensor, k: int):
-        """-> (scores fp64 (Q,k), idx int64 (Q,k)), exact order: score desc, index asc."""
+    def search(self, q32: torch.Tensor, k: int, out=None):
+        """-> (scores fp64 (Q,k), idx int64 (Q,k)), exact order: score desc, index asc.
+        out: optional (2,Q,k) int64 buffer that receives [score bits, indices] (the all-gather payload)."""
         _chk(q32, torch.float32, "q32")
         nq = q32.shape[0]
-        scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
-        idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
+        if out is not None:
+            _chk(out, torch.int64, "out")
+            assert tuple(out.shape) == (2, nq, k)
+            scores, idx = out[0].view(torch.float64), out[1]
+        else:
+            scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
+            idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
         lib.call("dirb200_index_search", self._h, _ptr(q32), nq, int(k), _ptr(scores), _ptr(idx), _stream())
         return scores, idx
 

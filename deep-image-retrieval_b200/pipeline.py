@@ -1,0 +1,276 @@
+"""The extraction / evaluation drivers of the reference, on the B200 path.
+
+Function names, keyword arguments and console output follow ``dirtorch/test_dir.py`` (``expand_descriptors`` :24-44,
+``extract_image_features`` :47-94, ``eval_model`` :97-180, ``load_model`` :183-191, CLI :194-259) and
+``dirtorch/extract_features.py`` (``extract_features`` :26-68, CLI :82-124).  What runs underneath:
+``net(imgs)`` is the libdirb200 network, multi-scale pooling / whitening / similarity / alpha-QE are libdirb200
+kernels; only AP bookkeeping (datasets.py) stays on the host, as in the reference.
+"""
+from __future__ import annotations
+
+import json
+import os
+import os.path as osp
+
+import numpy as np
+import torch
+import tqdm
+
+from . import common, datasets, nets, ops
+from .common import matmul, pool, tonumpy
+from .loader import get_loader
+
+
+def mkdir(fname, isfile="auto"):
+    if isfile == "auto":
+        isfile = bool(os.path.splitext(fname)[1])
+    directory = os.path.split(fname)[0] if isfile else fname
+    if directory and not os.path.isdir(directory):
+        os.makedirs(directory)
+
+
+def _dev_f32(x):
+    if isinstance(x, torch.Tensor):
+        return x.to("cuda", torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).cuda()
+
+
+def expand_descriptors(descs, db=None, alpha=0, k=0):
+    """alpha query expansion (db given) / database augmentation (db=None): test_dir.py:24-44.
+    q' = normalize(mean([q] + [db_j * sim_ij^alpha for the k nearest j])).  Returns a host ndarray."""
+    assert k >= 0 and alpha >= 0, "k and alpha must be non-negative"
+    if k == 0:
+        return descs
+    q = _dev_f32(descs)
+    if db is not None:
+        d = _dev_f32(db)
+        s, i = ops.Index(d).search(q, k)
+    else:
+        # the reference zeroes the diagonal of the self-similarity (test_dir.py:33-34): drop each row from its
+        # own neighbour list
+        d = q
+        s1, i1 = ops.Index(d).search(q, min(k + 1, d.shape[0]))
+        s1, i1 = s1.cpu().numpy(), i1.cpu().numpy()
+        rows = np.arange(q.shape[0])[:, None]
+        keep = np.argsort(i1 == rows, axis=1, kind="stable")[:, :k]       # non-self entries first, order preserved
+        s = torch.from_numpy(np.take_along_axis(s1, keep, 1).copy()).cuda()
+        i = torch.from_numpy(np.take_along_axis(i1, keep, 1).copy()).cuda()
+    out = ops.aqe_expand(q, d, i.contiguous(), s.contiguous(), float(alpha))
+    return out.cpu().numpy()
+
+
+def extract_image_features(dataset, transforms, net, ret_imgs=False, same_size=False, flip=None,
+                           desc="Extract feats...", iscuda=True, threads=8, batch_size=8):
+    """Descriptors of every image of `dataset`, (N, D) on the GPU (test_dir.py:47-94)."""
+    if not same_size:
+        batch_size = 1
+    loader = get_loader(dataset, trf_chain=transforms, preprocess=net.preprocess, iscuda=iscuda, output=["img"],
+                        batch_size=batch_size, threads=threads, shuffle=False)
+    if hasattr(net, "eval"):
+        net.eval()
+    tocpu = (lambda x: x.cpu()) if ret_imgs == "cpu" else (lambda x: x)
+    img_feats, trf_images = [], []
+    for inputs in tqdm.tqdm(loader, desc, total=1 + (len(dataset) - 1) // batch_size):
+        imgs = inputs[0]
+        for i in range(len(imgs)):
+            if flip and flip.pop(0):
+                imgs[i] = imgs[i].flip(2)
+        imgs = common.variables(inputs[:1], net.iscuda)[0]
+        d = net(imgs)
+        if ret_imgs:
+            trf_images.append(tocpu(imgs))
+        if d.dim() == 1:
+            d = d.unsqueeze(0)
+        img_feats.append(d)
+    img_feats = torch.cat(img_feats, dim=0)
+    if ret_imgs:
+        if same_size:
+            trf_images = torch.cat(trf_images, dim=0)
+        return trf_images, img_feats
+    return img_feats
+
+
+def _pool_and_normalize(descs, pooling, gemp):
+    """pool() over transform chains followed by F.normalize(p=2, dim=1): test_dir.py:121-122."""
+    if len(descs) == 1:
+        return ops.l2_normalize(_dev_f32(descs[0]))
+    if pooling not in ("mean", "gem"):
+        raise ValueError("Bad pooling mode: " + str(pooling))
+    return ops.pool_scales([_dev_f32(d) for d in descs], pooling, gemp, l2=True)
+
+
+def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=None, aqe=None, adba=None, threads=8,
+               batch_size=16, save_feats=None, load_feats=None, dbg=()):
+    """Evaluate a network on a retrieval dataset (test_dir.py:97-180).  aqe / adba: dict(k=..., alpha=...)."""
+    print("\n>> Evaluation...")
+    query_db = db.get_query_db()
+    bdescs, qdescs = [], []
+    if not load_feats:
+        trfs_list = [trfs] if isinstance(trfs, str) else trfs
+        for trf in trfs_list:
+            kw = dict(iscuda=net.iscuda, threads=threads, batch_size=batch_size, same_size="Pad" in trf or "Crop" in trf)
+            bdescs.append(extract_image_features(db, trf, net, desc="DB", **kw))
+            qdescs.append(bdescs[-1] if db is query_db else extract_image_features(query_db, trf, net, desc="query", **kw))
+        bdescs = _pool_and_normalize(bdescs, pooling, gemp)
+        qdescs = _pool_and_normalize(qdescs, pooling, gemp)
+    else:
+        bdescs = np.load(os.path.join(load_feats, "feats.bdescs.npy"))
+        qdescs = np.load(os.path.join(load_feats, "feats.qdescs.npy")) if query_db is not db else bdescs
+    if save_feats:
+        mkdir(save_feats, isfile=False)
+        np.save(os.path.join(save_feats, "feats.bdescs.npy"), tonumpy(bdescs))
+        if query_db is not db:
+            np.save(os.path.join(save_feats, "feats.qdescs.npy"), tonumpy(qdescs))
+    if whiten is not None:
+        bdescs = common.whiten_features(tonumpy(bdescs), net.pca, **whiten)
+        qdescs = common.whiten_features(tonumpy(qdescs), net.pca, **whiten)
+    if adba is not None:
+        bdescs = expand_descriptors(bdescs, **adba)
+    if aqe is not None:
+        qdescs = expand_descriptors(qdescs, db=bdescs, **aqe)
+    scores = matmul(tonumpy(qdescs), tonumpy(bdescs))
+    del bdescs, qdescs
+    res = {}
+    try:
+        aps = [db.eval_query_AP(q, s) for q, s in enumerate(tqdm.tqdm(scores, desc="AP"))]
+        if not isinstance(aps[0], dict):
+            aps = [float(e) for e in aps]
+            if detailed:
+                res["APs"] = aps
+            res["mAP"] = float(np.mean([e for e in aps if e >= 0]))      # AP = -1: query without relevants
+        else:
+            for mode in aps[0].keys():
+                apst = [float(e[mode]) for e in aps]
+                if detailed:
+                    res["APs-" + mode] = apst
+                res["mAP-" + mode] = float(np.mean([e for e in apst if e >= 0]))
+    except NotImplementedError:
+        print(" AP not implemented!")
+    try:
+        tops = [db.eval_query_top(q, s) for q, s in enumerate(tqdm.tqdm(scores, desc="top1"))]
+        if detailed:
+            res["tops"] = tops
+        for k in tops[0]:
+            res["top%d" % k] = float(np.mean([top[k] for top in tops]))
+    except NotImplementedError:
+        pass
+    return res
+
+
+def extract_features(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=None, threads=8, batch_size=16,
+                     output=None, dbg=()):
+    """Extract (and optionally whiten) descriptors and save them as .npy (extract_features.py:26-68)."""
+    print("\n>> Extracting features...")
+    try:
+        query_db = db.get_query_db()
+    except NotImplementedError:
+        query_db = None
+    bdescs, qdescs = [], []
+    trfs_list = [trfs] if isinstance(trfs, str) else trfs
+    for trf in trfs_list:
+        kw = dict(iscuda=net.iscuda, threads=threads, batch_size=batch_size, same_size="Pad" in trf or "Crop" in trf)
+        bdescs.append(extract_image_features(db, trf, net, desc="DB", **kw))
+        if query_db is not None:
+            qdescs.append(bdescs[-1] if db is query_db else extract_image_features(query_db, trf, net, desc="query", **kw))
+    bdescs = tonumpy(_pool_and_normalize(bdescs, pooling, gemp))
+    if query_db is not None:
+        qdescs = tonumpy(_pool_and_normalize(qdescs, pooling, gemp))
+    if whiten is not None:
+        bdescs = common.whiten_features(bdescs, net.pca, **whiten)
+        if query_db is not None:
+            qdescs = common.whiten_features(qdescs, net.pca, **whiten)
+    mkdir(output, isfile=True)
+    if query_db is db or query_db is None:
+        np.save(output, bdescs)
+    else:
+        o = osp.splitext(output)
+        np.save(o[0] + ".qdescs" + o[1], qdescs)
+        np.save(o[0] + ".dbdescs" + o[1], bdescs)
+    print("Features extracted.")
+
+
+def load_model(path, iscuda):
+    """Build the network from a checkpoint dict (test_dir.py:183-191)."""
+    checkpoint = common.load_checkpoint(path, iscuda)
+    net = nets.create_model(pretrained="", **checkpoint["model_options"])
+    net = common.switch_model_to_cuda(net, iscuda, checkpoint)
+    net.load_state_dict(checkpoint["state_dict"])
+    net.preprocess = checkpoint.get("preprocess", net.preprocess)
+    if "pca" in checkpoint:
+        net.pca = checkpoint.get("pca")
+    return net
+
+
+def _common_args(parser, whiten_default, whitenp_default):
+    parser.add_argument("--dataset", "-d", type=str, required=True, help="Command to load dataset")
+    parser.add_argument("--checkpoint", type=str, required=True, help="path to weights")
+    parser.add_argument("--trfs", type=str, required=False, default="", nargs="+", help="test transforms (can be several)")
+    parser.add_argument("--pooling", type=str, default="gem", help="pooling scheme if several trf chains")
+    parser.add_argument("--gemp", type=int, default=3, help="GeM pooling power")
+    parser.add_argument("--out-json", type=str, default="", help="path to output json")
+    parser.add_argument("--detailed", action="store_true", help="return detailed evaluation")
+    parser.add_argument("--threads", type=int, default=8, help="number of thread workers")
+    parser.add_argument("--dbg", default=(), nargs="*", help="debugging options")
+    parser.add_argument("--whiten", type=str, default=whiten_default, help="applies whitening")
+    parser.add_argument("--whitenp", type=float, default=whitenp_default, help="whitening power")
+    parser.add_argument("--whitenv", type=int, default=None, help="number of components, default is None (all)")
+    parser.add_argument("--whitenm", type=float, default=1.0, help="whitening multiplier")
+
+
+def _select_pca(net, args):
+    if args.whiten:
+        net.pca = net.pca[args.whiten]
+        return {"whitenp": args.whitenp, "whitenv": args.whitenv, "whitenm": args.whitenm}
+    net.pca = None
+    return None
+
+
+def test_dir_main(argv=None):
+    """python -m dirtorch.test_dir (test_dir.py:194-259).  --aqe / --adba also accept a float alpha."""
+    import argparse
+    parser = argparse.ArgumentParser(description="Evaluate a model")
+    _common_args(parser, whiten_default="Landmarks_clean", whitenp_default=0.25)
+    parser.add_argument("--save-feats", type=str, default="", help="path to output features")
+    parser.add_argument("--load-feats", type=str, default="", help="path to load features from")
+    parser.add_argument("--gpu", type=int, default=0, nargs="+", help="GPU ids")
+    parser.add_argument("--aqe", type=float, nargs="+", help="alpha-query expansion parameters: k alpha")
+    parser.add_argument("--adba", type=float, nargs="+", help="alpha-database augmentation parameters: k alpha")
+    args = parser.parse_args(argv)
+    args.iscuda = common.torch_set_gpu(args.gpu)
+    aqe = {"k": int(args.aqe[0]), "alpha": args.aqe[1]} if args.aqe is not None else None
+    adba = {"k": int(args.adba[0]), "alpha": args.adba[1]} if args.adba is not None else None
+    dataset = datasets.create(args.dataset)
+    print("Test dataset:", dataset)
+    net = load_model(args.checkpoint, args.iscuda)
+    whiten = _select_pca(net, args)
+    res = eval_model(dataset, net, args.trfs, pooling=args.pooling, gemp=args.gemp, detailed=args.detailed,
+                     threads=args.threads, dbg=args.dbg, whiten=whiten, aqe=aqe, adba=adba,
+                     save_feats=args.save_feats, load_feats=args.load_feats)
+    print(" * " + "\n * ".join(["%s = %g" % p for p in res.items()]))
+    if args.out_json:
+        try:
+            data = json.load(open(args.out_json))
+        except IOError:
+            data = {}
+        data[args.dataset] = res
+        mkdir(args.out_json)
+        open(args.out_json, "w").write(json.dumps(data, indent=1))
+        print("saved to " + args.out_json)
+    return res
+
+
+def extract_features_main(argv=None):
+    """python -m dirtorch.extract_features (extract_features.py:82-124)."""
+    import argparse
+    parser = argparse.ArgumentParser(description="Extract features")
+    _common_args(parser, whiten_default=None, whitenp_default=0.5)
+    parser.add_argument("--output", type=str, default="", help="path to output features")
+    parser.add_argument("--gpu", type=int, nargs="+", help="GPU ids")
+    args = parser.parse_args(argv)
+    args.iscuda = common.torch_set_gpu(args.gpu if args.gpu is not None else [0])
+    dataset = datasets.create(args.dataset)
+    print("Dataset:", dataset)
+    net = load_model(args.checkpoint, args.iscuda)
+    whiten = _select_pca(net, args)
+    extract_features(dataset, net, args.trfs, pooling=args.pooling, gemp=args.gemp, detailed=args.detailed,
+                     threads=args.threads, dbg=args.dbg, whiten=whiten, output=args.output)

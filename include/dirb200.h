@@ -137,18 +137,23 @@ int dirb200_index_search(dirb200_index* idx, const float* q32_dev, int Q, int k,
 int dirb200_index_last_stats(dirb200_index* idx, int64_t stats[5]);
 int dirb200_index_destroy(dirb200_index* idx);
 
-/* Merge G per-shard top-k lists ([G][Q][k] scores fp64 + global indices int64, as produced by an
- * all-gather of dirb200_index_search outputs) into the global top-k with the same ordering rule. */
-int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, double* out_scores_dev,
-                       int64_t* out_idx_dev, void* stream);
+/* Merge G per-shard top-k lists (scores fp64 + global indices int64, as produced by an all-gather of
+ * dirb200_index_search outputs) into the global top-k with the same ordering rule.  Shard g's [Q][k] block starts
+ * shard_stride elements after shard g-1's (0 = dense [G][Q][k]); a packed all-gather buffer [G][2][Q][k] uses
+ * shard_stride = 2*Q*k with idx_dev = scores_dev + Q*k. */
+int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, int64_t shard_stride,
+                       double* out_scores_dev, int64_t* out_idx_dev, void* stream);
 /* Full exact score matrix (fp64 accumulate, fp32 out): the literal common.matmul for small evaluation sets. */
 int dirb200_scores_exact(const float* q_dev, int Q, const float* db_dev, int64_t N, int D, float* out_dev,
                          void* stream);
 /* Alpha query expansion, test_dir.py:24-44:  out_i = normalize(mean([q_i] + [db_j * s_ij^alpha, j in topk(i)])).
- * nn_idx_dev/nn_scores_dev: [Q][k] neighbours (LOCAL row numbers into db32_dev, -1 = none) and their scores.
- * partial != 0 writes the un-normalised SUM over the local neighbours only (for a cross-GPU all-reduce). */
+ * nn_idx_dev/nn_scores_dev: [Q][k] neighbour indices (-1 = none) and their scores.  With n_rows > 0 the indices
+ * are GLOBAL and db32_dev holds the rows [row_offset, row_offset+n_rows) of a sharded database: neighbours owned
+ * by other shards are skipped; with n_rows <= 0 the indices are plain rows of db32_dev.
+ * partial != 0 writes the un-normalised SUM over the (owned) neighbours only, for a cross-GPU all-reduce. */
 int dirb200_aqe_expand(const float* q_dev, int Q, int D, const float* db32_dev, const int64_t* nn_idx_dev,
-                       const double* nn_scores_dev, int k, double alpha, int partial, float* out_dev, void* stream);
+                       const double* nn_scores_dev, int k, double alpha, int partial, int64_t row_offset, int64_t n_rows,
+                       float* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

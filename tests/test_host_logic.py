@@ -1,0 +1,156 @@
+"""CPU tests of the host-side logic: dataset / AP bookkeeping against the reference's golden values, the
+transform chain, CLI surface, and the multi-rank top-k exchange under gloo (world_size 2)."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import dirb200.synth as synth
+from conftest import REPO
+from oracle import dir_oracle as O
+
+
+def _gt_dataset(tmp_path, g, revisited=False):
+    from dirtorch.datasets import ImageListRelevants
+    db, q, pos = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                          db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    gnd = synth.oxford_gt(pos, n_junk=int(g["n_junk"]), n_db=int(g["n_db"]), seed=int(g["gt_seed"]))
+    if revisited:
+        gnd = [{"bbx": e["bbx"], "easy": e["ok"][:2], "hard": e["ok"][2:], "junk": e["junk"]} for e in gnd]
+    imlist = ["im%04d" % i for i in range(int(g["n_db"]))]
+    f = tmp_path / ("gnd%d.pkl" % revisited)
+    with open(f, "wb") as fh:
+        pickle.dump({"imlist": imlist, "qimlist": imlist[:int(g["n_q"])], "gnd": gnd}, fh)
+    return ImageListRelevants(str(f), root=str(tmp_path)), db, q
+
+
+def test_dataset_ap_matches_reference(golden, tmp_path):
+    g = golden("rank_ap.npz")
+    ds, db, q = _gt_dataset(tmp_path, g)
+    assert ds.nimg == 400 and ds.nquery == 6 and ds.get_key(3) == "im0003.jpg"
+    assert ds.get_query_db().nimg == 6
+    for i in range(6):
+        assert abs(ds.eval_query_AP(i, g["scores"][i]) - g["aps"][i]) < 1e-12
+    ds2, _, _ = _gt_dataset(tmp_path, g, revisited=True)
+    for i in range(6):
+        ap = ds2.eval_query_AP(i, g["scores"][i])
+        assert abs(ap["easy"] - g["aps_easy"][i]) < 1e-12
+        assert abs(ap["medium"] - g["aps_medium"][i]) < 1e-12
+        assert abs(ap["hard"] - g["aps_hard"][i]) < 1e-12
+    with pytest.raises(AssertionError):
+        ds.eval_query_AP(0, g["scores"][0][:10])           # wrong shape, generic.py:201
+
+
+def test_transforms_and_loader(tmp_path):
+    from PIL import Image
+    from dirb200.loader import Scale, create_transforms, get_loader
+    from dirtorch.datasets import ImageList
+    assert Scale(0.7).get_params((1024, 1024)) == (717, 717)          # int(0.5 + s*w), transforms.py:168
+    assert Scale(1.4).get_params((1024, 768)) == (1434, 1075)
+    assert Scale(256).get_params((512, 1024)) == (256, 512)
+    u8 = synth.make_images_u8(3, 40, 56, seed=2)
+    names = []
+    for i in range(3):
+        Image.fromarray(u8[i]).save(tmp_path / ("a%d.png" % i))
+        names.append("a%d.png" % i)
+    ds = ImageList(imgs=names, root=str(tmp_path))
+    pre = dict(mean=synth.RGB_MEANS, std=synth.RGB_STDS, input_size=224)
+    batches = [b[0] for b in get_loader(ds, "", False, preprocess=pre, output=["img"], batch_size=3, threads=1)]
+    assert torch.allclose(batches[0], synth.normalise_images(u8), atol=1e-6)     # ToTensor + Normalize, transforms.py:27
+    scaled = [b[0] for b in get_loader(ds, "Scale(0.5)", False, preprocess=pre, output=["img"], batch_size=1, threads=1)]
+    assert tuple(scaled[0].shape) == (1, 3, 20, 28)
+    with pytest.raises(SyntaxError):
+        create_transforms("Bogus(3)", to_tensor=True, **pre)
+
+
+def test_cli_surface_and_no_cpu_path():
+    from dirtorch import extract_features, test_dir
+    from dirtorch.utils import common
+    for fn in ("expand_descriptors", "extract_image_features", "eval_model", "load_model"):
+        assert callable(getattr(test_dir, fn))
+    assert callable(extract_features.extract_features) and callable(extract_features.load_model)
+    for fn in ("tonumpy", "matmul", "pool", "transform", "whiten_features", "torch_set_gpu", "load_checkpoint",
+               "switch_model_to_cuda", "variables"):
+        assert callable(getattr(common, fn))
+    with pytest.raises(RuntimeError):
+        common.torch_set_gpu([-1])                                   # the reference would run on CPU here
+    with pytest.raises(TypeError):
+        common.matmul([1, 2], [3, 4])                                # common.py:37
+    x = [torch.zeros(2, 4), torch.zeros(2, 4)]
+    with pytest.raises(ValueError):
+        common.pool(x, "bogus")                                       # common.py:55
+    assert common.pool(x[:1], "gem") is x[0]                          # single chain: identity, common.py:42-43
+    import inspect
+    sig = inspect.signature(test_dir.eval_model)
+    assert list(sig.parameters)[:3] == ["db", "net", "trfs"] and sig.parameters["pooling"].default == "mean"
+    assert inspect.signature(test_dir.extract_image_features).parameters["batch_size"].default == 8
+    assert inspect.signature(test_dir.expand_descriptors).parameters["alpha"].default == 0
+    # CLI flags of the reference (test_dir.py:198-221 / extract_features.py:86-105)
+    with pytest.raises(SystemExit):
+        test_dir.test_dir_main(["--help"])
+    with pytest.raises(SystemExit):
+        extract_features.extract_features_main(["--dataset", "x"])   # --checkpoint is required
+
+
+def test_shard_rows_cover():
+    from dirb200.dist import shard_rows
+    for n, w in ((1_000_000, 8), (100, 8), (7, 3), (5, 8)):
+        rs = [shard_rows(n, w, r) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+    assert shard_rows(1_000_000, 8, 3) == (375000, 500000)
+
+
+def _gloo_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    import dirb200.synth as synth
+    from dirb200.dist import all_gather_packed, shard_rows
+    from oracle import dir_oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    db, q, _ = synth.make_descriptor_db(3000, 11, dim=64, n_pos=4, db_seed=1, q_seed=2)
+    k = 16
+    s0, s1 = shard_rows(db.shape[0], world, rank)
+    ls, li = O.topk(q, db[s0:s1], k)                                   # stands in for dirb200_index_search
+    packed = torch.empty((2, q.shape[0], k), dtype=torch.int64)
+    packed[0] = torch.from_numpy(ls).view(torch.int64)
+    packed[1] = torch.from_numpy(li + s0)                              # global indices = local row + offset
+    gathered = all_gather_packed(packed)
+    assert tuple(gathered.shape) == (world, 2, q.shape[0], k)
+    sc = [gathered[g, 0].view(torch.float64).numpy() for g in range(world)]
+    ix = [gathered[g, 1].numpy() for g in range(world)]
+    ms, mi = O.merge_topk(sc, ix, k)
+    rs, ri = O.topk(q, db, k)
+    ok = bool(np.array_equal(mi, ri) and np.allclose(ms, rs, atol=1e-15))
+    # alpha-QE partial sums: every rank sums the neighbours it owns, all-reduce, add the query, normalise
+    part = np.zeros_like(q, dtype=np.float64)
+    for i in range(q.shape[0]):
+        for j in range(2):
+            r = ri[i, j]
+            if s0 <= r < s1:
+                part[i] += db[r].astype(np.float64) * rs[i, j] ** 0.5
+    t = torch.from_numpy(part)
+    dist.all_reduce(t)
+    out = t.numpy() + q
+    out /= np.linalg.norm(out, axis=1, keepdims=True)
+    ref = O.expand_descriptors(q, db=db, k=2, alpha=0.5)
+    ok = ok and float(np.abs(out - ref).max()) < 1e-6
+    with open(os.path.join(tmp, "ok%d" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_topk_exchange_gloo_world2(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
