@@ -41,6 +41,25 @@ struct Block {
 
 }  // namespace
 
+// Per-launch CUDA-event timing of one forward (option "profile"): class 0 = tcgen05 conv, 1 = stem conv (mma.sync),
+// 2 = layout/maxpool, 3 = head.  Events sit on the launch stream, so they time exactly the kernels between them.
+struct Profiler {
+  struct Rec { cudaEvent_t a, b; int cls; double flops, bytes; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get() {
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[used++];
+  }
+  void reset() { recs.clear(); used = 0; }
+  ~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
 struct dirb200_net {
   int device = 0;
   std::string arch;
@@ -73,6 +92,24 @@ struct dirb200_net {
   int debug_taps = 0;
   int64_t last_launches = 0;
   double last_flops = 0;
+  int profile = 0;
+  Profiler prof;
+  // pipelined host entry point
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> pipe_events;
+  int host_chunk = 16;
+};
+
+struct ProfScope {
+  dirb200_net* n; cudaStream_t st; bool on;
+  ProfScope(dirb200_net* n_, cudaStream_t st_, int cls, double flops, double bytes) : n(n_), st(st_), on(n_->profile != 0) {
+    if (on) {
+      Profiler::Rec r{n->prof.get(), n->prof.get(), cls, flops, bytes};
+      cudaEventRecord(r.a, st);
+      n->prof.recs.push_back(r);
+    }
+  }
+  ~ProfScope() { if (on) cudaEventRecord(n->prof.recs.back().b, st); }
 };
 
 static int dev_alloc(dirb200_net* n, void** p, size_t bytes) {
@@ -153,8 +190,14 @@ static ConvLayer make_layer(const std::string& conv, const std::string& bn, int 
 static int run_conv(dirb200_net* n, const ConvLayer& L, const __half* in, int B, int H, int W, const __half* res,
                     int relu, __half* out, cudaStream_t stream, int force_mma = 0) {
   ConvShape s{B, H, W, L.CinPad, L.Cout, L.K, L.K, L.stride, L.pad};
-  n->last_flops += 2.0 * B * s.Ho() * s.Wo() * static_cast<double>(L.Cout) * L.K * L.K * L.Cin;
-  if (force_mma || n->conv_impl == 1 || L.CinPad % 64 != 0)
+  const double flops = 2.0 * B * s.Ho() * s.Wo() * static_cast<double>(L.Cout) * L.K * L.K * L.Cin;
+  // algorithmic bytes: input + output (+ residual) activations once, weights once
+  const double bytes = 2.0 * (static_cast<double>(B) * H * W * L.CinPad + static_cast<double>(B) * s.Ho() * s.Wo() * L.Cout * (res ? 2 : 1) +
+                              static_cast<double>(L.Cout) * L.K * L.K * L.CinPad);
+  n->last_flops += flops;
+  const bool mma = force_mma || n->conv_impl == 1 || L.CinPad % 64 != 0;
+  ProfScope ps(n, stream, mma ? 1 : 0, flops, bytes);
+  if (mma)
     return conv_mma(s, in, L.w, L.Kpad, L.scale, L.shift, res, relu, out, stream);
   if (n->conv_impl == 2) return conv_tc_np(s, in, L.w, L.scale, L.shift, res, relu, out, stream);
   return conv_tc(s, in, L.w, L.scale, L.shift, res, relu, out, stream);
@@ -189,6 +232,8 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "conv_impl") n->conv_impl = static_cast<int>(value);
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
   else if (k == "debug_taps") n->debug_taps = value != 0;
+  else if (k == "profile") n->profile = value != 0;
+  else if (k == "host_chunk") n->host_chunk = std::max(1, static_cast<int>(value));
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown net option '%s'", key);
   return 0;
 }
@@ -262,42 +307,34 @@ int dirb200_net_finalize(dirb200_net* n) {
 }
 
 static int auto_chunk(int B, int H, int W) {
-  // keep (chunk x largest activation = layer1 output, 256 ch at H/4 x W/4 fp16) around 1/2 of the 126 MB L2,
-  // but give every launch at least ~2 waves of tiles.
-  const double per_img = 256.0 * (H / 4.0) * (W / 4.0) * 2.0;
-  int c = static_cast<int>(64e6 / per_img);
-  const double px_per_img = (H / 32.0) * (W / 32.0);  // layer4 pixels: the smallest GEMM M
-  const int min_for_fill = static_cast<int>(ceil(148.0 * 128.0 / (px_per_img * 4.0)));
-  if (c < min_for_fill) c = min_for_fill;
+  // Large chunks keep every launch at many tiles per SM (the persistent kernels lose ~1/waves to the tail);
+  // bound the activation workspace to ~24 GB of the 180 GB HBM.
+  const double per_img = 2.0 * (static_cast<double>(H) * W * 8 + (H / 2.0) * (W / 2.0) * 64 + 5.0 * (H / 4.0) * (W / 4.0) * 256);
+  int c = static_cast<int>(24e9 / per_img);
   if (c < 1) c = 1;
+  if (c > 64) c = 64;
   if (c > B) c = B;
   return c;
 }
 
-int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int W, float* desc_dev, void* desc16_dev,
-                        void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DIRB_REQUIRE(n && imgs_dev && desc_dev, DIRB200_EINVAL, "null argument");
-  DIRB_REQUIRE(n->finalized, DIRB200_ESTATE, "dirb200_net_finalize has not been called");
-  DIRB_REQUIRE(B >= 1 && H >= 32 && W >= 32, DIRB200_ENOTSUP, "need B >= 1 and H, W >= 32 (got %d, %d, %d)", B, H, W);
-  DIRB_CUDA(cudaSetDevice(n->device));
-  const int64_t launches0 = launches_total();
-  n->last_flops = 0;
-  const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
-  const int D = n->without_fc ? 2048 : n->out_dim;
+namespace {
+struct Workspace {
+  __half* in8; __half* stem_out; __half* act[5]; float* head_ws;
+  int H1, W1, H2, W2;
+};
+}  // namespace
 
-  // ---- spatial sizes
-  const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;     // stem conv
-  const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1;   // maxpool
-  // ---- workspace: in8, stem, and five rotating activation buffers sized for the largest tensor of the trunk
+static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w) {
+  w->H1 = (H + 6 - 7) / 2 + 1; w->W1 = (W + 6 - 7) / 2 + 1;       // stem conv
+  w->H2 = (w->H1 + 2 - 3) / 2 + 1; w->W2 = (w->W1 + 2 - 3) / 2 + 1;   // maxpool
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   const size_t o_in8 = carve(static_cast<size_t>(chunk) * H * W * 8 * 2);
-  const size_t o_stem = carve(static_cast<size_t>(chunk) * H1 * W1 * 64 * 2);
-  const size_t act_max = static_cast<size_t>(chunk) * H2 * W2 * 256 * 2;   // layer1 output is the largest
+  const size_t o_stem = carve(static_cast<size_t>(chunk) * w->H1 * w->W1 * 64 * 2);
+  const size_t act_max = static_cast<size_t>(chunk) * w->H2 * w->W2 * 256 * 2;   // layer1 output is the largest
   size_t o_act[5];
   for (int i = 0; i < 5; ++i) o_act[i] = carve(act_max);
-  int Hf = H2, Wf = W2;
+  int Hf = w->H2, Wf = w->W2;
   for (int li = 1; li < 4; ++li) { Hf = (Hf + 2 - 3) / 2 + 1; Wf = (Wf + 2 - 3) / 2 + 1; }
   const size_t o_head = carve(head_workspace_floats(chunk, Hf * Wf, 2048, n->out_dim) * 4);
   if (off > n->ws_bytes) {
@@ -307,61 +344,105 @@ int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int
     n->ws_bytes = off;
   }
   uint8_t* ws = static_cast<uint8_t*>(n->ws);
-  __half* in8 = reinterpret_cast<__half*>(ws + o_in8);
-  __half* stem_out = reinterpret_cast<__half*>(ws + o_stem);
-  __half* act[5];
-  for (int i = 0; i < 5; ++i) act[i] = reinterpret_cast<__half*>(ws + o_act[i]);
-  float* head_ws = reinterpret_cast<float*>(ws + o_head);
+  w->in8 = reinterpret_cast<__half*>(ws + o_in8);
+  w->stem_out = reinterpret_cast<__half*>(ws + o_stem);
+  for (int i = 0; i < 5; ++i) w->act[i] = reinterpret_cast<__half*>(ws + o_act[i]);
+  w->head_ws = reinterpret_cast<float*>(ws + o_head);
+  return 0;
+}
 
+// One pass of the network over `cb` images (NCHW fp32 on the device) -> cb descriptors.
+static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, int cb, int H, int W, float* desc_dev,
+                     __half* desc16_dev, cudaStream_t stream) {
+  const int D = n->without_fc ? 2048 : n->out_dim;
+  {
+    ProfScope ps(n, stream, 2, 0, static_cast<double>(cb) * H * W * (12 + 16));
+    DIRB_TRY(nchw_to_nhwc8(imgs_dev, cb, H, W, w.in8, stream));
+  }
+  DIRB_TRY(run_conv(n, n->stem, w.in8, cb, H, W, nullptr, 1, w.stem_out, stream, /*force_mma=*/1));
+  __half* x = w.act[0];
+  {
+    ProfScope ps(n, stream, 2, 0, 2.0 * cb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.H2) * w.W2));
+    DIRB_TRY(maxpool_3x3s2(w.stem_out, cb, w.H1, w.W1, 64, x, stream));
+  }
+  DIRB_TRY(record_tap(n, "stem", x, cb, w.H2, w.W2, 64, stream));
+  int h = w.H2, wd = w.W2, cur = 0, layer = 0;
+  for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
+    const Block& blk = n->blocks[bi];
+    __half* t1 = w.act[(cur + 1) % 5];
+    __half* t2 = w.act[(cur + 2) % 5];
+    __half* rs = w.act[(cur + 3) % 5];
+    __half* y = w.act[(cur + 4) % 5];
+    const int s = blk.c2.stride;
+    const int ho = (h + 2 - 3) / s + 1, wo = (wd + 2 - 3) / s + 1;
+    DIRB_TRY(run_conv(n, blk.c1, x, cb, h, wd, nullptr, 1, t1, stream));
+    DIRB_TRY(run_conv(n, blk.c2, t1, cb, h, wd, nullptr, 1, t2, stream));
+    const __half* res = x;
+    if (blk.has_down) {
+      DIRB_TRY(run_conv(n, blk.down, x, cb, h, wd, nullptr, 0, rs, stream));
+      res = rs;
+    }
+    DIRB_TRY(run_conv(n, blk.c3, t2, cb, ho, wo, res, 1, y, stream));
+    x = y;
+    cur = (cur + 4) % 5;
+    h = ho;
+    wd = wo;
+    if (static_cast<int>(bi) + 1 == n->layer_end[layer]) {
+      DIRB_TRY(record_tap(n, "layer" + std::to_string(layer + 1), x, cb, h, wd, blk.c3.Cout, stream));
+      ++layer;
+    }
+  }
+  {
+    ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * cb * 2048.0 * n->out_dim, 2.0 * cb * h * wd * 2048.0);
+    DIRB_TRY(head_pool_fc_l2(x, cb, h * wd, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
+                             n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, w.head_ws, desc_dev,
+                             desc16_dev, stream));
+  }
+  if (!n->without_fc) n->last_flops += 2.0 * cb * 2048.0 * n->out_dim;
+  return 0;
+}
+
+static int check_forward_args(dirb200_net* n, int B, int H, int W) {
+  DIRB_REQUIRE(n->finalized, DIRB200_ESTATE, "dirb200_net_finalize has not been called");
+  DIRB_REQUIRE(B >= 1 && H >= 32 && W >= 32, DIRB200_ENOTSUP, "need B >= 1 and H, W >= 32 (got %d, %d, %d)", B, H, W);
+  return 0;
+}
+
+int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int W, float* desc_dev, void* desc16_dev,
+                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(n && imgs_dev && desc_dev, DIRB200_EINVAL, "null argument");
+  DIRB_TRY(check_forward_args(n, B, H, W));
+  DIRB_CUDA(cudaSetDevice(n->device));
+  const int64_t launches0 = launches_total();
+  n->last_flops = 0;
+  n->prof.reset();
+  const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
+  const int D = n->without_fc ? 2048 : n->out_dim;
+  Workspace w;
+  DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int cb = std::min(chunk, B - b0);
-    DIRB_TRY(nchw_to_nhwc8(imgs_dev + static_cast<size_t>(b0) * 3 * H * W, cb, H, W, in8, stream));
-    DIRB_TRY(run_conv(n, n->stem, in8, cb, H, W, nullptr, 1, stem_out, stream, /*force_mma=*/1));
-    __half* x = act[0];
-    DIRB_TRY(maxpool_3x3s2(stem_out, cb, H1, W1, 64, x, stream));
-    DIRB_TRY(record_tap(n, "stem", x, cb, H2, W2, 64, stream));
-    int h = H2, w = W2, cur = 0, layer = 0;
-    for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
-      const Block& blk = n->blocks[bi];
-      __half* t1 = act[(cur + 1) % 5];
-      __half* t2 = act[(cur + 2) % 5];
-      __half* rs = act[(cur + 3) % 5];
-      __half* y = act[(cur + 4) % 5];
-      const int s = blk.c2.stride;
-      const int ho = (h + 2 - 3) / s + 1, wo = (w + 2 - 3) / s + 1;
-      DIRB_TRY(run_conv(n, blk.c1, x, cb, h, w, nullptr, 1, t1, stream));
-      DIRB_TRY(run_conv(n, blk.c2, t1, cb, h, w, nullptr, 1, t2, stream));
-      const __half* res = x;
-      if (blk.has_down) {
-        DIRB_TRY(run_conv(n, blk.down, x, cb, h, w, nullptr, 0, rs, stream));
-        res = rs;
-      }
-      DIRB_TRY(run_conv(n, blk.c3, t2, cb, ho, wo, res, 1, y, stream));
-      x = y;
-      cur = (cur + 4) % 5;
-      h = ho;
-      w = wo;
-      if (static_cast<int>(bi) + 1 == n->layer_end[layer]) {
-        DIRB_TRY(record_tap(n, "layer" + std::to_string(layer + 1), x, cb, h, w, blk.c3.Cout, stream));
-        ++layer;
-      }
-    }
-    DIRB_TRY(head_pool_fc_l2(x, cb, h * w, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
-                             n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, head_ws,
-                             desc_dev + static_cast<size_t>(b0) * D,
-                             desc16_dev ? static_cast<__half*>(desc16_dev) + static_cast<size_t>(b0) * D : nullptr,
-                             stream));
-    if (!n->without_fc) n->last_flops += 2.0 * cb * 2048.0 * n->out_dim;
+    DIRB_TRY(run_chunk(n, w, imgs_dev + static_cast<size_t>(b0) * 3 * H * W, cb, H, W,
+                       desc_dev + static_cast<size_t>(b0) * D,
+                       desc16_dev ? static_cast<__half*>(desc16_dev) + static_cast<size_t>(b0) * D : nullptr, stream));
   }
   n->last_launches = launches_total() - launches0;
   return 0;
 }
 
+// Host buffers in, host descriptors out.  The batch is cut into chunks of `host_chunk` images; the H2D copy of
+// chunk i+1 (copy stream) overlaps the network pass over chunk i (compute stream), two device input buffers.
 int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int H, int W, float* desc_host) {
   DIRB_REQUIRE(n && imgs_host && desc_host, DIRB200_EINVAL, "null argument");
+  DIRB_TRY(check_forward_args(n, B, H, W));
   DIRB_CUDA(cudaSetDevice(n->device));
   if (!n->own_stream) DIRB_CUDA(cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking));
-  const size_t in_bytes = static_cast<size_t>(B) * 3 * H * W * 4;
+  if (!n->copy_stream) DIRB_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
+  const int chunk = std::min(B, n->chunk > 0 ? n->chunk : n->host_chunk);
+  const int nchunks = (B + chunk - 1) / chunk;
+  const size_t img_bytes = static_cast<size_t>(3) * H * W * 4;
+  const size_t in_bytes = 2 * static_cast<size_t>(chunk) * img_bytes;
   const int D = n->without_fc ? 2048 : n->out_dim;
   const size_t out_bytes = static_cast<size_t>(B) * D * 4;
   if (in_bytes > n->h2d_bytes) {
@@ -376,10 +457,46 @@ int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int 
     DIRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&n->d_desc), out_bytes));
     n->d_desc_bytes = out_bytes;
   }
-  DIRB_CUDA(cudaMemcpyAsync(n->h2d, imgs_host, in_bytes, cudaMemcpyHostToDevice, n->own_stream));
-  DIRB_TRY(dirb200_net_forward(n, n->h2d, B, H, W, n->d_desc, nullptr, n->own_stream));
+  while (n->pipe_events.size() < static_cast<size_t>(2 * nchunks)) {
+    cudaEvent_t e;
+    DIRB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    n->pipe_events.push_back(e);
+  }
+  const int64_t launches0 = launches_total();
+  n->last_flops = 0;
+  n->prof.reset();
+  Workspace w;
+  DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * chunk, cb = std::min(chunk, B - b0);
+    float* dst = n->h2d + static_cast<size_t>(c & 1) * chunk * (img_bytes / 4);
+    cudaEvent_t copied = n->pipe_events[2 * c], done = n->pipe_events[2 * c + 1];
+    if (c >= 2) DIRB_CUDA(cudaStreamWaitEvent(n->copy_stream, n->pipe_events[2 * (c - 2) + 1], 0));   // buffer free
+    DIRB_CUDA(cudaMemcpyAsync(dst, imgs_host + static_cast<size_t>(b0) * (img_bytes / 4), static_cast<size_t>(cb) * img_bytes,
+                              cudaMemcpyHostToDevice, n->copy_stream));
+    DIRB_CUDA(cudaEventRecord(copied, n->copy_stream));
+    DIRB_CUDA(cudaStreamWaitEvent(n->own_stream, copied, 0));
+    DIRB_TRY(run_chunk(n, w, dst, cb, H, W, n->d_desc + static_cast<size_t>(b0) * D, nullptr, n->own_stream));
+    DIRB_CUDA(cudaEventRecord(done, n->own_stream));
+  }
   DIRB_CUDA(cudaMemcpyAsync(desc_host, n->d_desc, out_bytes, cudaMemcpyDeviceToHost, n->own_stream));
   DIRB_CUDA(cudaStreamSynchronize(n->own_stream));
+  n->last_launches = launches_total() - launches0;
+  return 0;
+}
+
+// Aggregated per-class timing of the last forward run with option "profile": out[4][4] = {launches, ms, flops, bytes}
+// for class 0 tcgen05 convs, 1 stem conv, 2 layout + maxpool, 3 head.  Synchronises the device.
+int dirb200_net_profile(dirb200_net* n, double* out16) {
+  DIRB_REQUIRE(n && out16, DIRB200_EINVAL, "null argument");
+  DIRB_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  for (auto& r : n->prof.recs) {
+    float ms = 0;
+    DIRB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    double* o = out16 + 4 * r.cls;
+    o[0] += 1; o[1] += ms; o[2] += r.flops; o[3] += r.bytes;
+  }
   return 0;
 }
 
@@ -413,6 +530,8 @@ int dirb200_net_destroy(dirb200_net* n) {
   if (n->h2d) cudaFree(n->h2d);
   if (n->d_desc) cudaFree(n->d_desc);
   if (n->own_stream) cudaStreamDestroy(n->own_stream);
+  if (n->copy_stream) cudaStreamDestroy(n->copy_stream);
+  for (auto e : n->pipe_events) cudaEventDestroy(e);
   delete n;
   return 0;
 }

@@ -226,6 +226,15 @@ class ResNetRMAC:
         n, hh, ww, c = [int(v) for v in dims]
         return buf[: n * hh * ww * c * 2].view(torch.float16).view(n, hh, ww, c).clone()
 
+    def profile(self):
+        """Per-class timing of the last forward (needs set_backend_option('profile', 1)):
+        {class: dict(launches, ms, flops, bytes)}."""
+        arr = (C.c_double * 16)()
+        lib.call("dirb200_net_profile", self._handle, arr)
+        names = ["conv_tcgen05", "stem_conv", "layout_maxpool", "head"]
+        return {nm: dict(launches=int(arr[4 * i]), ms=arr[4 * i + 1], flops=arr[4 * i + 2], bytes=arr[4 * i + 3])
+                for i, nm in enumerate(names)}
+
     def last_launch_stats(self):
         n, f = C.c_int64(), C.c_double()
         lib.call("dirb200_net_last_launches", self._handle, C.byref(n), C.byref(f))

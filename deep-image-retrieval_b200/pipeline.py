@@ -246,7 +246,8 @@ def test_dir_main(argv=None):
     res = eval_model(dataset, net, args.trfs, pooling=args.pooling, gemp=args.gemp, detailed=args.detailed,
                      threads=args.threads, dbg=args.dbg, whiten=whiten, aqe=aqe, adba=adba,
                      save_feats=args.save_feats, load_feats=args.load_feats)
-    print(" * " + "\n * ".join(["%s = %g" % p for p in res.items()]))
+    # (the reference's '%s = %g' line raises on the list-valued entries that --detailed adds; print scalars only)
+    print(" * " + "\n * ".join(["%s = %g" % p for p in res.items() if isinstance(p[1], (int, float))]))
     if args.out_json:
         try:
             data = json.load(open(args.out_json))

@@ -53,7 +53,8 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out);
  * "without_fc" 0/1; "out_dim"; "chunk" images processed per pass (0 = auto);
  * "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path),
  * 2 = one-tile-per-CTA tcgen05 kernel (A/B baseline);
- * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage. */
+ * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage; "profile" 1 = time every launch
+ * with CUDA events (dirb200_net_profile); "host_chunk" images per pipeline stage of dirb200_net_forward_host. */
 int dirb200_net_set_option(dirb200_net* net, const char* key, double value);
 /* One state_dict tensor by its reference key ("layer3.5.bn2.running_var", "adpool.p", "fc.weight" ...),
  * fp32 host memory, reference shape (conv OIHW).  "num_batches_tracked" keys are ignored. */
@@ -66,12 +67,18 @@ int dirb200_net_finalize(dirb200_net* net);
 int dirb200_net_forward(dirb200_net* net, const float* imgs_dev, int B, int H, int W, float* desc_dev,
                         void* desc16_dev, void* stream);
 /* Same through HOST buffers: H2D copy of the images, forward, D2H copy of the descriptors, stream sync
- * (the common.variables() -> net() -> tonumpy() sequence, common.py:205-218,23-27). */
+ * (the common.variables() -> net() -> tonumpy() sequence, common.py:205-218,23-27).  The batch is processed in
+ * chunks of "host_chunk" images (option, default 16) with the H2D copy of the next chunk overlapping the compute
+ * of the current one; pass pinned memory for the overlap to take effect. */
 int dirb200_net_forward_host(dirb200_net* net, const float* imgs_host, int B, int H, int W, float* desc_host);
 /* Debug tap (needs option "debug_taps"): copy the NHWC fp16 activation after stage `what` ("stem","layer1".."layer4")
  * of the LAST chunk of the last forward into dst_dev (capacity in bytes); returns its dims as {n,h,w,c}. */
 int dirb200_net_debug_stage(dirb200_net* net, const char* what, void* dst_dev, size_t capacity, int dims[4],
                             void* stream);
+/* Per-class CUDA-event timing of the last forward run with option "profile" = 1: out16 = 4 rows of
+ * {launches, milliseconds, algorithmic FLOPs, algorithmic bytes} for 0 tcgen05 convolutions, 1 stem convolution,
+ * 2 layout + maxpool, 3 head.  Synchronises the device. */
+int dirb200_net_profile(dirb200_net* net, double* out16);
 /* Number of kernels the last forward launched / algorithmic conv+fc FLOPs of the last forward. */
 int dirb200_net_last_launches(dirb200_net* net, int64_t* launches, double* flops);
 int dirb200_net_destroy(dirb200_net* net);

@@ -1,0 +1,52 @@
+"""Synthetic Oxford-layout dataset + checkpoint for the end-to-end CLI test (config 1 of BASELINE.json, reduced)."""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+import dirb200.synth as synth
+
+
+def build(root, n_groups=8, n_extra=8, size=(160, 192), seed=3, arch="resnet50_rmac"):
+    """Writes $root/oxford5k/jpg/*.png + gnd_oxford5k.pkl and $root/ckpt.pt.  Returns (gnd, names, state_dict)."""
+    from PIL import Image
+    h, w = size
+    r = np.random.RandomState(seed)
+    base = synth.make_images_u8(n_groups + n_extra, h, w, seed=seed).astype(np.float32)
+    # low-frequency structure so that different images are far apart, copies close
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for i in range(base.shape[0]):
+        f = r.uniform(1, 5, (3, 2))
+        ph = r.uniform(0, 6.28, (3, 2))
+        wave = np.stack([np.sin(6.28 * f[c, 0] * yy / h + ph[c, 0]) * np.cos(6.28 * f[c, 1] * xx / w + ph[c, 1]) for c in range(3)], -1)
+        base[i] = np.clip(0.3 * base[i] + 0.7 * (127.5 + 110 * wave), 0, 255)
+    imgs, names, gnd, qnames = [], [], [], []
+    for g in range(n_groups):
+        first = len(imgs)
+        imgs.append(base[g])
+        for sigma in (3.0, 10.0, 18.0):
+            imgs.append(np.clip(base[g] + sigma * r.standard_normal(base[g].shape), 0, 255))
+        if g < 4:
+            gnd.append({"bbx": (0, 0, w, h), "ok": [first + 1, first + 2, first + 3], "junk": [first]})
+            qnames.append(first)
+    for e in range(n_extra):
+        imgs.append(base[n_groups + e])
+    d = os.path.join(root, "oxford5k", "jpg")
+    os.makedirs(d, exist_ok=True)
+    for i, im in enumerate(imgs):
+        names.append("im%03d.png" % i)
+        Image.fromarray(im.astype(np.uint8)).save(os.path.join(d, names[-1]))
+    with open(os.path.join(root, "oxford5k", "gnd_oxford5k.pkl"), "wb") as f:
+        pickle.dump({"imlist": names, "qimlist": [names[i] for i in qnames], "gnd": gnd}, f)
+    sd = synth.make_state_dict(arch, seed=0)
+    return gnd, names, qnames, sd
+
+
+def load_normalised(root, names):
+    from PIL import Image
+    out = []
+    for n in names:
+        a = np.array(Image.open(os.path.join(root, "oxford5k", "jpg", n)).convert("RGB"), dtype=np.uint8)
+        out.append(synth.normalise_images(a[None]))
+    return out

@@ -1,0 +1,132 @@
+"""The reference-facing surface on the GPU: dirtorch.utils.common / test_dir functions, both CLIs end to end on a
+synthetic Oxford-layout dataset (BASELINE config 1, reduced), and the sharded search.  -m gpu."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import dirb200.synth as synth
+from conftest import REPO, rel_l2
+from oracle import dir_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    from dirb200 import ops
+    ops.require_gpu(0)
+
+
+def test_common_functions(golden):
+    _gpu()
+    from dirtorch.utils import common
+    g = golden("rank_ap.npz")
+    db, q, _ = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                        db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    sc = common.matmul(q, db)                                         # numpy in -> numpy (Q,N) out
+    assert isinstance(sc, np.ndarray) and sc.shape == (6, 400)
+    np.testing.assert_allclose(sc, g["scores"], atol=2e-6)
+    sc2 = common.matmul(torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda())
+    np.testing.assert_array_equal(sc, sc2)
+    w = golden("whiten.npz")
+    from types import SimpleNamespace
+    pca = SimpleNamespace(mean_=w["mean_f64"], components_=w["comp_f64"], explained_variance_=w["var_f64"], whiten=True)
+    assert rel_l2(common.whiten_features(w["X"], pca, whitenp=0.25), w["w_p025_f64"]) < 1e-5
+    assert rel_l2(common.whiten_features(w["X"], pca, whitenp=0.5, whitenv=32, whitenm=2.0), w["w_p05_v32_m2_f64"]) < 1e-5
+    assert rel_l2(common.transform(pca, w["X"], whitenp=0.25), w["w_nol2_f64"]) < 1e-5
+    p = golden("pool.npz")
+    xs = [torch.from_numpy(p[k]).cuda() for k in ("x0", "x1", "x2")]
+    np.testing.assert_allclose(common.tonumpy(common.pool(xs, "gem", 3)), p["gem3"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(common.tonumpy(common.pool(xs, "mean")), p["mean"], rtol=1e-6, atol=1e-7)
+
+
+def test_expand_descriptors(golden):
+    _gpu()
+    from dirtorch.test_dir import expand_descriptors
+    g = golden("aqe.npz")
+    db, q, _ = synth.make_descriptor_db(int(g["n_db"]), int(g["n_q"]), dim=int(g["dim"]), n_pos=int(g["n_pos"]),
+                                        db_seed=int(g["db_seed"]), q_seed=int(g["q_seed"]))
+    pad = lambda a: np.concatenate([a, np.zeros((a.shape[0], 64 - a.shape[1]), np.float32)], 1)   # dim 48 -> 64 (zeros: same scores)
+    for k, alpha, key in ((2, 0.5, "aqe_k2_a05"), (3, 1, "aqe_k3_a1")):
+        out = expand_descriptors(pad(q), db=pad(db), k=k, alpha=alpha)
+        assert rel_l2(out[:, :48], g[key]) < 1e-5
+    assert expand_descriptors(q, db=db, k=0, alpha=1) is q
+    out = expand_descriptors(pad(g["dba_in"]), db=None, k=2, alpha=1)       # database-side augmentation
+    assert rel_l2(out[:, :48], g["dba_k2_a1"]) < 1e-5
+    with pytest.raises(AssertionError):
+        expand_descriptors(q, db=db, k=-1, alpha=1)
+
+
+def test_sharded_index_single_rank():
+    _gpu()
+    from dirb200.dist import ShardedIndex
+    db, q, _ = synth.make_descriptor_db(5000, 17, dim=256, n_pos=5)
+    sh = ShardedIndex(torch.from_numpy(db).cuda(), row_offset=0)
+    s, i = sh.search(torch.from_numpy(q).cuda(), 30)
+    rs, ri = O.topk(q, db, 30)
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+    out = sh.expand_queries(torch.from_numpy(q).cuda(), 2, 0.5)
+    assert rel_l2(out.cpu().numpy(), O.expand_descriptors(q, db=db, k=2, alpha=0.5)) < 1e-5
+
+
+def test_cli_end_to_end(tmp_path, monkeypatch, capsys):
+    """extract_features + test_dir CLIs on a synthetic Oxford-layout DB_ROOT vs the oracle pipeline."""
+    _gpu()
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import e2e_data
+    from sklearn.decomposition import PCA
+    root = str(tmp_path)
+    gnd, names, qn, sd = e2e_data.build(root)
+    # ---- oracle pipeline (CPU): descriptors -> PCA fit -> whitening -> scores -> mAP
+    xs = e2e_data.load_normalised(root, names)
+    with torch.no_grad():
+        D = np.stack([O.extract(x, sd, "resnet50_rmac").numpy() for x in xs])
+    pca = PCA(n_components=32, whiten=True).fit(D)
+    W = O.whiten_features(D, pca, whitenp=0.25)
+    ref_map, ref_aps = O.mean_ap(O.scores_exact(W[qn], W), gnd)
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()},
+                "model_options": dict(arch="resnet50_rmac", out_dim=2048, pooling="gem", gemp=3),
+                "pca": {"Landmarks_clean": pca}}, os.path.join(root, "ckpt.pt"))
+    monkeypatch.setenv("DB_ROOT", root)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    from dirtorch import extract_features, test_dir
+    # ---- extract_features CLI, no whitening: raw descriptors within 1e-3
+    with open(os.path.join(root, "list.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    out_npy = os.path.join(root, "out", "feats.npy")
+    extract_features.extract_features_main(["--dataset", 'ImageList("%s/list.txt", "%s/oxford5k/jpg")' % (root, root),
+                                            "--checkpoint", os.path.join(root, "ckpt.pt"), "--output", out_npy,
+                                            "--gpu", "0", "--threads", "2"])
+    feats = np.load(out_npy)
+    assert feats.shape == (len(names), 2048) and feats.dtype == np.float32
+    assert rel_l2(feats, D) < 1e-3
+    # ---- test_dir CLI with whitening: same mAP as the oracle, and the literal console line
+    res = test_dir.test_dir_main(["--dataset", "Oxford5K", "--checkpoint", os.path.join(root, "ckpt.pt"),
+                                  "--whiten", "Landmarks_clean", "--whitenp", "0.25", "--gpu", "0", "--threads", "2",
+                                  "--save-feats", os.path.join(root, "saved"), "--detailed"])
+    assert res["mAP"] == ref_map
+    assert res["APs"] == [float(a) for a in ref_aps]
+    assert " * mAP = %g" % ref_map in capsys.readouterr().out
+    saved = np.load(os.path.join(root, "saved", "feats.bdescs.npy"))
+    assert rel_l2(saved, D) < 1e-3
+    # ---- alpha-QE through the CLI (float alpha accepted) and --load-feats
+    res2 = test_dir.test_dir_main(["--dataset", "Oxford5K", "--checkpoint", os.path.join(root, "ckpt.pt"),
+                                   "--whiten", "Landmarks_clean", "--gpu", "0", "--load-feats", os.path.join(root, "saved"),
+                                   "--aqe", "2", "0.5"])
+    Wq = O.expand_descriptors(O.whiten_features(saved[qn], pca, whitenp=0.25), db=O.whiten_features(saved, pca, whitenp=0.25), k=2, alpha=0.5)
+    ref2, _ = O.mean_ap(O.scores_exact(Wq, O.whiten_features(saved, pca, whitenp=0.25)), gnd)
+    assert res2["mAP"] == ref2
+
+
+def test_two_gpu_sharded_search(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, OUT_DIR=str(tmp_path))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(REPO, "tools", "dist_check.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "DIST-OK" in p.stdout

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): row-sharded search + one all-gather + merge and
+sharded alpha-QE against the single-process CPU oracle."""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import dirb200.synth as synth
+from dirb200.dist import ShardedIndex, shard_rows
+from oracle import dir_oracle as O
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+db, q, pos = synth.make_descriptor_db(40000, 70, dim=2048, n_pos=10)
+s0, s1 = shard_rows(db.shape[0], world, rank)
+index = ShardedIndex(torch.from_numpy(db[s0:s1]).cuda(), row_offset=s0)
+index.local.set_option("sample_rows", 2048)
+qd = torch.from_numpy(q).cuda()
+s, i = index.search(qd, 100)
+ok = True
+if rank == 0:
+    rs, ri = O.topk(q, db, 100)
+    ok = bool(np.array_equal(i.cpu().numpy(), ri) and np.abs(s.cpu().numpy() - rs).max() < 1e-12)
+out = index.expand_queries(qd, 2, 0.5)
+if rank == 0:
+    ref = O.expand_descriptors(q, db=db, k=2, alpha=0.5)
+    ok = ok and float(np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref)) < 1e-5
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("DIST-OK" if int(flag.item()) == 1 else "DIST-FAIL", "world", world)
+dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
