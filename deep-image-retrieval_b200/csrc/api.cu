@@ -29,6 +29,21 @@ int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const 
                   H16(out_dev), ST(stream));
 }
 
+size_t dirb200_stem_workspace_bytes(int B, int H, int W) { return stem_workspace_bytes(B, H, W); }
+
+int dirb200_stem_pack_weight(const float* w_oihw_host, void* w2_host) {
+  DIRB_REQUIRE(w_oihw_host && w2_host, DIRB200_EINVAL, "null argument");
+  pack_stem_w2(w_oihw_host, static_cast<__half*>(w2_host));
+  return 0;
+}
+
+int dirb200_stem_conv(const float* imgs_dev, int B, int H, int W, const void* w2_dev, const float* scale_dev,
+                      const float* shift_dev, void* ws_dev, void* out_dev, void* stream) {
+  DIRB_REQUIRE(imgs_dev && w2_dev && scale_dev && shift_dev && ws_dev && out_dev, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(B > 0 && H >= 7 && W >= 7, DIRB200_EINVAL, "bad shape");
+  return stem_tc(imgs_dev, B, H, W, CH16(w2_dev), scale_dev, shift_dev, H16(ws_dev), H16(out_dev), ST(stream));
+}
+
 int dirb200_maxpool_3x3s2(const void* in_dev, int B, int H, int W, int C, void* out_dev, void* stream) {
   DIRB_REQUIRE(in_dev && out_dev && B > 0 && H > 0 && W > 0, DIRB200_EINVAL, "bad arguments");
   return maxpool_3x3s2(CH16(in_dev), B, H, W, C, H16(out_dev), ST(stream));

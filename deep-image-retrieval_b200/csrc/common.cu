@@ -74,6 +74,36 @@ int encode_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int 
   return 0;
 }
 
+int encode_tmap_nhwc16(CUtensorMap* m, const void* base, int B, int H, int W, int tw, int th, int nb) {
+  EncodeTiledFn enc = get_encode();
+  DIRB_REQUIRE(enc != nullptr, DIRB200_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {32, (cuuint64_t)W * 32, (cuuint64_t)H * W * 32};
+  cuuint32_t box[4] = {16, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DIRB_REQUIRE(r == CUDA_SUCCESS, DIRB200_EDRIVER, "cuTensorMapEncodeTiled(nhwc16) failed: %d (B=%d H=%d W=%d box=%d,%d,%d)",
+               (int)r, B, H, W, tw, th, nb);
+  return 0;
+}
+
+int encode_tmap_2d_sw32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  DIRB_REQUIRE(enc != nullptr, DIRB200_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {16, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DIRB_REQUIRE(r == CUDA_SUCCESS, DIRB200_EDRIVER, "cuTensorMapEncodeTiled(2d sw32) failed: %d", (int)r);
+  return 0;
+}
+
 }  // namespace dirb
 
 extern "C" {

@@ -43,6 +43,11 @@ int encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t ou
 // fp16 NHWC activation viewed as (C, W, H, B); box (64, tw*es, th*es, nb) traversed with element stride es
 // on W and H (es = conv stride), 128-byte swizzle, out-of-bounds elements read as zero.
 int encode_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tw, int th, int nb, int es);
+// Same for 16-channel (32-byte) pixels: box (16, tw, th, nb), 32-byte swizzle (space-to-depth stem input).
+int encode_tmap_nhwc16(CUtensorMap* m, const void* base, int B, int H, int W, int tw, int th, int nb);
+// fp16 row-major [outer][inner] matrix, box = 16 x box_outer, 32-byte swizzle.
+int encode_tmap_2d_sw32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_outer);
 
 // Launch counter (the "gpu_launches" the benchmark reports): every kernel launch of this library bumps it.
 void count_launch(int n = 1);

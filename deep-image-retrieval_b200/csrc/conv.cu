@@ -7,6 +7,7 @@
 
 #include "conv_pers.cuh"
 #include "gemm_tc.cuh"
+#include "stem_pers.cuh"
 
 namespace dirb {
 
@@ -89,7 +90,7 @@ int conv_tc_np(const ConvShape& s, const __half* in, const __half* w, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ persistent tcgen05 path
-static int num_sms() {
+int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -142,7 +143,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
   const int64_t total = m_tiles * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
   p.total_tiles = static_cast<int>(total);
-  return conv_pers_launch<BN, STAGES>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
+  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
 }
 
 int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
@@ -153,6 +154,94 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
   if (s.Cout % 256 == 0) return conv_pers_bn<256, 3>(s, in, w, scale, shift, res, relu, out, stream);
   if (s.Cout % 128 == 0) return conv_pers_bn<128, 4>(s, in, w, scale, shift, res, relu, out, stream);
   return conv_pers_bn<64, 4>(s, in, w, scale, shift, res, relu, out, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ tcgen05 stem
+// NCHW fp32 -> zero-padded space-to-depth NHWC16 fp16 (see stem_pers.cuh): one thread per 2x2 block.
+__global__ void s2d_kernel(const float* __restrict__ in, __half* __restrict__ out, int H, int W, int Hs, int Ws,
+                           int64_t total) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int X = static_cast<int>(i % Ws);
+  const int Y = static_cast<int>((i / Ws) % Hs);
+  const int64_t n = i / (static_cast<int64_t>(Ws) * Hs);
+  const float* img = in + n * 3 * static_cast<int64_t>(H) * W;
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  uint32_t o[8];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int y = 2 * Y + dy - 3, x = 2 * X + dx - 3;
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const int64_t off = static_cast<int64_t>(y) * W + x;
+        c0 = __ldg(img + off);
+        c1 = __ldg(img + plane + off);
+        c2 = __ldg(img + 2 * plane + off);
+      }
+      o[(dy * 2 + dx) * 2] = pack_h2(c0, c1);
+      o[(dy * 2 + dx) * 2 + 1] = pack_h2(c2, 0.f);
+    }
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+static void stem_dims(int H, int W, int* Ho, int* Wo, int* Hs, int* Ws) {
+  *Ho = (H + 6 - 7) / 2 + 1;
+  *Wo = (W + 6 - 7) / 2 + 1;
+  *Hs = *Ho + 3;
+  *Ws = *Wo + 3;
+}
+
+size_t stem_workspace_bytes(int B, int H, int W) {
+  int Ho, Wo, Hs, Ws;
+  stem_dims(H, W, &Ho, &Wo, &Hs, &Ws);
+  return static_cast<size_t>(B) * Hs * Ws * 32;
+}
+
+void pack_stem_w2(const float* w, __half* out) {
+  for (int co = 0; co < 64; ++co)
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b)
+        for (int dy = 0; dy < 2; ++dy)
+          for (int dx = 0; dx < 2; ++dx)
+            for (int c = 0; c < 4; ++c) {
+              const int kh = 2 * a + dy, kw = 2 * b + dx;
+              float v = 0.f;
+              if (c < 3 && kh < 7 && kw < 7) v = w[((co * 3 + c) * 7 + kh) * 7 + kw];
+              out[co * 256 + (a * 4 + b) * 16 + (dy * 2 + dx) * 4 + c] = __float2half_rn(v);
+            }
+}
+
+int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const float* scale, const float* shift,
+            __half* s2d_ws, __half* out, cudaStream_t stream) {
+  int Ho, Wo, Hs, Ws;
+  stem_dims(H, W, &Ho, &Wo, &Hs, &Ws);
+  const int64_t total = static_cast<int64_t>(B) * Hs * Ws;
+  s2d_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(imgs, s2d_ws, H, W, Hs, Ws, total);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  StemParams p{};
+  pick_patch(B, Ho, Wo, &p.tw, &p.th, &p.nb);
+  p.tiles_w = (int)ceil_div(Wo, p.tw);
+  p.tiles_h = (int)ceil_div(Ho, p.th);
+  const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * ceil_div(B, p.nb);
+  DIRB_REQUIRE(tiles > 0 && tiles < (int64_t(1) << 31), DIRB200_ENOTSUP, "stem tile count out of range");
+  p.total_tiles = static_cast<int>(tiles);
+  p.scale = scale;
+  p.shift = shift;
+  CUtensorMap tmS, tmW, tmO;
+  DIRB_TRY(encode_tmap_nhwc16(&tmS, s2d_ws, B, Hs, Ws, p.tw, p.th, p.nb));
+  DIRB_TRY(encode_tmap_2d_sw32(&tmW, w2, 256, 64, 512, 64));
+  DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, 64, p.tw, p.th, p.nb, 1));
+  DIRB_CUDA(cudaFuncSetAttribute(stem_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::TOTAL));
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  stem_pers_kernel<<<grid, 256, StemSmem::TOTAL, stream>>>(tmS, tmW, tmO, p);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ mma.sync path

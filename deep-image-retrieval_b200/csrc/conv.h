@@ -21,7 +21,16 @@ int conv_tc_np(const ConvShape& s, const __half* in, const __half* w, const floa
 int conv_mma(const ConvShape& s, const __half* in, const __half* w, int Kpad, const float* scale, const float* shift,
              const __half* res, int relu, __half* out, cudaStream_t stream);
 
+int num_sms();
 int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_t stream);
+
+// Stem 7x7/s2/p3 (3 -> 64) + BN + ReLU on tensor cores (stem_pers.cuh).  imgs: NCHW fp32; w2: [64][256] fp16 in the
+// space-to-depth tap order (pack_stem_w2); s2d_ws: scratch of stem_workspace_bytes(B,H,W); out NHWC fp16 (B,Ho,Wo,64).
+size_t stem_workspace_bytes(int B, int H, int W);
+int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const float* scale, const float* shift,
+            __half* s2d_ws, __half* out, cudaStream_t stream);
+// OIHW fp32 [64][3][7][7] -> [64][256] fp16 (host).
+void pack_stem_w2(const float* w_oihw, __half* out);
 int maxpool_3x3s2(const __half* in, int B, int H, int W, int C, __half* out, cudaStream_t stream);
 
 size_t head_workspace_floats(int B, int HW, int C, int out_dim);

@@ -21,25 +21,37 @@
 
 namespace dirb {
 
+enum { PERS_EPI_CONV = 0, PERS_EPI_SIM_DENSE = 1, PERS_EPI_SIM_FILTER = 2 };
+
 struct ConvPersParams {
   int a_spatial, taps, kw_taps, cin_blocks, stride, pad;
   int tw, th, nb, tiles_w, tiles_h;
   int n_tiles, total_tiles;
+  int m_fastest, m_tiles;      // tile order: 0 = n-tile fastest (convolutions: CTAs share the activation tile),
+                               // 1 = m-tile fastest (search: CTAs running together share the streamed database tile)
   int has_res, relu;
   const float* scale;
   const float* shift;
+  // similarity epilogues (search.cu): D[q][n] = <query q, database row n>
+  int M, N;                    // valid queries / database rows of this launch
+  float* dense;                // [M][dense_ld] fp32 scores                     (PERS_EPI_SIM_DENSE)
+  int64_t dense_ld;
+  const float* thr;            // [M] per-query threshold                       (PERS_EPI_SIM_FILTER)
+  unsigned long long* cand;    // [M][cand_cap] packed (score bits << 32 | row)
+  int* cand_cnt;               // [M]
+  int cand_cap;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = 0>
 struct ConvPersSmem {
-  static constexpr int NBUF = 4;
+  static constexpr int NBUF = (EPI == 0) ? 4 : 0;   // staging buffers exist only for the convolution epilogue
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 128 * 128;                      // 128 rows x 64 channels fp16
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = STG_OFF + NBUF * STG_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NBUF;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * 4;
   static constexpr int TOTAL = BAR_OFF + 8 * NUM_BARS + 16 + 1024;  // + tmem slot + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                          // two accumulators
 };
@@ -49,8 +61,13 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvPersParams& p, int t) {
   TileCoord c;
-  c.n_tile = t % p.n_tiles;
-  c.m_tile = t / p.n_tiles;
+  if (p.m_fastest) {
+    c.m_tile = t % p.m_tiles;
+    c.n_tile = t / p.m_tiles;
+  } else {
+    c.n_tile = t % p.n_tiles;
+    c.m_tile = t / p.n_tiles;
+  }
   c.wo0 = c.ho0 = c.n0 = 0;
   if (p.a_spatial) {
     const int tx = c.m_tile % p.tiles_w;
@@ -63,13 +80,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvPersParams& p, int t)
   return c;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(256, 1)
 conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvPersParams p) {
-  using L = ConvPersSmem<BN, STAGES>;
-  constexpr int NBUF = L::NBUF;
+  using L = ConvPersSmem<BN, STAGES, EPI>;
+  constexpr int NBUF = 4;
   constexpr int CHUNKS = BN / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,8 +106,8 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO);
-    if (p.has_res) tma_prefetch_desc(&tmR);
+    if (EPI == PERS_EPI_CONV) tma_prefetch_desc(&tmO);
+    if (EPI == PERS_EPI_CONV && p.has_res) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -161,7 +178,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 2) {
-    if (lane == 0 && p.has_res) {
+    if (EPI == PERS_EPI_CONV && lane == 0 && p.has_res) {
       // ------------------------------------------------------------ residual producer
       uint32_t cc = 0;  // staging chunk counter, runs across tiles
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -191,6 +208,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&acc_full[a], (i >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (EPI == PERS_EPI_CONV) {
 #pragma unroll 1
       for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
         const int b = cc % NBUF;
@@ -260,8 +278,48 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      } else {
+        // ---------------------------------------------------------- similarity epilogues: row = query
+        const int64_t qi = static_cast<int64_t>(c.m_tile) * 128 + row;
+        const bool valid = qi < p.M;
+        const float t_q = (EPI == PERS_EPI_SIM_FILTER && valid) ? __ldg(p.thr + qi) : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          if (c0 + 32 == BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+          }
+          const int nb0 = c.n_tile * BN + c0;
+          if (!valid || nb0 >= p.N) continue;
+          if (EPI == PERS_EPI_SIM_DENSE) {
+            float* dp = p.dense + qi * p.dense_ld + nb0;
+            if (nb0 + 32 <= p.N) {
+              float4* d4 = reinterpret_cast<float4*>(dp);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) d4[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nb0 + j < p.N) dp[j] = v[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] >= t_q && nb0 + j < p.N) {
+                const int pos = atomicAdd(p.cand_cnt + qi, 1);
+                if (pos < p.cand_cap)
+                  p.cand[qi * p.cand_cap + pos] = (static_cast<unsigned long long>(__float_as_uint(v[j])) << 32) |
+                                                  static_cast<unsigned int>(nb0 + j);
+              }
+            }
+          }
+        }
+      }
     }
-    if (leader) bulk_wait<0>();                             // all output bytes written before the CTA retires
+    if (EPI == PERS_EPI_CONV && leader) bulk_wait<0>();     // all output bytes written before the CTA retires
   }
 
   tc_fence_before();
@@ -272,11 +330,11 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 int conv_pers_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                      const ConvPersParams& p, int num_sms, cudaStream_t stream) {
-  using L = ConvPersSmem<BN, STAGES>;
-  auto kern = conv_pers_kernel<BN, STAGES>;
+  using L = ConvPersSmem<BN, STAGES, EPI>;
+  auto kern = conv_pers_kernel<BN, STAGES, EPI>;
   DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   kern<<<grid, 256, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);

@@ -72,6 +72,7 @@ struct dirb200_net {
   bool finalized = false;
   // device weights
   ConvLayer stem;
+  __half* stem_w2 = nullptr;      // [64][256] space-to-depth tap layout for the tcgen05 stem
   std::vector<Block> blocks;      // flattened over layer1..4
   std::vector<int> layer_end;     // index (exclusive) of the last block of each layer
   float* fc_w = nullptr;
@@ -262,6 +263,14 @@ int dirb200_net_finalize(dirb200_net* n) {
   DIRB_CUDA(cudaSetDevice(n->device));
   n->stem = make_layer("conv1", "bn1", 3, 64, 7, 2, 3);          // resnet.py:115-117
   DIRB_TRY(pack_conv(n, n->stem));
+  {
+    const HostTensor* w;
+    DIRB_TRY(get_tensor(n, "conv1.weight", &w, 64 * 3 * 7 * 7));
+    std::vector<__half> w2(64 * 256);
+    pack_stem_w2(w->data.data(), w2.data());
+    DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&n->stem_w2), w2.size() * sizeof(__half)));
+    DIRB_CUDA(cudaMemcpy(n->stem_w2, w2.data(), w2.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   int inplanes = 64;
   const int planes_per_layer[4] = {64, 128, 256, 512};           // resnet.py:120-123
   for (int li = 0; li < 4; ++li) {
@@ -329,7 +338,7 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
   w->H2 = (w->H1 + 2 - 3) / 2 + 1; w->W2 = (w->W1 + 2 - 3) / 2 + 1;   // maxpool
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
-  const size_t o_in8 = carve(static_cast<size_t>(chunk) * H * W * 8 * 2);
+  const size_t o_in8 = carve(std::max(static_cast<size_t>(chunk) * H * W * 8 * 2, stem_workspace_bytes(chunk, H, W)));
   const size_t o_stem = carve(static_cast<size_t>(chunk) * w->H1 * w->W1 * 64 * 2);
   const size_t act_max = static_cast<size_t>(chunk) * w->H2 * w->W2 * 256 * 2;   // layer1 output is the largest
   size_t o_act[5];
@@ -355,11 +364,18 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
 static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, int cb, int H, int W, float* desc_dev,
                      __half* desc16_dev, cudaStream_t stream) {
   const int D = n->without_fc ? 2048 : n->out_dim;
-  {
-    ProfScope ps(n, stream, 2, 0, static_cast<double>(cb) * H * W * (12 + 16));
-    DIRB_TRY(nchw_to_nhwc8(imgs_dev, cb, H, W, w.in8, stream));
+  if (n->conv_impl == 1) {
+    {
+      ProfScope ps(n, stream, 2, 0, static_cast<double>(cb) * H * W * (12 + 16));
+      DIRB_TRY(nchw_to_nhwc8(imgs_dev, cb, H, W, w.in8, stream));
+    }
+    DIRB_TRY(run_conv(n, n->stem, w.in8, cb, H, W, nullptr, 1, w.stem_out, stream, /*force_mma=*/1));
+  } else {
+    const double flops = 2.0 * cb * w.H1 * w.W1 * 64.0 * 147.0;
+    n->last_flops += flops;
+    ProfScope ps(n, stream, 1, flops, static_cast<double>(cb) * (12.0 * H * W + 2.0 * stem_workspace_bytes(1, H, W) + 128.0 * w.H1 * w.W1));
+    DIRB_TRY(stem_tc(imgs_dev, cb, H, W, n->stem_w2, n->stem.scale, n->stem.shift, w.in8, w.stem_out, stream));
   }
-  DIRB_TRY(run_conv(n, n->stem, w.in8, cb, H, W, nullptr, 1, w.stem_out, stream, /*force_mma=*/1));
   __half* x = w.act[0];
   {
     ProfScope ps(n, stream, 2, 0, 2.0 * cb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.H2) * w.W2));

@@ -23,7 +23,7 @@
 #include <vector>
 
 #include "conv.h"
-#include "gemm_tc.cuh"
+#include "conv_pers.cuh"
 
 namespace dirb {
 namespace {
@@ -311,21 +311,36 @@ struct dirb200_index {
   int64_t stats[5] = {0, 0, 0, 0, 0};
 };
 
-static int sim_gemm(int epi, const __half* q16, int Q, const __half* db16, int64_t rows, int D, GemmTcParams p,
+// Similarity GEMM on the persistent tcgen05 kernel (conv_pers.cuh): A = queries [Q][D], B = database rows [rows][D],
+// 128 x 256 tiles, K = D.  Tiles are ordered database-tile-fastest, so CTAs running at the same time share the
+// query tile (L2) and stream disjoint database rows.
+struct SimArgs {
+  float* dense = nullptr; int64_t dense_ld = 0;
+  const float* thr = nullptr; unsigned long long* cand = nullptr; int* cand_cnt = nullptr; int cand_cap = 0;
+};
+static int sim_gemm(int epi, const __half* q16, int Q, const __half* db16, int64_t rows, int D, const SimArgs& a,
                     cudaStream_t stream) {
-  constexpr int BN = 128;
+  constexpr int BN = 256;
   CUtensorMap tmA, tmB;
   DIRB_TRY(encode_tmap_2d(&tmA, q16, D, Q, (uint64_t)D * 2, 64, 128));
   DIRB_TRY(encode_tmap_2d(&tmB, db16, D, rows, (uint64_t)D * 2, 64, BN));
+  ConvPersParams p{};
   p.a_spatial = 0;
   p.taps = 1; p.kw_taps = 1; p.cin_blocks = D / 64; p.stride = 1; p.pad = 0;
   p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
   p.M = Q;
   p.N = static_cast<int>(rows);
   p.n_tiles = static_cast<int>(ceil_div(rows, BN));
-  const int64_t m_tiles = ceil_div(Q, 128);
-  if (epi == EPI_SIM_DENSE) return gemm_tc_launch<BN, 3, EPI_SIM_DENSE, 2>(tmA, tmB, p, m_tiles, stream);
-  return gemm_tc_launch<BN, 3, EPI_SIM_FILTER, 2>(tmA, tmB, p, m_tiles, stream);
+  p.m_tiles = static_cast<int>(ceil_div(Q, 128));
+  p.m_fastest = 1;
+  const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  DIRB_REQUIRE(total < (int64_t(1) << 31), DIRB200_ENOTSUP, "too many tiles");
+  p.total_tiles = static_cast<int>(total);
+  p.dense = a.dense; p.dense_ld = a.dense_ld;
+  p.thr = a.thr; p.cand = a.cand; p.cand_cnt = a.cand_cnt; p.cand_cap = a.cand_cap;
+  if (epi == PERS_EPI_SIM_DENSE)
+    return conv_pers_launch<BN, 4, PERS_EPI_SIM_DENSE>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
+  return conv_pers_launch<BN, 4, PERS_EPI_SIM_FILTER>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
 }
 
 extern "C" {
@@ -446,11 +461,10 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   DIRB_TRY(f32_to_f16(q32, static_cast<int64_t>(Q) * D, q16, stream));
   // ---- 2. seed pass over the first S rows
   {
-    GemmTcParams p{};
-    p.dense = dense;
-    p.dense_ld = S_ld;
-    p.n_offset = 0;
-    DIRB_TRY(sim_gemm(EPI_SIM_DENSE, q16, Q, h->db16, S, D, p, stream));
+    SimArgs a;
+    a.dense = dense;
+    a.dense_ld = S_ld;
+    DIRB_TRY(sim_gemm(PERS_EPI_SIM_DENSE, q16, Q, h->db16, S, D, a, stream));
     const int kk = static_cast<int>(std::min<int64_t>(k, S));
     kth_dense_kernel<<<Q, SEL_THREADS, 0, stream>>>(dense, S_ld, static_cast<int>(S), kk, band, thr);
     count_launch();
@@ -465,13 +479,12 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
       dense_compact_kernel<<<g, 256, 0, stream>>>(dense, S_ld, static_cast<int>(N), thr, cand, cnt, cap);
       count_launch();
     } else {
-      GemmTcParams p{};
-      p.thr = thr;
-      p.cand = cand;
-      p.cand_cnt = cnt;
-      p.cand_cap = cap;
-      p.n_offset = 0;
-      DIRB_TRY(sim_gemm(EPI_SIM_FILTER, q16, Q, h->db16, N, D, p, stream));
+      SimArgs a;
+      a.thr = thr;
+      a.cand = cand;
+      a.cand_cnt = cnt;
+      a.cand_cap = cap;
+      DIRB_TRY(sim_gemm(PERS_EPI_SIM_FILTER, q16, Q, h->db16, N, D, a, stream));
     }
     // ---- 4. select survivors
     cand_select_kernel<<<Q, SEL_THREADS, 0, stream>>>(cand, cnt, cap, k, band, sidx, scnt, cap2, thr, flags, N);

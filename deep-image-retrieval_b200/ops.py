@@ -72,6 +72,23 @@ def conv_bn_act(x, w_packed, cout, kh, kw, stride, pad, scale, shift, res=None, 
     return out
 
 
+def stem_conv(x_nchw, w_oihw, scale, shift):
+    """Conv 7x7/s2/p3 (3->64) + BN + ReLU on tensor cores: NCHW fp32 (B,3,H,W) -> NHWC fp16 (B,Ho,Wo,64)."""
+    _chk(x_nchw, torch.float32, "x_nchw")
+    b, c, h, w = x_nchw.shape
+    assert c == 3 and tuple(w_oihw.shape) == (64, 3, 7, 7)
+    wh = np.ascontiguousarray(w_oihw.detach().cpu().numpy().astype(np.float32))
+    w2 = np.empty((64, 256), dtype=np.float16)
+    lib.call("dirb200_stem_pack_weight", wh.ctypes.data_as(C.c_void_p), w2.ctypes.data_as(C.c_void_p))
+    w2d = torch.from_numpy(w2).to(x_nchw.device)
+    ws = torch.empty(lib.raw("dirb200_stem_workspace_bytes")(b, h, w), dtype=torch.uint8, device=x_nchw.device)
+    ho, wo = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    out = torch.empty((b, ho, wo, 64), dtype=torch.float16, device=x_nchw.device)
+    lib.call("dirb200_stem_conv", _ptr(x_nchw), b, h, w, _ptr(w2d), _ptr(_chk(scale, torch.float32, "scale")),
+             _ptr(_chk(shift, torch.float32, "shift")), _ptr(ws), _ptr(out), _stream())
+    return out
+
+
 def maxpool_3x3s2(x):
     _chk(x, torch.float16, "x")
     b, h, w, c = x.shape

@@ -41,9 +41,16 @@ def expand_descriptors(descs, db=None, alpha=0, k=0):
     assert k >= 0 and alpha >= 0, "k and alpha must be non-negative"
     if k == 0:
         return descs
-    q = _dev_f32(descs)
+    dim = np.shape(descs)[1]
+    pad = (-dim) % 64                      # the tensor-core search wants D % 64 == 0; zero columns change no score
+
+    def _padded(x):
+        x = _dev_f32(x)
+        return torch.nn.functional.pad(x, (0, pad)).contiguous() if pad else x
+
+    q = _padded(descs)
     if db is not None:
-        d = _dev_f32(db)
+        d = _padded(db)
         s, i = ops.Index(d).search(q, k)
     else:
         # the reference zeroes the diagonal of the self-similarity (test_dir.py:33-34): drop each row from its
@@ -56,7 +63,7 @@ def expand_descriptors(descs, db=None, alpha=0, k=0):
         s = torch.from_numpy(np.take_along_axis(s1, keep, 1).copy()).cuda()
         i = torch.from_numpy(np.take_along_axis(i1, keep, 1).copy()).cuda()
     out = ops.aqe_expand(q, d, i.contiguous(), s.contiguous(), float(alpha))
-    return out.cpu().numpy()
+    return out[:, :dim].cpu().numpy()
 
 
 def extract_image_features(dataset, transforms, net, ret_imgs=False, same_size=False, flip=None,

@@ -95,6 +95,14 @@ int dirb200_nchw_to_nhwc8(const float* in_dev, int B, int H, int W, void* out_de
 int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const void* w_dev, int Cout, int KH,
                         int KW, int stride, int pad, const float* scale_dev, const float* shift_dev,
                         const void* res_dev, int relu, int impl, void* out_dev, void* stream);
+/* The stem on tensor cores: Conv2d(3, 64, 7, stride 2, pad 3, bias=False) + folded BN + ReLU, resnet.py:115-118.
+ * imgs_dev NCHW fp32 (B,3,H,W); w2_dev = the [64][256] fp16 weight layout produced (on the host) by
+ * dirb200_stem_pack_weight from the OIHW fp32 [64][3][7][7] tensor; ws_dev scratch of
+ * dirb200_stem_workspace_bytes(B,H,W) bytes; out_dev NHWC fp16 (B,Ho,Wo,64). */
+size_t dirb200_stem_workspace_bytes(int B, int H, int W);
+int dirb200_stem_pack_weight(const float* w_oihw_host, void* w2_host);
+int dirb200_stem_conv(const float* imgs_dev, int B, int H, int W, const void* w2_dev, const float* scale_dev,
+                      const float* shift_dev, void* ws_dev, void* out_dev, void* stream);
 /* MaxPool2d(3, stride 2, pad 1) on NHWC fp16.  resnet.py:119,161. */
 int dirb200_maxpool_3x3s2(const void* in_dev, int B, int H, int W, int C, void* out_dev, void* stream);
 /* Global pooling + (L2 over C) + FC + L2: rmac_resnet.py:59-68, pooling.py:38-40.

@@ -96,6 +96,24 @@ def test_stem_and_maxpool():
     assert torch.equal(yp.float().cpu(), refp)            # max of fp16 values is exact
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 63, 65), (3, 224, 224), (2, 130, 70)], ids=lambda s: "x".join(map(str, s)))
+def test_stem_tcgen05(shape):
+    """conv 7x7/s2/p3 + BN + ReLU through the space-to-depth tcgen05 kernel vs the fp32 oracle conv."""
+    ops = _ops()
+    b, h, w = shape
+    x = synth.make_images(b, h, w, seed=4)
+    sd = synth.make_state_dict("resnet50_rmac", seed=0)
+    wgt = sd["conv1.weight"]
+    s = sd["bn1.weight"] / torch.sqrt(sd["bn1.running_var"] + 1e-5)
+    sh = sd["bn1.bias"] - sd["bn1.running_mean"] * s
+    y = ops.stem_conv(x.to(DEV), wgt, s.to(DEV), sh.to(DEV))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.half().float(), wgt.half().float(), None, stride=2, padding=3) * s.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    ref = ref.permute(0, 2, 3, 1)
+    assert tuple(y.shape) == tuple(ref.shape)
+    assert (y.float().cpu() - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("kw", [dict(pooling="gem", p=3.0), dict(pooling="gem", p=2.5), dict(pooling="max"),
                                 dict(pooling="avg"), dict(pooling="gem", p=3.0, norm_features=True),
                                 dict(pooling="gem", p=3.0, without_fc=True)],
