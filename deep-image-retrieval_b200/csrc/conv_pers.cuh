@@ -21,7 +21,7 @@
 
 namespace dirb {
 
-enum { PERS_EPI_CONV = 0, PERS_EPI_SIM_DENSE = 1, PERS_EPI_SIM_FILTER = 2 };
+enum { PERS_EPI_CONV = 0, PERS_EPI_SIM_DENSE = 1, PERS_EPI_SIM_FILTER = 2, PERS_EPI_SIM_GMAX = 3 };
 
 struct ConvPersParams {
   int a_spatial, taps, kw_taps, cin_blocks, stride, pad;
@@ -295,7 +295,14 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const int nb0 = c.n_tile * BN + c0;
           if (!valid || nb0 >= p.N) continue;
-          if (EPI == PERS_EPI_SIM_DENSE) {
+          if (EPI == PERS_EPI_SIM_GMAX) {
+            // maximum of each group of 32 database rows: the k-th largest group maximum is a valid lower bound on
+            // the k-th best score (k distinct rows reach it) and costs 1/32 of the dense write + select
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = (nb0 + j < p.N) ? fmaxf(m, v[j]) : m;
+            p.dense[qi * p.dense_ld + (nb0 >> 5)] = m;
+          } else if (EPI == PERS_EPI_SIM_DENSE) {
             float* dp = p.dense + qi * p.dense_ld + nb0;
             if (nb0 + 32 <= p.N) {
               float4* d4 = reinterpret_cast<float4*>(dp);
@@ -306,13 +313,20 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (nb0 + j < p.N) dp[j] = v[j];
             }
           } else {
+            // one atomic per thread per 32-score group: reserve a run of slots for all matches of the group
+            uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] >= t_q && nb0 + j < p.N) {
-                const int pos = atomicAdd(p.cand_cnt + qi, 1);
-                if (pos < p.cand_cap)
-                  p.cand[qi * p.cand_cap + pos] = (static_cast<unsigned long long>(__float_as_uint(v[j])) << 32) |
-                                                  static_cast<unsigned int>(nb0 + j);
+            for (int j = 0; j < 32; ++j) mask |= (v[j] >= t_q && nb0 + j < p.N) ? (1u << j) : 0u;
+            if (mask) {
+              int pos = atomicAdd(p.cand_cnt + qi, __popc(mask));
+              unsigned long long* dst = p.cand + qi * p.cand_cap;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (mask & (1u << j)) {
+                  if (pos < p.cand_cap)
+                    dst[pos] = (static_cast<unsigned long long>(__float_as_uint(v[j])) << 32) | static_cast<unsigned int>(nb0 + j);
+                  ++pos;
+                }
               }
             }
           }

@@ -57,9 +57,17 @@ __device__ float block_kth_largest(Acc acc, int n, int k, uint32_t* hist /*[256]
     const int shift = pass * 8;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint32_t key = f2key(acc(i));
-      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    // similarity scores share their high bits, so most keys of a pass land in one or two bins: aggregate the
+    // lanes of a warp that hit the same bin and let one of them add the whole group
+    const int n_round = (n + 31) & ~31;
+    for (int i = threadIdx.x; i < n_round; i += blockDim.x) {
+      uint32_t bin = 0xffffffffu;
+      if (i < n) {
+        const uint32_t key = f2key(acc(i));
+        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xffffffffu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], static_cast<uint32_t>(__popc(peers)));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -309,6 +317,9 @@ struct dirb200_index {
   int* h_flags = nullptr;  // pinned
   int h_flags_n = 0;
   int64_t stats[5] = {0, 0, 0, 0, 0};
+  int profile = 0;                 // option "profile": time the phases of a search with CUDA events
+  cudaEvent_t ev[10] = {};
+  double phase_ms[9] = {};
 };
 
 // Similarity GEMM on the persistent tcgen05 kernel (conv_pers.cuh): A = queries [Q][D], B = database rows [rows][D],
@@ -340,6 +351,8 @@ static int sim_gemm(int epi, const __half* q16, int Q, const __half* db16, int64
   p.thr = a.thr; p.cand = a.cand; p.cand_cnt = a.cand_cnt; p.cand_cap = a.cand_cap;
   if (epi == PERS_EPI_SIM_DENSE)
     return conv_pers_launch<BN, 4, PERS_EPI_SIM_DENSE>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
+  if (epi == PERS_EPI_SIM_GMAX)
+    return conv_pers_launch<BN, 4, PERS_EPI_SIM_GMAX>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
   return conv_pers_launch<BN, 4, PERS_EPI_SIM_FILTER>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
 }
 
@@ -373,6 +386,7 @@ int dirb200_index_set_option(dirb200_index* h, const char* key, double value) {
   if (k == "eps16") h->eps16 = value;
   else if (k == "sample_rows") h->sample_rows = static_cast<int64_t>(value);
   else if (k == "cand_cap") h->cand_cap = static_cast<int>(value);
+  else if (k == "profile") h->profile = value != 0;
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown index option '%s'", key);
   return 0;
 }
@@ -383,8 +397,15 @@ int dirb200_index_last_stats(dirb200_index* h, int64_t stats[5]) {
   return 0;
 }
 
+int dirb200_index_last_profile(dirb200_index* h, double out9[9]) {
+  DIRB_REQUIRE(h && out9, DIRB200_EINVAL, "null");
+  for (int i = 0; i < 9; ++i) out9[i] = h->phase_ms[i];
+  return 0;
+}
+
 int dirb200_index_destroy(dirb200_index* h) {
   if (!h) return 0;
+  for (auto e : h->ev) if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   delete h;
@@ -416,6 +437,9 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   S = std::max<int64_t>(S, std::min<int64_t>(N, 4 * k));
   const bool small = (N <= S);
   if (small) S = N;
+  if (!small && S / 32 < k) S = std::min<int64_t>(N, std::max<int64_t>(S, 32 * static_cast<int64_t>(k)));
+  // seed threshold from group maxima (1/32 of the dense traffic) whenever there are at least k groups
+  const bool use_gmax = !small && (S / 32 >= k);
   const int64_t S_ld = ceil_div(S, 128) * 128;   // dense row stride (16-byte aligned rows)
   const double expect = small ? (2.0 * k + 64) : (1.5 * k * static_cast<double>(N) / S);
   int cap = static_cast<int>(std::min<double>(std::max<double>(4096, 4 * expect), 1 << 18));
@@ -457,17 +481,28 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   int* scnt = reinterpret_cast<int*>(w + o_scnt);
   int* flags = reinterpret_cast<int*>(w + o_flags);
 
+  int mark_i = 0;
+  auto mark = [&]() {
+    if (!h->profile) return;
+    if (!h->ev[mark_i]) cudaEventCreate(&h->ev[mark_i]);
+    cudaEventRecord(h->ev[mark_i++], stream);
+  };
+  mark();  // 0
   // ---- 1. queries to fp16
   DIRB_TRY(f32_to_f16(q32, static_cast<int64_t>(Q) * D, q16, stream));
+  mark();  // 1: convert
   // ---- 2. seed pass over the first S rows
   {
     SimArgs a;
     a.dense = dense;
     a.dense_ld = S_ld;
-    DIRB_TRY(sim_gemm(PERS_EPI_SIM_DENSE, q16, Q, h->db16, S, D, a, stream));
-    const int kk = static_cast<int>(std::min<int64_t>(k, S));
-    kth_dense_kernel<<<Q, SEL_THREADS, 0, stream>>>(dense, S_ld, static_cast<int>(S), kk, band, thr);
+    DIRB_TRY(sim_gemm(use_gmax ? PERS_EPI_SIM_GMAX : PERS_EPI_SIM_DENSE, q16, Q, h->db16, S, D, a, stream));
+    mark();  // 2: seed GEMM
+    const int n_vals = use_gmax ? static_cast<int>(ceil_div(S, 32)) : static_cast<int>(S);
+    const int kk = static_cast<int>(std::min<int64_t>(k, n_vals));
+    kth_dense_kernel<<<Q, SEL_THREADS, 0, stream>>>(dense, S_ld, n_vals, kk, band, thr);
     count_launch();
+    mark();  // 3: k-th of the seed scores
   }
   DIRB_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(Q) * 4, stream));
   int retries = 0;
@@ -486,9 +521,11 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
       a.cand_cap = cap;
       DIRB_TRY(sim_gemm(PERS_EPI_SIM_FILTER, q16, Q, h->db16, N, D, a, stream));
     }
+    if (retries == 0) mark();  // 4: filter pass
     // ---- 4. select survivors
     cand_select_kernel<<<Q, SEL_THREADS, 0, stream>>>(cand, cnt, cap, k, band, sidx, scnt, cap2, thr, flags, N);
     count_launch();
+    if (retries == 0) mark();  // 5: candidate selection
     DIRB_CUDA(cudaMemcpyAsync(h->h_flags, flags, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
     DIRB_CUDA(cudaStreamSynchronize(stream));
     bool cand_over = false, surv_over = false;
@@ -511,12 +548,15 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   // ---- 5. exact rescoring + ordering
   {
     dim3 g(static_cast<unsigned>(ceil_div(cap2, 8)), static_cast<unsigned>(Q));
+    mark();  // 6: flags round trip
     rescore_kernel<<<g, 256, 0, stream>>>(q32, h->db32, D, sidx, scnt, cap2, sscore);
+    mark();  // 7: exact re-scoring
     const size_t smem = static_cast<size_t>(cap2) * 16;
     DIRB_CUDA(cudaFuncSetAttribute(sort_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
     sort_topk_kernel<<<Q, 1024, smem, stream>>>(sscore, sidx, nullptr, scnt, 0, cap2, h->offset, k, scores_dev, idx_dev);
     count_launch(2);
     DIRB_CUDA(cudaGetLastError());
+    mark();  // 8: sort
   }
   {
     std::vector<int> hc(Q), hs(Q);
@@ -526,6 +566,13 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
     for (int i = 0; i < Q; ++i) {
       cand_total += hc[i];
       surv_total += hs[i];
+    }
+  }
+  if (h->profile && mark_i == 9) {
+    for (int i = 0; i < 8; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+      h->phase_ms[i] = ms;
     }
   }
   h->stats[0] = S;

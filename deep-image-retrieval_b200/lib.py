@@ -63,6 +63,7 @@ SIGNATURES = {
     "dirb200_index_set_option": (i32, [p, C.c_char_p, f64]),
     "dirb200_index_search": (i32, [p, p, i32, i32, p, p, p]),
     "dirb200_index_last_stats": (i32, [p, C.POINTER(i64)]),
+    "dirb200_index_last_profile": (i32, [p, C.POINTER(f64)]),
     "dirb200_index_destroy": (i32, [p]),
     "dirb200_topk_merge": (i32, [p, p, i32, i32, i32, i64, p, p, p]),
     "dirb200_scores_exact": (i32, [p, i32, p, i64, i32, p, p]),

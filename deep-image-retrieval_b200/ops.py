@@ -239,6 +239,12 @@ class Index:
         lib.call("dirb200_index_last_stats", self._h, arr)
         return dict(zip(["dense_rows", "candidates", "survivors", "retries", "launches"], [int(v) for v in arr]))
 
+    def profile(self):
+        arr = (C.c_double * 9)()
+        lib.call("dirb200_index_last_profile", self._h, arr)
+        names = ["to_f16", "seed_gemm", "seed_kth", "filter_gemm", "cand_select", "flags_roundtrip", "rescore", "sort"]
+        return {n: float(arr[i]) for i, n in enumerate(names)}
+
     def close(self):
         if self._h:
             lib.raw("dirb200_index_destroy")(self._h)

@@ -150,6 +150,10 @@ int dirb200_index_search(dirb200_index* idx, const float* q32_dev, int Q, int k,
                          int64_t* idx_dev, void* stream);
 /* Statistics of the last search: {dense_rows, candidates_total, survivors_total, retries, launches}. */
 int dirb200_index_last_stats(dirb200_index* idx, int64_t stats[5]);
+/* With option "profile" = 1: CUDA-event milliseconds of the phases of the last search, out9[0..7] = {query fp16
+ * conversion, seed GEMM, seed k-th select, filter GEMM, candidate select, flag round trip to the host, exact
+ * re-scoring, sort}. */
+int dirb200_index_last_profile(dirb200_index* idx, double out9[9]);
 int dirb200_index_destroy(dirb200_index* idx);
 
 /* Merge G per-shard top-k lists (scores fp64 + global indices int64, as produced by an all-gather of
