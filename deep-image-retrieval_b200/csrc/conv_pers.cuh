@@ -8,7 +8,8 @@
 //   warp 2  residual TMA   prefetches the residual tile (same box as the output tile) 64 channels at a time into
 //                          the staging buffers, up to NBUF chunks ahead of the epilogue
 //   warp 3  TMEM allocator
-//   warps 4-7 epilogue     tcgen05.ld (one accumulator row per thread) -> scale/shift (+ residual read from the
+//   warps 4-11 epilogue    (two warps per TMEM lane quarter, each taking 32 of the 64 channels of a chunk)
+//                          tcgen05.ld (one accumulator row per thread) -> scale/shift (+ residual read from the
 //                          staging buffer) (+ ReLU) -> fp16, written back IN PLACE into the 128-byte-swizzled
 //                          staging buffer -> one TMA store per 64-channel chunk (clips ragged edges by itself)
 //
@@ -80,8 +81,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvPersParams& p, int t)
   return c;
 }
 
+// Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
+// convolutions), 4 for the light similarity epilogues.
+template <int EPI>
+struct PersThreads {
+  static constexpr int EPI_WARPS = (EPI == 0) ? 8 : 4;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+};
+
 template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(PersThreads<EPI>::THREADS, 1)
 conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvPersParams p) {
@@ -114,7 +123,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);      // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], PersThreads<EPI>::EPI_WARPS);      // one arrival per epilogue warp
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&res_full[b], 1);
@@ -195,8 +204,10 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------------------- epilogue (128 threads)
-    const int quarter = warp - 4;
+    // -------------------------------------------------------------- epilogue
+    constexpr int EPI_THREADS = 32 * PersThreads<EPI>::EPI_WARPS;
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+    const int hsel = (warp - 4) >> 2;                  // conv epilogue: which 32-channel half of a chunk
     const int row = quarter * 32 + lane;
     const bool leader = (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
@@ -217,15 +228,15 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&res_full[b], (cc / NBUF) & 1);       // residual chunk has landed in `buf`
         } else {
           if (leader) bulk_wait_read<NBUF - 1>();           // the store issued NBUF chunks ago has left `buf`
-          named_bar_sync(1, 128);
+          named_bar_sync(1, EPI_THREADS);
         }
         const int col0 = c.n_tile * BN + ch * 64;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
+          const int half = hsel;
           float v[32];
           tmem_ld32(taddr + ch * 64 + half * 32, v);
           tmem_ld_wait();
-          if (ch == CHUNKS - 1 && half == 1) {             // last TMEM read of this tile: release the accumulator
+          if (ch == CHUNKS - 1) {                          // last TMEM read of this tile: release the accumulator
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -267,7 +278,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(2, 128);
+        named_bar_sync(2, EPI_THREADS);
         if (leader) {
           if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
           else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
@@ -351,7 +362,7 @@ int conv_pers_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   auto kern = conv_pers_kernel<BN, STAGES, EPI>;
   DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, 256, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);
+  kern<<<grid, PersThreads<EPI>::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   return 0;

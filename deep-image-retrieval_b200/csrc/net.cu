@@ -95,6 +95,8 @@ struct dirb200_net {
   double last_flops = 0;
   int profile = 0;
   Profiler prof;
+  int sub[5] = {0, 0, 0, 0, 0};   // images per sub-chunk of stage 0..4 (0 = auto)
+  int stage_sched = 0;            // 0 = every stage over the whole chunk (fastest measured), 1 = per-stage sub-chunks
   // pipelined host entry point
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> pipe_events;
@@ -234,6 +236,8 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
   else if (k == "debug_taps") n->debug_taps = value != 0;
   else if (k == "profile") n->profile = value != 0;
+  else if (k == "stage_sched") n->stage_sched = static_cast<int>(value);
+  else if (k.size() == 4 && k.compare(0, 3, "sub") == 0 && k[3] >= '0' && k[3] <= '4') n->sub[k[3] - '0'] = static_cast<int>(value);
   else if (k == "host_chunk") n->host_chunk = std::max(1, static_cast<int>(value));
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown net option '%s'", key);
   return 0;
@@ -327,25 +331,58 @@ static int auto_chunk(int B, int H, int W) {
 }
 
 namespace {
+// Stage schedule.  The network is cut into 5 stages: 0 = stem + maxpool, 1..4 = layer1..layer4 (+ head after 4).
+// A stage runs over the chunk in sub-chunks of sub[s] images: the tensors passed between the blocks of a stage are
+// then small enough to stay in the 126 MB L2, while the stage outputs of the whole chunk live in HBM buffers.
 struct Workspace {
-  __half* in8; __half* stem_out; __half* act[5]; float* head_ws;
-  int H1, W1, H2, W2;
+  __half* stem_ws;        // s2d / nhwc8 staging of one stem sub-chunk
+  __half* stem_out;       // stem conv output of one sub-chunk (before the maxpool)
+  __half* stage_out[4];   // outputs of stage 0..3 for the whole chunk
+  __half* scratch[4];     // rotating tensors inside a stage
+  float* head_ws;
+  int H1, W1;             // stem conv output size
+  int h[5], w[5];         // spatial size of the output of stage 0..4
+  int sub[5];
 };
+
+const int kStageCh[5] = {64, 256, 512, 1024, 2048};
 }  // namespace
 
 static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w) {
-  w->H1 = (H + 6 - 7) / 2 + 1; w->W1 = (W + 6 - 7) / 2 + 1;       // stem conv
-  w->H2 = (w->H1 + 2 - 3) / 2 + 1; w->W2 = (w->W1 + 2 - 3) / 2 + 1;   // maxpool
+  w->H1 = (H + 6 - 7) / 2 + 1; w->W1 = (W + 6 - 7) / 2 + 1;                 // stem conv
+  w->h[0] = (w->H1 + 2 - 3) / 2 + 1; w->w[0] = (w->W1 + 2 - 3) / 2 + 1;     // maxpool
+  w->h[1] = w->h[0]; w->w[1] = w->w[0];                                     // layer1: stride 1
+  for (int s = 2; s < 5; ++s) { w->h[s] = (w->h[s - 1] + 2 - 3) / 2 + 1; w->w[s] = (w->w[s - 1] + 2 - 3) / 2 + 1; }
+  // sub-chunk sizes: option "subN", else auto = enough images for ~2 tiles per SM in the stage's smallest GEMM,
+  // but not more than keeps one stage tensor around 32 MB
+  for (int s = 0; s < 5; ++s) {
+    int v = n->sub[s];
+    if (v <= 0) {
+      if (n->stage_sched == 0) {
+        v = chunk;                              // flat schedule: every stage over the whole chunk
+      } else {
+        // enough images for ~2 waves of 128-pixel tiles in the stage's narrowest GEMM
+        const double px = static_cast<double>(w->h[s]) * w->w[s];
+        v = std::max(1, static_cast<int>(ceil(2.0 * 148.0 * 128.0 / px)));
+        if (s == 0) v = std::max(v, 2);
+      }
+    }
+    w->sub[s] = std::max(1, std::min(v, chunk));
+  }
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
-  const size_t o_in8 = carve(std::max(static_cast<size_t>(chunk) * H * W * 8 * 2, stem_workspace_bytes(chunk, H, W)));
-  const size_t o_stem = carve(static_cast<size_t>(chunk) * w->H1 * w->W1 * 64 * 2);
-  const size_t act_max = static_cast<size_t>(chunk) * w->H2 * w->W2 * 256 * 2;   // layer1 output is the largest
-  size_t o_act[5];
-  for (int i = 0; i < 5; ++i) o_act[i] = carve(act_max);
-  int Hf = w->H2, Wf = w->W2;
-  for (int li = 1; li < 4; ++li) { Hf = (Hf + 2 - 3) / 2 + 1; Wf = (Wf + 2 - 3) / 2 + 1; }
-  const size_t o_head = carve(head_workspace_floats(chunk, Hf * Wf, 2048, n->out_dim) * 4);
+  const size_t o_sws = carve(std::max(static_cast<size_t>(w->sub[0]) * H * W * 8 * 2, stem_workspace_bytes(w->sub[0], H, W)));
+  const size_t o_stem = carve(static_cast<size_t>(w->sub[0]) * w->H1 * w->W1 * 64 * 2);
+  size_t o_stage[4], o_scr[4];
+  for (int s = 0; s < 4; ++s) o_stage[s] = carve(static_cast<size_t>(chunk) * w->h[s] * w->w[s] * kStageCh[s] * 2);
+  size_t scr = 0;   // largest tensor inside any stage = the stage's sub-chunk at the stage's INPUT resolution x output channels / or input
+  for (int s = 1; s < 5; ++s) {
+    const size_t in_px = static_cast<size_t>(w->h[s - 1]) * w->w[s - 1];
+    scr = std::max(scr, static_cast<size_t>(w->sub[s]) * in_px * (kStageCh[s] / 4) * 2);          // conv1 output at input resolution
+    scr = std::max(scr, static_cast<size_t>(w->sub[s]) * w->h[s] * w->w[s] * kStageCh[s] * 2);    // block output
+  }
+  for (int i = 0; i < 4; ++i) o_scr[i] = carve(scr);
+  const size_t o_head = carve(head_workspace_floats(w->sub[4], w->h[4] * w->w[4], 2048, n->out_dim) * 4);
   if (off > n->ws_bytes) {
     if (n->ws) DIRB_CUDA(cudaFree(n->ws));
     n->ws = nullptr;
@@ -353,9 +390,10 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
     n->ws_bytes = off;
   }
   uint8_t* ws = static_cast<uint8_t*>(n->ws);
-  w->in8 = reinterpret_cast<__half*>(ws + o_in8);
+  w->stem_ws = reinterpret_cast<__half*>(ws + o_sws);
   w->stem_out = reinterpret_cast<__half*>(ws + o_stem);
-  for (int i = 0; i < 5; ++i) w->act[i] = reinterpret_cast<__half*>(ws + o_act[i]);
+  for (int s = 0; s < 4; ++s) w->stage_out[s] = reinterpret_cast<__half*>(ws + o_stage[s]);
+  for (int i = 0; i < 4; ++i) w->scratch[i] = reinterpret_cast<__half*>(ws + o_scr[i]);
   w->head_ws = reinterpret_cast<float*>(ws + o_head);
   return 0;
 }
@@ -364,57 +402,72 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
 static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, int cb, int H, int W, float* desc_dev,
                      __half* desc16_dev, cudaStream_t stream) {
   const int D = n->without_fc ? 2048 : n->out_dim;
-  if (n->conv_impl == 1) {
-    {
-      ProfScope ps(n, stream, 2, 0, static_cast<double>(cb) * H * W * (12 + 16));
-      DIRB_TRY(nchw_to_nhwc8(imgs_dev, cb, H, W, w.in8, stream));
+  // ---------------------------------------------------------------- stage 0: stem + maxpool
+  for (int b0 = 0; b0 < cb; b0 += w.sub[0]) {
+    const int sb = std::min(w.sub[0], cb - b0);
+    const float* img = imgs_dev + static_cast<size_t>(b0) * 3 * H * W;
+    if (n->conv_impl == 1) {
+      {
+        ProfScope ps(n, stream, 2, 0, static_cast<double>(sb) * H * W * (12 + 16));
+        DIRB_TRY(nchw_to_nhwc8(img, sb, H, W, w.stem_ws, stream));
+      }
+      DIRB_TRY(run_conv(n, n->stem, w.stem_ws, sb, H, W, nullptr, 1, w.stem_out, stream, /*force_mma=*/1));
+    } else {
+      const double flops = 2.0 * sb * w.H1 * w.W1 * 64.0 * 147.0;
+      n->last_flops += flops;
+      ProfScope ps(n, stream, 1, flops, static_cast<double>(sb) * (12.0 * H * W + 2.0 * stem_workspace_bytes(1, H, W) + 128.0 * w.H1 * w.W1));
+      DIRB_TRY(stem_tc(img, sb, H, W, n->stem_w2, n->stem.scale, n->stem.shift, w.stem_ws, w.stem_out, stream));
     }
-    DIRB_TRY(run_conv(n, n->stem, w.in8, cb, H, W, nullptr, 1, w.stem_out, stream, /*force_mma=*/1));
-  } else {
-    const double flops = 2.0 * cb * w.H1 * w.W1 * 64.0 * 147.0;
-    n->last_flops += flops;
-    ProfScope ps(n, stream, 1, flops, static_cast<double>(cb) * (12.0 * H * W + 2.0 * stem_workspace_bytes(1, H, W) + 128.0 * w.H1 * w.W1));
-    DIRB_TRY(stem_tc(imgs_dev, cb, H, W, n->stem_w2, n->stem.scale, n->stem.shift, w.in8, w.stem_out, stream));
+    ProfScope ps(n, stream, 2, 0, 2.0 * sb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.h[0]) * w.w[0]));
+    DIRB_TRY(maxpool_3x3s2(w.stem_out, sb, w.H1, w.W1, 64,
+                           w.stage_out[0] + static_cast<size_t>(b0) * w.h[0] * w.w[0] * 64, stream));
   }
-  __half* x = w.act[0];
-  {
-    ProfScope ps(n, stream, 2, 0, 2.0 * cb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.H2) * w.W2));
-    DIRB_TRY(maxpool_3x3s2(w.stem_out, cb, w.H1, w.W1, 64, x, stream));
-  }
-  DIRB_TRY(record_tap(n, "stem", x, cb, w.H2, w.W2, 64, stream));
-  int h = w.H2, wd = w.W2, cur = 0, layer = 0;
-  for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
-    const Block& blk = n->blocks[bi];
-    __half* t1 = w.act[(cur + 1) % 5];
-    __half* t2 = w.act[(cur + 2) % 5];
-    __half* rs = w.act[(cur + 3) % 5];
-    __half* y = w.act[(cur + 4) % 5];
-    const int s = blk.c2.stride;
-    const int ho = (h + 2 - 3) / s + 1, wo = (wd + 2 - 3) / s + 1;
-    DIRB_TRY(run_conv(n, blk.c1, x, cb, h, wd, nullptr, 1, t1, stream));
-    DIRB_TRY(run_conv(n, blk.c2, t1, cb, h, wd, nullptr, 1, t2, stream));
-    const __half* res = x;
-    if (blk.has_down) {
-      DIRB_TRY(run_conv(n, blk.down, x, cb, h, wd, nullptr, 0, rs, stream));
-      res = rs;
+  DIRB_TRY(record_tap(n, "stem", w.stage_out[0], cb, w.h[0], w.w[0], 64, stream));
+  // ---------------------------------------------------------------- stages 1..4: layer1..layer4 (+ head)
+  int first = 0;
+  for (int s = 1; s < 5; ++s) {
+    const int last = n->layer_end[s - 1];       // blocks [first, last)
+    const int hi = w.h[s - 1], wi = w.w[s - 1], ho = w.h[s], wo = w.w[s];
+    const __half* stage_in = w.stage_out[s - 1];
+    for (int b0 = 0; b0 < cb; b0 += w.sub[s]) {
+      const int sb = std::min(w.sub[s], cb - b0);
+      const __half* x = stage_in + static_cast<size_t>(b0) * hi * wi * kStageCh[s - 1];
+      int h = hi, wd = wi;
+      for (int bi = first; bi < last; ++bi) {
+        const Block& blk = n->blocks[bi];
+        const int j = bi - first;
+        __half* t1 = w.scratch[0];
+        __half* t2 = w.scratch[1];
+        __half* rs = w.scratch[2];
+        __half* y = (j % 2 == 0) ? w.scratch[3] : w.scratch[2];
+        if (bi == last - 1 && s < 4) y = w.stage_out[s] + static_cast<size_t>(b0) * ho * wo * kStageCh[s];
+        const int st = blk.c2.stride;
+        const int h2 = (h + 2 - 3) / st + 1, w2 = (wd + 2 - 3) / st + 1;
+        DIRB_TRY(run_conv(n, blk.c1, x, sb, h, wd, nullptr, 1, t1, stream));
+        DIRB_TRY(run_conv(n, blk.c2, t1, sb, h, wd, nullptr, 1, t2, stream));
+        const __half* res = x;
+        if (blk.has_down) {
+          DIRB_TRY(run_conv(n, blk.down, x, sb, h, wd, nullptr, 0, rs, stream));
+          res = rs;
+        }
+        DIRB_TRY(run_conv(n, blk.c3, t2, sb, h2, w2, res, 1, y, stream));
+        x = y;
+        h = h2;
+        wd = w2;
+      }
+      if (s == 4) {
+        if (b0 + sb >= cb) DIRB_TRY(record_tap(n, "layer4", x, sb, ho, wo, 2048, stream));
+        ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * 2048.0 * n->out_dim, 2.0 * sb * ho * wo * 2048.0);
+        DIRB_TRY(head_pool_fc_l2(x, sb, ho * wo, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
+                                 n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, w.head_ws,
+                                 desc_dev + static_cast<size_t>(b0) * D,
+                                 desc16_dev ? desc16_dev + static_cast<size_t>(b0) * D : nullptr, stream));
+        if (!n->without_fc) n->last_flops += 2.0 * sb * 2048.0 * n->out_dim;
+      }
     }
-    DIRB_TRY(run_conv(n, blk.c3, t2, cb, ho, wo, res, 1, y, stream));
-    x = y;
-    cur = (cur + 4) % 5;
-    h = ho;
-    wd = wo;
-    if (static_cast<int>(bi) + 1 == n->layer_end[layer]) {
-      DIRB_TRY(record_tap(n, "layer" + std::to_string(layer + 1), x, cb, h, wd, blk.c3.Cout, stream));
-      ++layer;
-    }
+    if (s < 4) DIRB_TRY(record_tap(n, "layer" + std::to_string(s), w.stage_out[s], cb, ho, wo, kStageCh[s], stream));
+    first = last;
   }
-  {
-    ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * cb * 2048.0 * n->out_dim, 2.0 * cb * h * wd * 2048.0);
-    DIRB_TRY(head_pool_fc_l2(x, cb, h * wd, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
-                             n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, w.head_ws, desc_dev,
-                             desc16_dev, stream));
-  }
-  if (!n->without_fc) n->last_flops += 2.0 * cb * 2048.0 * n->out_dim;
   return 0;
 }
 

@@ -144,6 +144,12 @@ class ResNetRMAC:
         self._opts[key] = float(value)
         self._release()
 
+    def set_backend_option_live(self, key, value):
+        """Change a tuning knob on the existing native handle (no weight re-upload)."""
+        self._opts[key] = float(value)
+        if self._handle is not None:
+            lib.call("dirb200_net_set_option", self._handle, key.encode(), float(value))
+
     # ------------------------------------------------------------------ native handle
     def _release(self):
         if self._handle is not None:
