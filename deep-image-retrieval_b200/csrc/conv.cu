@@ -101,7 +101,7 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NB>
 static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
                         const __half* res, int relu, __half* out, cudaStream_t stream) {
   const int Ho = s.Ho(), Wo = s.Wo();
@@ -143,7 +143,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
   const int64_t total = m_tiles * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
   p.total_tiles = static_cast<int>(total);
-  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
+  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, NB>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
 }
 
 int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
@@ -151,9 +151,17 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
   DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
                "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
   DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
-  if (s.Cout % 256 == 0) return conv_pers_bn<256, 3>(s, in, w, scale, shift, res, relu, out, stream);
-  if (s.Cout % 128 == 0) return conv_pers_bn<128, 4>(s, in, w, scale, shift, res, relu, out, stream);
-  return conv_pers_bn<64, 4>(s, in, w, scale, shift, res, relu, out, stream);
+  // Shared memory split: convolutions with a residual keep 4 staging buffers (residual prefetch depth) and a
+  // shorter operand ring; the others trade two staging buffers for one more ring slot (deeper TMA lookahead).
+  if (s.Cout % 256 == 0) {
+    if (res) return conv_pers_bn<256, 3, 4>(s, in, w, scale, shift, res, relu, out, stream);
+    return conv_pers_bn<256, 4, 2>(s, in, w, scale, shift, res, relu, out, stream);
+  }
+  if (s.Cout % 128 == 0) {
+    if (res) return conv_pers_bn<128, 5, 4>(s, in, w, scale, shift, res, relu, out, stream);
+    return conv_pers_bn<128, 6, 2>(s, in, w, scale, shift, res, relu, out, stream);
+  }
+  return conv_pers_bn<64, 6, 4>(s, in, w, scale, shift, res, relu, out, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ tcgen05 stem

@@ -43,9 +43,9 @@ struct ConvPersParams {
   int cand_cap;
 };
 
-template <int BN, int STAGES, int EPI = 0>
+template <int BN, int STAGES, int EPI = 0, int NB = 4>
 struct ConvPersSmem {
-  static constexpr int NBUF = (EPI == 0) ? 4 : 0;   // staging buffers exist only for the convolution epilogue
+  static constexpr int NBUF = (EPI == 0) ? NB : 0;  // staging buffers exist only for the convolution epilogue
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -89,13 +89,13 @@ struct PersThreads {
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
 };
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int NB = 4>
 __global__ void __launch_bounds__(PersThreads<EPI>::THREADS, 1)
 conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvPersParams p) {
-  using L = ConvPersSmem<BN, STAGES, EPI>;
-  constexpr int NBUF = 4;
+  using L = ConvPersSmem<BN, STAGES, EPI, NB>;
+  constexpr int NBUF = NB;
   constexpr int CHUNKS = BN / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -355,11 +355,12 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int NB = 4>
 int conv_pers_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                      const ConvPersParams& p, int num_sms, cudaStream_t stream) {
-  using L = ConvPersSmem<BN, STAGES, EPI>;
-  auto kern = conv_pers_kernel<BN, STAGES, EPI>;
+  using L = ConvPersSmem<BN, STAGES, EPI, NB>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  auto kern = conv_pers_kernel<BN, STAGES, EPI, NB>;
   DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   kern<<<grid, PersThreads<EPI>::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);
