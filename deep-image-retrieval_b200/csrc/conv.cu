@@ -5,6 +5,7 @@
 // :115-118 (stem).  BatchNorm (eval) is folded by the caller into scale = gamma/sqrt(var+eps), shift = beta-mean*scale.
 #include "conv.h"
 
+#include "conv_halo.cuh"
 #include "conv_pers.cuh"
 #include "gemm_tc.cuh"
 #include "stem_pers.cuh"
@@ -146,11 +147,49 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
   return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, NB>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
 }
 
+static int g_conv_halo = 1;
+void set_conv_halo(int on) { g_conv_halo = on; }
+
+// 3x3 / stride 1 / pad 1 with the halo patch loaded once per tile (conv_halo.cuh).
+template <int BN, int BSTAGES, bool BRES>
+static int conv_halo_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
+                        const __half* res, int relu, __half* out, cudaStream_t stream) {
+  ConvPersParams p{};
+  p.a_spatial = 1;
+  p.taps = 9; p.kw_taps = 3;
+  p.cin_blocks = s.Cin / 64;
+  p.stride = 1; p.pad = 1;
+  p.tw = 8; p.th = 16; p.nb = 1;
+  p.tiles_w = (int)ceil_div(s.W, 8);
+  p.tiles_h = (int)ceil_div(s.H, 16);
+  p.n_tiles = s.Cout / BN;
+  p.has_res = res != nullptr;
+  p.relu = relu;
+  p.scale = scale;
+  p.shift = shift;
+  const int64_t total = (int64_t)p.tiles_w * p.tiles_h * s.B * p.n_tiles;
+  DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
+  p.total_tiles = static_cast<int>(total);
+  CUtensorMap tmA, tmB, tmR, tmO;
+  DIRB_TRY(encode_tmap_nhwc(&tmA, in, s.B, s.H, s.W, s.Cin, 10, 18, 1, 1));          // halo box 10 x 18 pixels
+  DIRB_TRY(encode_tmap_nhwc(&tmO, out, s.B, s.H, s.W, s.Cout, 8, 16, 1, 1));
+  if (res) DIRB_TRY(encode_tmap_nhwc(&tmR, res, s.B, s.H, s.W, s.Cout, 8, 16, 1, 1));
+  else tmR = tmO;
+  DIRB_TRY(encode_tmap_2d(&tmB, w, 9 * s.Cin, s.Cout, (uint64_t)9 * s.Cin * 2, 64, BN));
+  return conv_halo_launch<BN, BSTAGES, 2, BRES>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
+}
+
 int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
             const __half* res, int relu, __half* out, cudaStream_t stream) {
   DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
                "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
   DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
+  if (g_conv_halo && s.KH == 3 && s.KW == 3 && s.stride == 1 && s.pad == 1 && s.H >= 16 && s.W >= 8 && res == nullptr) {
+    if (s.Cout == 64 && s.Cin == 64) return conv_halo_bn<64, 9, true>(s, in, w, scale, shift, res, relu, out, stream);
+    if (s.Cout % 256 == 0) return conv_halo_bn<256, 4, false>(s, in, w, scale, shift, res, relu, out, stream);
+    if (s.Cout % 128 == 0) return conv_halo_bn<128, 6, false>(s, in, w, scale, shift, res, relu, out, stream);
+    return conv_halo_bn<64, 8, false>(s, in, w, scale, shift, res, relu, out, stream);
+  }
   // Shared memory split: convolutions with a residual keep 4 staging buffers (residual prefetch depth) and a
   // shorter operand ring; the others trade two staging buffers for one more ring slot (deeper TMA lookahead).
   if (s.Cout % 256 == 0) {

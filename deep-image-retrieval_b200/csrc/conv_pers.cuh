@@ -81,6 +81,87 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvPersParams& p, int t)
   return c;
 }
 
+// Convolution epilogue of one output tile: for each 64-channel chunk read the accumulator row of this thread from
+// TMEM, apply BN scale/shift (+ residual from the staging buffer) (+ ReLU), write fp16 in place into the swizzled
+// staging buffer and let the leader thread TMA-store it.  `cc` counts staging chunks across tiles.
+template <int BN, int NBUF, int EPI_THREADS>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
+                                                   uint8_t* stg, uint64_t* res_full, uint64_t* res_empty,
+                                                   uint64_t* acc_empty_a, uint32_t& cc, uint32_t row_off, uint32_t sw,
+                                                   int hsel, int lane, bool leader, const CUtensorMap& tmO) {
+  constexpr int CHUNKS = BN / 64;
+  constexpr int STG_BYTES = 128 * 128;
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
+        const int b = cc % NBUF;
+        uint8_t* buf = stg + b * STG_BYTES;
+        if (p.has_res) {
+          mbar_wait(&res_full[b], (cc / NBUF) & 1);       // residual chunk has landed in `buf`
+        } else {
+          if (leader) bulk_wait_read<NBUF - 1>();           // the store issued NBUF chunks ago has left `buf`
+          named_bar_sync(1, EPI_THREADS);
+        }
+        const int col0 = c.n_tile * BN + ch * 64;
+        {
+          const int half = hsel;
+          float v[32];
+          tmem_ld32(taddr + ch * 64 + half * 32, v);
+          tmem_ld_wait();
+          if (ch == CHUNKS - 1) {                          // last TMEM read of this tile: release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_a);
+          }
+          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
+            v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                    // 4 x 16-byte chunks (8 channels each) of this half
+            const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+            uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
+            if (p.has_res) {
+              const uint4 r = *sp;
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_h2(rr[e]);
+                v[j * 8 + e * 2] += f.x;
+                v[j * 8 + e * 2 + 1] += f.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
+            }
+            uint4 o;
+            o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
+            o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
+            o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
+            o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
+            *sp = o;
+          }
+        }
+        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(2, EPI_THREADS);
+        if (leader) {
+          if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
+          else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
+          bulk_commit();
+          if (p.has_res && cc >= 1) {                       // the previous chunk's store has finished reading its
+            bulk_wait_read<1>();                            // buffer -> hand that buffer back to the residual producer
+            mbar_arrive(&res_empty[(cc - 1) % NBUF]);
+          }
+        }
+      }
+}
+
 // Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
 // convolutions), 4 for the light similarity epilogues.
 template <int EPI>
@@ -220,75 +301,8 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       if (EPI == PERS_EPI_CONV) {
-#pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
-        const int b = cc % NBUF;
-        uint8_t* buf = stg + b * L::STG_BYTES;
-        if (p.has_res) {
-          mbar_wait(&res_full[b], (cc / NBUF) & 1);       // residual chunk has landed in `buf`
-        } else {
-          if (leader) bulk_wait_read<NBUF - 1>();           // the store issued NBUF chunks ago has left `buf`
-          named_bar_sync(1, EPI_THREADS);
-        }
-        const int col0 = c.n_tile * BN + ch * 64;
-        {
-          const int half = hsel;
-          float v[32];
-          tmem_ld32(taddr + ch * 64 + half * 32, v);
-          tmem_ld_wait();
-          if (ch == CHUNKS - 1) {                          // last TMEM read of this tile: release the accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
-          }
-          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
-            v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
-            v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
-            v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
-            v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {                    // 4 x 16-byte chunks (8 channels each) of this half
-            const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
-            uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
-            if (p.has_res) {
-              const uint4 r = *sp;
-              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_h2(rr[e]);
-                v[j * 8 + e * 2] += f.x;
-                v[j * 8 + e * 2 + 1] += f.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
-            }
-            uint4 o;
-            o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
-            o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
-            o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
-            o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
-            *sp = o;
-          }
-        }
-        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(2, EPI_THREADS);
-        if (leader) {
-          if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
-          else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
-          bulk_commit();
-          if (p.has_res && cc >= 1) {                       // the previous chunk's store has finished reading its
-            bulk_wait_read<1>();                            // buffer -> hand that buffer back to the residual producer
-            mbar_arrive(&res_empty[(cc - 1) % NBUF]);
-          }
-        }
-      }
+        conv_epilogue_tile<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off, sw,
+                                                  hsel, lane, leader, tmO);
       } else {
         // ---------------------------------------------------------- similarity epilogues: row = query
         const int64_t qi = static_cast<int64_t>(c.m_tile) * 128 + row;

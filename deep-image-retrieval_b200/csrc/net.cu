@@ -236,6 +236,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
   else if (k == "debug_taps") n->debug_taps = value != 0;
   else if (k == "profile") n->profile = value != 0;
+  else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "stage_sched") n->stage_sched = static_cast<int>(value);
   else if (k.size() == 4 && k.compare(0, 3, "sub") == 0 && k[3] >= '0' && k[3] <= '4') n->sub[k[3] - '0'] = static_cast<int>(value);
   else if (k == "host_chunk") n->host_chunk = std::max(1, static_cast<int>(value));

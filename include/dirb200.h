@@ -53,7 +53,8 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out);
  * "without_fc" 0/1; "out_dim"; "chunk" images processed per pass (0 = auto);
  * "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path),
  * 2 = one-tile-per-CTA tcgen05 kernel (A/B baseline);
- * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage; "profile" 1 = time every launch
+ * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage; "halo" 1 (default) / 0 = 3x3 stride-1 convolutions load their input patch once per tile
+ * (conv_halo.cuh) or tap by tap (process-wide A/B switch); "profile" 1 = time every launch
  * with CUDA events (dirb200_net_profile); "host_chunk" images per pipeline stage of dirb200_net_forward_host. */
 int dirb200_net_set_option(dirb200_net* net, const char* key, double value);
 /* One state_dict tensor by its reference key ("layer3.5.bn2.running_var", "adpool.p", "fc.weight" ...),

@@ -79,3 +79,36 @@ def test_extract_r101_large_image_vs_oracle():
     assert rel_l2(d[:1], ref) < TOL
     d_alone = net(x[1:2].cuda()).cpu().numpy()
     assert np.array_equal(d_alone, d[1])
+
+
+def test_full_size_1024_vs_oracle_and_batch_properties():
+    """BASELINE configs[1] geometry (ResNet-101, 1024x1024): one image against the CPU oracle, and the
+    size-independent properties at batch level: batch-composition invariance, unit norm, determinism."""
+    net, sd = _net("resnet101_rmac", 0)
+    x = synth.make_images(6, 1024, 1024, seed=21)
+    xc = x.cuda()
+    d = net(xc).cpu().numpy()
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+    ref = O.extract(x[2:3], sd, "resnet101_rmac", squeeze=False).numpy()
+    assert rel_l2(d[2:3], ref) < TOL
+    assert np.array_equal(net(xc[2:3]).cpu().numpy(), d[2])              # alone == inside the batch
+    assert np.array_equal(net(xc[[4, 2, 0]]).cpu().numpy(), d[[4, 2, 0]])  # order / neighbours do not matter
+    assert np.array_equal(net(xc).cpu().numpy(), d)                      # run-to-run deterministic
+    launches, flops = net.last_launch_stats()
+    assert abs(flops / 6 / 325.99e9 - 1.0) < 0.01                        # SURVEY 8d: 325.99 GFLOP per image
+
+
+def test_multiscale_pool_matches_oracle():
+    """BASELINE configs[4] structure at reduced size: Scale(0.7), identity, Scale(1.4) chains -> gem pool -> L2."""
+    from dirb200 import ops
+    net, sd = _net("resnet50_rmac", 0)
+    base = synth.make_images(3, 160, 192, seed=8)
+    sizes = [(int(0.5 + 0.7 * 160), int(0.5 + 0.7 * 192)), (160, 192), (int(0.5 + 1.4 * 160), int(0.5 + 1.4 * 192))]
+    descs_gpu, descs_ref = [], []
+    for (h, w) in sizes:
+        xs = torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=False)
+        descs_gpu.append(net(xs.cuda()))
+        descs_ref.append(O.extract(xs, sd, "resnet50_rmac").numpy())
+    pooled = ops.pool_scales(descs_gpu, "gem", 3, l2=True).cpu().numpy()
+    ref = O.l2n(O.pool_scales(descs_ref, "gem", 3))
+    assert rel_l2(pooled, ref) < TOL

@@ -64,6 +64,12 @@ CONV_CASES = [
     (3, 96, 96, 64, 64, 3, 1, 1, False, True),       # BN = 64
     (4, 64, 64, 512, 512, 1, 1, 0, True, True),      # 2 n-tiles per m-tile, residual
     (5, 30, 30, 256, 512, 1, 2, 0, False, False),    # stride-2 projection, ragged patches
+    # 3x3/s1 through the halo kernel (8x16 patches, one input patch load per tile): ragged sizes, several
+    # channel blocks, two n-tiles, resident and streamed weights
+    (2, 33, 21, 64, 64, 3, 1, 1, False, True),
+    (2, 17, 9, 128, 256, 3, 1, 1, False, True),
+    (1, 40, 24, 512, 512, 3, 1, 1, False, False),
+    (2, 32, 48, 64, 128, 3, 1, 1, False, True),
 ]
 
 
