@@ -147,6 +147,45 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
   return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, NB>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
 }
 
+// conv3 (1x1) of block 0 fused with the projection shortcut: out = relu([t2 | x_strided] . [W3*s3 | Wd*sd]^T + shift).
+// t2: (B,Ho,Wo,Cmid); x: (B,Hx,Wx,Cx) read with spatial stride `xstride`; wcat: [Cout][Cmid + Cx] fp16.
+template <int BN, int STAGES>
+static int conv_fused_ds_bn(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
+                            const __half* x, const __half* wcat, int Cout, const float* scale, const float* shift,
+                            __half* out, cudaStream_t stream) {
+  ConvPersParams p{};
+  p.a_spatial = 1;
+  p.taps = 1; p.kw_taps = 1;
+  p.cin_blocks = (Cmid + Cx) / 64;
+  p.k_split = Cmid / 64;
+  p.a2_stride = xstride;
+  p.stride = 1; p.pad = 0;
+  pick_patch(B, Ho, Wo, &p.tw, &p.th, &p.nb);
+  p.tiles_w = (int)ceil_div(Wo, p.tw);
+  p.tiles_h = (int)ceil_div(Ho, p.th);
+  p.n_tiles = Cout / BN;
+  p.has_res = 0;
+  p.relu = 1;
+  p.scale = scale;
+  p.shift = shift;
+  const int64_t total = (int64_t)p.tiles_w * p.tiles_h * ceil_div(B, p.nb) * p.n_tiles;
+  DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
+  p.total_tiles = static_cast<int>(total);
+  CUtensorMap tmA, tmB, tmX, tmO;
+  DIRB_TRY(encode_tmap_nhwc(&tmA, t2, B, Ho, Wo, Cmid, p.tw, p.th, p.nb, 1));
+  DIRB_TRY(encode_tmap_nhwc(&tmX, x, B, Hx, Wx, Cx, p.tw, p.th, p.nb, xstride));
+  DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, Cout, p.tw, p.th, p.nb, 1));
+  DIRB_TRY(encode_tmap_2d(&tmB, wcat, Cmid + Cx, Cout, (uint64_t)(Cmid + Cx) * 2, 64, BN));
+  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, 2>(tmA, tmB, tmX, tmO, p, num_sms(), stream);
+}
+
+int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
+                  const __half* x, const __half* wcat, int Cout, const float* scale, const float* shift, __half* out,
+                  cudaStream_t stream) {
+  DIRB_REQUIRE(Cmid % 64 == 0 && Cx % 64 == 0 && Cout % 256 == 0, DIRB200_ENOTSUP, "fused shortcut needs 64-multiples");
+  return conv_fused_ds_bn<256, 4>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
+}
+
 static int g_conv_halo = 1;
 void set_conv_halo(int on) { g_conv_halo = on; }
 

@@ -14,6 +14,10 @@ struct ConvShape {
 // w: [Cout][KH*KW*Cin] fp16 (K index = (kh*KW + kw)*Cin + c).
 int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
             const __half* res, int relu, __half* out, cudaStream_t stream);
+// conv3 of a block fused with its 1x1 projection shortcut (see conv.cu).
+int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
+                  const __half* x, const __half* wcat, int Cout, const float* scale, const float* shift, __half* out,
+                  cudaStream_t stream);
 // The earlier one-tile-per-CTA tcgen05 kernel (gemm_tc.cuh), kept as an A/B baseline (impl 2).
 int conv_tc_np(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
                const __half* res, int relu, __half* out, cudaStream_t stream);

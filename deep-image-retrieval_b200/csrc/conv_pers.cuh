@@ -31,6 +31,10 @@ struct ConvPersParams {
   int m_fastest, m_tiles;      // tile order: 0 = n-tile fastest (convolutions: CTAs share the activation tile),
                                // 1 = m-tile fastest (search: CTAs running together share the streamed database tile)
   int has_res, relu;
+  // fused projection shortcut (block 0 of a layer): k-iterations >= k_split read their A tile from a SECOND
+  // activation tensor (tensor map tmR, spatial boxes with element stride a2_stride baked into the map) - the
+  // block input x of the 1x1 downsample conv - while the weights are the K-concatenation [W3*s3 | Wd*sd].
+  int k_split, a2_stride;
   const float* scale;
   const float* shift;
   // similarity epilogues (search.cu): D[q][n] = <query q, database row n>
@@ -197,7 +201,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI == PERS_EPI_CONV) tma_prefetch_desc(&tmO);
-    if (EPI == PERS_EPI_CONV && p.has_res) tma_prefetch_desc(&tmR);
+    if (EPI == PERS_EPI_CONV && (p.has_res || p.k_split > 0)) tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -231,7 +235,9 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           const int tap = it / p.cin_blocks;
           const int kc = it - tap * p.cin_blocks;
-          if (p.a_spatial) {
+          if (p.k_split > 0 && it >= p.k_split) {
+            tma_load_4d(sa, &tmR, &full_bar[s], (it - p.k_split) * 64, c.wo0 * p.a2_stride, c.ho0 * p.a2_stride, c.n0);
+          } else if (p.a_spatial) {
             const int kh = tap / p.kw_taps;
             const int kw = tap - kh * p.kw_taps;
             tma_load_4d(sa, &tmA, &full_bar[s], kc * 64, c.wo0 * p.stride + kw - p.pad,

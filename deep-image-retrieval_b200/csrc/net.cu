@@ -37,6 +37,11 @@ struct ConvLayer {
 struct Block {
   ConvLayer c1, c2, c3, down;
   bool has_down = false;
+  // block 0 of a layer: conv3 + projection shortcut as ONE GEMM over K = [conv2 output | block input]:
+  // wcat[o] = [scale3[o] * W3[o][:], scale_d[o] * Wd[o][:]] (fp16), shift = shift3 + shift_d, scale = 1.
+  __half* wcat = nullptr;
+  float* cat_shift = nullptr;
+  float* ones = nullptr;
 };
 
 }  // namespace
@@ -95,6 +100,7 @@ struct dirb200_net {
   double last_flops = 0;
   int profile = 0;
   Profiler prof;
+  int fuse_ds = 1;                // fuse the projection shortcut into conv3 of block 0 (tcgen05 path only)
   int sub[5] = {0, 0, 0, 0, 0};   // images per sub-chunk of stage 0..4 (0 = auto)
   int stage_sched = 0;            // 0 = every stage over the whole chunk (fastest measured), 1 = per-stage sub-chunks
   // pipelined host entry point
@@ -237,6 +243,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "debug_taps") n->debug_taps = value != 0;
   else if (k == "profile") n->profile = value != 0;
   else if (k == "halo") set_conv_halo(value != 0);
+  else if (k == "fuse_ds") n->fuse_ds = value != 0;
   else if (k == "stage_sched") n->stage_sched = static_cast<int>(value);
   else if (k.size() == 4 && k.compare(0, 3, "sub") == 0 && k[3] >= '0' && k[3] <= '4') n->sub[k[3] - '0'] = static_cast<int>(value);
   else if (k == "host_chunk") n->host_chunk = std::max(1, static_cast<int>(value));
@@ -294,6 +301,29 @@ int dirb200_net_finalize(dirb200_net* n) {
       if (blk.has_down) {
         blk.down = make_layer(p + "downsample.0", p + "downsample.1", inplanes, planes * 4, 1, stride, 0);
         DIRB_TRY(pack_conv(n, blk.down));
+        // K-concatenated, BN-scaled weights for the fused conv3 + shortcut
+        const HostTensor *w3, *wd;
+        const int cout = planes * 4, kcat = planes + inplanes;
+        DIRB_TRY(get_tensor(n, p + "conv3.weight", &w3, static_cast<size_t>(cout) * planes));
+        DIRB_TRY(get_tensor(n, p + "downsample.0.weight", &wd, static_cast<size_t>(cout) * inplanes));
+        std::vector<float> s3(cout), sh3(cout), sd(cout), shd(cout);
+        DIRB_CUDA(cudaMemcpy(s3.data(), blk.c3.scale, cout * 4, cudaMemcpyDeviceToHost));
+        DIRB_CUDA(cudaMemcpy(sh3.data(), blk.c3.shift, cout * 4, cudaMemcpyDeviceToHost));
+        DIRB_CUDA(cudaMemcpy(sd.data(), blk.down.scale, cout * 4, cudaMemcpyDeviceToHost));
+        DIRB_CUDA(cudaMemcpy(shd.data(), blk.down.shift, cout * 4, cudaMemcpyDeviceToHost));
+        std::vector<__half> wc(static_cast<size_t>(cout) * kcat);
+        std::vector<float> shc(cout), one(cout, 1.0f);
+        for (int o = 0; o < cout; ++o) {
+          for (int c = 0; c < planes; ++c) wc[static_cast<size_t>(o) * kcat + c] = __float2half_rn(s3[o] * w3->data[static_cast<size_t>(o) * planes + c]);
+          for (int c = 0; c < inplanes; ++c) wc[static_cast<size_t>(o) * kcat + planes + c] = __float2half_rn(sd[o] * wd->data[static_cast<size_t>(o) * inplanes + c]);
+          shc[o] = sh3[o] + shd[o];
+        }
+        DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&blk.wcat), wc.size() * sizeof(__half)));
+        DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&blk.cat_shift), cout * 4));
+        DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&blk.ones), cout * 4));
+        DIRB_CUDA(cudaMemcpy(blk.wcat, wc.data(), wc.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        DIRB_CUDA(cudaMemcpy(blk.cat_shift, shc.data(), cout * 4, cudaMemcpyHostToDevice));
+        DIRB_CUDA(cudaMemcpy(blk.ones, one.data(), cout * 4, cudaMemcpyHostToDevice));
       }
       n->blocks.push_back(blk);
       inplanes = planes * 4;
@@ -447,6 +477,20 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
         DIRB_TRY(run_conv(n, blk.c1, x, sb, h, wd, nullptr, 1, t1, stream));
         DIRB_TRY(run_conv(n, blk.c2, t1, sb, h, wd, nullptr, 1, t2, stream));
         const __half* res = x;
+        if (blk.has_down && n->fuse_ds && n->conv_impl == 0 && blk.c3.Cout % 256 == 0) {
+          const double flops = 2.0 * sb * h2 * w2 * static_cast<double>(blk.c3.Cout) * (blk.c3.Cin + blk.down.Cin);
+          const double bytes = 2.0 * (static_cast<double>(sb) * h2 * w2 * (blk.c3.Cin + blk.c3.Cout) +
+                                      static_cast<double>(sb) * h * wd * blk.down.Cin +
+                                      static_cast<double>(blk.c3.Cout) * (blk.c3.Cin + blk.down.Cin));
+          n->last_flops += flops;
+          ProfScope ps(n, stream, 0, flops, bytes);
+          DIRB_TRY(conv_fused_ds(sb, h2, w2, blk.c3.Cin, t2, h, wd, blk.down.Cin, st, x, blk.wcat, blk.c3.Cout, blk.ones,
+                                 blk.cat_shift, y, stream));
+          x = y;
+          h = h2;
+          wd = w2;
+          continue;
+        }
         if (blk.has_down) {
           DIRB_TRY(run_conv(n, blk.down, x, sb, h, wd, nullptr, 0, rs, stream));
           res = rs;
