@@ -310,7 +310,7 @@ int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const floa
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   StemParams p{};
-  pick_patch(B, Ho, Wo, &p.tw, &p.th, &p.nb);
+  p.tw = 8; p.th = 16; p.nb = 1;               // fixed patch: the kernel reads taps as views of one 11 x 19 halo box
   p.tiles_w = (int)ceil_div(Wo, p.tw);
   p.tiles_h = (int)ceil_div(Ho, p.th);
   const int64_t tiles = (int64_t)p.tiles_w * p.tiles_h * ceil_div(B, p.nb);
@@ -319,7 +319,7 @@ int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const floa
   p.scale = scale;
   p.shift = shift;
   CUtensorMap tmS, tmW, tmO;
-  DIRB_TRY(encode_tmap_nhwc16(&tmS, s2d_ws, B, Hs, Ws, p.tw, p.th, p.nb));
+  DIRB_TRY(encode_tmap_nhwc16(&tmS, s2d_ws, B, Hs, Ws, 11, 19, 1));
   DIRB_TRY(encode_tmap_2d_sw32(&tmW, w2, 256, 64, 512, 64));
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, 64, p.tw, p.th, p.nb, 1));
   DIRB_CUDA(cudaFuncSetAttribute(stem_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::TOTAL));

@@ -553,8 +553,27 @@ int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int 
   DIRB_CUDA(cudaSetDevice(n->device));
   if (!n->own_stream) DIRB_CUDA(cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking));
   if (!n->copy_stream) DIRB_CUDA(cudaStreamCreateWithFlags(&n->copy_stream, cudaStreamNonBlocking));
-  const int chunk = std::min(B, n->chunk > 0 ? n->chunk : n->host_chunk);
-  const int nchunks = (B + chunk - 1) / chunk;
+  // Chunk schedule: small chunks first so that compute starts after a short copy, then doubling sizes (large chunks
+  // run the network more efficiently): host_chunk/2, host_chunk/2, host_chunk, 2*host_chunk, ... (option "chunk"
+  // forces a uniform size).
+  std::vector<int> sizes;
+  {
+    int left = B;
+    if (n->chunk > 0) {
+      while (left > 0) { sizes.push_back(std::min(left, n->chunk)); left -= sizes.back(); }
+    } else {
+      int c = std::max(1, n->host_chunk / 2);
+      int reps = 2;
+      while (left > 0) {
+        const int v = std::min(left, c);
+        sizes.push_back(v);
+        left -= v;
+        if (--reps == 0) { c = std::min(c * 2, 2 * n->host_chunk); reps = 1; }
+      }
+    }
+  }
+  const int nchunks = static_cast<int>(sizes.size());
+  const int chunk = *std::max_element(sizes.begin(), sizes.end());
   const size_t img_bytes = static_cast<size_t>(3) * H * W * 4;
   const size_t in_bytes = 2 * static_cast<size_t>(chunk) * img_bytes;
   const int D = n->without_fc ? 2048 : n->out_dim;
@@ -581,8 +600,9 @@ int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int 
   n->prof.reset();
   Workspace w;
   DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
+  int b0 = 0;
   for (int c = 0; c < nchunks; ++c) {
-    const int b0 = c * chunk, cb = std::min(chunk, B - b0);
+    const int cb = sizes[c];
     float* dst = n->h2d + static_cast<size_t>(c & 1) * chunk * (img_bytes / 4);
     cudaEvent_t copied = n->pipe_events[2 * c], done = n->pipe_events[2 * c + 1];
     if (c >= 2) DIRB_CUDA(cudaStreamWaitEvent(n->copy_stream, n->pipe_events[2 * (c - 2) + 1], 0));   // buffer free
@@ -592,6 +612,7 @@ int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int 
     DIRB_CUDA(cudaStreamWaitEvent(n->own_stream, copied, 0));
     DIRB_TRY(run_chunk(n, w, dst, cb, H, W, n->d_desc + static_cast<size_t>(b0) * D, nullptr, n->own_stream));
     DIRB_CUDA(cudaEventRecord(done, n->own_stream));
+    b0 += cb;
   }
   DIRB_CUDA(cudaMemcpyAsync(desc_host, n->d_desc, out_bytes, cudaMemcpyDeviceToHost, n->own_stream));
   DIRB_CUDA(cudaStreamSynchronize(n->own_stream));

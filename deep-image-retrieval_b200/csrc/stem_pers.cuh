@@ -6,11 +6,14 @@
 // with 16 fp16 channels per 2x2 pixel block.  The 7x7/s2 convolution over img is then a 4x4/s1 convolution over S:
 //     out[ho][wo][co] = sum_{a,b in 0..3} sum_{j<16} S[ho+a][wo+b][j] * W2[co][a][b][j],
 //     W2[co][a][b][(dy*2+dx)*4+c] = w[co][c][2a+dy][2b+dx]              (0 where 2a+dy or 2b+dx = 7, or c = 3)
-// i.e. an implicit GEMM with K = 16 taps x 16 = 256.  Each tap is ONE tcgen05.mma (M=128, N=64, K=16) whose A operand
-// is a (nb x th x tw) patch of S shifted by (a,b) - a plain 4-D TMA box of 32-byte rows (SWIZZLE_32B) - and whose B
-// operand is the 64 x 16 slice of W2 for that tap; all 16 slices (32 KB) stay resident in shared memory.
+// i.e. an implicit GEMM with K = 16 taps x 16 = 256.  Each tap is ONE tcgen05.mma (M=128, N=64, K=16) whose B
+// operand is the 64 x 16 slice of W2 for that tap (all 16 slices, 32 KB, stay resident in shared memory) and whose
+// A operand is a VIEW of the tile's input patch: the output tile is 8 x 16 pixels, ONE 4-D TMA box brings the
+// 11 x 19 halo patch of S (32-byte pixels, SWIZZLE_32B, 6.5 KB) into shared memory, and tap (a,b) reads it through
+// a UMMA descriptor starting (a*11 + b) * 32 B into the patch with 8-pixel core matrices 11 * 32 B apart
+// (same shifted-view mechanism as conv_halo.cuh) - the patch crosses the L2 -> SM path once instead of 16 times.
 //
-//   warp 0  TMA producer   weights once; per tile 4 ring slots (one per a), each = 4 boxes (b = 0..3) of 128 x 32 B
+//   warp 0  TMA producer   weights once; per tile one halo patch into a ring slot
 //   warp 1  MMA issuer     16 MMAs per tile into one of two TMEM accumulators (64 columns each)
 //   warp 3  TMEM allocator
 //   warps 4-7 epilogue     TMEM -> scale/shift/ReLU -> fp16 into a 128-byte-swizzled staging tile -> TMA store
@@ -27,9 +30,10 @@ struct StemParams {
 };
 
 struct StemSmem {
-  static constexpr int STAGES = 6;                       // ring slots (one slot = one kernel row a = 4 taps)
-  static constexpr int TAP_BYTES = 128 * 32;             // 128 pixels x 16 channels fp16
-  static constexpr int SLOT_BYTES = 4 * TAP_BYTES;       // 16 KB
+  static constexpr int STAGES = 4;                       // ring slots (one slot = the halo patch of one tile)
+  static constexpr int HALO_W = 11, HALO_H = 19;
+  static constexpr int HALO_DATA = HALO_W * HALO_H * 32; // 6 688 B landed by TMA
+  static constexpr int SLOT_BYTES = 7 * 1024;
   static constexpr int W_BYTES = 16 * 64 * 32;           // 16 taps x (64 x 16 fp16)
   static constexpr int STG_BYTES = 128 * 128;            // 128 pixels x 64 channels fp16
   static constexpr int W_OFF = STAGES * SLOT_BYTES;
@@ -39,12 +43,12 @@ struct StemSmem {
   static constexpr int TOTAL = BAR_OFF + 8 * NUM_BARS + 16 + 1024;
 };
 
-// K-major operand with rows of 16 halfs (32 B), 32-byte swizzle: 8-row groups 256 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+// K-major operand with rows of 16 halfs (32 B), 32-byte swizzle: 8-row groups `sbo` bytes apart (256 when dense).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t sbo = 256) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(6) << 61;   // SWIZZLE_32B
   return d;
@@ -107,14 +111,11 @@ stem_pers_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int wo0, ho0, n0;
         tile_origin(t, wo0, ho0, n0);
-        for (int a = 0; a < 4; ++a, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], L::SLOT_BYTES);
-          uint8_t* slot = smem + s * L::SLOT_BYTES;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) tma_load_4d(slot + b * L::TAP_BYTES, &tmS, &full_bar[s], 0, wo0 + b, ho0 + a, n0);
-        }
+        const int s = g % STAGES;
+        mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], L::HALO_DATA);
+        tma_load_4d(smem + s * L::SLOT_BYTES, &tmS, &full_bar[s], 0, wo0, ho0, n0);
+        ++g;
       }
     }
   } else if (warp == 1) {
@@ -129,18 +130,19 @@ stem_pers_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 64;
-        for (int a = 0; a < 4; ++a, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(&full_bar[s], (g / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t slot = smem_u32(smem + s * L::SLOT_BYTES);
+        const int s = g % STAGES;
+        mbar_wait(&full_bar[s], (g / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t slot = smem_u32(smem + s * L::SLOT_BYTES);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            umma_f16(d_tmem, umma_desc_sw32(slot + b * L::TAP_BYTES), umma_desc_sw32(w_addr + (a * 4 + b) * 2048), idesc,
-                     (a | b) != 0);
-          umma_commit(&empty_bar[s]);
-        }
+            umma_f16(d_tmem, umma_desc_sw32(slot + static_cast<uint32_t>(a * L::HALO_W + b) * 32u, L::HALO_W * 32u),
+                     umma_desc_sw32(w_addr + (a * 4 + b) * 2048), idesc, (a | b) != 0);
+        umma_commit(&empty_bar[s]);
         umma_commit(&acc_full[acc]);
+        ++g;
       }
     }
   } else if (warp >= 4) {
