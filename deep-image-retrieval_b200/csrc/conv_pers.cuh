@@ -22,7 +22,7 @@
 
 namespace dirb {
 
-enum { PERS_EPI_CONV = 0, PERS_EPI_SIM_DENSE = 1, PERS_EPI_SIM_FILTER = 2, PERS_EPI_SIM_GMAX = 3 };
+enum { PERS_EPI_CONV = 0, PERS_EPI_SIM_DENSE = 1, PERS_EPI_SIM_FILTER = 2, PERS_EPI_SIM_GMAX = 3, PERS_EPI_F32 = 4 };
 
 struct ConvPersParams {
   int a_spatial, taps, kw_taps, cin_blocks, stride, pad;
@@ -35,6 +35,10 @@ struct ConvPersParams {
   // activation tensor (tensor map tmR, spatial boxes with element stride a2_stride baked into the map) - the
   // block input x of the 1x1 downsample conv - while the weights are the K-concatenation [W3*s3 | Wd*sd].
   int k_split, a2_stride;
+  // PERS_EPI_F32 (whitening): fp32-accurate product from fp16 hi/lo splits, K = 3 parts of k_per_part blocks:
+  // (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi) with A_lo in tensor map tmR and B_lo in tmO; epilogue = column scale,
+  // fp32 store to dense[M][dense_ld].
+  int k_per_part;
   const float* scale;
   const float* shift;
   // similarity epilogues (search.cu): D[q][n] = <query q, database row n>
@@ -202,6 +206,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     if (EPI == PERS_EPI_CONV) tma_prefetch_desc(&tmO);
     if (EPI == PERS_EPI_CONV && (p.has_res || p.k_split > 0)) tma_prefetch_desc(&tmR);
+    if (EPI == PERS_EPI_F32) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmO); }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -235,6 +240,13 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           const int tap = it / p.cin_blocks;
           const int kc = it - tap * p.cin_blocks;
+          if (EPI == PERS_EPI_F32) {
+            const int part = it / p.k_per_part;
+            const int kk = it - part * p.k_per_part;
+            tma_load_2d(sa, part == 2 ? &tmR : &tmA, &full_bar[s], kk * 64, c.m_tile * 128);
+            tma_load_2d(sa + L::A_BYTES, part == 1 ? &tmO : &tmB, &full_bar[s], kk * 64, c.n_tile * BN);
+            continue;
+          }
           if (p.k_split > 0 && it >= p.k_split) {
             tma_load_4d(sa, &tmR, &full_bar[s], (it - p.k_split) * 64, c.wo0 * p.a2_stride, c.ho0 * p.a2_stride, c.n0);
           } else if (p.a_spatial) {
@@ -326,7 +338,20 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           const int nb0 = c.n_tile * BN + c0;
           if (!valid || nb0 >= p.N) continue;
-          if (EPI == PERS_EPI_SIM_GMAX) {
+          if (EPI == PERS_EPI_F32) {
+            float* dp = p.dense + qi * p.dense_ld + nb0;
+            const bool vec = (nb0 + 32 <= p.N) && ((p.dense_ld & 3) == 0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= (p.scale != nullptr && nb0 + j < p.N) ? __ldg(p.scale + nb0 + j) : 1.0f;
+            if (vec) {
+              float4* d4 = reinterpret_cast<float4*>(dp);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) d4[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nb0 + j < p.N) dp[j] = v[j];
+            }
+          } else if (EPI == PERS_EPI_SIM_GMAX) {
             // maximum of each group of 32 database rows: the k-th largest group maximum is a valid lower bound on
             // the k-th best score (k distinct rows reach it) and costs 1/32 of the dense write + select
             float m = -INFINITY;

@@ -1,6 +1,7 @@
 // Small memory-bound operators around the convolution stack and the descriptor post-processing.
 // All of them are HBM-bound: one coalesced 16-byte access per thread per element group, fp32 arithmetic.
 #include "conv.h"
+#include "conv_pers.cuh"
 #include "ptx.cuh"
 
 namespace dirb {
@@ -387,15 +388,85 @@ __global__ void __launch_bounds__(256) whiten_gemm_kernel(const float* __restric
 }
 }  // namespace
 
+// x - mean -> fp16 hi + fp16 lo (hi + lo reproduces the fp32 value to ~2^-22 relative)
+__global__ void split_f16_kernel(const float* __restrict__ x, const float* __restrict__ mean, int D, int64_t total,
+                                 __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+  if (i >= total) return;
+  float4 v = *reinterpret_cast<const float4*>(x + i);
+  if (mean) {
+    const float4 m = *reinterpret_cast<const float4*>(mean + (i % D));
+    v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+  }
+  const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+  uint2 oh, ol;
+  oh.x = pack_h2(__half2float(h0), __half2float(h1));
+  oh.y = pack_h2(__half2float(h2), __half2float(h3));
+  ol.x = pack_h2(v.x - __half2float(h0), v.y - __half2float(h1));
+  ol.y = pack_h2(v.z - __half2float(h2), v.w - __half2float(h3));
+  *reinterpret_cast<uint2*>(hi + i) = oh;
+  *reinterpret_cast<uint2*>(lo + i) = ol;
+}
+
+// Tensor-core whitening: Y = ((X - mean) . comp^T) * colscale through three fp16 GEMM passes over hi/lo splits
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) - fp32-level accuracy at tensor-core speed.
+static int whiten_tc(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale,
+                     int Dout, float* y, cudaStream_t stream) {
+  __half *xh = nullptr, *xl = nullptr, *ch = nullptr, *cl = nullptr;
+  const size_t xe = static_cast<size_t>(N) * D, ce = static_cast<size_t>(Dout) * D;
+  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xh), xe * 2, stream));
+  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xl), xe * 2, stream));
+  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ch), ce * 2, stream));
+  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&cl), ce * 2, stream));
+  split_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(xe, 4), 256)), 256, 0, stream>>>(x, mean, D, xe, xh, xl);
+  split_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(ce, 4), 256)), 256, 0, stream>>>(comp, nullptr, D, ce, ch, cl);
+  count_launch(2);
+  DIRB_CUDA(cudaGetLastError());
+  constexpr int BN = 256;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  DIRB_TRY(encode_tmap_2d(&tmAh, xh, D, N, (uint64_t)D * 2, 64, 128));
+  DIRB_TRY(encode_tmap_2d(&tmAl, xl, D, N, (uint64_t)D * 2, 64, 128));
+  DIRB_TRY(encode_tmap_2d(&tmBh, ch, D, Dout, (uint64_t)D * 2, 64, BN));
+  DIRB_TRY(encode_tmap_2d(&tmBl, cl, D, Dout, (uint64_t)D * 2, 64, BN));
+  ConvPersParams p{};
+  p.a_spatial = 0;
+  p.taps = 1; p.kw_taps = 1;
+  p.k_per_part = D / 64;
+  p.cin_blocks = 3 * p.k_per_part;
+  p.stride = 1; p.pad = 0;
+  p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
+  p.M = static_cast<int>(N);
+  p.N = Dout;
+  p.n_tiles = static_cast<int>(ceil_div(Dout, BN));
+  p.m_tiles = static_cast<int>(ceil_div(N, 128));
+  p.m_fastest = 0;
+  const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  DIRB_REQUIRE(total < (int64_t(1) << 31) && N < (int64_t(1) << 31), DIRB200_ENOTSUP, "whiten: shape too large");
+  p.total_tiles = static_cast<int>(total);
+  p.dense = y;
+  p.dense_ld = Dout;
+  p.scale = colscale;
+  DIRB_TRY((conv_pers_launch<BN, 4, PERS_EPI_F32>(tmAh, tmBh, tmAl, tmBl, p, num_sms(), stream)));
+  DIRB_CUDA(cudaFreeAsync(xh, stream));
+  DIRB_CUDA(cudaFreeAsync(xl, stream));
+  DIRB_CUDA(cudaFreeAsync(ch, stream));
+  DIRB_CUDA(cudaFreeAsync(cl, stream));
+  return 0;
+}
+
 int whiten(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale, int Dout,
            int l2norm, float* y, __half* y16, cudaStream_t stream) {
   DIRB_REQUIRE(D % WK == 0, DIRB200_ENOTSUP, "whiten needs D %% 16 == 0 (got %d)", D);
   if (N == 0) return 0;
-  dim3 grid((unsigned)ceil_div(N, WT), (unsigned)ceil_div(Dout, WT));
-  DIRB_REQUIRE(ceil_div(N, WT) < (int64_t(1) << 31) && grid.y < 65536u, DIRB200_ENOTSUP, "whiten: shape too large");
-  whiten_gemm_kernel<<<grid, 256, 0, stream>>>(x, comp, mean, colscale, y, N, D, Dout);
-  count_launch();
-  DIRB_CUDA(cudaGetLastError());
+  if (D % 64 == 0 && N >= 64) {
+    DIRB_TRY(whiten_tc(x, N, D, comp, mean, colscale, Dout, y, stream));
+  } else {
+    dim3 grid((unsigned)ceil_div(N, WT), (unsigned)ceil_div(Dout, WT));
+    DIRB_REQUIRE(ceil_div(N, WT) < (int64_t(1) << 31) && grid.y < 65536u, DIRB200_ENOTSUP, "whiten: shape too large");
+    whiten_gemm_kernel<<<grid, 256, 0, stream>>>(x, comp, mean, colscale, y, N, D, Dout);
+    count_launch();
+    DIRB_CUDA(cudaGetLastError());
+  }
   if (l2norm) return l2_normalize(y, N, Dout, 0.f, y, y16, stream);
   if (y16) return f32_to_f16(y, N * Dout, y16, stream);
   return 0;

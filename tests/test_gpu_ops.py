@@ -145,6 +145,21 @@ def test_head(shape, kw):
     assert rel_l2(out.cpu().numpy(), ref) < 2e-5
 
 
+def test_whiten_tensor_core_path_large():
+    """5000 x 2048 rows through the tcgen05 hi/lo-split whitening vs the fp64 oracle, ragged row count."""
+    ops = _ops()
+    pca64 = synth.make_pca(2048, seed=3, dtype=np.float64)
+    pca32 = synth.make_pca(2048, seed=3, dtype=np.float32)
+    X = synth._unit_rows(np.random.RandomState(6).standard_normal((5000, 2048))).astype(np.float32)
+    ref = O.whiten_features(X.astype(np.float64), pca64, whitenp=0.25, whitenv=1000)
+    cs = (1.0 / np.power(pca64.explained_variance_[:1000], 0.25)).astype(np.float32)
+    y = ops.whiten(torch.from_numpy(X).to(DEV), torch.from_numpy(pca32.components_[:1000].copy()).to(DEV),
+                   torch.from_numpy(pca32.mean_).to(DEV), torch.from_numpy(cs).to(DEV))
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (5000, 1000)
+    assert rel_l2(y.cpu().numpy(), ref) < 2e-5
+
+
 def test_pool_scales_l2_whiten(golden):
     ops = _ops()
     g = golden("pool.npz")
@@ -175,6 +190,6 @@ def test_pool_scales_l2_whiten(golden):
     csb = (1.0 / np.power(pca.explained_variance_.astype(np.float64), 0.25)).astype(np.float32)
     yb, yb16 = ops.whiten(torch.from_numpy(Xb).to(DEV), torch.from_numpy(pca.components_).to(DEV),
                           torch.from_numpy(pca.mean_).to(DEV), torch.from_numpy(csb).to(DEV), want_f16=True)
-    assert rel_l2(yb.cpu().numpy(), ref) < 1e-3            # north-star tolerance; fp32 SIMT gives ~1e-6
+    assert rel_l2(yb.cpu().numpy(), ref) < 1e-3            # north-star tolerance; the hi/lo split GEMM gives ~1e-6
     assert rel_l2(yb.cpu().numpy(), ref) < 2e-5
     assert rel_l2(yb16.float().cpu().numpy(), ref) < 1e-3

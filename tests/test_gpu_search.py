@@ -151,4 +151,4 @@ def test_full_size_1m_properties():
     np.testing.assert_array_equal(i_h[pick], best_i)
     np.testing.assert_allclose(s_h[pick], best_s, rtol=0, atol=1e-12)
     st = index.stats()
-    assert st["retries"] == 0 and st["candidates"] < 20 * Q * K
+    assert st["retries"] == 0 and st["candidates"] < 40 * Q * K

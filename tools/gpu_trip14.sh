@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1
+echo "== pytest rc=$?"; tail -4 gpurun_out/pytest_all.log
+timeout 1200 python bench.py > gpurun_out/bench_full.log 2>&1
+echo "== bench rc=$?"; tail -1 gpurun_out/bench_full.log | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print("extract", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "conv TF", d["roofline"]["achieved"], d["roofline"]["classes_ms"], d["clocks"]); print("search", d["search"]["value"], d["search"]["ms_per_step"], d["search"]["whiten"])'

@@ -20,9 +20,11 @@ for li, (pl, nb) in enumerate(zip([64, 128, 256, 512], [3, 4, 23, 3])):
         ho = h // s
         seq.append(("L%d c1 1x1 %d->%d" % (li + 1, inpl, pl), 2 * B * h * h * inpl * pl, B * h * h * (inpl + pl) * 2))
         seq.append(("L%d c2 3x3 %d s%d" % (li + 1, pl, s), 2 * B * ho * ho * pl * pl * 9, B * (h * h + ho * ho) * pl * 2))
-        if b == 0:
-            seq.append(("L%d ds 1x1 %d->%d s%d" % (li + 1, inpl, pl * 4, s), 2 * B * ho * ho * inpl * pl * 4, B * (h * h * inpl + ho * ho * pl * 4) * 2))
-        seq.append(("L%d c3 1x1 %d->%d +res" % (li + 1, pl, pl * 4), 2 * B * ho * ho * pl * pl * 4, B * ho * ho * (pl + pl * 8) * 2))
+        if b == 0:   # conv3 fused with the projection shortcut: K = [conv2 output | block input]
+            seq.append(("L%d c3+ds 1x1 [%d|%d]->%d" % (li + 1, pl, inpl, pl * 4), 2 * B * ho * ho * (pl + inpl) * pl * 4,
+                        B * (ho * ho * (pl + pl * 4) + h * h * inpl) * 2))
+        else:
+            seq.append(("L%d c3 1x1 %d->%d +res" % (li + 1, pl, pl * 4), 2 * B * ho * ho * pl * pl * 4, B * ho * ho * (pl + pl * 8) * 2))
         inpl, h = pl * 4, ho
 seq += [("head", 0, 0)] * 4
 per = len(seq)
