@@ -190,7 +190,7 @@ static int g_conv_halo = 1;
 void set_conv_halo(int on) { g_conv_halo = on; }
 
 // 3x3 / stride 1 / pad 1 with the halo patch loaded once per tile (conv_halo.cuh).
-template <int BN, int BSTAGES, bool BRES>
+template <int BN, int BSTAGES, bool BRES, int NA>
 static int conv_halo_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
                         const __half* res, int relu, __half* out, cudaStream_t stream) {
   ConvPersParams p{};
@@ -215,7 +215,7 @@ static int conv_halo_bn(const ConvShape& s, const __half* in, const __half* w, c
   if (res) DIRB_TRY(encode_tmap_nhwc(&tmR, res, s.B, s.H, s.W, s.Cout, 8, 16, 1, 1));
   else tmR = tmO;
   DIRB_TRY(encode_tmap_2d(&tmB, w, 9 * s.Cin, s.Cout, (uint64_t)9 * s.Cin * 2, 64, BN));
-  return conv_halo_launch<BN, BSTAGES, 2, BRES>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
+  return conv_halo_launch<BN, BSTAGES, 2, BRES, NA>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
 }
 
 int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
@@ -224,10 +224,11 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
                "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
   DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
   if (g_conv_halo && s.KH == 3 && s.KW == 3 && s.stride == 1 && s.pad == 1 && s.H >= 16 && s.W >= 8 && res == nullptr) {
-    if (s.Cout == 64 && s.Cin == 64) return conv_halo_bn<64, 9, true>(s, in, w, scale, shift, res, relu, out, stream);
-    if (s.Cout % 256 == 0) return conv_halo_bn<256, 4, false>(s, in, w, scale, shift, res, relu, out, stream);
-    if (s.Cout % 128 == 0) return conv_halo_bn<128, 6, false>(s, in, w, scale, shift, res, relu, out, stream);
-    return conv_halo_bn<64, 8, false>(s, in, w, scale, shift, res, relu, out, stream);
+    // halo slots (input prefetch depth): short tiles need more patches in flight to cover the HBM latency
+    if (s.Cout == 64 && s.Cin == 64) return conv_halo_bn<64, 9, true, 4>(s, in, w, scale, shift, res, relu, out, stream);
+    if (s.Cout % 256 == 0) return conv_halo_bn<256, 4, false, 2>(s, in, w, scale, shift, res, relu, out, stream);
+    if (s.Cout % 128 == 0) return conv_halo_bn<128, 6, false, 3>(s, in, w, scale, shift, res, relu, out, stream);
+    return conv_halo_bn<64, 8, false, 4>(s, in, w, scale, shift, res, relu, out, stream);
   }
   // Shared memory split: convolutions with a residual keep 4 staging buffers (residual prefetch depth) and a
   // shorter operand ring; the others trade two staging buffers for one more ring slot (deeper TMA lookahead).

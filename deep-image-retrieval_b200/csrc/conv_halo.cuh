@@ -16,12 +16,12 @@
 
 namespace dirb {
 
-template <int BN, int BSTAGES, int NB>
+template <int BN, int BSTAGES, int NB, int NA_ = 2>
 struct ConvHaloSmem {
   static constexpr int HALO_W = 10, HALO_H = 18;
   static constexpr int HALO_DATA = HALO_W * HALO_H * 128;          // 23 040 B landed by TMA
   static constexpr int HALO_SLOT = 24 * 1024;                      // 1024-byte aligned slot
-  static constexpr int NA = 2;                                     // halo slots
+  static constexpr int NA = NA_;                                   // halo slots (prefetch depth of the input patches)
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STG_BYTES = 128 * 128;
   static constexpr int B_OFF = NA * HALO_SLOT;
@@ -42,12 +42,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
 }
 
 // p: tw = 8, th = 16, nb = 1, taps = 9, a_spatial = 1; tmA = halo map (box 64 x 10 x 18 x 1).
-template <int BN, int BSTAGES, int NB, bool BRES>
+template <int BN, int BSTAGES, int NB, bool BRES, int NA_>
 __global__ void __launch_bounds__(PersThreads<0>::THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvPersParams p) {
-  using L = ConvHaloSmem<BN, BSTAGES, NB>;
+  using L = ConvHaloSmem<BN, BSTAGES, NB, NA_>;
   constexpr int NA = L::NA;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,7 +72,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    if (p.has_res) tma_prefetch_desc(&tmR);
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], PersThreads<0>::EPI_WARPS); }
@@ -87,17 +86,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      // ------------------------------------------------------------ producer: halo patches + weight tiles
-      uint32_t ga = 0, gb = 0;
+      // ------------------------------------------------------------ producer 1: weight tiles
+      uint32_t gb = 0;
       bool first = true;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
-        for (int kc = 0; kc < p.cin_blocks; ++kc, ++ga) {
-          const int sa = ga % NA;
-          mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1);
-          mbar_expect_tx(&a_full[sa], L::HALO_DATA);
-          tma_load_4d(smem + sa * L::HALO_SLOT, &tmA, &a_full[sa], kc * 64, c.wo0 - 1, c.ho0 - 1, c.n0);
-          if (!BRES || first) {
+        if (!BRES || first) {
+          for (int kc = 0; kc < p.cin_blocks; ++kc) {
             for (int tap = 0; tap < 9; ++tap, ++gb) {
               const int sb = BRES ? (kc * 9 + tap) : static_cast<int>(gb % BSTAGES);
               if (!BRES) mbar_wait(&b_empty[sb], ((gb / BSTAGES) & 1) ^ 1);
@@ -107,6 +102,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         first = false;
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ producer 2: input halo patches, running up to NA
+      // patches ahead of the MMA warp independently of the weight stream (3x3 convolutions carry no residual, so
+      // this warp has no residual tiles to prefetch)
+      uint32_t ga = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        for (int kc = 0; kc < p.cin_blocks; ++kc, ++ga) {
+          const int sa = ga % NA;
+          mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1);
+          mbar_expect_tx(&a_full[sa], L::HALO_DATA);
+          tma_load_4d(smem + sa * L::HALO_SLOT, &tmA, &a_full[sa], kc * 64, c.wo0 - 1, c.ho0 - 1, c.n0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -124,42 +135,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int sa = ga % NA;
           mbar_wait(&a_full[sa], (ga / NA) & 1);
           tc_fence_after();
-          const uint32_t halo = smem_u32(smem + sa * L::HALO_SLOT);
+          // One thread issues every MMA, so its instruction count per MMA bounds small-N tiles (a 128x64x16 MMA
+          // occupies the tensor core for only 32 cycles): build the two base descriptors once and reach every
+          // (tap, k) operand by adding a compile-time constant to the 14-bit start-address field.
+          const uint64_t adesc0 = umma_desc_sw128_sbo(smem_u32(smem + sa * L::HALO_SLOT), L::HALO_W * 128u);
+          const uint64_t bdesc0 = umma_desc_sw128(smem_u32(bsm));
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap, ++gb) {
             const int sb = BRES ? (kc * 9 + tap) : static_cast<int>(gb % BSTAGES);
             if (!BRES) {
               mbar_wait(&b_full[sb], (gb / BSTAGES) & 1);
+              tc_fence_after();
             } else if (first) {
               mbar_wait(&b_full[sb], 0);
+              tc_fence_after();
             }
-            tc_fence_after();
             const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t a_addr = halo + static_cast<uint32_t>(kh * L::HALO_W + kw) * 128u;
-            const uint64_t bdesc = umma_desc_sw128(smem_u32(bsm + sb * L::B_BYTES));
+            const uint64_t ad = adesc0 + static_cast<uint64_t>((kh * L::HALO_W + kw) * 8);      // * 128 B >> 4
+            const uint64_t bd = bdesc0 + static_cast<uint64_t>(sb) * (L::B_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d_tmem, umma_desc_sw128_sbo(a_addr + 32u * k, L::HALO_W * 128u), bdesc + 2 * k, idesc,
-                       (kc | tap | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0);
             if (!BRES) umma_commit(&b_empty[sb]);
           }
           umma_commit(&a_empty[sa]);
         }
         umma_commit(&acc_full[a]);
         first = false;
-      }
-    }
-  } else if (warp == 2) {
-    if (lane == 0 && p.has_res) {
-      constexpr int CHUNKS = BN / 64;
-      uint32_t cc = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(p, t);
-        for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
-          const int b = cc % NB;
-          mbar_wait(&res_empty[b], ((cc / NB) & 1) ^ 1);
-          mbar_expect_tx(&res_full[b], L::STG_BYTES);
-          tma_load_4d(stg + b * L::STG_BYTES, &tmR, &res_full[b], c.n_tile * BN + ch * 64, c.wo0, c.ho0, c.n0);
-        }
       }
     }
   } else if (warp >= 4) {
@@ -191,12 +192,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int BSTAGES, int NB, bool BRES>
+template <int BN, int BSTAGES, int NB, bool BRES, int NA_>
 int conv_halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                      const ConvPersParams& p, int num_sms, cudaStream_t stream) {
-  using L = ConvHaloSmem<BN, BSTAGES, NB>;
+  using L = ConvHaloSmem<BN, BSTAGES, NB, NA_>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  auto kern = conv_halo_kernel<BN, BSTAGES, NB, BRES>;
+  auto kern = conv_halo_kernel<BN, BSTAGES, NB, BRES, NA_>;
   DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   kern<<<grid, PersThreads<0>::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);

@@ -133,13 +133,15 @@ stem_pers_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
         const int s = g % STAGES;
         mbar_wait(&full_bar[s], (g / STAGES) & 1);
         tc_fence_after();
-        const uint32_t slot = smem_u32(smem + s * L::SLOT_BYTES);
+        // base descriptors once per tile; every tap is a compile-time offset in the start-address field
+        const uint64_t adesc0 = umma_desc_sw32(smem_u32(smem + s * L::SLOT_BYTES), L::HALO_W * 32u);
+        const uint64_t bdesc0 = umma_desc_sw32(w_addr);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            umma_f16(d_tmem, umma_desc_sw32(slot + static_cast<uint32_t>(a * L::HALO_W + b) * 32u, L::HALO_W * 32u),
-                     umma_desc_sw32(w_addr + (a * 4 + b) * 2048), idesc, (a | b) != 0);
+            umma_f16(d_tmem, adesc0 + static_cast<uint64_t>((a * L::HALO_W + b) * 2), bdesc0 + static_cast<uint64_t>((a * 4 + b) * 128),
+                     idesc, (a | b) != 0);
         umma_commit(&empty_bar[s]);
         umma_commit(&acc_full[acc]);
         ++g;
