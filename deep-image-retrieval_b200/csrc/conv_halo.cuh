@@ -121,47 +121,67 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-      uint32_t ga = 0, gb = 0, i = 0;
-      bool first = true;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const uint32_t a = i & 1;
-        mbar_wait(&acc_empty[a], ((i >> 1) & 1) ^ 1);
+    // -------------------------------------------------------------- MMA issuer (whole warp walks the loop, one
+    // elected lane issues; see conv_pers.cuh)
+    constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+    uint32_t ga = 0, gb = 0, i = 0;
+    bool first = true;
+    const uint64_t bdesc0 = umma_desc_sw128(smem_u32(bsm));
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const uint32_t a = i & 1;
+      mbar_wait(&acc_empty[a], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * BN;
+      for (int kc = 0; kc < p.cin_blocks; ++kc, ++ga) {
+        const int sa = ga % NA;
+        mbar_wait(&a_full[sa], (ga / NA) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * BN;
-        for (int kc = 0; kc < p.cin_blocks; ++kc, ++ga) {
-          const int sa = ga % NA;
-          mbar_wait(&a_full[sa], (ga / NA) & 1);
-          tc_fence_after();
-          // One thread issues every MMA, so its instruction count per MMA bounds small-N tiles (a 128x64x16 MMA
-          // occupies the tensor core for only 32 cycles): build the two base descriptors once and reach every
-          // (tap, k) operand by adding a compile-time constant to the 14-bit start-address field.
-          const uint64_t adesc0 = umma_desc_sw128_sbo(smem_u32(smem + sa * L::HALO_SLOT), L::HALO_W * 128u);
-          const uint64_t bdesc0 = umma_desc_sw128(smem_u32(bsm));
+        // One thread issues every MMA, so its instruction count per MMA bounds small-N tiles (a 128x64x16 MMA
+        // occupies the tensor core for only 32 cycles): build the base descriptors once and reach every (tap, k)
+        // operand by adding a compile-time constant to the 14-bit start-address field.
+        const uint64_t adesc0 = umma_desc_sw128_sbo(smem_u32(smem + sa * L::HALO_SLOT), L::HALO_W * 128u);
+        const bool last_kc = (kc == p.cin_blocks - 1);
+        if (BRES) {
+          if (first) {
+            for (int tap = 0; tap < 9; ++tap) mbar_wait(&b_full[kc * 9 + tap], 0);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const uint64_t ad = adesc0 + static_cast<uint64_t>((kh * L::HALO_W + kw) * 8);      // * 128 B >> 4
+              const uint64_t bd = bdesc0 + static_cast<uint64_t>(kc * 9 + tap) * (L::B_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0);
+            }
+            umma_commit(&a_empty[sa]);
+            if (last_kc) umma_commit(&acc_full[a]);
+          }
+          __syncwarp();
+        } else {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap, ++gb) {
-            const int sb = BRES ? (kc * 9 + tap) : static_cast<int>(gb % BSTAGES);
-            if (!BRES) {
-              mbar_wait(&b_full[sb], (gb / BSTAGES) & 1);
-              tc_fence_after();
-            } else if (first) {
-              mbar_wait(&b_full[sb], 0);
-              tc_fence_after();
-            }
+            const int sb = static_cast<int>(gb % BSTAGES);
+            mbar_wait(&b_full[sb], (gb / BSTAGES) & 1);
+            tc_fence_after();
             const int kh = tap / 3, kw = tap - kh * 3;
-            const uint64_t ad = adesc0 + static_cast<uint64_t>((kh * L::HALO_W + kw) * 8);      // * 128 B >> 4
+            const uint64_t ad = adesc0 + static_cast<uint64_t>((kh * L::HALO_W + kw) * 8);
             const uint64_t bd = bdesc0 + static_cast<uint64_t>(sb) * (L::B_BYTES >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0);
-            if (!BRES) umma_commit(&b_empty[sb]);
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0);
+              umma_commit(&b_empty[sb]);
+              if (tap == 8) {
+                umma_commit(&a_empty[sa]);
+                if (last_kc) umma_commit(&acc_full[a]);
+              }
+            }
+            __syncwarp();
           }
-          umma_commit(&a_empty[sa]);
         }
-        umma_commit(&acc_full[a]);
-        first = false;
       }
+      first = false;
     }
   } else if (warp >= 4) {
     constexpr int EPI_THREADS = 32 * PersThreads<0>::EPI_WARPS;

@@ -262,27 +262,30 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-      uint32_t g = 0, i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const uint32_t a = i & 1;
-        mbar_wait(&acc_empty[a], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+    // -------------------------------------------------------------- MMA issuer
+    // The whole warp walks the loop (uniform control flow keeps descriptors and TMEM addresses in uniform
+    // registers); one elected lane issues the MMAs and the commits of a ring slot.
+    constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+    uint32_t g = 0, i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const uint32_t a = i & 1;
+      mbar_wait(&acc_empty[a], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * BN;
+      for (int it = 0; it < k_iters; ++it, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(&full_bar[s], (g / STAGES) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * BN;
-        for (int it = 0; it < k_iters; ++it, ++g) {
-          const int s = g % STAGES;
-          mbar_wait(&full_bar[s], (g / STAGES) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
           umma_commit(&empty_bar[s]);
+          if (it == k_iters - 1) umma_commit(&acc_full[a]);
         }
-        umma_commit(&acc_full[a]);
+        __syncwarp();
       }
     }
   } else if (warp == 2) {

@@ -119,33 +119,31 @@ stem_pers_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, 64);
-      mbar_wait(w_bar, 0);
+    // whole warp walks the loop (uniform operands), one elected lane issues the 16 MMAs + commits of a tile
+    constexpr uint32_t idesc = umma_idesc_f16(128, 64);
+    mbar_wait(w_bar, 0);
+    tc_fence_after();
+    const uint64_t bdesc0 = umma_desc_sw32(smem_u32(wsm));
+    uint32_t g = 0, i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i, ++g) {
+      const uint32_t acc = i & 1;
+      mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
+      const int s = g % STAGES;
+      mbar_wait(&full_bar[s], (g / STAGES) & 1);
       tc_fence_after();
-      const uint32_t w_addr = smem_u32(wsm);
-      uint32_t g = 0, i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
-        const uint32_t acc = i & 1;
-        mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 64;
-        const int s = g % STAGES;
-        mbar_wait(&full_bar[s], (g / STAGES) & 1);
-        tc_fence_after();
-        // base descriptors once per tile; every tap is a compile-time offset in the start-address field
-        const uint64_t adesc0 = umma_desc_sw32(smem_u32(smem + s * L::SLOT_BYTES), L::HALO_W * 32u);
-        const uint64_t bdesc0 = umma_desc_sw32(w_addr);
+      const uint32_t d_tmem = tmem_base + acc * 64;
+      const uint64_t adesc0 = umma_desc_sw32(smem_u32(smem + s * L::SLOT_BYTES), L::HALO_W * 32u);
+      if (elect_one()) {
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b)
-            umma_f16(d_tmem, adesc0 + static_cast<uint64_t>((a * L::HALO_W + b) * 2), bdesc0 + static_cast<uint64_t>((a * 4 + b) * 128),
-                     idesc, (a | b) != 0);
+            umma_f16(d_tmem, adesc0 + static_cast<uint64_t>((a * L::HALO_W + b) * 2),
+                     bdesc0 + static_cast<uint64_t>((a * 4 + b) * 128), idesc, (a | b) != 0);
         umma_commit(&empty_bar[s]);
         umma_commit(&acc_full[acc]);
-        ++g;
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int quarter = warp - 4;
