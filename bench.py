@@ -229,6 +229,16 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * e2e_steps / e2e_s
+    # same, from uint8 HWC host images (what a decoder yields): ToTensor + Normalize run inside the stem, 4x fewer bytes
+    host8 = torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8).pin_memory()
+    net.forward_host_u8(host8.numpy(), device=local)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        net.forward_host_u8(host8.numpy(), device=local)
+    barrier()
+    e2e_u8_value = world * B * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+    del host8
 
     # ---- roofline of the dominant kernel (the persistent tcgen05 convolution), timed live with CUDA events on the
     #      launch stream during one extra, instrumented step
@@ -266,7 +276,9 @@ def main():
                    "weights": "random init (synth.make_state_dict seed 0)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                 "d2h_bytes_per_step": B * net.descriptor_dim * 4, "steps": e2e_steps,
-                "api": "dirb200_net_forward_host (pinned host buffers, H2D of chunk i+1 overlaps compute of chunk i)"},
+                "api": "dirb200_net_forward_host (pinned host buffers, H2D of chunk i+1 overlaps compute of chunk i)",
+                "uint8_input": {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S,
+                                "api": "dirb200_net_forward_host_u8 (uint8 HWC pixels, normalisation fused into the stem)"}},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(),
         "roofline": roofline,

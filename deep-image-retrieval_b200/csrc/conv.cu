@@ -275,6 +275,38 @@ __global__ void s2d_kernel(const float* __restrict__ in, __half* __restrict__ ou
   dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
+// Same from uint8 HWC pixels (what an image decoder yields): ToTensor (x / 255) and Normalize ((v - mean) / std) of
+// dirtorch/utils/transforms.py:27 are applied on the fly in fp32, in torch's order and with true divisions, so the
+// fp16 values are bit-identical to those of the fp32-input path.
+__global__ void s2d_u8_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, int H, int W, int Hs, int Ws,
+                              int64_t total, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int X = static_cast<int>(i % Ws);
+  const int Y = static_cast<int>((i / Ws) % Hs);
+  const int64_t n = i / (static_cast<int64_t>(Ws) * Hs);
+  const uint8_t* img = in + n * 3 * static_cast<int64_t>(H) * W;
+  uint32_t o[8];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int y = 2 * Y + dy - 3, x = 2 * X + dx - 3;
+      float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        const uint8_t* px = img + (static_cast<int64_t>(y) * W + x) * 3;
+        c0 = __fdiv_rn(__fdiv_rn(static_cast<float>(px[0]), 255.0f) - m0, s0);
+        c1 = __fdiv_rn(__fdiv_rn(static_cast<float>(px[1]), 255.0f) - m1, s1);
+        c2 = __fdiv_rn(__fdiv_rn(static_cast<float>(px[2]), 255.0f) - m2, s2);
+      }
+      o[(dy * 2 + dx) * 2] = pack_h2(c0, c1);
+      o[(dy * 2 + dx) * 2 + 1] = pack_h2(c2, 0.f);
+    }
+  uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 static void stem_dims(int H, int W, int* Ho, int* Wo, int* Hs, int* Ws) {
   *Ho = (H + 6 - 7) / 2 + 1;
   *Wo = (W + 6 - 7) / 2 + 1;
@@ -303,11 +335,15 @@ void pack_stem_w2(const float* w, __half* out) {
 }
 
 int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const float* scale, const float* shift,
-            __half* s2d_ws, __half* out, cudaStream_t stream) {
+            __half* s2d_ws, __half* out, cudaStream_t stream, const uint8_t* imgs_u8, const float* mean_std) {
   int Ho, Wo, Hs, Ws;
   stem_dims(H, W, &Ho, &Wo, &Hs, &Ws);
   const int64_t total = static_cast<int64_t>(B) * Hs * Ws;
-  s2d_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(imgs, s2d_ws, H, W, Hs, Ws, total);
+  if (imgs_u8 != nullptr)
+    s2d_u8_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(
+        imgs_u8, s2d_ws, H, W, Hs, Ws, total, mean_std[0], mean_std[1], mean_std[2], mean_std[3], mean_std[4], mean_std[5]);
+  else
+    s2d_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(imgs, s2d_ws, H, W, Hs, Ws, total);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   StemParams p{};

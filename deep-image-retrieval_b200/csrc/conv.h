@@ -33,8 +33,10 @@ int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_
 // Stem 7x7/s2/p3 (3 -> 64) + BN + ReLU on tensor cores (stem_pers.cuh).  imgs: NCHW fp32; w2: [64][256] fp16 in the
 // space-to-depth tap order (pack_stem_w2); s2d_ws: scratch of stem_workspace_bytes(B,H,W); out NHWC fp16 (B,Ho,Wo,64).
 size_t stem_workspace_bytes(int B, int H, int W);
+// imgs_u8 != nullptr: the input is uint8 HWC (B,H,W,3) and is normalised on the fly with mean_std = {mean[3], std[3]}.
 int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const float* scale, const float* shift,
-            __half* s2d_ws, __half* out, cudaStream_t stream);
+            __half* s2d_ws, __half* out, cudaStream_t stream, const uint8_t* imgs_u8 = nullptr,
+            const float* mean_std = nullptr);
 // OIHW fp32 [64][3][7][7] -> [64][256] fp16 (host).
 void pack_stem_w2(const float* w_oihw, __half* out);
 int maxpool_3x3s2(const __half* in, int B, int H, int W, int C, __half* out, cudaStream_t stream);

@@ -100,6 +100,7 @@ struct dirb200_net {
   double last_flops = 0;
   int profile = 0;
   Profiler prof;
+  float mean_std[6] = {0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f};   // preprocess of resnet.py:110-111
   int fuse_ds = 1;                // fuse the projection shortcut into conv3 of block 0 (tcgen05 path only)
   int sub[5] = {0, 0, 0, 0, 0};   // images per sub-chunk of stage 0..4 (0 = auto)
   int stage_sched = 0;            // 0 = every stage over the whole chunk (fastest measured), 1 = per-stage sub-chunks
@@ -244,6 +245,8 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "profile") n->profile = value != 0;
   else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "fuse_ds") n->fuse_ds = value != 0;
+  else if (k.size() == 5 && k.compare(0, 4, "mean") == 0 && k[4] >= '0' && k[4] <= '2') n->mean_std[k[4] - '0'] = static_cast<float>(value);
+  else if (k.size() == 4 && k.compare(0, 3, "std") == 0 && k[3] >= '0' && k[3] <= '2') n->mean_std[3 + k[3] - '0'] = static_cast<float>(value);
   else if (k == "stage_sched") n->stage_sched = static_cast<int>(value);
   else if (k.size() == 4 && k.compare(0, 3, "sub") == 0 && k[3] >= '0' && k[3] <= '4') n->sub[k[3] - '0'] = static_cast<int>(value);
   else if (k == "host_chunk") n->host_chunk = std::max(1, static_cast<int>(value));
@@ -431,13 +434,15 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
 
 // One pass of the network over `cb` images (NCHW fp32 on the device) -> cb descriptors.
 static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, int cb, int H, int W, float* desc_dev,
-                     __half* desc16_dev, cudaStream_t stream) {
+                     __half* desc16_dev, cudaStream_t stream, const uint8_t* imgs_u8 = nullptr) {
   const int D = n->without_fc ? 2048 : n->out_dim;
   // ---------------------------------------------------------------- stage 0: stem + maxpool
   for (int b0 = 0; b0 < cb; b0 += w.sub[0]) {
     const int sb = std::min(w.sub[0], cb - b0);
-    const float* img = imgs_dev + static_cast<size_t>(b0) * 3 * H * W;
+    const float* img = imgs_dev ? imgs_dev + static_cast<size_t>(b0) * 3 * H * W : nullptr;
+    const uint8_t* img8 = imgs_u8 ? imgs_u8 + static_cast<size_t>(b0) * 3 * H * W : nullptr;
     if (n->conv_impl == 1) {
+      DIRB_REQUIRE(img8 == nullptr, DIRB200_ENOTSUP, "uint8 input needs the tcgen05 stem (conv_impl 0)");
       {
         ProfScope ps(n, stream, 2, 0, static_cast<double>(sb) * H * W * (12 + 16));
         DIRB_TRY(nchw_to_nhwc8(img, sb, H, W, w.stem_ws, stream));
@@ -447,7 +452,8 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
       const double flops = 2.0 * sb * w.H1 * w.W1 * 64.0 * 147.0;
       n->last_flops += flops;
       ProfScope ps(n, stream, 1, flops, static_cast<double>(sb) * (12.0 * H * W + 2.0 * stem_workspace_bytes(1, H, W) + 128.0 * w.H1 * w.W1));
-      DIRB_TRY(stem_tc(img, sb, H, W, n->stem_w2, n->stem.scale, n->stem.shift, w.stem_ws, w.stem_out, stream));
+      DIRB_TRY(stem_tc(img, sb, H, W, n->stem_w2, n->stem.scale, n->stem.shift, w.stem_ws, w.stem_out, stream, img8,
+                       n->mean_std));
     }
     ProfScope ps(n, stream, 2, 0, 2.0 * sb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.h[0]) * w.w[0]));
     DIRB_TRY(maxpool_3x3s2(w.stem_out, sb, w.H1, w.W1, 64,
@@ -547,7 +553,41 @@ int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int
 
 // Host buffers in, host descriptors out.  The batch is cut into chunks of `host_chunk` images; the H2D copy of
 // chunk i+1 (copy stream) overlaps the network pass over chunk i (compute stream), two device input buffers.
+static int forward_host_impl(dirb200_net* n, const void* imgs_host, int is_u8, int B, int H, int W, float* desc_host);
+
 int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int H, int W, float* desc_host) {
+  return forward_host_impl(n, imgs_host, 0, B, H, W, desc_host);
+}
+
+int dirb200_net_forward_host_u8(dirb200_net* n, const uint8_t* imgs_host, int B, int H, int W, float* desc_host) {
+  return forward_host_impl(n, imgs_host, 1, B, H, W, desc_host);
+}
+
+int dirb200_net_forward_u8(dirb200_net* n, const uint8_t* imgs_dev, int B, int H, int W, float* desc_dev, void* desc16_dev,
+                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(n && imgs_dev && desc_dev, DIRB200_EINVAL, "null argument");
+  DIRB_TRY(check_forward_args(n, B, H, W));
+  DIRB_CUDA(cudaSetDevice(n->device));
+  const int64_t launches0 = launches_total();
+  n->last_flops = 0;
+  n->prof.reset();
+  const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
+  const int D = n->without_fc ? 2048 : n->out_dim;
+  Workspace w;
+  DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int cb = std::min(chunk, B - b0);
+    DIRB_TRY(run_chunk(n, w, nullptr, cb, H, W, desc_dev + static_cast<size_t>(b0) * D,
+                       desc16_dev ? static_cast<__half*>(desc16_dev) + static_cast<size_t>(b0) * D : nullptr, stream,
+                       imgs_dev + static_cast<size_t>(b0) * 3 * H * W));
+  }
+  n->last_launches = launches_total() - launches0;
+  return 0;
+}
+
+static int forward_host_impl(dirb200_net* n, const void* imgs_host_, int is_u8, int B, int H, int W, float* desc_host) {
+  const uint8_t* imgs_host = static_cast<const uint8_t*>(imgs_host_);
   DIRB_REQUIRE(n && imgs_host && desc_host, DIRB200_EINVAL, "null argument");
   DIRB_TRY(check_forward_args(n, B, H, W));
   DIRB_CUDA(cudaSetDevice(n->device));
@@ -574,7 +614,7 @@ int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int 
   }
   const int nchunks = static_cast<int>(sizes.size());
   const int chunk = *std::max_element(sizes.begin(), sizes.end());
-  const size_t img_bytes = static_cast<size_t>(3) * H * W * 4;
+  const size_t img_bytes = static_cast<size_t>(3) * H * W * (is_u8 ? 1 : 4);
   const size_t in_bytes = 2 * static_cast<size_t>(chunk) * img_bytes;
   const int D = n->without_fc ? 2048 : n->out_dim;
   const size_t out_bytes = static_cast<size_t>(B) * D * 4;
@@ -603,14 +643,15 @@ int dirb200_net_forward_host(dirb200_net* n, const float* imgs_host, int B, int 
   int b0 = 0;
   for (int c = 0; c < nchunks; ++c) {
     const int cb = sizes[c];
-    float* dst = n->h2d + static_cast<size_t>(c & 1) * chunk * (img_bytes / 4);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(n->h2d) + static_cast<size_t>(c & 1) * chunk * img_bytes;
     cudaEvent_t copied = n->pipe_events[2 * c], done = n->pipe_events[2 * c + 1];
     if (c >= 2) DIRB_CUDA(cudaStreamWaitEvent(n->copy_stream, n->pipe_events[2 * (c - 2) + 1], 0));   // buffer free
-    DIRB_CUDA(cudaMemcpyAsync(dst, imgs_host + static_cast<size_t>(b0) * (img_bytes / 4), static_cast<size_t>(cb) * img_bytes,
+    DIRB_CUDA(cudaMemcpyAsync(dst, imgs_host + static_cast<size_t>(b0) * img_bytes, static_cast<size_t>(cb) * img_bytes,
                               cudaMemcpyHostToDevice, n->copy_stream));
     DIRB_CUDA(cudaEventRecord(copied, n->copy_stream));
     DIRB_CUDA(cudaStreamWaitEvent(n->own_stream, copied, 0));
-    DIRB_TRY(run_chunk(n, w, dst, cb, H, W, n->d_desc + static_cast<size_t>(b0) * D, nullptr, n->own_stream));
+    DIRB_TRY(run_chunk(n, w, is_u8 ? nullptr : reinterpret_cast<const float*>(dst), cb, H, W,
+                       n->d_desc + static_cast<size_t>(b0) * D, nullptr, n->own_stream, is_u8 ? dst : nullptr));
     DIRB_CUDA(cudaEventRecord(done, n->own_stream));
     b0 += cb;
   }

@@ -222,6 +222,34 @@ class ResNetRMAC:
         lib.call("dirb200_net_forward_host", h, a.ctypes.data_as(C.c_void_p), b, hgt, wid, out.ctypes.data_as(C.c_void_p))
         return out
 
+    def forward_u8(self, imgs_u8: torch.Tensor):
+        """uint8 HWC CUDA tensor (B,H,W,3) -> descriptors; ToTensor + Normalize(self.preprocess) run inside the stem."""
+        if not (imgs_u8.is_cuda and imgs_u8.dtype == torch.uint8 and imgs_u8.dim() == 4 and imgs_u8.shape[3] == 3):
+            raise TypeError("expected a (B,H,W,3) uint8 CUDA tensor")
+        x = imgs_u8.contiguous()
+        b, hgt, wid, _ = x.shape
+        h = self._ensure_with_preprocess(x.device.index or 0)
+        desc = torch.empty((b, self.descriptor_dim), dtype=torch.float32, device=x.device)
+        lib.call("dirb200_net_forward_u8", h, C.c_void_p(x.data_ptr()), b, hgt, wid, C.c_void_p(desc.data_ptr()),
+                 C.c_void_p(0), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return desc[0] if b == 1 else desc
+
+    def forward_host_u8(self, imgs_u8: np.ndarray, device=0) -> np.ndarray:
+        """Host uint8 HWC array (B,H,W,3) in, host descriptors out (H2D of 3 bytes/pixel instead of 12)."""
+        a = np.ascontiguousarray(imgs_u8, dtype=np.uint8)
+        b, hgt, wid, _ = a.shape
+        h = self._ensure_with_preprocess(device)
+        out = np.empty((b, self.descriptor_dim), dtype=np.float32)
+        lib.call("dirb200_net_forward_host_u8", h, a.ctypes.data_as(C.c_void_p), b, hgt, wid, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def _ensure_with_preprocess(self, device_index):
+        h = self._ensure(device_index)
+        for i in range(3):
+            lib.call("dirb200_net_set_option", h, ("mean%d" % i).encode(), float(self.preprocess["mean"][i]))
+            lib.call("dirb200_net_set_option", h, ("std%d" % i).encode(), float(self.preprocess["std"][i]))
+        return h
+
     def debug_stage(self, what):
         """NHWC fp16 activation after 'stem' / 'layer1'..'layer4' of the last chunk of the last forward."""
         dims = (C.c_int * 4)()

@@ -72,6 +72,13 @@ int dirb200_net_forward(dirb200_net* net, const float* imgs_dev, int B, int H, i
  * chunks of "host_chunk" images (option, default 16) with the H2D copy of the next chunk overlapping the compute
  * of the current one; pass pinned memory for the overlap to take effect. */
 int dirb200_net_forward_host(dirb200_net* net, const float* imgs_host, int B, int H, int W, float* desc_host);
+/* uint8 input (what an image decoder yields): imgs = HWC uint8 pixels (B,H,W,3); ToTensor + Normalize(mean,std)
+ * (dirtorch/utils/transforms.py:27; options "mean0".."mean2", "std0".."std2", default = ImageNet values of
+ * resnet.py:110-111) are applied on the fly in the stem's input stage, bit-identically to the fp32 entry points.
+ * 4x fewer host->device bytes than the fp32 path (first step). */
+int dirb200_net_forward_u8(dirb200_net* net, const uint8_t* imgs_dev, int B, int H, int W, float* desc_dev,
+                           void* desc16_dev, void* stream);
+int dirb200_net_forward_host_u8(dirb200_net* net, const uint8_t* imgs_host, int B, int H, int W, float* desc_host);
 /* Debug tap (needs option "debug_taps"): copy the NHWC fp16 activation after stage `what` ("stem","layer1".."layer4")
  * of the LAST chunk of the last forward into dst_dev (capacity in bytes); returns its dims as {n,h,w,c}. */
 int dirb200_net_debug_stage(dirb200_net* net, const char* what, void* dst_dev, size_t capacity, int dims[4],

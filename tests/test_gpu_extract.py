@@ -112,3 +112,16 @@ def test_multiscale_pool_matches_oracle():
     pooled = ops.pool_scales(descs_gpu, "gem", 3, l2=True).cpu().numpy()
     ref = O.l2n(O.pool_scales(descs_ref, "gem", 3))
     assert rel_l2(pooled, ref) < TOL
+
+
+def test_uint8_input_is_bit_identical_to_fp32_input():
+    """ToTensor + Normalize fused into the stem input stage (uint8 HWC in): same descriptors, bit for bit."""
+    net, sd = _net("resnet50_rmac", 0)
+    u8 = synth.make_images_u8(3, 130, 174, seed=12)
+    x = synth.normalise_images(u8)
+    d_f32 = net(x.cuda()).cpu().numpy()
+    d_u8 = net.forward_u8(torch.from_numpy(u8).cuda()).cpu().numpy()
+    assert np.array_equal(d_u8, d_f32)
+    assert np.array_equal(net.forward_host_u8(u8), d_f32)
+    ref = O.extract(x, sd, "resnet50_rmac").numpy()
+    assert rel_l2(d_u8, ref) < TOL
