@@ -6,6 +6,7 @@
 
 namespace dirb {
 
+int g_use_pdl = 1;
 static thread_local char g_err[1024] = "";
 static std::atomic<int64_t> g_launches{0};
 

@@ -49,6 +49,24 @@ int encode_tmap_nhwc16(CUtensorMap* m, const void* base, int B, int H, int W, in
 int encode_tmap_2d_sw32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                         uint32_t box_outer);
 
+// Launch `kern` with programmatic stream serialization (PDL): its CTAs may start while the previous kernel of the
+// stream drains; the kernel must call pdl_wait() before touching data produced by its predecessor.
+extern int g_use_pdl;
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // Launch counter (the "gpu_launches" the benchmark reports): every kernel launch of this library bumps it.
 void count_launch(int n = 1);
 int64_t launches_total();

@@ -361,9 +361,8 @@ int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const floa
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, 64, p.tw, p.th, p.nb, 1));
   DIRB_CUDA(cudaFuncSetAttribute(stem_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::TOTAL));
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  stem_pers_kernel<<<grid, 256, StemSmem::TOTAL, stream>>>(tmS, tmW, tmO, p);
+  DIRB_CUDA(launch_pdl(stem_pers_kernel, dim3(grid), dim3(256), StemSmem::TOTAL, stream, tmS, tmW, tmO, p));
   count_launch();
-  DIRB_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -83,6 +83,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may start its own prologue while this one runs / drains
+  pdl_wait();                // everything below reads tensors written by the previous kernel of the stream
 
   if (warp == 0) {
     if (lane == 0) {
@@ -220,9 +222,8 @@ int conv_halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   auto kern = conv_halo_kernel<BN, BSTAGES, NB, BRES, NA_>;
   DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  kern<<<grid, PersThreads<0>::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmR, tmO, p);
+  DIRB_CUDA(launch_pdl(kern, dim3(grid), dim3(PersThreads<0>::THREADS), L::TOTAL, stream, tmA, tmB, tmR, tmO, p));
   count_launch();
-  DIRB_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -93,6 +93,8 @@ stem_pers_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may start its own prologue while this one runs / drains
+  pdl_wait();                // everything below reads tensors written by the previous kernel of the stream
 
   auto tile_origin = [&](int t, int& wo0, int& ho0, int& n0) {
     const int tx = t % p.tiles_w;
