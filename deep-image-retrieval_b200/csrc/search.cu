@@ -112,18 +112,20 @@ __global__ void dense_compact_kernel(const float* __restrict__ dense, int64_t ld
   }
 }
 
-// Per query: exact k-th largest candidate score, survivors = candidates >= kth - band.
-// flags[q]: bit0 = candidate overflow (cnt > cap), bit1 = survivor overflow.  On candidate overflow the new
-// (tighter, still valid) threshold kth(captured) - band is written to thr[q]; otherwise thr[q] = +inf so that a
-// re-run of the filter pass leaves this query alone.
-__global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(const unsigned long long* __restrict__ cand,
-                                                                  const int* __restrict__ cnt, int cap, int k, float band,
-                                                                  int* __restrict__ surv_idx, int* __restrict__ surv_cnt,
-                                                                  int cap2, float* __restrict__ thr,
-                                                                  int* __restrict__ flags, int64_t n_rows) {
+// Per query: exact k-th and k_shard-th largest candidate scores (fp16-path scores).
+//   kth_k[q]  : local k-th best - always a valid lower bound on the global k-th best
+//   sel[q]    : local k_shard-th best (k_shard = ceil(k / shards)); the MINIMUM of this value over all shards is a
+//               valid and much tighter lower bound on the global k-th best (every shard holds >= k_shard rows at or
+//               above its own value, hence >= k rows lie at or above the minimum) - the caller min-reduces it.
+// flags[q] bit0 = candidate overflow (cnt > cap): the tighter threshold kth(captured) - band is written to thr[q];
+// otherwise thr[q] = +inf so that a re-run of the filter pass leaves this query alone.
+__global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned long long* __restrict__ cand,
+                                                               const int* __restrict__ cnt, int cap, int k, int k_shard,
+                                                               float band, float* __restrict__ kth_k,
+                                                               float* __restrict__ sel, float* __restrict__ thr,
+                                                               int* __restrict__ flags, int64_t n_rows) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bc[2];
-  __shared__ int s_n;
   const int q = blockIdx.x;
   const int total = cnt[q];
   const int n = min(total, cap);
@@ -134,13 +136,36 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(const unsigned
     if (threadIdx.x == 0) {
       thr[q] = t - band;
       flags[q] = 1;
-      surv_cnt[q] = 0;
     }
     return;
   }
+  float ts = t;
+  if (k_shard < kk) {
+    __syncthreads();
+    ts = block_kth_largest(CandAcc{c}, n, k_shard, hist, bc);
+  }
+  if (threadIdx.x == 0) {
+    kth_k[q] = t;
+    sel[q] = ts;
+    flags[q] = 0;
+    thr[q] = INFINITY;
+  }
+}
+
+// Survivors = candidates with score >= max(sel[q], kth_k[q]) - band.  flags[q] bit1 = more than cap2 survivors.
+__global__ void __launch_bounds__(SEL_THREADS) cand_survivors_kernel(const unsigned long long* __restrict__ cand,
+                                                                     const int* __restrict__ cnt, int cap,
+                                                                     const float* __restrict__ kth_k,
+                                                                     const float* __restrict__ sel, float band,
+                                                                     int* __restrict__ surv_idx, int* __restrict__ surv_cnt,
+                                                                     int cap2, int* __restrict__ flags) {
+  __shared__ int s_n;
+  const int q = blockIdx.x;
+  const int n = min(cnt[q], cap);
+  const unsigned long long* c = cand + static_cast<int64_t>(q) * cap;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  const float t2 = t - band;
+  const float t2 = fmaxf(sel[q], kth_k[q]) - band;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long e = c[i];
     if (__uint_as_float(static_cast<uint32_t>(e >> 32)) >= t2) {
@@ -152,7 +177,6 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_select_kernel(const unsigned
   if (threadIdx.x == 0) {
     surv_cnt[q] = min(s_n, cap2);
     flags[q] = (s_n > cap2) ? 2 : 0;
-    thr[q] = INFINITY;
   }
 }
 
@@ -181,10 +205,13 @@ __global__ void rescore_kernel(const float* __restrict__ q32, const float* __res
 
 // Per query: bitonic sort of (score desc, index asc), write the first k.  Also used to merge shard lists.
 // in_idx is int32 local rows (+offset) when idx32 != nullptr, else int64 global indices from idx64.
+// With shard_k > 0 the input is G shard lists read in place: entry i of query q = element (i % shard_k) of shard
+// (i / shard_k), i.e. in[(i / shard_k) * shard_stride + q * shard_k + i % shard_k] (the all-gather buffer layout).
 __global__ void __launch_bounds__(1024) sort_topk_kernel(const double* __restrict__ in_score, const int* __restrict__ idx32,
                                                          const int64_t* __restrict__ idx64, const int* __restrict__ cnts,
                                                          int fixed_cnt, int stride, int64_t offset, int k,
-                                                         double* __restrict__ out_score, int64_t* __restrict__ out_idx) {
+                                                         double* __restrict__ out_score, int64_t* __restrict__ out_idx,
+                                                         int shard_k = 0, int64_t shard_stride = 0) {
   extern __shared__ uint8_t sm[];
   const int q = blockIdx.x;
   const int n = cnts ? cnts[q] : fixed_cnt;
@@ -195,9 +222,10 @@ __global__ void __launch_bounds__(1024) sort_topk_kernel(const double* __restric
   int64_t* ix = reinterpret_cast<int64_t*>(sc + P);
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     if (i < n) {
-      sc[i] = in_score[static_cast<int64_t>(q) * stride + i];
-      ix[i] = idx32 ? (static_cast<int64_t>(idx32[static_cast<int64_t>(q) * stride + i]) + offset)
-                    : idx64[static_cast<int64_t>(q) * stride + i];
+      const int64_t src = shard_k > 0 ? (static_cast<int64_t>(i / shard_k) * shard_stride + static_cast<int64_t>(q) * shard_k + i % shard_k)
+                                      : (static_cast<int64_t>(q) * stride + i);
+      sc[i] = in_score[src];
+      ix[i] = idx32 ? (static_cast<int64_t>(idx32[src]) + offset) : idx64[src];
       if (ix[i] < 0) sc[i] = -INFINITY;  // empty slots of a shard list
     } else {
       sc[i] = -INFINITY;
@@ -317,6 +345,19 @@ struct dirb200_index {
   int* h_flags = nullptr;  // pinned
   int h_flags_n = 0;
   int64_t stats[5] = {0, 0, 0, 0, 0};
+  float* sel_own = nullptr;        // selection thresholds of the single-shard entry point
+  size_t sel_bytes = 0;
+  // state of a search between dirb200_index_search_begin and _finish
+  struct Pending {
+    bool active = false;
+    int Q = 0, k = 0, cap = 0, cap2 = 0, retries = 0, mark_i = 0;
+    int64_t S = 0, launches0 = 0;
+    float band = 0;
+    int *cnt = nullptr, *sidx = nullptr, *scnt = nullptr, *flags = nullptr;
+    unsigned long long* cand = nullptr;
+    double* sscore = nullptr;
+    float *kth_k = nullptr, *sel = nullptr;
+  } pend;
   int profile = 0;                 // option "profile": time the phases of a search with CUDA events
   cudaEvent_t ev[10] = {};
   double phase_ms[9] = {};
@@ -407,27 +448,42 @@ int dirb200_index_destroy(dirb200_index* h) {
   if (!h) return 0;
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
+  if (h->sel_own) cudaFree(h->sel_own);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   delete h;
   return 0;
 }
 
-int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, double* scores_dev, int64_t* idx_dev,
-                         void* stream_) {
+static void mark_phase(dirb200_index* h, cudaStream_t stream) {
+  if (!h->profile || h->pend.mark_i >= 10) return;
+  if (!h->ev[h->pend.mark_i]) cudaEventCreate(&h->ev[h->pend.mark_i]);
+  cudaEventRecord(h->ev[h->pend.mark_i++], stream);
+}
+
+// Phase 1: fp16 queries, seed pass, filter pass (with overflow retries), local k-th / k_shard-th candidate scores.
+// sel_dev[Q] receives the local k_shard-th best fp16-path score per query; with several shards the caller
+// MIN-reduces it over the shards before phase 2 (k_shard = ceil(k / shards)); with one shard k_shard = k.
+int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k, int k_shard, float* sel_dev,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DIRB_REQUIRE(h && q32 && scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(h && q32 && sel_dev, DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(h->db32 != nullptr, DIRB200_ESTATE, "index has no database attached");
   DIRB_REQUIRE(Q > 0 && k > 0 && k <= 1024, DIRB200_ENOTSUP, "need 0 < Q and 0 < k <= 1024 (got Q=%d k=%d)", Q, k);
+  DIRB_REQUIRE(k_shard >= 1 && k_shard <= k, DIRB200_EINVAL, "k_shard must be in [1, k]");
   DIRB_CUDA(cudaSetDevice(h->device));
   const int D = h->dim;
   const int64_t N = h->N;
-  const int64_t launches0 = launches_total();
-  const int cap2 = (k > 256) ? 2048 : 1024;
-  if (N == 0) {
-    std::vector<double> s(static_cast<size_t>(Q) * k, -INFINITY);
-    std::vector<int64_t> ix(static_cast<size_t>(Q) * k, -1);
-    DIRB_CUDA(cudaMemcpyAsync(scores_dev, s.data(), s.size() * 8, cudaMemcpyHostToDevice, stream));
-    DIRB_CUDA(cudaMemcpyAsync(idx_dev, ix.data(), ix.size() * 8, cudaMemcpyHostToDevice, stream));
+  auto& P = h->pend;
+  P = dirb200_index::Pending();
+  P.active = true;
+  P.Q = Q;
+  P.k = k;
+  P.launches0 = launches_total();
+  P.cap2 = (k > 256) ? 2048 : 1024;
+  const int cap2 = P.cap2;
+  if (N == 0) {   // empty shard: nothing can be selected; +inf never lowers the MIN over the shards
+    std::vector<float> inf(Q, INFINITY);
+    DIRB_CUDA(cudaMemcpyAsync(sel_dev, inf.data(), static_cast<size_t>(Q) * 4, cudaMemcpyHostToDevice, stream));
     DIRB_CUDA(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -446,6 +502,9 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   if (h->cand_cap > 0) cap = std::max(h->cand_cap, 2 * k);
   cap = (cap + 255) / 256 * 256;
   const float band = static_cast<float>(2.0 * h->eps16);
+  P.S = S;
+  P.cap = cap;
+  P.band = band;
 
   // ---- workspace carve-up
   size_t off = 0;
@@ -459,6 +518,7 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   const size_t o_sscore = carve(static_cast<size_t>(Q) * cap2 * 8);
   const size_t o_scnt = carve(static_cast<size_t>(Q) * 4);
   const size_t o_flags = carve(static_cast<size_t>(Q) * 4);
+  const size_t o_kthk = carve(static_cast<size_t>(Q) * 4);
   if (off > h->ws_bytes) {
     if (h->ws) DIRB_CUDA(cudaFree(h->ws));
     h->ws = nullptr;
@@ -474,39 +534,35 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   __half* q16 = reinterpret_cast<__half*>(w + o_q16);
   float* dense = reinterpret_cast<float*>(w + o_dense);
   float* thr = reinterpret_cast<float*>(w + o_thr);
-  int* cnt = reinterpret_cast<int*>(w + o_cnt);
-  unsigned long long* cand = reinterpret_cast<unsigned long long*>(w + o_cand);
-  int* sidx = reinterpret_cast<int*>(w + o_sidx);
-  double* sscore = reinterpret_cast<double*>(w + o_sscore);
-  int* scnt = reinterpret_cast<int*>(w + o_scnt);
-  int* flags = reinterpret_cast<int*>(w + o_flags);
+  P.cnt = reinterpret_cast<int*>(w + o_cnt);
+  P.cand = reinterpret_cast<unsigned long long*>(w + o_cand);
+  P.sidx = reinterpret_cast<int*>(w + o_sidx);
+  P.sscore = reinterpret_cast<double*>(w + o_sscore);
+  P.scnt = reinterpret_cast<int*>(w + o_scnt);
+  P.flags = reinterpret_cast<int*>(w + o_flags);
+  P.kth_k = reinterpret_cast<float*>(w + o_kthk);
+  P.sel = sel_dev;
+  int* cnt = P.cnt;
+  unsigned long long* cand = P.cand;
 
-  int mark_i = 0;
-  auto mark = [&]() {
-    if (!h->profile) return;
-    if (!h->ev[mark_i]) cudaEventCreate(&h->ev[mark_i]);
-    cudaEventRecord(h->ev[mark_i++], stream);
-  };
-  mark();  // 0
+  mark_phase(h, stream);  // 0
   // ---- 1. queries to fp16
   DIRB_TRY(f32_to_f16(q32, static_cast<int64_t>(Q) * D, q16, stream));
-  mark();  // 1: convert
+  mark_phase(h, stream);  // 1: convert
   // ---- 2. seed pass over the first S rows
   {
     SimArgs a;
     a.dense = dense;
     a.dense_ld = S_ld;
     DIRB_TRY(sim_gemm(use_gmax ? PERS_EPI_SIM_GMAX : PERS_EPI_SIM_DENSE, q16, Q, h->db16, S, D, a, stream));
-    mark();  // 2: seed GEMM
+    mark_phase(h, stream);  // 2: seed GEMM
     const int n_vals = use_gmax ? static_cast<int>(ceil_div(S, 32)) : static_cast<int>(S);
     const int kk = static_cast<int>(std::min<int64_t>(k, n_vals));
     kth_dense_kernel<<<Q, SEL_THREADS, 0, stream>>>(dense, S_ld, n_vals, kk, band, thr);
     count_launch();
-    mark();  // 3: k-th of the seed scores
+    mark_phase(h, stream);  // 3: k-th of the seed scores
   }
   DIRB_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(Q) * 4, stream));
-  int retries = 0;
-  int64_t cand_total = 0, surv_total = 0;
   for (;;) {
     // ---- 3. candidates
     if (small) {
@@ -521,66 +577,105 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
       a.cand_cap = cap;
       DIRB_TRY(sim_gemm(PERS_EPI_SIM_FILTER, q16, Q, h->db16, N, D, a, stream));
     }
-    if (retries == 0) mark();  // 4: filter pass
-    // ---- 4. select survivors
-    cand_select_kernel<<<Q, SEL_THREADS, 0, stream>>>(cand, cnt, cap, k, band, sidx, scnt, cap2, thr, flags, N);
+    if (P.retries == 0) mark_phase(h, stream);  // 4: filter pass
+    // ---- 4. local k-th / k_shard-th candidate scores
+    cand_kth_kernel<<<Q, SEL_THREADS, 0, stream>>>(cand, cnt, cap, k, std::min<int>(k_shard, static_cast<int>(std::min<int64_t>(k, N))), band,
+                                                   P.kth_k, sel_dev, thr, P.flags, N);
     count_launch();
-    if (retries == 0) mark();  // 5: candidate selection
-    DIRB_CUDA(cudaMemcpyAsync(h->h_flags, flags, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
+    if (P.retries == 0) mark_phase(h, stream);  // 5: candidate selection
+    DIRB_CUDA(cudaMemcpyAsync(h->h_flags, P.flags, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
     DIRB_CUDA(cudaStreamSynchronize(stream));
-    bool cand_over = false, surv_over = false;
+    bool cand_over = false;
+    for (int i = 0; i < Q; ++i) cand_over |= (h->h_flags[i] & 1) != 0;
+    if (!cand_over) break;
+    DIRB_REQUIRE(P.retries < 4, DIRB200_EOVERFLOW, "candidate buffer overflow not resolved after %d retries", P.retries);
+    ++P.retries;
+    // Overflowed queries restart from an empty list with the tightened threshold that cand_kth wrote.  Finished
+    // queries have thr = +inf, so the re-run appends nothing for them and the (idempotent) selection reproduces
+    // their values from the unchanged list.
+    for (int i = 0; i < Q; ++i)
+      if (h->h_flags[i] & 1) DIRB_CUDA(cudaMemsetAsync(cnt + i, 0, 4, stream));
+  }
+  mark_phase(h, stream);  // 6: flags round trip
+  return 0;
+}
+
+// Phase 2: survivors (candidates within the band of max(sel, local k-th)), exact re-scoring, ordered output.
+int dirb200_index_search_finish(dirb200_index* h, const float* q32, const float* sel_dev, double* scores_dev,
+                                int64_t* idx_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(h && q32 && sel_dev && scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
+  auto& P = h->pend;
+  DIRB_REQUIRE(P.active, DIRB200_ESTATE, "dirb200_index_search_finish without a matching _begin");
+  DIRB_CUDA(cudaSetDevice(h->device));
+  const int Q = P.Q, k = P.k, cap2 = P.cap2;
+  P.active = false;
+  if (h->N == 0) {
+    std::vector<double> s(static_cast<size_t>(Q) * k, -INFINITY);
+    std::vector<int64_t> ix(static_cast<size_t>(Q) * k, -1);
+    DIRB_CUDA(cudaMemcpyAsync(scores_dev, s.data(), s.size() * 8, cudaMemcpyHostToDevice, stream));
+    DIRB_CUDA(cudaMemcpyAsync(idx_dev, ix.data(), ix.size() * 8, cudaMemcpyHostToDevice, stream));
+    DIRB_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  cand_survivors_kernel<<<Q, SEL_THREADS, 0, stream>>>(P.cand, P.cnt, P.cap, P.kth_k, sel_dev, P.band, P.sidx, P.scnt, cap2,
+                                                       P.flags);
+  {
+    dim3 g(static_cast<unsigned>(ceil_div(cap2, 8)), static_cast<unsigned>(Q));
+    rescore_kernel<<<g, 256, 0, stream>>>(q32, h->db32, h->dim, P.sidx, P.scnt, cap2, P.sscore);
+    mark_phase(h, stream);  // 7: survivors + exact re-scoring
+    const size_t smem = static_cast<size_t>(cap2) * 16;
+    DIRB_CUDA(cudaFuncSetAttribute(sort_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+    sort_topk_kernel<<<Q, 1024, smem, stream>>>(P.sscore, P.sidx, nullptr, P.scnt, 0, cap2, h->offset, k, scores_dev, idx_dev);
+    count_launch(3);
+    DIRB_CUDA(cudaGetLastError());
+    mark_phase(h, stream);  // 8: sort
+  }
+  int64_t cand_total = 0, surv_total = 0;
+  {
+    std::vector<int> hc(Q), hs(Q);
+    DIRB_CUDA(cudaMemcpyAsync(hc.data(), P.cnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
+    DIRB_CUDA(cudaMemcpyAsync(hs.data(), P.scnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
+    DIRB_CUDA(cudaMemcpyAsync(h->h_flags, P.flags, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
+    DIRB_CUDA(cudaStreamSynchronize(stream));
+    bool surv_over = false;
     for (int i = 0; i < Q; ++i) {
-      cand_over |= (h->h_flags[i] & 1) != 0;
+      cand_total += hc[i];
+      surv_total += hs[i];
       surv_over |= (h->h_flags[i] & 2) != 0;
     }
     DIRB_REQUIRE(!surv_over, DIRB200_EOVERFLOW,
                  "more than %d rows within 2*eps16=%g of the k-th score for some query (near-duplicate rows?)", cap2,
-                 (double)band);
-    if (!cand_over) break;
-    DIRB_REQUIRE(retries < 4, DIRB200_EOVERFLOW, "candidate buffer overflow not resolved after %d retries", retries);
-    ++retries;
-    // Overflowed queries restart from an empty list with the tightened threshold that cand_select wrote.  Finished
-    // queries have thr = +inf, so the re-run appends nothing for them and the (idempotent) select reproduces
-    // their survivors from the unchanged list.
-    for (int i = 0; i < Q; ++i)
-      if (h->h_flags[i] & 1) DIRB_CUDA(cudaMemsetAsync(cnt + i, 0, 4, stream));
+                 (double)P.band);
   }
-  // ---- 5. exact rescoring + ordering
-  {
-    dim3 g(static_cast<unsigned>(ceil_div(cap2, 8)), static_cast<unsigned>(Q));
-    mark();  // 6: flags round trip
-    rescore_kernel<<<g, 256, 0, stream>>>(q32, h->db32, D, sidx, scnt, cap2, sscore);
-    mark();  // 7: exact re-scoring
-    const size_t smem = static_cast<size_t>(cap2) * 16;
-    DIRB_CUDA(cudaFuncSetAttribute(sort_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-    sort_topk_kernel<<<Q, 1024, smem, stream>>>(sscore, sidx, nullptr, scnt, 0, cap2, h->offset, k, scores_dev, idx_dev);
-    count_launch(2);
-    DIRB_CUDA(cudaGetLastError());
-    mark();  // 8: sort
-  }
-  {
-    std::vector<int> hc(Q), hs(Q);
-    DIRB_CUDA(cudaMemcpyAsync(hc.data(), cnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
-    DIRB_CUDA(cudaMemcpyAsync(hs.data(), scnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
-    DIRB_CUDA(cudaStreamSynchronize(stream));
-    for (int i = 0; i < Q; ++i) {
-      cand_total += hc[i];
-      surv_total += hs[i];
-    }
-  }
-  if (h->profile && mark_i == 9) {
+  if (h->profile && P.mark_i == 9) {
     for (int i = 0; i < 8; ++i) {
       float ms = 0;
       cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
       h->phase_ms[i] = ms;
     }
   }
-  h->stats[0] = S;
+  h->stats[0] = P.S;
   h->stats[1] = cand_total;
   h->stats[2] = surv_total;
-  h->stats[3] = retries;
-  h->stats[4] = launches_total() - launches0;
+  h->stats[3] = P.retries;
+  h->stats[4] = launches_total() - P.launches0;
   return 0;
+}
+
+// Single-shard search = phase 1 with k_shard = k followed directly by phase 2.
+int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, double* scores_dev, int64_t* idx_dev,
+                         void* stream_) {
+  DIRB_REQUIRE(h && q32 && scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(Q > 0, DIRB200_ENOTSUP, "need Q > 0");
+  if (static_cast<size_t>(Q) * 4 > h->sel_bytes) {
+    if (h->sel_own) cudaFree(h->sel_own);
+    h->sel_own = nullptr;
+    DIRB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->sel_own), static_cast<size_t>(Q) * 4));
+    h->sel_bytes = static_cast<size_t>(Q) * 4;
+  }
+  DIRB_TRY(dirb200_index_search_begin(h, q32, Q, k, k, h->sel_own, stream_));
+  return dirb200_index_search_finish(h, q32, h->sel_own, scores_dev, idx_dev, stream_);
 }
 
 int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, int64_t shard_stride,
@@ -589,30 +684,16 @@ int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, 
   DIRB_REQUIRE(scores_dev && idx_dev && out_scores_dev && out_idx_dev, DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(G >= 1 && Q >= 1 && k >= 1 && static_cast<int64_t>(G) * k <= 4096, DIRB200_ENOTSUP,
                "merge supports G*k <= 4096 (got G=%d k=%d)", G, k);
-  // shard g holds [Q][k] at element offset g*shard_stride; the kernel wants the G lists of one query contiguous
+  // shard g holds [Q][k] at element offset g*shard_stride; the sort kernel gathers the G lists of a query in place
   if (shard_stride <= 0) shard_stride = static_cast<int64_t>(Q) * k;
   const int n = G * k;
-  double* tmp_s = nullptr;
-  int64_t* tmp_i = nullptr;
-  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp_s), static_cast<size_t>(Q) * n * 8, stream));
-  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp_i), static_cast<size_t>(Q) * n * 8, stream));
-  for (int g = 0; g < G; ++g) {
-    DIRB_CUDA(cudaMemcpy2DAsync(tmp_s + static_cast<size_t>(g) * k, static_cast<size_t>(n) * 8,
-                                scores_dev + static_cast<size_t>(g) * shard_stride, static_cast<size_t>(k) * 8,
-                                static_cast<size_t>(k) * 8, Q, cudaMemcpyDeviceToDevice, stream));
-    DIRB_CUDA(cudaMemcpy2DAsync(tmp_i + static_cast<size_t>(g) * k, static_cast<size_t>(n) * 8,
-                                idx_dev + static_cast<size_t>(g) * shard_stride, static_cast<size_t>(k) * 8,
-                                static_cast<size_t>(k) * 8, Q, cudaMemcpyDeviceToDevice, stream));
-  }
   int P = 2;
   while (P < n) P <<= 1;
   DIRB_CUDA(cudaFuncSetAttribute(sort_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-  sort_topk_kernel<<<Q, 1024, static_cast<size_t>(P) * 16, stream>>>(tmp_s, nullptr, tmp_i, nullptr, n, n, 0, k,
-                                                                    out_scores_dev, out_idx_dev);
+  sort_topk_kernel<<<Q, 1024, static_cast<size_t>(P) * 16, stream>>>(scores_dev, nullptr, idx_dev, nullptr, n, n, 0, k,
+                                                                    out_scores_dev, out_idx_dev, k, shard_stride);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
-  DIRB_CUDA(cudaFreeAsync(tmp_s, stream));
-  DIRB_CUDA(cudaFreeAsync(tmp_i, stream));
   return 0;
 }
 

@@ -45,8 +45,19 @@ class ShardedIndex:
         return packed
 
     def search(self, q32: torch.Tensor, k: int):
-        """Global exact top-k: local search -> one all-gather -> merge.  Returns (scores fp64, idx int64), (Q,k)."""
-        packed = self.search_local(q32, k)
+        """Global exact top-k.  Phase 1 on every shard (tensor-core passes) -> MIN all-reduce of the per-query
+        selection thresholds (4*Q bytes: the local ceil(k/G)-th best scores bound the global k-th best, so each shard
+        re-scores only ~k/G rows) -> phase 2 (exact re-scoring) -> one all-gather of the per-shard lists -> merge.
+        Returns (scores fp64, idx int64), (Q,k)."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            packed = self.search_local(q32, k)
+            return self.ops.topk_merge_packed(packed.unsqueeze(0), k)
+        k_shard = -(-k // world)
+        sel = self.local.search_begin(q32, k, k_shard)
+        dist.all_reduce(sel, op=dist.ReduceOp.MIN, group=self.group)
+        packed = torch.empty((2, q32.shape[0], k), dtype=torch.int64, device=q32.device)
+        self.local.search_finish(q32, k, sel, out=packed)
         gathered = all_gather_packed(packed, self.group)
         return self.ops.topk_merge_packed(gathered, k)
 

@@ -64,6 +64,8 @@ SIGNATURES = {
     "dirb200_index_set_db": (i32, [p, p, p, i64, i64]),
     "dirb200_index_set_option": (i32, [p, C.c_char_p, f64]),
     "dirb200_index_search": (i32, [p, p, i32, i32, p, p, p]),
+    "dirb200_index_search_begin": (i32, [p, p, i32, i32, i32, p, p]),
+    "dirb200_index_search_finish": (i32, [p, p, p, p, p, p]),
     "dirb200_index_last_stats": (i32, [p, C.POINTER(i64)]),
     "dirb200_index_last_profile": (i32, [p, C.POINTER(f64)]),
     "dirb200_index_destroy": (i32, [p]),

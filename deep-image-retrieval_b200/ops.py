@@ -234,6 +234,25 @@ class Index:
         lib.call("dirb200_index_search", self._h, _ptr(q32), nq, int(k), _ptr(scores), _ptr(idx), _stream())
         return scores, idx
 
+    def search_begin(self, q32: torch.Tensor, k: int, k_shard: int):
+        """Phase 1 of a sharded search -> sel (Q,) fp32: local k_shard-th best fp16-path score (MIN-reduce it)."""
+        _chk(q32, torch.float32, "q32")
+        sel = torch.empty(q32.shape[0], dtype=torch.float32, device=q32.device)
+        lib.call("dirb200_index_search_begin", self._h, _ptr(q32), q32.shape[0], int(k), int(k_shard), _ptr(sel), _stream())
+        return sel
+
+    def search_finish(self, q32: torch.Tensor, k: int, sel: torch.Tensor, out=None):
+        """Phase 2: exact re-scoring of the rows within the band of the (reduced) threshold -> ordered local list."""
+        nq = q32.shape[0]
+        if out is not None:
+            scores, idx = out[0].view(torch.float64), out[1]
+        else:
+            scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
+            idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
+        lib.call("dirb200_index_search_finish", self._h, _ptr(q32), _ptr(_chk(sel, torch.float32, "sel")), _ptr(scores),
+                 _ptr(idx), _stream())
+        return scores, idx
+
     def stats(self):
         arr = (C.c_int64 * 5)()
         lib.call("dirb200_index_last_stats", self._h, arr)

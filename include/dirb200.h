@@ -156,11 +156,21 @@ int dirb200_index_set_option(dirb200_index* idx, const char* key, double value);
  * If N < k the tail is filled with score -inf / index -1.  Synchronises the stream (overflow check). */
 int dirb200_index_search(dirb200_index* idx, const float* q32_dev, int Q, int k, double* scores_dev,
                          int64_t* idx_dev, void* stream);
+/* The same search in two phases, for a database sharded over several GPUs.  Phase 1 runs the tensor-core passes and
+ * writes to sel_dev[Q] (caller-owned) the local k_shard-th best fp16-path score per query, k_shard = ceil(k / shards).
+ * The caller MIN-reduces sel_dev over the shards (ncclAllReduce, 4*Q bytes): every shard holds >= k_shard rows at or
+ * above its own value, so >= k rows of the whole database lie at or above the minimum - a valid, tight lower bound
+ * on the global k-th best that lets each shard re-score only ~1.4 * k / shards rows instead of ~1.4 * k.  Phase 2
+ * re-scores the rows within the band of max(sel_dev[q], local k-th) exactly and returns the shard's ordered list. */
+int dirb200_index_search_begin(dirb200_index* idx, const float* q32_dev, int Q, int k, int k_shard, float* sel_dev,
+                               void* stream);
+int dirb200_index_search_finish(dirb200_index* idx, const float* q32_dev, const float* sel_dev, double* scores_dev,
+                                int64_t* idx_dev, void* stream);
 /* Statistics of the last search: {dense_rows, candidates_total, survivors_total, retries, launches}. */
 int dirb200_index_last_stats(dirb200_index* idx, int64_t stats[5]);
 /* With option "profile" = 1: CUDA-event milliseconds of the phases of the last search, out9[0..7] = {query fp16
- * conversion, seed GEMM, seed k-th select, filter GEMM, candidate select, flag round trip to the host, exact
- * re-scoring, sort}. */
+ * conversion, seed GEMM, seed k-th select, filter GEMM, candidate k-th select, flag round trip to the host (+ any
+ * cross-shard exchange between the phases), survivors + exact re-scoring, sort}. */
 int dirb200_index_last_profile(dirb200_index* idx, double out9[9]);
 int dirb200_index_destroy(dirb200_index* idx);
 

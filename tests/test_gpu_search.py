@@ -152,3 +152,38 @@ def test_full_size_1m_properties():
     np.testing.assert_allclose(s_h[pick], best_s, rtol=0, atol=1e-12)
     st = index.stats()
     assert st["retries"] == 0 and st["candidates"] < 40 * Q * K
+
+
+def test_two_phase_sharded_search_single_gpu():
+    """The sharded protocol with all shards on one GPU: phase 1 per shard (k_shard = ceil(k/G)), MIN over the shards'
+    selection thresholds (what the all-reduce does), phase 2 per shard, merge == oracle.  Shards re-score far fewer
+    rows than a stand-alone search would."""
+    ops = _ops()
+    db, q, pos = synth.make_descriptor_db(48000, 40, dim=512, n_pos=8, db_seed=77, q_seed=78)
+    k, G = 60, 4
+    qd = torch.from_numpy(q).to(DEV)
+    bounds = [(g * 12000, (g + 1) * 12000) for g in range(G)]
+    shards = [ops.Index(torch.from_numpy(db[a:b]).to(DEV), index_offset=a) for a, b in bounds]
+    for sh in shards:
+        sh.set_option("sample_rows", 2048)
+    sels = [sh.search_begin(qd, k, -(-k // G)) for sh in shards]
+    sel = torch.stack(sels).min(dim=0).values.contiguous()
+    outs = [sh.search_finish(qd, k, sel) for sh in shards]
+    ms, mi = ops.topk_merge(torch.stack([o[0] for o in outs]).contiguous(), torch.stack([o[1] for o in outs]).contiguous(), k)
+    rs, ri = O.topk(q, db, k)
+    np.testing.assert_array_equal(mi.cpu().numpy(), ri)
+    np.testing.assert_allclose(ms.cpu().numpy(), rs, rtol=0, atol=1e-12)
+    surv_two_phase = sum(sh.stats()["survivors"] for sh in shards)
+    alone = 0
+    for sh in shards:
+        sh.search(qd, k)
+        alone += sh.stats()["survivors"]
+    assert surv_two_phase < 0.6 * alone, (surv_two_phase, alone)
+    # an empty shard and a skewed split must not break the bound
+    tiny = ops.Index(torch.from_numpy(db[:70]).to(DEV), index_offset=0)
+    rest = ops.Index(torch.from_numpy(db[70:]).to(DEV), index_offset=70)
+    s2 = [tiny.search_begin(qd, k, 30), rest.search_begin(qd, k, 30)]
+    sel2 = torch.minimum(s2[0], s2[1]).contiguous()
+    o2 = [tiny.search_finish(qd, k, sel2), rest.search_finish(qd, k, sel2)]
+    ms2, mi2 = ops.topk_merge(torch.stack([o[0] for o in o2]).contiguous(), torch.stack([o[1] for o in o2]).contiguous(), k)
+    np.testing.assert_array_equal(mi2.cpu().numpy(), ri)
