@@ -1,5 +1,6 @@
 // Convolution + folded BatchNorm (+ residual) (+ ReLU) on NHWC fp16 activations.
-//   impl 0: tcgen05 implicit GEMM (gemm_tc.cuh) - every Bottleneck conv (Cin % 64 == 0)
+//   impl 0: persistent tcgen05 implicit GEMM (conv_pers.cuh, conv_halo.cuh for 3x3/s1) - every Bottleneck conv
+//   impl 2: one-tile-per-CTA tcgen05 kernel (gemm_tc.cuh), kept as an A/B baseline
 //   impl 1: mma.sync implicit GEMM            - the 7x7 stem (Cin padded 3 -> 8) and the validation path
 // Reference semantics: dirtorch/nets/backbones/resnet.py:56-63 (convs, bias=False), :70-85 (BN, ReLU, residual add),
 // :115-118 (stem).  BatchNorm (eval) is folded by the caller into scale = gamma/sqrt(var+eps), shift = beta-mean*scale.

@@ -65,7 +65,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int b_iters = 9 * p.cin_blocks;                 // weight tiles per output tile
   const int cin = p.cin_blocks * 64;
 
   if (warp == 0 && lane == 0) {
