@@ -256,7 +256,7 @@ def main():
     conv = prof["conv_tcgen05"]
     conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] else 0.0
     tot_ms = sum(v["ms"] for v in prof.values())
-    roofline = {"bound": "tensor", "kernel": "conv_pers_kernel<BN,STAGES> (all %d Bottleneck convolutions of the step)" % conv["launches"],
+    roofline = {"bound": "tensor", "kernel": "conv_pers_kernel + conv_halo_kernel (all %d Bottleneck convolution launches of the step)" % conv["launches"],
                 "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf, "traffic": None,
                 "peak_source": peak_src + ", sustained dense 16-bit",
                 "avg_launch_ms": conv["ms"] / max(1, conv["launches"]), "flops_per_launch": conv["flops"] / max(1, conv["launches"]),
@@ -337,7 +337,7 @@ def main():
             "config": {"workload": "%d queries x %d x %d fp16 database, k=%d, exact fp64 re-scoring" % (Q, N, D, K),
                        "sharding": "rows / %d ranks, one all-gather of (score,index)[Q][k], %d B per rank" % (world, 16 * Q * K)},
             "e2e": {"value": Q / s_e2e, "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * K * 16},
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<128,3,EPI_SIM_*> (seed + filter passes)",
+            "roofline": {"bound": "tensor", "kernel": "conv_pers_kernel<256,4,PERS_EPI_SIM_*> (seed + filter passes)",
                          "achieved": flops / world / (s_ms * 1e-3) / 1e12, "peak": peak_tf_burst, "unit": "TFLOP/s",
                          "frac": flops / world / (s_ms * 1e-3) / 1e12 / peak_tf_burst,
                          "note": "whole search step per GPU (GEMM passes + selection + re-scoring) vs burst dense 16-bit peak",
