@@ -189,6 +189,8 @@ int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int
 
 static int g_conv_halo = 1;
 void set_conv_halo(int on) { g_conv_halo = on; }
+static int g_res_variant = 0;   // tuning knob: shared-memory split of the residual (conv3) kernel, see conv_tc
+void set_res_variant(int v) { g_res_variant = v; }
 
 // 3x3 / stride 1 / pad 1 with the halo patch loaded once per tile (conv_halo.cuh).
 template <int BN, int BSTAGES, bool BRES, int NA>
@@ -234,7 +236,11 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
   // Shared memory split: convolutions with a residual keep 4 staging buffers (residual prefetch depth) and a
   // shorter operand ring; the others trade two staging buffers for one more ring slot (deeper TMA lookahead).
   if (s.Cout % 256 == 0) {
-    if (res) return conv_pers_bn<256, 3, 4>(s, in, w, scale, shift, res, relu, out, stream);
+    if (res) {
+      if (g_res_variant == 1) return conv_pers_bn<256, 2, 6>(s, in, w, scale, shift, res, relu, out, stream);
+      if (g_res_variant == 2) return conv_pers_bn<128, 4, 6>(s, in, w, scale, shift, res, relu, out, stream);
+      return conv_pers_bn<256, 3, 4>(s, in, w, scale, shift, res, relu, out, stream);
+    }
     return conv_pers_bn<256, 4, 2>(s, in, w, scale, shift, res, relu, out, stream);
   }
   if (s.Cout % 128 == 0) {

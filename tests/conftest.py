@@ -10,6 +10,20 @@ if REPO not in sys.path:
 GOLDEN = os.path.join(REPO, "tests", "golden")
 
 
+def _ensure_library():
+    """The C-ABI library is a build artefact (git-ignored): compile it in-tree if this is a fresh checkout."""
+    lib = os.path.join(REPO, "deep-image-retrieval_b200", "libdirb200.so")
+    if not os.path.exists(lib):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("dirb200_build_ext", os.path.join(REPO, "deep-image-retrieval_b200", "build_ext.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+
+
+_ensure_library()
+
+
 def pytest_configure(config):
     import torch
     torch.set_num_threads(min(16, os.cpu_count() or 1))   # oracle convs: many-core boxes oversubscribe badly

@@ -125,3 +125,16 @@ def test_uint8_input_is_bit_identical_to_fp32_input():
     assert np.array_equal(net.forward_host_u8(u8), d_f32)
     ref = O.extract(x, sd, "resnet50_rmac").numpy()
     assert rel_l2(d_u8, ref) < TOL
+
+
+@pytest.mark.parametrize("size", [(717, 717), (1434, 1434), (64, 48), (333, 517)], ids=lambda s: "%dx%d" % s)
+def test_odd_and_multiscale_sizes_vs_oracle(size):
+    """BASELINE configs[4] scales of a 1024^2 image (Scale(0.7) -> 717, Scale(1.4) -> 1434, transforms.py:168) plus tiny
+    and odd rectangular inputs: every stage has ragged tiles; one image against the CPU oracle."""
+    net, sd = _net("resnet101_rmac", 3)
+    h, w = size
+    x = synth.make_images(2, h, w, seed=31)
+    d = net(x.cuda()).cpu().numpy()
+    ref = O.extract(x[:1], sd, "resnet101_rmac", squeeze=False).numpy()
+    assert rel_l2(d[:1], ref) < TOL
+    assert np.array_equal(net(x[:1].cuda()).cpu().numpy(), d[0])
