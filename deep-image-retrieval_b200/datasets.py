@@ -152,6 +152,35 @@ class ImageListRelevants(Dataset):
             return self._ap(query_idx, scores, "classic")
         return {m: self._ap(query_idx, scores, m) for m in ("easy", "medium", "hard")}
 
+    # ---- the same AP from a ranked PREFIX (top-k engine) instead of a full score row
+    def _ap_from_ranking(self, q, ranked_idx, mode):
+        rel = set(int(i) for i in self.get_relevants(q, mode))
+        junk = set(int(i) for i in self.get_junk(q, mode))
+        rel -= junk                                  # a label set to 0 (junk) after 1 wins, as in get_query_groundtruth
+        if mode != "classic" and not rel:
+            return -1
+        ranks, pos, found = [], 0, 0
+        for i in ranked_idx:
+            i = int(i)
+            if i < 0 or i in junk:
+                continue
+            if i in rel:
+                ranks.append(pos)
+                found += 1
+                if found == len(rel):
+                    break
+            pos += 1
+        if found < len(rel):
+            return None                              # prefix too short: some positive ranks are unknown
+        return compute_average_precision(ranks)
+
+    def eval_query_AP_from_ranking(self, query_idx, ranked_idx):
+        """AP of `eval_query_AP` computed from the first entries of the ranking (database indices, best first).
+        Returns None (or a dict containing None) when the prefix does not reach every positive."""
+        if self.relevants:
+            return self._ap_from_ranking(query_idx, ranked_idx, "classic")
+        return {m: self._ap_from_ranking(query_idx, ranked_idx, m) for m in ("easy", "medium", "hard")}
+
 
 def _db_root():
     return os.environ["DB_ROOT"]

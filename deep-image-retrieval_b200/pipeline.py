@@ -106,9 +106,30 @@ def _pool_and_normalize(descs, pooling, gemp):
     return ops.pool_scales([_dev_f32(d) for d in descs], pooling, gemp, l2=True)
 
 
+def _aps_from_topk(db, qdescs, bdescs, k):
+    """Per-query AP from the exact top-k ranking (dirb200_index_search); dense score row only where needed."""
+    dim = qdescs.shape[1]
+    pad = (-dim) % 64
+    f = lambda a: torch.nn.functional.pad(_dev_f32(a), (0, pad)).contiguous() if pad else _dev_f32(a)
+    qd, bd = f(qdescs), f(bdescs)
+    k = min(k, bd.shape[0], 1024)
+    _, idx = ops.Index(bd).search(qd, k)
+    idx = idx.cpu().numpy()
+    aps = []
+    for q in range(qd.shape[0]):
+        ap = db.eval_query_AP_from_ranking(q, idx[q])
+        incomplete = ap is None or (isinstance(ap, dict) and any(v is None for v in ap.values()))
+        if incomplete:
+            row = ops.scores_exact(qd[q:q + 1].contiguous(), bd).cpu().numpy()[0]
+            ap = db.eval_query_AP(q, row)
+        aps.append(ap)
+    return aps
+
+
 def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=None, aqe=None, adba=None, threads=8,
-               batch_size=16, save_feats=None, load_feats=None, dbg=()):
-    """Evaluate a network on a retrieval dataset (test_dir.py:97-180).  aqe / adba: dict(k=..., alpha=...)."""
+               batch_size=16, save_feats=None, load_feats=None, dbg=(), rank_topk=0):
+    """Evaluate a network on a retrieval dataset (test_dir.py:97-180).  aqe / adba: dict(k=..., alpha=...).
+    rank_topk > 0 (extension): rank with the exact top-k search instead of the dense Q x N score matrix."""
     print("\n>> Evaluation...")
     query_db = db.get_query_db()
     bdescs, qdescs = [], []
@@ -135,11 +156,20 @@ def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=Non
         bdescs = expand_descriptors(bdescs, **adba)
     if aqe is not None:
         qdescs = expand_descriptors(qdescs, db=bdescs, **aqe)
-    scores = matmul(tonumpy(qdescs), tonumpy(bdescs))
-    del bdescs, qdescs
     res = {}
+    qn, bn = tonumpy(qdescs), tonumpy(bdescs)
+    if rank_topk and hasattr(db, "eval_query_AP_from_ranking"):
+        # Large databases: rank with the exact top-k engine instead of materialising the Q x N score matrix; a
+        # query whose positives are not all inside the top-k falls back to its exact dense score row.
+        aps = _aps_from_topk(db, qn, bn, int(rank_topk))
+        scores = None
+    else:
+        scores = matmul(qn, bn)
+        aps = None
+    del bdescs, qdescs
     try:
-        aps = [db.eval_query_AP(q, s) for q, s in enumerate(tqdm.tqdm(scores, desc="AP"))]
+        if aps is None:
+            aps = [db.eval_query_AP(q, s) for q, s in enumerate(tqdm.tqdm(scores, desc="AP"))]
         if not isinstance(aps[0], dict):
             aps = [float(e) for e in aps]
             if detailed:
@@ -154,6 +184,8 @@ def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=Non
     except NotImplementedError:
         print(" AP not implemented!")
     try:
+        if scores is None:
+            raise NotImplementedError()
         tops = [db.eval_query_top(q, s) for q, s in enumerate(tqdm.tqdm(scores, desc="top1"))]
         if detailed:
             res["tops"] = tops
@@ -242,6 +274,8 @@ def test_dir_main(argv=None):
     parser.add_argument("--gpu", type=int, default=0, nargs="+", help="GPU ids")
     parser.add_argument("--aqe", type=float, nargs="+", help="alpha-query expansion parameters: k alpha")
     parser.add_argument("--adba", type=float, nargs="+", help="alpha-database augmentation parameters: k alpha")
+    parser.add_argument("--rank-topk", type=int, default=0,
+                        help="(extension) rank with the exact top-k search (k <= 1024) instead of the dense score matrix")
     args = parser.parse_args(argv)
     args.iscuda = common.torch_set_gpu(args.gpu)
     aqe = {"k": int(args.aqe[0]), "alpha": args.aqe[1]} if args.aqe is not None else None
@@ -252,7 +286,7 @@ def test_dir_main(argv=None):
     whiten = _select_pca(net, args)
     res = eval_model(dataset, net, args.trfs, pooling=args.pooling, gemp=args.gemp, detailed=args.detailed,
                      threads=args.threads, dbg=args.dbg, whiten=whiten, aqe=aqe, adba=adba,
-                     save_feats=args.save_feats, load_feats=args.load_feats)
+                     save_feats=args.save_feats, load_feats=args.load_feats, rank_topk=args.rank_topk)
     # (the reference's '%s = %g' line raises on the list-valued entries that --detailed adds; print scalars only)
     print(" * " + "\n * ".join(["%s = %g" % p for p in res.items() if isinstance(p[1], (int, float))]))
     if args.out_json:

@@ -112,6 +112,12 @@ def test_cli_end_to_end(tmp_path, monkeypatch, capsys):
     assert " * mAP = %g" % ref_map in capsys.readouterr().out
     saved = np.load(os.path.join(root, "saved", "feats.bdescs.npy"))
     assert rel_l2(saved, D) < 1e-3
+    # ---- the top-k evaluation path (no Q x N score matrix): same mAP, with and without the dense fallback
+    for rk in ("16", "2"):
+        res_k = test_dir.test_dir_main(["--dataset", "Oxford5K", "--checkpoint", os.path.join(root, "ckpt.pt"),
+                                        "--whiten", "Landmarks_clean", "--gpu", "0", "--load-feats", os.path.join(root, "saved"),
+                                        "--rank-topk", rk])
+        assert res_k["mAP"] == ref_map
     # ---- alpha-QE through the CLI (float alpha accepted) and --load-feats
     res2 = test_dir.test_dir_main(["--dataset", "Oxford5K", "--checkpoint", os.path.join(root, "ckpt.pt"),
                                    "--whiten", "Landmarks_clean", "--gpu", "0", "--load-feats", os.path.join(root, "saved"),

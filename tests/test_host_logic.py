@@ -44,6 +44,25 @@ def test_dataset_ap_matches_reference(golden, tmp_path):
         ds.eval_query_AP(0, g["scores"][0][:10])           # wrong shape, generic.py:201
 
 
+def test_ap_from_ranked_prefix_equals_ap_from_scores(golden, tmp_path):
+    """The top-k evaluation path: AP from the first entries of the ranking == AP from the full score row."""
+    g = golden("rank_ap.npz")
+    for revisited in (False, True):
+        ds, db, q = _gt_dataset(tmp_path, g, revisited=revisited)
+        for i in range(6):
+            full = ds.eval_query_AP(i, g["scores"][i])
+            order = O.rank_desc(g["scores"][i])
+            worst = max(int(np.where(order == p)[0][0]) for p in synth.oxford_gt(
+                synth.make_descriptor_db(400, 6, dim=32, n_pos=5, db_seed=21, q_seed=22)[2], n_junk=3, n_db=400, seed=5)[i]["ok"])
+            got = ds.eval_query_AP_from_ranking(i, order[:worst + 1])
+            if isinstance(full, dict):
+                assert all(abs(got[m] - full[m]) < 1e-12 for m in full)
+            else:
+                assert abs(got - full) < 1e-12
+            short = ds.eval_query_AP_from_ranking(i, order[:1])          # prefix too short -> unknown
+            assert short is None or (isinstance(short, dict) and any(v is None for v in short.values())) or worst == 0
+
+
 def test_transforms_and_loader(tmp_path):
     from PIL import Image
     from dirb200.loader import Scale, create_transforms, get_loader
