@@ -1,6 +1,7 @@
 // Persistent tcgen05 implicit-GEMM convolution + BN + residual + ReLU for sm_100a.
 //
-// One CTA per SM loops over output tiles (128 pixels x BN channels, BN up to 256); 8 warps, each with one job:
+// One CTA per SM loops over output tiles (128 pixels x BN channels, BN up to 256); 12 warps (4 + 8 epilogue warps;
+// the similarity / whitening epilogues use 4), each with one job:
 //
 //   warp 0  TMA producer   A (128x64 activation patch) and B (BNx64 weights) into a STAGES-deep smem ring
 //   warp 1  MMA issuer     tcgen05.mma (M=128, N=BN, K=16) x 4 per ring slot into one of TWO TMEM accumulators,
@@ -60,7 +61,7 @@ struct ConvPersSmem {
   static constexpr int STG_BYTES = 128 * 128;                      // 128 rows x 64 channels fp16
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = STG_OFF + NBUF * STG_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * (NB > 4 ? NB : 4);   // ring, accumulators, residual ring
   static constexpr int TOTAL = BAR_OFF + 8 * NUM_BARS + 16 + 1024;  // + tmem slot + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                          // two accumulators
 };
