@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["common.cu", "conv.cu", "ops.cu", "search.cu", "net.cu", "api.cu"]
+SOURCES = ["common.cu", "conv.cu", "ops.cu", "search.cu", "net.cu", "api.cu", "resize.cu"]
 LIB = os.path.join(HERE, "libdirb200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

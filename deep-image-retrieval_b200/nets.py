@@ -234,6 +234,25 @@ class ResNetRMAC:
                  C.c_void_p(0), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return desc[0] if b == 1 else desc
 
+    def forward_u8_multiscale(self, imgs_u8: torch.Tensor, scales=(0.7, 1.0, 1.4), pooling="gem", gemp=3):
+        """Multi-scale descriptors entirely on the GPU (BASELINE configs[4]): for every scale s the uint8 batch is
+        resized like the reference's `Scale(s)` transform (PIL bilinear, output size int(0.5 + s*w), bit-exact on the
+        GPU), run through the network, and the per-scale descriptors are pooled (common.pool) and L2-normalised
+        (test_dir.py:121-122)."""
+        from . import ops
+        b, h, w, _ = imgs_u8.shape
+        descs = []
+        for sc in scales:
+            if float(sc) == 1.0:
+                x = imgs_u8
+            else:
+                x = ops.resize_bilinear_u8(imgs_u8.contiguous(), (int(0.5 + sc * h), int(0.5 + sc * w)))
+            d = self.forward_u8(x)
+            descs.append(d if d.dim() == 2 else d.unsqueeze(0))
+        if len(descs) == 1:
+            return ops.l2_normalize(descs[0])
+        return ops.pool_scales(descs, pooling, gemp, l2=True)
+
     def forward_host_u8(self, imgs_u8: np.ndarray, device=0) -> np.ndarray:
         """Host uint8 HWC array (B,H,W,3) in, host descriptors out (H2D of 3 bytes/pixel instead of 12)."""
         a = np.ascontiguousarray(imgs_u8, dtype=np.uint8)

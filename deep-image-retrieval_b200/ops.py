@@ -89,6 +89,28 @@ def stem_conv(x_nchw, w_oihw, scale, shift):
     return out
 
 
+def resize_bilinear_u8(x_u8, size):
+    """uint8 HWC CUDA tensor (B,H,W,3) -> (B,Ho,Wo,3), byte-identical to PIL Image.resize((Wo,Ho), BILINEAR)."""
+    _chk(x_u8, torch.uint8, "x_u8")
+    b, h, w, c = x_u8.shape
+    assert c == 3
+    ho, wo = int(size[0]), int(size[1])
+    out = torch.empty((b, ho, wo, 3), dtype=torch.uint8, device=x_u8.device)
+    lib.call("dirb200_resize_bilinear_u8", _ptr(x_u8), b, h, w, ho, wo, _ptr(out), _stream())
+    return out
+
+
+def resize_coeffs(in_size, out_size):
+    """Host-only: PIL's fixed-point bilinear coefficient table of one axis -> (bounds [out,2], kk [out,ksize])."""
+    ks = C.c_int()
+    lib.call("dirb200_resize_coeffs", int(in_size), int(out_size), C.c_void_p(0), C.c_void_p(0), C.byref(ks))
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ks.value), dtype=np.int32)
+    lib.call("dirb200_resize_coeffs", int(in_size), int(out_size), bounds.ctypes.data_as(C.c_void_p),
+             kk.ctypes.data_as(C.c_void_p), C.byref(ks))
+    return bounds, kk
+
+
 def maxpool_3x3s2(x):
     _chk(x, torch.float16, "x")
     b, h, w, c = x.shape

@@ -79,6 +79,13 @@ int dirb200_net_forward_host(dirb200_net* net, const float* imgs_host, int B, in
 int dirb200_net_forward_u8(dirb200_net* net, const uint8_t* imgs_dev, int B, int H, int W, float* desc_dev,
                            void* desc16_dev, void* stream);
 int dirb200_net_forward_host_u8(dirb200_net* net, const uint8_t* imgs_host, int B, int H, int W, float* desc_host);
+/* Bilinear resize of uint8 HWC RGB images (B,H,W,3) -> (B,Ho,Wo,3), byte-identical to PIL's
+ * Image.resize((Wo,Ho), Image.BILINEAR) - the `Scale` transform of dirtorch/utils/transforms.py:133-185 - so that
+ * multi-scale extraction (Scale(0.7), Scale(1.4)) can stay on the GPU in front of dirb200_net_forward_u8.
+ * dirb200_resize_coeffs is the host-only coefficient table of one axis (bounds_out [2*out], kk_out [out*ksize];
+ * call with kk_out == NULL to query ksize). */
+int dirb200_resize_bilinear_u8(const uint8_t* in_dev, int B, int H, int W, int Ho, int Wo, uint8_t* out_dev, void* stream);
+int dirb200_resize_coeffs(int in_size, int out_size, int* bounds_out, int* kk_out, int* ksize_out);
 /* Debug tap (needs option "debug_taps"): copy the NHWC fp16 activation after stage `what` ("stem","layer1".."layer4")
  * of the LAST chunk of the last forward into dst_dev (capacity in bytes); returns its dims as {n,h,w,c}. */
 int dirb200_net_debug_stage(dirb200_net* net, const char* what, void* dst_dev, size_t capacity, int dims[4],

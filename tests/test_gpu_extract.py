@@ -138,3 +138,22 @@ def test_odd_and_multiscale_sizes_vs_oracle(size):
     ref = O.extract(x[:1], sd, "resnet101_rmac", squeeze=False).numpy()
     assert rel_l2(d[:1], ref) < TOL
     assert np.array_equal(net(x[:1].cuda()).cpu().numpy(), d[0])
+
+
+def test_gpu_multiscale_equals_pil_resize_path():
+    """Scale(0.7) / identity / Scale(1.4) with the resize on the GPU == the same chains with PIL's resize on the CPU
+    (bit-identical pixels -> bit-identical descriptors), and the pooled result matches the oracle."""
+    from PIL import Image
+    from dirb200 import ops
+    net, sd = _net("resnet50_rmac", 0)
+    u8 = synth.make_images_u8(2, 150, 210, seed=14)
+    pooled = net.forward_u8_multiscale(torch.from_numpy(u8).cuda(), scales=(0.7, 1.0, 1.4), pooling="gem", gemp=3).cpu().numpy()
+    per_scale_gpu, per_scale_ref = [], []
+    for s in (0.7, 1.0, 1.4):
+        wo, ho = int(0.5 + s * 210), int(0.5 + s * 150)
+        res = np.stack([np.array(Image.fromarray(u8[i]).resize((wo, ho), Image.BILINEAR)) if s != 1.0 else u8[i] for i in range(2)])
+        per_scale_gpu.append(net.forward_u8(torch.from_numpy(res).cuda()))
+        per_scale_ref.append(O.extract(synth.normalise_images(res), sd, "resnet50_rmac").numpy())
+    same = ops.pool_scales(per_scale_gpu, "gem", 3, l2=True).cpu().numpy()
+    assert np.array_equal(pooled, same)
+    assert rel_l2(pooled, O.l2n(O.pool_scales(per_scale_ref, "gem", 3))) < TOL

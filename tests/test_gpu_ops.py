@@ -193,3 +193,18 @@ def test_pool_scales_l2_whiten(golden):
     assert rel_l2(yb.cpu().numpy(), ref) < 1e-3            # north-star tolerance; the hi/lo split GEMM gives ~1e-6
     assert rel_l2(yb.cpu().numpy(), ref) < 2e-5
     assert rel_l2(yb16.float().cpu().numpy(), ref) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 53, 0.7), (1, 100, 80, 1.4), (3, 64, 64, 0.5), (1, 333, 517, 0.7), (2, 224, 224, 1.4)],
+                         ids=lambda s: "x".join(str(v) for v in s))
+def test_resize_bilinear_matches_pil(shape):
+    """GPU bilinear resize == PIL Image.resize(BILINEAR) byte for byte (the `Scale(float)` transform, transforms.py:168,183)."""
+    from PIL import Image
+    ops = _ops()
+    b, h, w, s = shape
+    ho, wo = int(0.5 + s * h), int(0.5 + s * w)
+    a = np.random.RandomState(1).randint(0, 256, (b, h, w, 3), dtype=np.uint8)
+    out = ops.resize_bilinear_u8(torch.from_numpy(a).to(DEV), (ho, wo)).cpu().numpy()
+    for i in range(b):
+        ref = np.array(Image.fromarray(a[i]).resize((wo, ho), Image.BILINEAR))
+        assert np.array_equal(out[i], ref)

@@ -173,3 +173,32 @@ def test_topk_exchange_gloo_world2(tmp_path):
     s.close()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
+
+
+def test_resize_coefficients_reproduce_pil():
+    """The host-side coefficient tables of the GPU resize (dirb200_resize_coeffs), applied in numpy integer
+    arithmetic, reproduce PIL's Image.resize(BILINEAR) byte for byte (the kernels do exactly this arithmetic)."""
+    from PIL import Image
+    from dirb200 import ops
+    r = np.random.RandomState(0)
+
+    def apply(a, ho, wo):
+        h, w, c = a.shape
+        bx, kx = ops.resize_coeffs(w, wo)
+        tmp = np.zeros((h, wo, c), dtype=np.uint8)
+        for xx in range(wo):
+            x0, n = bx[xx]
+            acc = (1 << 21) + (a[:, x0:x0 + n, :].astype(np.int64) * kx[xx, :n][None, :, None]).sum(axis=1)
+            tmp[:, xx, :] = np.clip(acc >> 22, 0, 255)
+        by, ky = ops.resize_coeffs(h, ho)
+        out = np.zeros((ho, wo, c), dtype=np.uint8)
+        for yy in range(ho):
+            y0, n = by[yy]
+            acc = (1 << 21) + (tmp[y0:y0 + n].astype(np.int64) * ky[yy, :n][:, None, None]).sum(axis=0)
+            out[yy] = np.clip(acc >> 22, 0, 255)
+        return out
+
+    for (h, w, ho, wo) in ((37, 53, 26, 37), (37, 53, 52, 74), (64, 64, 45, 45), (100, 80, 33, 200), (50, 50, 50, 70)):
+        a = r.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.array(Image.fromarray(a).resize((wo, ho), Image.BILINEAR))
+        assert np.array_equal(apply(a, ho, wo), ref), (h, w, ho, wo)
