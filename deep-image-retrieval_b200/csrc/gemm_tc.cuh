@@ -12,17 +12,19 @@
 // from the tensor map's element stride.  smem tiles are K-major rows of 128 B with the 128-byte swizzle, which
 // is exactly what the UMMA smem descriptor (ptx.cuh: umma_desc_sw128) describes.
 //
-// Epilogues:
-//   EPI_CONV        y = acc*scale[c] + shift[c] (+ residual) (ReLU) -> fp16 NHWC           (conv + BN + add + ReLU)
-//   EPI_SIM_DENSE   fp32 scores written to dense[q][n]                                      (threshold seeding pass)
-//   EPI_SIM_FILTER  scores >= thr[q] appended to a per-query candidate list (score, row)    (filtered search pass)
+// Epilogue: y = acc*scale[c] + shift[c] (+ residual) (ReLU) -> fp16 NHWC, one output row per thread, direct
+// global stores (conv + BN + add + ReLU).
+//
+// This one-tile-per-CTA kernel was the first working tcgen05 path and is kept as the A/B baseline (conv_impl = 2)
+// and as the simplest statement of the TMA -> UMMA -> TMEM pipeline; the production kernels are the persistent
+// ones in conv_pers.cuh / conv_halo.cuh / stem_pers.cuh.
 #pragma once
 #include "common.h"
 #include "ptx.cuh"
 
 namespace dirb {
 
-enum { EPI_CONV = 0, EPI_SIM_DENSE = 1, EPI_SIM_FILTER = 2 };
+enum { EPI_CONV = 0 };
 
 struct GemmTcParams {
   // A addressing
@@ -42,14 +44,6 @@ struct GemmTcParams {
   const __half* res;
   __half* out;
   int relu;
-  // EPI_SIM_*
-  float* dense;                // [M][dense_ld]
-  int64_t dense_ld;
-  int n_offset;                // column offset of this launch inside the dense matrix / local row base
-  const float* thr;            // [M]
-  unsigned long long* cand;    // [M][cand_cap] packed (score bits << 32 | row)
-  int* cand_cnt;               // [M]
-  int cand_cap;
 };
 
 template <int BN, int STAGES>
@@ -213,34 +207,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o.z = pack_h2(v[q * 8 + 4], v[q * 8 + 5]);
             o.w = pack_h2(v[q * 8 + 6], v[q * 8 + 7]);
             op[q] = o;
-          }
-        }
-      } else if (EPI == EPI_SIM_DENSE) {
-        if (valid) {
-          const int nb0 = n_tile * BN + c0;
-          float* dp = p.dense + pix * p.dense_ld + p.n_offset + nb0;
-          if (nb0 + 32 <= p.N) {
-            float4* d4 = reinterpret_cast<float4*>(dp);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nb0 + j < p.N) dp[j] = v[j];
-          }
-        }
-      } else {  // EPI_SIM_FILTER
-        if (valid) {
-          const float t = __ldg(p.thr + pix);
-          const int nb0 = n_tile * BN + c0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (v[j] >= t && nb0 + j < p.N) {
-              const int pos = atomicAdd(p.cand_cnt + pix, 1);
-              if (pos < p.cand_cap)
-                p.cand[pix * p.cand_cap + pos] =
-                    (static_cast<unsigned long long>(__float_as_uint(v[j])) << 32) |
-                    static_cast<unsigned int>(p.n_offset + nb0 + j);
-            }
           }
         }
       }
