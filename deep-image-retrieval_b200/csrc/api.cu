@@ -59,6 +59,11 @@ int dirb200_head_pool_fc_l2(const void* feat_dev, int B, int HW, int C, int pool
                          fc_w_dev ? out_dim : C, ws_dev, desc_dev, H16(desc16_dev), ST(stream));
 }
 
+int dirb200_center_bias(void* feat_dev, int B, int H, int W, int C, float b, void* stream) {
+  DIRB_REQUIRE(feat_dev && B > 0 && H > 0 && W > 0, DIRB200_EINVAL, "bad arguments");
+  return center_bias(H16(feat_dev), B, H, W, C, b, ST(stream));
+}
+
 int dirb200_pool_scales(const float* xs_dev, int S, int64_t N, int D, int mode, float gemp, int l2, float* out_dev,
                         void* stream) {
   DIRB_REQUIRE(xs_dev && out_dev, DIRB200_EINVAL, "null argument");

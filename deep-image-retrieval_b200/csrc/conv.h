@@ -50,6 +50,7 @@ int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float
 int pool_scales(const float* xs, int S, int64_t N, int D, int mode, float gemp, int l2, float* out,
                 cudaStream_t stream);
 int l2_normalize(const float* x, int64_t N, int D, float eps, float* out, __half* out16, cudaStream_t stream);
+int center_bias(__half* x, int B, int H, int W, int C, float b, cudaStream_t stream);
 int f32_to_f16(const float* x, int64_t n, __half* out, cudaStream_t stream);
 int whiten(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale, int Dout,
            int l2norm, float* y, __half* y16, cudaStream_t stream);

@@ -72,6 +72,7 @@ struct dirb200_net {
   // options
   int pooling = 0, norm_features = 0, without_fc = 0, out_dim = 2048, chunk = 0, conv_impl = 0;
   float gem_p = 3.0f, gem_eps = 1e-6f;
+  float center_bias = 0.0f;       // rmac_resnet.py:52-56
   // host state dict
   std::map<std::string, HostTensor> sd;
   bool finalized = false;
@@ -223,9 +224,10 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out) {
   n->arch = arch;
   if (n->arch == "resnet50_rmac") n->nblocks = {3, 4, 6, 3};          // rmac_resnet.py:80
   else if (n->arch == "resnet101_rmac") n->nblocks = {3, 4, 23, 3};   // rmac_resnet.py:84
+  else if (n->arch == "resnet152_rmac") n->nblocks = {3, 8, 36, 3};   // rmac_resnet.py:88
   else {
     delete n;
-    DIRB_REQUIRE(false, DIRB200_ENOTSUP, "unknown model architecture '%s' (supported: resnet50_rmac, resnet101_rmac)", arch);
+    DIRB_REQUIRE(false, DIRB200_ENOTSUP, "unknown model architecture '%s' (supported: resnet50_rmac, resnet101_rmac, resnet152_rmac)", arch);
   }
   *out = n;
   return 0;
@@ -241,6 +243,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "chunk") n->chunk = static_cast<int>(value);
   else if (k == "conv_impl") n->conv_impl = static_cast<int>(value);
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
+  else if (k == "center_bias") n->center_bias = static_cast<float>(value);
   else if (k == "debug_taps") n->debug_taps = value != 0;
   else if (k == "profile") n->profile = value != 0;
   else if (k == "halo") set_conv_halo(value != 0);
@@ -511,6 +514,8 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
       if (s == 4) {
         if (b0 + sb >= cb) DIRB_TRY(record_tap(n, "layer4", x, sb, ho, wo, 2048, stream));
         ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * 2048.0 * n->out_dim, 2.0 * sb * ho * wo * 2048.0);
+        if (n->center_bias > 0.0f)   // x is a scratch buffer whose only remaining reader is the pooling below
+          DIRB_TRY(center_bias(const_cast<__half*>(x), sb, ho, wo, 2048, n->center_bias, stream));
         DIRB_TRY(head_pool_fc_l2(x, sb, ho * wo, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
                                  n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, w.head_ws,
                                  desc_dev + static_cast<size_t>(b0) * D,

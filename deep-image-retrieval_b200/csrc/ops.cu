@@ -254,6 +254,53 @@ int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// center_bias (rmac_resnet.py:52-56): x[n][h][w][:] *= 1 + bilinear(align_corners=True) of the 4x4 map that is b on
+// its central 2x2 and 0 on its border, resized to (H, W).  In place on the fp16 NHWC layer4 map, 8 channels / thread.
+__device__ __forceinline__ float center_bias_axis(int i, int n, int& i0, int& i1, float& l1) {
+  const float scale = n > 1 ? 3.0f / static_cast<float>(n - 1) : 0.0f;   // (in - 1) / (out - 1), in = 4
+  const float src = scale * static_cast<float>(i);
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < 3 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+  return 1.0f - l1;
+}
+
+__global__ void center_bias_kernel(__half* __restrict__ x, int H, int W, int C8, float b, int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t pix = i / C8;
+  const int wq = static_cast<int>(pix % W);
+  const int hq = static_cast<int>((pix / W) % H);
+  int h0, h1, w0, w1;
+  float lh1, lw1;
+  const float lh0 = center_bias_axis(hq, H, h0, h1, lh1);
+  const float lw0 = center_bias_axis(wq, W, w0, w1, lw1);
+  auto tab = [b](int r, int c) { return (r == 1 || r == 2) && (c == 1 || c == 2) ? b : 0.0f; };
+  const float m = 1.0f + (lh0 * (lw0 * tab(h0, w0) + lw1 * tab(h0, w1)) + lh1 * (lw0 * tab(h1, w0) + lw1 * tab(h1, w1)));
+  uint4* ptr = reinterpret_cast<uint4*>(x) + i;
+  uint4 v = *ptr;
+  __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __half22float2(hv[e]);
+    f.x *= m;
+    f.y *= m;
+    hv[e] = __floats2half2_rn(f.x, f.y);
+  }
+  *ptr = v;
+}
+
+int center_bias(__half* x, int B, int H, int W, int C, float b, cudaStream_t stream) {
+  DIRB_REQUIRE(C % 8 == 0, DIRB200_ENOTSUP, "center_bias needs C %% 8 == 0 (got %d)", C);
+  const int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  if (total == 0 || b == 0.0f) return 0;
+  center_bias_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(x, H, W, C / 8, b, total);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int l2_normalize(const float* x, int64_t N, int D, float eps, float* out, __half* out16, cudaStream_t stream) {
   if (N == 0) return 0;
   l2_rows_kernel<<<static_cast<unsigned>(N), 256, 0, stream>>>(x, out, out16, D, eps);

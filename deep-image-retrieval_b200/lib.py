@@ -60,6 +60,7 @@ SIGNATURES = {
     "dirb200_head_pool_fc_l2": (i32, [p, i32, i32, i32, i32, f32, f32, i32, p, p, i32, p, p, p, p]),
     "dirb200_pool_scales": (i32, [p, i32, i64, i32, i32, f32, i32, p, p]),
     "dirb200_l2_normalize": (i32, [p, i64, i32, f32, p, p, p]),
+    "dirb200_center_bias": (i32, [p, i32, i32, i32, i32, f32, p]),
     "dirb200_whiten": (i32, [p, i64, i32, p, p, p, i32, i32, p, p, p]),
     "dirb200_f32_to_f16": (i32, [p, i64, p, p]),
     "dirb200_index_create": (i32, [i32, i32, C.POINTER(p)]),

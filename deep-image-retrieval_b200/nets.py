@@ -21,7 +21,8 @@ import torch
 
 from . import lib, synth
 
-_ARCH_BLOCKS = {"resnet50_rmac": [3, 4, 6, 3], "resnet101_rmac": [3, 4, 23, 3]}
+_ARCH_BLOCKS = {"resnet50_rmac": [3, 4, 6, 3], "resnet101_rmac": [3, 4, 23, 3],     # rmac_resnet.py:78-88
+                "resnet152_rmac": [3, 8, 36, 3]}
 model_names = set(_ARCH_BLOCKS)
 
 
@@ -75,8 +76,6 @@ class ResNetRMAC:
             raise NameError("unknown model architecture '%s'\nSelect one in %s" % (arch, ",".join(sorted(model_names))))
         if not (pooling in ("max", "avg") or pooling.startswith("gem")):
             raise ValueError(pooling)                            # rmac_resnet.py:30-31
-        if center_bias:
-            raise NotImplementedError("center_bias > 0 (rmac_resnet.py:52-56) is not supported by the B200 path")
         self.arch = arch
         self.model_name = arch.split("_")[0]
         self.rgb_means = list(synth.RGB_MEANS)                   # resnet.py:110-112
@@ -171,7 +170,7 @@ class ResNetRMAC:
         try:
             mode = 0 if self.pooling.startswith("gem") else (1 if self.pooling == "max" else 2)
             for k, v in [("pooling", mode), ("norm_features", self.norm_features), ("without_fc", self.without_fc),
-                         ("out_dim", self.out_dim)] + list(self._opts.items()):
+                         ("out_dim", self.out_dim), ("center_bias", max(0.0, float(self.center_bias)))] + list(self._opts.items()):
                 lib.call("dirb200_net_set_option", h, k.encode(), float(v))
             for name, t in self._sd.items():
                 if name.endswith("num_batches_tracked"):
@@ -300,6 +299,10 @@ def resnet50_rmac(**kwargs):
 
 def resnet101_rmac(**kwargs):
     return ResNetRMAC("resnet101_rmac", **kwargs)
+
+
+def resnet152_rmac(**kwargs):
+    return ResNetRMAC("resnet152_rmac", **kwargs)
 
 
 def create_model(arch, pretrained="", delete_fc=False, *args, **kwargs):

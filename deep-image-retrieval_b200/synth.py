@@ -26,7 +26,7 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
-BLOCKS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3]}
+BLOCKS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3], "resnet152": [3, 8, 36, 3]}
 RGB_MEANS = [0.485, 0.456, 0.406]
 RGB_STDS = [0.229, 0.224, 0.225]
 

@@ -128,6 +128,10 @@ int dirb200_head_pool_fc_l2(const void* feat_dev, int B, int HW, int C, int pool
                             int norm_features, const float* fc_w_dev, const float* fc_b_dev, int out_dim,
                             float* ws_dev, float* desc_dev, void* desc16_dev, void* stream);
 
+/* center_bias option, rmac_resnet.py:52-56: feat[n][h][w][:] *= 1 + bilinear(align_corners) resize to (H,W) of the
+ * 4x4 map holding b on its central 2x2; in place on the NHWC fp16 map that feeds the global pooling. */
+int dirb200_center_bias(void* feat_dev, int B, int H, int W, int C, float b, void* stream);
+
 /* ------------------------------------------------------------------ descriptor post-processing */
 
 /* common.pool + F.normalize: common.py:41-55, test_dir.py:121-122.  xs_dev: (S,N,D) fp32 stacked;

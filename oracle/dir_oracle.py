@@ -24,7 +24,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-BLOCKS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3]}
+BLOCKS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3], "resnet152": [3, 8, 36, 3]}  # rmac_resnet.py:78-88
 BN_EPS = 1e-5  # torch.nn.BatchNorm2d default, used by resnet.py:57,60,63,117,140
 
 
@@ -73,8 +73,17 @@ def gem(x, p, eps=1e-6):
     return x.clamp(min=eps).pow(p).mean(dim=(2, 3)).pow(1.0 / p)
 
 
-def head(feat, sd, pooling="gem", norm_features=False, without_fc=False, squeeze=True):
-    """Global pooling -> (L2 over C) -> squeeze -> fc -> L2, rmac_resnet.py:59-69."""
+def center_bias_map(b, h, w):
+    """1 + bilinear(align_corners=True) resize to (h, w) of the 4x4 map with b on its central 2x2, rmac_resnet.py:52-55."""
+    m = torch.zeros(1, 1, 4, 4)
+    m[0, 0, 1:3, 1:3] = float(b)
+    return F.interpolate(1 + m, size=(h, w), mode="bilinear", align_corners=True)
+
+
+def head(feat, sd, pooling="gem", norm_features=False, without_fc=False, squeeze=True, center_bias=0):
+    """(center bias) -> global pooling -> (L2 over C) -> squeeze -> fc -> L2, rmac_resnet.py:52-69."""
+    if center_bias > 0:
+        feat = feat * center_bias_map(center_bias, feat.shape[2], feat.shape[3])
     if pooling == "max":
         x = feat.amax(dim=(2, 3))
     elif pooling == "avg":

@@ -100,6 +100,19 @@ def gold_extract():
 
 
 @torch.no_grad()
+def gold_extract_extra():
+    """resnet152_rmac (rmac_resnet.py:86-88) and the center_bias option (rmac_resnet.py:52-56)."""
+    net = ref_model("resnet152_rmac", seed=4)
+    x = synth.make_images(1, 96, 128, seed=41)
+    out = {"desc_r152": net(x).numpy()}
+    xs = synth.make_images(2, 128, 160, seed=6)
+    for tag, b in (("cb05", 0.5), ("cb2", 2.0)):
+        out["desc_" + tag] = ref_model("resnet50_rmac", seed=3, center_bias=b)(xs).numpy()
+    save("extract_extra.npz", r152_seed=4, r152_img_seed=41, r152_img_shape=np.array([1, 96, 128]),
+         cb_seed=3, cb_img_seed=6, cb_img_shape=np.array([2, 128, 160]), **out)
+
+
+@torch.no_grad()
 def gold_gem():
     r = np.random.RandomState(3)
     x = torch.from_numpy(r.standard_normal((2, 8, 5, 7)).astype(np.float32))
@@ -170,9 +183,13 @@ def gold_aqe():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["extra"]:               # only the files added after the first batch
+        gold_extract_extra()
+        sys.exit(0)
     gold_gem()
     gold_pool()
     gold_whiten()
     gold_rank_ap()
     gold_aqe()
     gold_extract()
+    gold_extract_extra()

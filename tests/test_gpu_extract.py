@@ -70,6 +70,19 @@ def test_extract_r101_golden(golden):
     assert rel_l2(net(x.cuda()).cpu().numpy(), g["desc"]) < TOL
 
 
+def test_extract_r152_and_center_bias_golden(golden):
+    g = golden("extract_extra.npz")
+    net, _ = _net("resnet152_rmac", int(g["r152_seed"]))
+    b, h, w = [int(v) for v in g["r152_img_shape"]]
+    d = net(synth.make_images(b, h, w, seed=int(g["r152_img_seed"])).cuda())
+    assert tuple(d.shape) == (2048,) and rel_l2(d.cpu().numpy(), g["desc_r152"]) < TOL
+    b, h, w = [int(v) for v in g["cb_img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["cb_img_seed"])).cuda()
+    for tag, cb in (("cb05", 0.5), ("cb2", 2.0)):                      # rmac_resnet.py:52-56
+        net, _ = _net("resnet50_rmac", int(g["cb_seed"]), center_bias=cb)
+        assert rel_l2(net(x).cpu().numpy(), g["desc_" + tag]) < TOL, tag
+
+
 def test_extract_r101_large_image_vs_oracle():
     # one 512x384 image against the CPU oracle, plus batch-composition invariance at that size
     net, sd = _net("resnet101_rmac", 2)

@@ -113,3 +113,18 @@ def test_extract_r50_options(golden):
 
 def test_extract_r101(golden):
     _check_extract(golden("extract_r101.npz"), "resnet101_rmac")
+
+
+def test_extract_r152_and_center_bias(golden):
+    g = golden("extract_extra.npz")
+    b, h, w = [int(v) for v in g["r152_img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["r152_img_seed"]))
+    sd = synth.make_state_dict("resnet152_rmac", seed=int(g["r152_seed"]))
+    d = O.extract(x, sd, "resnet152_rmac").numpy()
+    assert d.shape == (2048,) and rel_l2(d, g["desc_r152"]) < 2e-5
+    b, h, w = [int(v) for v in g["cb_img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["cb_img_seed"]))
+    sd = synth.make_state_dict("resnet50_rmac", seed=int(g["cb_seed"]))
+    for tag, cb in (("cb05", 0.5), ("cb2", 2.0)):
+        assert rel_l2(O.extract(x, sd, "resnet50_rmac", center_bias=cb).numpy(), g["desc_" + tag]) < 2e-5, tag
+    assert rel_l2(O.extract(x, sd, "resnet50_rmac").numpy(), g["desc_cb2"]) > 1e-3   # the option is not a no-op
