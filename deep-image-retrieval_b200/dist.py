@@ -39,6 +39,16 @@ class ShardedIndex:
         self.row_offset = int(row_offset)
         self.local = ops.Index(db32_local, index_offset=row_offset, db16=db16_local)
 
+    @classmethod
+    def from_store(cls, store, device, group=None, chunk_rows: int = 65536):
+        """Load this rank's row range of an on-disk descriptor store (store.py) and index it.  The split is
+        ``shard_rows`` over the CURRENT world size, whatever shard files the store was written in."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        start, end = shard_rows(len(store), world, rank)
+        d32, d16 = store.load_rows_to_device(start, end, device, chunk_rows)
+        return cls(d32, start, group, db16_local=d16)
+
     def search_local(self, q32: torch.Tensor, k: int):
         packed = torch.empty((2, q32.shape[0], k), dtype=torch.int64, device=q32.device)
         self.local.search(q32, k, out=packed)

@@ -19,6 +19,7 @@ import tqdm
 from . import common, datasets, nets, ops
 from .common import matmul, pool, tonumpy
 from .loader import get_loader
+from .store import DescriptorStore
 
 
 def mkdir(fname, isfile="auto"):
@@ -141,6 +142,11 @@ def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=Non
             qdescs.append(bdescs[-1] if db is query_db else extract_image_features(query_db, trf, net, desc="query", **kw))
         bdescs = _pool_and_normalize(bdescs, pooling, gemp)
         qdescs = _pool_and_normalize(qdescs, pooling, gemp)
+    elif DescriptorStore.is_store(os.path.join(load_feats, "bdescs")):
+        # extension: row-sharded descriptor store (store.py) instead of one .npy per side
+        bdescs = DescriptorStore(os.path.join(load_feats, "bdescs")).read_all().astype(np.float32, copy=False)
+        qdescs = (DescriptorStore(os.path.join(load_feats, "qdescs")).read_all().astype(np.float32, copy=False)
+                  if query_db is not db else bdescs)
     else:
         bdescs = np.load(os.path.join(load_feats, "feats.bdescs.npy"))
         qdescs = np.load(os.path.join(load_feats, "feats.qdescs.npy")) if query_db is not db else bdescs

@@ -72,6 +72,29 @@ def test_sharded_index_single_rank():
     assert rel_l2(out.cpu().numpy(), O.expand_descriptors(q, db=db, k=2, alpha=0.5)) < 1e-5
 
 
+def test_sharded_index_from_store(tmp_path):
+    """Disk -> pinned staging -> HBM -> exact top-k: same ranking as the in-memory database (fp32 store), and exact
+    for the STORED values with an fp16 store."""
+    _gpu()
+    from dirb200.dist import ShardedIndex
+    from dirb200 import store as S
+    db, q, _ = synth.make_descriptor_db(5000, 17, dim=256, n_pos=5)
+    qd = torch.from_numpy(q).cuda()
+    st = S.write_store(str(tmp_path / "f32"), db, rows_per_shard=1234)
+    sh = ShardedIndex.from_store(st, "cuda:0", chunk_rows=1000)
+    assert sh.local.n == 5000 and sh.row_offset == 0
+    s, i = sh.search(qd, 30)
+    rs, ri = O.topk(q, db, 30)
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=0, atol=1e-12)
+    st16 = S.write_store(str(tmp_path / "f16"), db, rows_per_shard=2048, dtype=np.float16)
+    sh16 = ShardedIndex.from_store(st16, "cuda:0")
+    s, i = sh16.search(qd, 30)
+    rs, ri = O.topk(q, db.astype(np.float16).astype(np.float32), 30)
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=0, atol=1e-12)
+
+
 def test_cli_end_to_end(tmp_path, monkeypatch, capsys):
     """extract_features + test_dir CLIs on a synthetic Oxford-layout DB_ROOT vs the oracle pipeline."""
     _gpu()
