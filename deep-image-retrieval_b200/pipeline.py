@@ -36,9 +36,10 @@ def _dev_f32(x):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).cuda()
 
 
-def expand_descriptors(descs, db=None, alpha=0, k=0):
+def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096):
     """alpha query expansion (db given) / database augmentation (db=None): test_dir.py:24-44.
-    q' = normalize(mean([q] + [db_j * sim_ij^alpha for the k nearest j])).  Returns a host ndarray."""
+    q' = normalize(mean([q] + [db_j * sim_ij^alpha for the k nearest j])).  Returns a host ndarray.
+    q_block (extension): queries searched per pass."""
     assert k >= 0 and alpha >= 0, "k and alpha must be non-negative"
     if k == 0:
         return descs
@@ -50,20 +51,24 @@ def expand_descriptors(descs, db=None, alpha=0, k=0):
         return torch.nn.functional.pad(x, (0, pad)).contiguous() if pad else x
 
     q = _padded(descs)
-    if db is not None:
-        d = _padded(db)
-        s, i = ops.Index(d).search(q, k)
-    else:
-        # the reference zeroes the diagonal of the self-similarity (test_dir.py:33-34): drop each row from its
-        # own neighbour list
-        d = q
-        s1, i1 = ops.Index(d).search(q, min(k + 1, d.shape[0]))
-        s1, i1 = s1.cpu().numpy(), i1.cpu().numpy()
-        rows = np.arange(q.shape[0])[:, None]
-        keep = np.argsort(i1 == rows, axis=1, kind="stable")[:, :k]       # non-self entries first, order preserved
-        s = torch.from_numpy(np.take_along_axis(s1, keep, 1).copy()).cuda()
-        i = torch.from_numpy(np.take_along_axis(i1, keep, 1).copy()).cuda()
-    out = ops.aqe_expand(q, d, i.contiguous(), s.contiguous(), float(alpha))
+    d = _padded(db) if db is not None else q
+    index = ops.Index(d)
+    out = torch.empty_like(q)
+    # Queries go through in blocks so that database augmentation (an N x N self-search) needs O(block) scratch.
+    for c0 in range(0, q.shape[0], q_block):
+        qc = q[c0:c0 + q_block].contiguous()
+        if db is not None:
+            s, i = index.search(qc, min(k, d.shape[0]))
+        else:
+            # the reference zeroes the diagonal of the self-similarity (test_dir.py:33-34): drop each row from its
+            # own neighbour list
+            s1, i1 = index.search(qc, min(k + 1, d.shape[0]))
+            s1, i1 = s1.cpu().numpy(), i1.cpu().numpy()
+            rows = np.arange(c0, c0 + qc.shape[0])[:, None]
+            keep = np.argsort(i1 == rows, axis=1, kind="stable")[:, :k]   # non-self entries first, order preserved
+            s = torch.from_numpy(np.take_along_axis(s1, keep, 1).copy()).cuda()
+            i = torch.from_numpy(np.take_along_axis(i1, keep, 1).copy()).cuda()
+        out[c0:c0 + qc.shape[0]] = ops.aqe_expand(qc, d, i.contiguous(), s.contiguous(), float(alpha))
     return out[:, :dim].cpu().numpy()
 
 

@@ -56,6 +56,10 @@ def test_expand_descriptors(golden):
     assert expand_descriptors(q, db=db, k=0, alpha=1) is q
     out = expand_descriptors(pad(g["dba_in"]), db=None, k=2, alpha=1)       # database-side augmentation
     assert rel_l2(out[:, :48], g["dba_k2_a1"]) < 1e-5
+    # blocked query passes (how a large N x N augmentation runs) give the same rows
+    assert np.array_equal(expand_descriptors(pad(g["dba_in"]), db=None, k=2, alpha=1, q_block=16), out)
+    assert np.array_equal(expand_descriptors(q, db=db, k=2, alpha=0.5, q_block=2),
+                          expand_descriptors(q, db=db, k=2, alpha=0.5))
     with pytest.raises(AssertionError):
         expand_descriptors(q, db=db, k=-1, alpha=1)
 
