@@ -236,6 +236,9 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out) {
 int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   DIRB_REQUIRE(n && key, DIRB200_EINVAL, "null argument");
   const std::string k(key);
+  // options that decide which tensors dirb200_net_finalize reads / packs cannot change afterwards
+  const bool structural = (k == "pooling" || k == "without_fc" || k == "out_dim");
+  DIRB_REQUIRE(!(structural && n->finalized), DIRB200_ESTATE, "option '%s' must be set before dirb200_net_finalize", key);
   if (k == "pooling") n->pooling = static_cast<int>(value);
   else if (k == "norm_features") n->norm_features = value != 0;
   else if (k == "without_fc") n->without_fc = value != 0;

@@ -4,18 +4,24 @@
 // per-query sort (datasets/generic.py:207,221) for the first k ranks, without materialising the Q x N matrix:
 //
 //   1. queries -> fp16                                                             (f32_to_f16)
-//   2. seed:   tcgen05 GEMM of the queries against the first S rows, scores written densely;
-//              per query the k-th largest fp16-path score t_S is a lower bound on the final k-th score
-//                                                                                  (gemm_tc EPI_SIM_DENSE + kth_dense)
+//   2. seed:   tcgen05 GEMM of the queries against the first S rows.  The epilogue keeps the maximum of every group
+//              of 32 consecutive rows (PERS_EPI_SIM_GMAX; 1/32 of the dense score traffic); per query the k-th largest
+//              group maximum t_S has >= k rows at or above it, so it is a lower bound on the final k-th score.
+//              (fewer than k groups: dense scores, PERS_EPI_SIM_DENSE)                 (kth_dense_kernel)
 //   3. filter: tcgen05 GEMM against all N rows; the epilogue appends (score,row) to the query's candidate list
-//              only when score >= t_S - 2*eps16                                     (gemm_tc EPI_SIM_FILTER)
-//      (for N <= S step 3 is a scan of the dense scores instead)
-//   4. select: exact k-th largest candidate score t; survivors = candidates with score >= t - 2*eps16
-//   5. rescore the survivors exactly (fp64 accumulation of the fp32 rows) and sort (score desc, index asc).
+//              only when score >= t_S - 2*eps16                                     (PERS_EPI_SIM_FILTER)
+//      (for N <= S step 3 is a scan of the dense scores instead: dense_compact_kernel)
+//   4. select: exact k-th largest candidate score t (radix select, cand_kth_kernel); survivors = candidates with
+//              score >= t - 2*eps16                                                    (cand_survivors_kernel)
+//   5. rescore the survivors exactly (fp64 accumulation of the fp32 rows, rescore_kernel) and sort
+//      (score desc, index asc: sort_topk_kernel).
 //
-// eps16 bounds |fp16-path score - exact score|; any row of the true top-k then satisfies the step-3 and step-4
-// conditions, so the result is the exact top-k (same argument twice).  Candidate-buffer overflow raises the
-// threshold from what was captured and re-runs the filter pass.
+// eps16 bounds |fp16-path score - exact score| (unit-norm rows: 2 * 2^-11 from the operand roundings + fp32
+// accumulation, default 1.2e-3); any row of the true top-k then satisfies the step-3 and step-4 conditions, so the
+// result is the exact top-k (same argument twice).  Candidate-buffer overflow raises the threshold from what was
+// captured and re-runs the filter pass.  With several shards the phases are split (search_begin / search_finish)
+// so that the caller can MIN-reduce the per-shard selection thresholds in between (see cand_kth_kernel).
+// The GEMMs run on the persistent warp-specialised kernel of conv_pers.cuh (128 x 256 tiles, K = D).
 #include <math.h>
 
 #include <algorithm>
@@ -446,6 +452,7 @@ int dirb200_index_last_profile(dirb200_index* h, double out9[9]) {
 
 int dirb200_index_destroy(dirb200_index* h) {
   if (!h) return 0;
+  cudaSetDevice(h->device);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
   if (h->ws) cudaFree(h->ws);
   if (h->sel_own) cudaFree(h->sel_own);
@@ -714,7 +721,8 @@ int dirb200_aqe_expand(const float* q_dev, int Q, int D, const float* db32_dev, 
                        float* out_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DIRB_REQUIRE(q_dev && db32_dev && nn_idx_dev && nn_scores_dev && out_dev, DIRB200_EINVAL, "null argument");
-  DIRB_REQUIRE(k >= 1 && k <= 4096 && alpha >= 0, DIRB200_EINVAL, "k and alpha must be non-negative (test_dir.py:25)");
+  DIRB_REQUIRE(k >= 1 && alpha >= 0, DIRB200_EINVAL, "k and alpha must be non-negative (test_dir.py:25)");
+  DIRB_REQUIRE(k <= 2048, DIRB200_ENOTSUP, "at most 2048 neighbours per query (got %d)", k);
   if (Q == 0) return 0;
   const size_t smem = static_cast<size_t>((k + 1) & ~1) * 4 + static_cast<size_t>(k) * 8;
   aqe_kernel<<<Q, 256, smem, stream>>>(q_dev, D, db32_dev, nn_idx_dev, nn_scores_dev, k, alpha, partial, row_offset,

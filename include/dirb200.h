@@ -47,15 +47,24 @@ int dirb200_device_check(int device);
  * dirtorch/nets/__init__.py:24-64, dirtorch/nets/rmac_resnet.py:12-69,
  * dirtorch/nets/backbones/resnet.py:46-87,102-174, dirtorch/nets/layers/pooling.py:38-54.   */
 
-/* arch: "resnet50_rmac" | "resnet101_rmac" (Bottleneck trunks, rmac_resnet.py:78-84). */
+/* arch: "resnet50_rmac" | "resnet101_rmac" | "resnet152_rmac" (Bottleneck trunks, rmac_resnet.py:78-88). */
 int dirb200_net_create(const char* arch, int device, dirb200_net** out);
-/* Options (rmac_resnet.py:15-37): "pooling" 0=gem 1=max 2=avg; "norm_features" 0/1;
- * "without_fc" 0/1; "out_dim"; "chunk" images processed per pass (0 = auto);
- * "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit GEMM (validation path),
- * 2 = one-tile-per-CTA tcgen05 kernel (A/B baseline);
- * "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage; "halo" 1 (default) / 0 = 3x3 stride-1 convolutions load their input patch once per tile
- * (conv_halo.cuh) or tap by tap (process-wide A/B switch); "profile" 1 = time every launch
- * with CUDA events (dirb200_net_profile); "host_chunk" images per pipeline stage of dirb200_net_forward_host. */
+/* Options.
+ * Model options of rmac_resnet.py:15-37 (the three marked * must be set BEFORE dirb200_net_finalize, later
+ * changes return DIRB200_ESTATE): "pooling"* 0=gem 1=max 2=avg; "without_fc"* 0/1; "out_dim"*; "norm_features" 0/1;
+ * "center_bias" b >= 0 (rmac_resnet.py:52-56); "gem_eps" (pooling.py:39, default 1e-6);
+ * "mean0".."mean2", "std0".."std2": Normalize constants of the uint8 entry points (default resnet.py:110-111).
+ * Scheduling: "chunk" images per pass of the network (0 = auto); "host_chunk" images per pipeline stage of
+ * dirb200_net_forward_host (default 16); "stage_sched" 1 = run each stage in L2-sized sub-chunks ("sub0".."sub4"
+ * images per sub-chunk of stem / layer1..4), 0 (default, faster as measured) = whole chunk per stage.
+ * Implementation A/B switches: "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit
+ * GEMM (validation path), 2 = one-tile-per-CTA tcgen05 kernel (baseline); "fuse_ds" 1 (default) = projection
+ * shortcut fused into conv3 as a K-concatenated GEMM.  PROCESS-WIDE (they select kernels, not handle state; set
+ * them once, not concurrently with a running forward): "halo" 1 (default) / 0 = 3x3 stride-1 convolutions load
+ * their input patch once per tile (conv_halo.cuh) or tap by tap; "pdl" 1 (default) = programmatic dependent
+ * launch between consecutive kernels; "res_variant" tile-variant selector of the residual 1x1 convolutions.
+ * Diagnostics: "debug_taps" 1 = keep copies of the stage outputs for dirb200_net_debug_stage; "profile" 1 = time
+ * every launch with CUDA events (dirb200_net_profile). */
 int dirb200_net_set_option(dirb200_net* net, const char* key, double value);
 /* One state_dict tensor by its reference key ("layer3.5.bn2.running_var", "adpool.p", "fc.weight" ...),
  * fp32 host memory, reference shape (conv OIHW).  "num_batches_tracked" keys are ignored. */
