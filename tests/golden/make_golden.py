@@ -182,9 +182,83 @@ def gold_aqe():
     save("aqe.npz", **out)
 
 
+def gold_cli():
+    for hard in (False, True):
+        _gold_cli(hard)
+
+
+def _gold_cli(hard):
+    """The reference's OWN command lines, unmodified, on the synthetic Oxford-layout DB_ROOT of tests/e2e_data.py:
+    `python -m dirtorch.extract_features` and `python -m dirtorch.test_dir` (CPU, --gpu -1), run as subprocesses
+    from a neutral working directory with only /root/reference on PYTHONPATH."""
+    import json
+    import subprocess
+    from sklearn.decomposition import PCA
+    sys.path.append(REPO)                      # after /root/reference: `dirtorch` stays the reference's
+    sys.path.append(os.path.join(REPO, "tests"))
+    import e2e_data
+    root = tempfile.mkdtemp(prefix="dbroot_cli_")
+    gnd, names, qn, sd = e2e_data.build(root, hard=hard)
+    env = dict(os.environ, PYTHONPATH=REF, DB_ROOT=root, TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD="1")
+    ckpt = os.path.join(root, "ckpt.pt")
+    opts = dict(arch="resnet50_rmac", out_dim=2048, pooling="gem", gemp=3)
+
+    def run(mod, *argv):
+        r = subprocess.run([sys.executable, "-m", mod] + list(argv), cwd=root, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return r.stdout
+
+    # 1. raw descriptors through the reference's extract_features CLI (checkpoint without PCA yet)
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}, "model_options": opts}, ckpt)
+    with open(os.path.join(root, "list.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    run("dirtorch.extract_features", "--dataset", 'ImageList("%s/list.txt", "%s/oxford5k/jpg")' % (root, root),
+        "--checkpoint", ckpt, "--output", os.path.join(root, "out", "feats.npy"), "--gpu", "-1", "--threads", "2")
+    D = np.load(os.path.join(root, "out", "feats.npy"))
+    # 2. PCA learnt on them, stored the way the released checkpoints do (ckpt['pca'][name]), test_dir CLI
+    pca = PCA(n_components=32, whiten=True).fit(D)
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}, "model_options": opts,
+                "pca": {"Landmarks_clean": pca}}, ckpt)
+    common_args = ["--dataset", "Oxford5K", "--checkpoint", ckpt, "--whiten", "Landmarks_clean", "--whitenp", "0.25",
+                   "--gpu", "-1", "--threads", "2"]
+    out1 = run("dirtorch.test_dir", *common_args, "--save-feats", os.path.join(root, "saved"),
+               "--out-json", os.path.join(root, "res1.json"))
+    out2 = run("dirtorch.test_dir", *common_args, "--load-feats", os.path.join(root, "saved"), "--aqe", "2", "1",
+               "--out-json", os.path.join(root, "res2.json"))
+    out3 = run("dirtorch.test_dir", *common_args, "--load-feats", os.path.join(root, "saved"), "--adba", "2", "1",
+               "--out-json", os.path.join(root, "res3.json"))
+    res = [json.load(open(os.path.join(root, "res%d.json" % i)))["Oxford5K"] for i in (1, 2, 3)]
+    lines = [[l for l in o.splitlines() if l.startswith(" * ")] for o in (out1, out2, out3)]
+    # 3. per-query APs (eval_model(detailed=True) cannot be printed by the reference's own CLI)
+    from dirtorch.datasets.generic import ImageListRelevants
+    ds = ImageListRelevants(os.path.join(root, "oxford5k", "gnd_oxford5k.pkl"), root=os.path.join(root, "oxford5k"))   # = Oxford5K(), oxford.py:8-11
+    net = ref_test_dir.load_model(ckpt, False)
+    net.pca = net.pca["Landmarks_clean"]
+    ref_test_dir.args = SimpleNamespace(aqe=None, adba=None)
+    det = ref_test_dir.eval_model(ds, net, "", detailed=True, whiten=dict(whitenp=0.25, whitenv=None, whitenm=1.0),
+                                  load_feats=os.path.join(root, "saved"), threads=2)
+    saved = np.load(os.path.join(root, "saved", "feats.bdescs.npy"))
+    W = common.whiten_features(saved, net.pca, whitenp=0.25)
+    # The fitted PCA in 13 KB instead of 270 KB: its components lie in the row space of the centred descriptors,
+    # components_ = coeff @ (D - mean(D)); the test rebuilds them from the oracle's descriptors (a PCA *refit* there
+    # would be ill-conditioned in the trailing components and is sklearn's business, not the path's).
+    Dc = D.astype(np.float64) - D.astype(np.float64).mean(0)
+    coeff = pca.components_.astype(np.float64) @ np.linalg.pinv(Dc, rcond=1e-10)
+    err_c, err_m = np.abs(coeff @ Dc - pca.components_).max(), np.abs(pca.mean_ - D.mean(0)).max()
+    print('PCA coefficient reconstruction error', err_c, err_m)
+    assert err_c < 1e-5 and err_m < 1e-6
+    save("cli_hard.npz" if hard else "cli_easy.npz", pca_coeff=coeff, pca_var=pca.explained_variance_, n_images=len(names), queries=np.array(qn), desc_head=D[:3], desc_norms=np.linalg.norm(D, axis=1),
+         saved_equals_extract=np.array(np.array_equal(saved, D)), whitened=W,
+         mAP=res[0]["mAP"], mAP_aqe_k2_a1=res[1]["mAP"], mAP_adba_k2_a1=res[2]["mAP"], APs=np.array(det["APs"]),
+         console=np.array([l for ls in lines for l in ls]))
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["extra"]:               # only the files added after the first batch
         gold_extract_extra()
+        sys.exit(0)
+    if sys.argv[1:] == ["cli"]:
+        gold_cli()
         sys.exit(0)
     gold_gem()
     gold_pool()
@@ -193,3 +267,4 @@ if __name__ == "__main__":
     gold_aqe()
     gold_extract()
     gold_extract_extra()
+    gold_cli()

@@ -1,6 +1,7 @@
 """Pin the CPU oracle (oracle/dir_oracle.py) against the golden vectors produced by the
 unmodified reference (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 import dirb200.synth as synth
@@ -128,3 +129,41 @@ def test_extract_r152_and_center_bias(golden):
     for tag, cb in (("cb05", 0.5), ("cb2", 2.0)):
         assert rel_l2(O.extract(x, sd, "resnet50_rmac", center_bias=cb).numpy(), g["desc_" + tag]) < 2e-5, tag
     assert rel_l2(O.extract(x, sd, "resnet50_rmac").numpy(), g["desc_cb2"]) > 1e-3   # the option is not a no-op
+
+
+@pytest.mark.parametrize("variant", ["easy", "hard"])
+def test_pipeline_matches_reference_command_lines(golden, tmp_path, variant):
+    """cli_*.npz hold what the reference's own `python -m dirtorch.extract_features` / `python -m dirtorch.test_dir`
+    (+ --aqe, --adba) print and save on the synthetic Oxford-layout dataset of tests/e2e_data.py.  The oracle pipeline
+    (extract -> whiten with the run's PCA -> scores -> AP) must reproduce them; tests/test_gpu_pipeline.py::test_cli_end_to_end
+    compares the GPU command lines with the same oracle pipeline on the same files."""
+    import os
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import e2e_data
+    g = golden("cli_%s.npz" % variant)
+    gnd, names, qn, sd = e2e_data.build(str(tmp_path), hard=(variant == "hard"))
+    assert len(names) == int(g["n_images"]) and list(qn) == list(g["queries"])
+    xs = e2e_data.load_normalised(str(tmp_path), names)
+    with torch.no_grad():
+        D = np.stack([O.extract(x, sd, "resnet50_rmac").numpy() for x in xs])
+    assert rel_l2(D[:3], g["desc_head"]) < 2e-5                                   # extract_features.py output
+    assert bool(g["saved_equals_extract"])                                        # --save-feats == --output rows
+    # the reference run's fitted PCA, rebuilt from its coefficients over the centred descriptors (see make_golden.py)
+    mean = D.astype(np.float64).mean(0)
+    pca = SimpleNamespace(mean_=mean.astype(np.float32), whiten=True, explained_variance_=g["pca_var"],
+                          components_=(g["pca_coeff"] @ (D.astype(np.float64) - mean)).astype(np.float32))
+    W = O.whiten_features(D, pca, whitenp=0.25)
+    assert rel_l2(W, g["whitened"]) < 1e-3
+    m, aps = O.mean_ap(O.scores_exact(W[qn], W), gnd)
+    np.testing.assert_allclose(aps, g["APs"], rtol=0, atol=1e-12)
+    assert abs(m - float(g["mAP"])) < 1e-12
+    assert " * mAP = %g" % m == str(g["console"][0])                              # test_dir.py:245
+    m_aqe, _ = O.mean_ap(O.scores_exact(O.expand_descriptors(W[qn], db=W, k=2, alpha=1), W), gnd)
+    assert abs(m_aqe - float(g["mAP_aqe_k2_a1"])) < 1e-12                          # --aqe 2 1
+    Wd = O.expand_descriptors(W, db=None, k=2, alpha=1)                            # --adba 2 1 (queries are NOT
+    m_dba, _ = O.mean_ap(O.scores_exact(W[qn], Wd), gnd)                           # re-drawn from the augmented rows)
+    assert abs(m_dba - float(g["mAP_adba_k2_a1"])) < 1e-12
+    if variant == "hard":
+        assert 0.5 < m < 0.95 and len(set(np.round(aps, 6))) >= 3                 # a ranking that can actually differ
