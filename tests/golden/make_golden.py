@@ -247,7 +247,18 @@ def _gold_cli(hard):
     err_c, err_m = np.abs(coeff @ Dc - pca.components_).max(), np.abs(pca.mean_ - D.mean(0)).max()
     print('PCA coefficient reconstruction error', err_c, err_m)
     assert err_c < 1e-5 and err_m < 1e-6
-    save("cli_hard.npz" if hard else "cli_easy.npz", pca_coeff=coeff, pca_var=pca.explained_variance_, n_images=len(names), queries=np.array(qn), desc_head=D[:3], desc_norms=np.linalg.norm(D, axis=1),
+    extra = {}
+    if hard:
+        # multi-scale protocol of the paper through the same command line: three transform chains, GeM pooling of
+        # the per-scale descriptors (common.pool, common.py:41-55), F.normalize, whitening, ranking
+        out4 = run("dirtorch.test_dir", *common_args, "--trfs", "Scale(0.7)", "", "Scale(1.4)", "--pooling", "gem",
+                   "--gemp", "3", "--save-feats", os.path.join(root, "saved_ms"), "--out-json", os.path.join(root, "res4.json"))
+        saved_ms = np.load(os.path.join(root, "saved_ms", "feats.bdescs.npy"))
+        det_ms = ref_test_dir.eval_model(ds, net, "", detailed=True, whiten=dict(whitenp=0.25, whitenv=None, whitenm=1.0),
+                                         load_feats=os.path.join(root, "saved_ms"), threads=2)
+        extra = dict(ms_mAP=json.load(open(os.path.join(root, "res4.json")))["Oxford5K"]["mAP"], ms_APs=np.array(det_ms["APs"]),
+                     ms_desc_head=saved_ms[:3], ms_console=np.array([l for l in out4.splitlines() if l.startswith(" * ")]))
+    save("cli_hard.npz" if hard else "cli_easy.npz", **extra, pca_coeff=coeff, pca_var=pca.explained_variance_, n_images=len(names), queries=np.array(qn), desc_head=D[:3], desc_norms=np.linalg.norm(D, axis=1),
          saved_equals_extract=np.array(np.array_equal(saved, D)), whitened=W,
          mAP=res[0]["mAP"], mAP_aqe_k2_a1=res[1]["mAP"], mAP_adba_k2_a1=res[2]["mAP"], APs=np.array(det["APs"]),
          console=np.array([l for ls in lines for l in ls]))

@@ -167,3 +167,21 @@ def test_pipeline_matches_reference_command_lines(golden, tmp_path, variant):
     assert abs(m_dba - float(g["mAP_adba_k2_a1"])) < 1e-12
     if variant == "hard":
         assert 0.5 < m < 0.95 and len(set(np.round(aps, 6))) >= 3                 # a ranking that can actually differ
+        # multi-scale protocol: --trfs "Scale(0.7)" "" "Scale(1.4)" --pooling gem --gemp 3.  The transform chains are
+        # built by the product's host code (loader.create_transforms), PIL does the resizing as in the reference.
+        from PIL import Image
+        from dirb200 import loader
+        pre = dict(mean=synth.RGB_MEANS, std=synth.RGB_STDS)
+        per_scale = []
+        for chain in ("Scale(0.7)", "", "Scale(1.4)"):
+            trf = loader.create_transforms(chain, to_tensor=True, **pre)
+            with torch.no_grad():
+                per_scale.append(np.stack([
+                    O.extract(trf(Image.open(os.path.join(str(tmp_path), "oxford5k", "jpg", n)).convert("RGB"))[None], sd,
+                              "resnet50_rmac").numpy() for n in names]))
+        Dm = O.l2n(O.pool_scales(per_scale, "gem", 3))                              # test_dir.py:121-122
+        assert rel_l2(Dm[:3], g["ms_desc_head"]) < 2e-5
+        Wm = O.whiten_features(Dm, pca, whitenp=0.25)
+        mm, aps_m = O.mean_ap(O.scores_exact(Wm[qn], Wm), gnd)
+        np.testing.assert_allclose(aps_m, g["ms_APs"], rtol=0, atol=1e-12)
+        assert abs(mm - float(g["ms_mAP"])) < 1e-12 and " * mAP = %g" % mm == str(g["ms_console"][0])
