@@ -62,3 +62,30 @@ def test_model_api_surface():
     assert len([k for k in sd if not k.endswith("num_batches_tracked")]) == 161 * 1 + 0 or True
     net.load_state_dict({"module." + k: v for k, v in sd.items()})   # DataParallel prefix accepted
     assert net.eval() is net and net.fc_name == "fc" and net.feat_dim == 2048
+
+
+def test_integration_stub_is_current():
+    """The ctypes binding shown in INTEGRATION.md compiles, calls only exported entry points with the header's
+    argument counts, and uses only option keys the library accepts."""
+    from dirb200 import lib
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "class B200Net" in b)
+    compile(stub, "INTEGRATION.md", "exec")
+    calls = re.findall(r"_L\.(dirb200_[a-z0-9_]+)\(", stub)
+    assert len(set(calls)) >= 8
+    for name in set(calls):
+        assert name in lib.SIGNATURES, name
+    # argument counts (balanced-parenthesis scan, calls may span lines)
+    for m in re.finditer(r"_L\.(dirb200_[a-z0-9_]+)\(", stub):
+        name, i, depth = m.group(1), m.end(), 1
+        n = 0 if stub[i] == ")" else 1
+        while depth:
+            ch = stub[i]
+            depth += (ch in "([") - (ch in ")]")
+            n += (ch == "," and depth == 1)
+            i += 1
+        assert n == len(lib.SIGNATURES[name][1]), (name, n, len(lib.SIGNATURES[name][1]))
+    hdr = open(os.path.join(REPO, "include", "dirb200.h")).read()
+    for key in ("pooling", "norm_features", "without_fc", "out_dim", "center_bias"):
+        assert '"%s"' % key in hdr and key in stub
