@@ -1,7 +1,8 @@
 """Minimal dataset layer behind the CLIs: image lists and Oxford-style retrieval ground truth.
 
 Mirrors the parts of ``dirtorch/datasets`` the evaluation path touches: ``ImageList`` (generic.py:13-30),
-``ImageListRelevants`` + ``eval_query_AP`` (generic.py:120-224), ``ImageListROIs`` (generic.py:226-250),
+``ImageListLabels`` / ``ImageListLabelsQ`` with the label-based AP and top-k of ``Dataset`` (generic.py:33-121,
+dataset.py:69-101), ``ImageListRelevants`` + ``eval_query_AP`` (generic.py:120-224), ``ImageListROIs`` (generic.py:226-250),
 the Oxford/Paris wrappers (oxford.py, paris.py) and ``create`` (create.py:19-24).  AP arithmetic follows
 ``utils/evaluation.py:46-82``.  File bookkeeping only - nothing here is on the GPU hot path.
 """
@@ -75,6 +76,99 @@ class ImageList(Dataset):
 
     def get_key(self, i):
         return self.imgs[i]
+
+
+class ImageListLabels(Dataset):
+    """Images with one class label each; every image is also a query and its positives are the other images of its
+    class (generic.py:44-77; ground truth and AP: dataset.py:69-92 with sklearn's average_precision_score,
+    evaluation.py:41-43).
+
+    Input: a text file with ``<image path> <label>`` per row, a json ``{path: label}``, or explicit lists."""
+
+    def __init__(self, img_list_path=None, root=None, imgs=None, labels=None, cls_idx=None):
+        self.root = root or ""
+        if imgs is None:
+            if osp.splitext(img_list_path)[1] == ".json":
+                import json
+                with open(img_list_path) as f:
+                    pairs = list(json.load(f).items())
+            else:
+                with open(img_list_path) as f:
+                    pairs = [row.split(" ")[:2] for row in (e.strip() for e in f) if row]
+            imgs, labels = [p[0] for p in pairs], [p[1] for p in pairs]
+        assert len(imgs) == len(labels), "one label per image"
+        self.imgs, self.labels = list(imgs), list(labels)
+        self.nimg = len(self.imgs)
+        self._index_classes(self.labels, cls_idx)
+
+    def _index_classes(self, all_labels, cls_idx=None):
+        # class ids in order of first appearance (callers may pin some ids through cls_idx)
+        self.cls_idx = dict(cls_idx or {})
+        free = (i for i in range(len(set(all_labels) | set(self.cls_idx))) if i not in set(self.cls_idx.values()))
+        for lab in all_labels:
+            if lab not in self.cls_idx:
+                self.cls_idx[lab] = next(free)
+        self.classes = [c for c, _ in sorted(self.cls_idx.items(), key=lambda kv: kv[1])]
+        self.nclass = len(self.classes)
+        self.c_relevant_idx = {}
+        for i, lab in enumerate(self.labels):
+            self.c_relevant_idx.setdefault(lab, []).append(i)
+
+    def get_key(self, i):
+        return self.imgs[i]
+
+    def get_label(self, i, toint=False):
+        return self.cls_idx[self.labels[i]] if toint else self.labels[i]
+
+    def get_query_db(self):
+        return self
+
+    def get_query_groundtruth(self, query_idx, what="AP"):
+        qdb = self.get_query_db()
+        qlabel = qdb.get_label(query_idx)
+        if what == "label":
+            return qlabel
+        if what != "AP":
+            raise ValueError("Unknown ground-truth type: %s" % what)
+        gt = -np.ones(self.nimg, dtype=np.int8)                  # negatives
+        gt[self.c_relevant_idx.get(qlabel, [])] = 1              # same class
+        if qdb is self:
+            gt[query_idx] = 0                                    # the query itself is ignored
+        return gt
+
+    def eval_query_AP(self, query_idx, scores):
+        from sklearn.metrics import average_precision_score
+        gt = self.get_query_groundtruth(query_idx, "AP")
+        scores = np.asarray(scores)
+        assert gt.shape == scores.shape, "scores should have shape %s" % str(gt.shape)
+        keep = gt != 0
+        if not (gt[keep] > 0).any():
+            return -1                                            # no relevant image: excluded from the mean
+        return average_precision_score(gt[keep] > 0, scores[keep])
+
+    def eval_query_top(self, query_idx, scores, k=(1, 5, 10, 20, 50, 100)):
+        qlabel = self.get_query_groundtruth(query_idx, "label")
+        correct = np.array([lab == qlabel for lab in self.labels], dtype=bool)[np.argsort(-np.asarray(scores))]
+        return {k_: float(correct[:k_].any()) for k_ in k if k_ < len(correct)}
+
+
+class ImageListLabelsQ(ImageListLabels):
+    """Labelled database + a separate labelled query list (generic.py:80-105)."""
+
+    def __init__(self, img_list_path, query_list_path, root=None):
+        with open(query_list_path) as f:
+            qpairs = [row.split(" ")[:2] for row in (e.strip() for e in f) if row]
+        self.qimgs, self.qlabels = [p[0] for p in qpairs], [p[1] for p in qpairs]
+        ImageListLabels.__init__(self, img_list_path, root=root)
+        self.nquery = len(self.qimgs)
+
+    def _index_classes(self, all_labels, cls_idx=None):
+        ImageListLabels._index_classes(self, list(all_labels) + list(self.qlabels), cls_idx)
+
+    def get_query_db(self):
+        if getattr(self, "_qdb", None) is None:
+            self._qdb = ImageListLabels(root=self.root, imgs=self.qimgs, labels=self.qlabels, cls_idx=self.cls_idx)
+        return self._qdb
 
 
 class ImageListROIs(Dataset):

@@ -182,6 +182,35 @@ def gold_aqe():
     save("aqe.npz", **out)
 
 
+def gold_labels():
+    """Label-based AP of Dataset.eval_query_AP (dataset.py:83-92 -> sklearn, evaluation.py:41-43) on labelled image
+    lists (generic.py:44-105): every image a query, and a separate query list."""
+    from dirtorch.datasets.generic import ImageListLabels, ImageListLabelsQ
+    r = np.random.RandomState(17)
+    n, nq = 60, 7
+    labels = ["c%d" % v for v in r.randint(0, 6, n)]
+    labels[5] = "lonely"                                      # a class of one: AP = -1 for that query
+    qlabels = ["c%d" % v for v in r.randint(0, 7, nq)]         # c6 never occurs in the database
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "db.txt"), "w") as f:
+        f.write("\n".join("im%03d.jpg %s" % (i, l) for i, l in enumerate(labels)) + "\n")
+    with open(os.path.join(tmp, "q.txt"), "w") as f:
+        f.write("\n".join("q%03d.jpg %s" % (i, l) for i, l in enumerate(qlabels)) + "\n")
+    scores = r.standard_normal((n, n)).astype(np.float32)
+    qscores = r.standard_normal((nq, n)).astype(np.float32)
+    ds = ImageListLabels(os.path.join(tmp, "db.txt"), root=tmp)
+    aps = np.array([ds.eval_query_AP(q, scores[q]) for q in range(n)], dtype=np.float64)
+    dsq = ImageListLabelsQ(os.path.join(tmp, "db.txt"), os.path.join(tmp, "q.txt"), root=tmp)
+    qaps = []
+    for q in range(nq):
+        try:
+            qaps.append(dsq.eval_query_AP(q, qscores[q]))
+        except KeyError:                                        # label absent from the database: c_relevant_idx[...] raises
+            qaps.append(np.nan)
+    save("label_ap.npz", labels=np.array(labels), qlabels=np.array(qlabels), scores=scores, qscores=qscores, aps=aps,
+         qaps=np.array(qaps, dtype=np.float64), gt0=ds.get_query_groundtruth(0), nclass=ds.nclass, nclass_q=dsq.nclass)
+
+
 def gold_cli():
     for hard in (False, True):
         _gold_cli(hard)
@@ -271,6 +300,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["cli"]:
         gold_cli()
         sys.exit(0)
+    if sys.argv[1:] == ["labels"]:
+        gold_labels()
+        sys.exit(0)
     gold_gem()
     gold_pool()
     gold_whiten()
@@ -279,3 +311,4 @@ if __name__ == "__main__":
     gold_extract()
     gold_extract_extra()
     gold_cli()
+    gold_labels()

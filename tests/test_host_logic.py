@@ -63,6 +63,41 @@ def test_ap_from_ranked_prefix_equals_ap_from_scores(golden, tmp_path):
             assert short is None or (isinstance(short, dict) and any(v is None for v in short.values())) or worst == 0
 
 
+def test_label_datasets_ap_matches_reference(golden, tmp_path):
+    """Label-based AP / top-k (dataset.py:69-101) on labelled image lists (generic.py:44-105) vs the reference."""
+    from dirtorch import datasets as D
+    g = golden("label_ap.npz")
+    labels, qlabels = [str(v) for v in g["labels"]], [str(v) for v in g["qlabels"]]
+    with open(tmp_path / "db.txt", "w") as f:
+        f.write("\n".join("im%03d.jpg %s" % (i, l) for i, l in enumerate(labels)) + "\n")
+    with open(tmp_path / "q.txt", "w") as f:
+        f.write("\n".join("q%03d.jpg %s" % (i, l) for i, l in enumerate(qlabels)) + "\n")
+    ds = D.create('ImageListLabels("%s", root="%s")' % (tmp_path / "db.txt", tmp_path))
+    assert len(ds) == 60 and ds.nclass == int(g["nclass"]) and ds.get_query_db() is ds
+    assert ds.get_key(3) == "im003.jpg" and ds.get_label(3) == labels[3] and ds.classes[ds.get_label(3, toint=True)] == labels[3]
+    np.testing.assert_array_equal(ds.get_query_groundtruth(0), g["gt0"])
+    aps = np.array([ds.eval_query_AP(q, g["scores"][q]) for q in range(60)], dtype=np.float64)
+    np.testing.assert_allclose(aps, g["aps"], rtol=0, atol=1e-12)
+    assert aps[5] == -1                                                           # a class of one image
+    dsq = D.ImageListLabelsQ(str(tmp_path / "db.txt"), str(tmp_path / "q.txt"), root=str(tmp_path))
+    qdb = dsq.get_query_db()
+    assert dsq.nquery == 7 and len(qdb) == 7 and qdb.get_key(2) == "q002.jpg" and dsq.nclass == int(g["nclass_q"]) == qdb.nclass
+    qaps = np.array([dsq.eval_query_AP(q, g["qscores"][q]) for q in range(7)], dtype=np.float64)
+    np.testing.assert_allclose(qaps, g["qaps"], rtol=0, atol=1e-12)
+    # top-k: the reference's own eval_query_top needs np.bool8 (gone in NumPy 2); checked against its definition
+    s = g["scores"][1]
+    order = np.argsort(-s)
+    top = ds.eval_query_top(1, s, k=(1, 5, 100))
+    assert set(top) == {1, 5} and top[5] == float(any(labels[j] == labels[1] for j in order[:5]))
+    with pytest.raises(ValueError):
+        ds.get_query_groundtruth(0, "bogus")
+    # a json list gives the same dataset
+    import json
+    json.dump({"im%03d.jpg" % i: l for i, l in enumerate(labels)}, open(tmp_path / "db.json", "w"))
+    dj = D.ImageListLabels(str(tmp_path / "db.json"), root=str(tmp_path))
+    assert dj.labels == labels and dj.cls_idx == ds.cls_idx
+
+
 def test_transforms_and_loader(tmp_path):
     from PIL import Image
     from dirb200.loader import Scale, create_transforms, get_loader
