@@ -239,6 +239,58 @@ def extract_features(db, net, trfs, pooling="mean", gemp=3, detailed=False, whit
     print("Features extracted.")
 
 
+class _RowRange:
+    """The images [start, end) of a dataset, seen as a dataset (what one rank of a sharded extraction owns)."""
+
+    def __init__(self, dataset, start, end):
+        self.dataset, self.start, self.nimg = dataset, int(start), int(end) - int(start)
+
+    def __len__(self):
+        return self.nimg
+
+    def get_key(self, i):
+        return self.dataset.get_key(self.start + i)
+
+    def get_filename(self, i, root=None):
+        return self.dataset.get_filename(self.start + i, root=root)
+
+    def get_image(self, i, resize=None):
+        return self.dataset.get_image(self.start + i, resize=resize)
+
+
+def extract_to_store(db, net, trfs, store_path, pooling="mean", gemp=3, whiten=None, threads=8, batch_size=16,
+                     dtype=np.float32, group=None):
+    """Multi-GPU extraction (extension; the reference's analogue is nn.DataParallel, common.py:155).  Run under
+    torchrun, one process per GPU: rank r extracts the contiguous image range ``shard_rows(len(db), world, r)`` with
+    its own network handle, pools over the transform chains, normalises and optionally whitens exactly as
+    ``extract_features`` does, and writes its rows as one shard of a descriptor store (store.py); rank 0 writes the
+    manifest.  Images are independent, so there is no data-path collective.  Returns the opened store; each rank can
+    then search its rows with ``ShardedIndex.from_store``."""
+    import torch.distributed as tdist
+    from .dist import shard_rows
+    from .store import write_distributed
+    on = tdist.is_available() and tdist.is_initialized()
+    rank, world = (tdist.get_rank(group), tdist.get_world_size(group)) if on else (0, 1)
+    start, end = shard_rows(len(db), world, rank)
+    part = _RowRange(db, start, end)
+    trfs_list = [trfs] if isinstance(trfs, str) else trfs
+    dim = net.descriptor_dim if hasattr(net, "descriptor_dim") else net.feat_dim
+    if len(part):
+        descs = []
+        for trf in trfs_list:
+            descs.append(extract_image_features(part, trf, net, desc="DB[%d/%d]" % (rank, world), iscuda=net.iscuda,
+                                                threads=threads, batch_size=batch_size,
+                                                same_size="Pad" in trf or "Crop" in trf))
+        rows = tonumpy(_pool_and_normalize(descs, pooling, gemp))
+        if whiten is not None:
+            rows = common.whiten_features(rows, net.pca, **whiten)
+    else:                                                     # more ranks than images
+        rows = np.zeros((0, dim), np.float32)
+    meta = dict(arch=getattr(net, "arch", ""), trfs=list(trfs_list), pooling=pooling, gemp=gemp, whiten=whiten or {},
+                n_images=len(db))
+    return write_distributed(store_path, rows, group=group, dtype=dtype, meta=meta)
+
+
 def load_model(path, iscuda):
     """Build the network from a checkpoint dict (test_dir.py:183-191)."""
     checkpoint = common.load_checkpoint(path, iscuda)

@@ -137,6 +137,24 @@ def finalize_rank_shards(path: str, world: int, meta: dict = None):
     return DescriptorStore(path)
 
 
+def write_distributed(path: str, rows_local, group=None, dtype=None, meta: dict = None):
+    """Collective write under torch.distributed (one process per GPU): every rank writes the rows it owns - in rank
+    order they must form the database order, as after ``dist.shard_rows`` - as its own shard file, then rank 0
+    assigns the offsets and writes the manifest.  Two barriers, no data-path collective: descriptors never leave
+    the rank that extracted them.  Without an initialised process group this is ``write_store`` with one shard."""
+    import torch.distributed as tdist
+    if not (tdist.is_available() and tdist.is_initialized()):
+        write_rank_shard(path, rows_local, 0, dtype)
+        return finalize_rank_shards(path, 1, meta)
+    rank, world = tdist.get_rank(group), tdist.get_world_size(group)
+    write_rank_shard(path, rows_local, rank, dtype)
+    tdist.barrier(group)                       # every shard file is complete
+    if rank == 0:
+        finalize_rank_shards(path, world, meta)
+    tdist.barrier(group)                       # the manifest exists
+    return DescriptorStore(path)
+
+
 class DescriptorStore:
     """Read side.  Shards are memory-mapped lazily; ``read_rows`` may span shard boundaries."""
 

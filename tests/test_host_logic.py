@@ -210,6 +210,85 @@ def test_topk_exchange_gloo_world2(tmp_path):
     assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
 
 
+class _FakeNet:
+    """Stands in for the GPU network in host-plumbing tests: descriptor = per-channel mean / std of the image."""
+    iscuda = False
+    arch = "fake"
+    descriptor_dim = 6
+    preprocess = dict(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225], input_size=224)
+    pca = None
+
+    def eval(self):
+        return self
+
+    def __call__(self, imgs):
+        return torch.cat([imgs.mean(dim=(2, 3)), imgs.std(dim=(2, 3))], dim=1)
+
+
+def _fake_pool_and_normalize(descs, pooling, gemp):
+    x = torch.stack([d.float() for d in descs]).mean(0)
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def _make_image_list(tmp, n):
+    from PIL import Image
+    from dirtorch.datasets import ImageList
+    r = np.random.RandomState(8)
+    names = []
+    for i in range(n):
+        names.append("im%02d.png" % i)
+        Image.fromarray(r.randint(0, 256, (24 + i, 30, 3), dtype=np.uint8)).save(os.path.join(tmp, names[-1]))
+    return ImageList(imgs=names, root=tmp)
+
+
+def _extract_store_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import torch.distributed as dist
+    import dirb200  # noqa: F401
+    from dirb200 import pipeline
+    import test_host_logic as T
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pipeline._pool_and_normalize = T._fake_pool_and_normalize      # the real one runs CUDA kernels
+    ds = T._make_image_list(tmp, 7) if rank == 0 else None
+    dist.barrier()
+    if ds is None:
+        from dirtorch.datasets import ImageList
+        ds = ImageList(imgs=["im%02d.png" % i for i in range(7)], root=tmp)
+    st = pipeline.extract_to_store(ds, T._FakeNet(), ["", "Scale(0.5)"], os.path.join(tmp, "store"), threads=1)
+    ok = len(st) == 7 and st.dim == 6 and [s["n_rows"] for s in st.shards] == [3, 4][:world] and st.meta["n_images"] == 7
+    with open(os.path.join(tmp, "ok%d" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_extract_to_store_gloo_world2_matches_single_process(tmp_path, monkeypatch):
+    """Sharded extraction plumbing (row ranges, per-rank shard files, manifest) with a stand-in network: two gloo
+    ranks write the same store as one process."""
+    import socket
+    import torch.multiprocessing as mp
+    from dirb200 import pipeline, store
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_extract_store_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
+    two = store.DescriptorStore(str(tmp_path / "store")).read_all()
+    monkeypatch.setattr(pipeline, "_pool_and_normalize", _fake_pool_and_normalize)
+    from dirtorch.datasets import ImageList
+    ds = ImageList(imgs=["im%02d.png" % i for i in range(7)], root=str(tmp_path))
+    one = pipeline.extract_to_store(ds, _FakeNet(), ["", "Scale(0.5)"], str(tmp_path / "single"), threads=1)
+    assert [s["n_rows"] for s in one.shards] == [7] and one.meta["trfs"] == ["", "Scale(0.5)"]
+    np.testing.assert_array_equal(one.read_all(), two)
+    np.testing.assert_allclose(np.linalg.norm(two, axis=1), 1.0, atol=1e-6)
+    # more ranks than images: empty shards are legal
+    tiny = pipeline.extract_to_store(ImageList(imgs=[], root=str(tmp_path)), _FakeNet(), "", str(tmp_path / "empty"))
+    assert len(tiny) == 0 and tiny.dim == 6
+
+
 def test_resize_coefficients_reproduce_pil():
     """The host-side coefficient tables of the GPU resize (dirb200_resize_coeffs), applied in numpy integer
     arithmetic, reproduce PIL's Image.resize(BILINEAR) byte for byte (the kernels do exactly this arithmetic)."""
