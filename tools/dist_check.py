@@ -31,15 +31,15 @@ out = index.expand_queries(qd, 2, 0.5)
 if rank == 0:
     ref = O.expand_descriptors(q, db=db, k=2, alpha=0.5)
     ok = ok and float(np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref)) < 1e-5
-# Persisted path: every rank writes its rows as a shard of a descriptor store, the store is re-read under the current
-# world size (row ranges come from the manifest, not from the shard files) and searched again.
-import tempfile
-from dirb200 import store as S
-path = os.environ.get("DIST_CHECK_STORE") or os.path.join(tempfile.gettempdir(), "dirb200_dist_check_store")
-st = S.write_distributed(path, db[s0:s1])
-index2 = ShardedIndex.from_store(st, "cuda:%d" % local)
-s2, i2 = index2.search(qd, 100)
-ok = ok and bool(torch.equal(i2, i) and torch.equal(s2, s))
+# Persisted path (opt-in: DIST_CHECK_STORE=<directory on a filesystem all ranks see>): every rank writes its rows as a
+# shard of a descriptor store, the store is re-read under the current world size (row ranges come from the manifest)
+# and searched again.
+if os.environ.get("DIST_CHECK_STORE"):
+    from dirb200 import store as S
+    st = S.write_distributed(os.environ["DIST_CHECK_STORE"], db[s0:s1])
+    index2 = ShardedIndex.from_store(st, "cuda:%d" % local)
+    s2, i2 = index2.search(qd, 100)
+    ok = ok and bool(torch.equal(i2, i) and torch.equal(s2, s))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
