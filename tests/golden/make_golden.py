@@ -287,6 +287,17 @@ def _gold_cli(hard):
                                          load_feats=os.path.join(root, "saved_ms"), threads=2)
         extra = dict(ms_mAP=json.load(open(os.path.join(root, "res4.json")))["Oxford5K"]["mAP"], ms_APs=np.array(det_ms["APs"]),
                      ms_desc_head=saved_ms[:3], ms_console=np.array([l for l in out4.splitlines() if l.startswith(" * ")]))
+    if hard:
+        # revisited protocol (easy / medium / hard, generic.py:150-170,210-224) through `--dataset ROxford5K`
+        gnd_r = [{"bbx": g_["bbx"], "easy": [g_["ok"][0], g_["ok"][2]], "hard": [g_["ok"][1]], "junk": g_["junk"]} for g_ in gnd]
+        gnd_r[3]["easy"], gnd_r[3]["hard"] = gnd[3]["ok"], []          # no hard positive: AP-hard = -1, left out of the mean
+        with open(os.path.join(root, "oxford5k", "gnd_roxford5k.pkl"), "wb") as f:
+            pickle.dump({"imlist": names, "qimlist": [names[i] for i in qn], "gnd": gnd_r}, f)
+        out5 = run("dirtorch.test_dir", "--dataset", "ROxford5K", *common_args[2:], "--load-feats", os.path.join(root, "saved"),
+                   "--out-json", os.path.join(root, "res5.json"))
+        r5 = json.load(open(os.path.join(root, "res5.json")))["ROxford5K"]
+        extra.update(rox_easy=r5["mAP-easy"], rox_medium=r5["mAP-medium"], rox_hard=r5["mAP-hard"],
+                     rox_console=np.array([l for l in out5.splitlines() if l.startswith(" * ")]))
     save("cli_hard.npz" if hard else "cli_easy.npz", **extra, pca_coeff=coeff, pca_var=pca.explained_variance_, n_images=len(names), queries=np.array(qn), desc_head=D[:3], desc_norms=np.linalg.norm(D, axis=1),
          saved_equals_extract=np.array(np.array_equal(saved, D)), whitened=W,
          mAP=res[0]["mAP"], mAP_aqe_k2_a1=res[1]["mAP"], mAP_adba_k2_a1=res[2]["mAP"], APs=np.array(det["APs"]),

@@ -132,7 +132,7 @@ def test_extract_r152_and_center_bias(golden):
 
 
 @pytest.mark.parametrize("variant", ["easy", "hard"])
-def test_pipeline_matches_reference_command_lines(golden, tmp_path, variant):
+def test_pipeline_matches_reference_command_lines(golden, tmp_path, variant, monkeypatch):
     """cli_*.npz hold what the reference's own `python -m dirtorch.extract_features` / `python -m dirtorch.test_dir`
     (+ --aqe, --adba) print and save on the synthetic Oxford-layout dataset of tests/e2e_data.py.  The oracle pipeline
     (extract -> whiten with the run's PCA -> scores -> AP) must reproduce them; tests/test_gpu_pipeline.py::test_cli_end_to_end
@@ -167,6 +167,26 @@ def test_pipeline_matches_reference_command_lines(golden, tmp_path, variant):
     assert abs(m_dba - float(g["mAP_adba_k2_a1"])) < 1e-12
     if variant == "hard":
         assert 0.5 < m < 0.95 and len(set(np.round(aps, 6))) >= 3                 # a ranking that can actually differ
+        # revisited protocol through `--dataset ROxford5K`: the oracle's AP per mode and the product's dataset class
+        # (host code, no GPU) on the oracle's scores, aggregated as test_dir.py:160-167
+        import pickle
+        gnd_r = [{"bbx": g_["bbx"], "easy": [g_["ok"][0], g_["ok"][2]], "hard": [g_["ok"][1]], "junk": g_["junk"]} for g_ in gnd]
+        gnd_r[3]["easy"], gnd_r[3]["hard"] = gnd[3]["ok"], []
+        with open(os.path.join(str(tmp_path), "oxford5k", "gnd_roxford5k.pkl"), "wb") as f:
+            pickle.dump({"imlist": names, "qimlist": [names[i] for i in qn], "gnd": gnd_r}, f)
+        sc = O.scores_exact(W[qn], W)
+        modes = {"easy": lambda g_: (g_["easy"], g_["junk"] + g_["hard"]), "medium": lambda g_: (g_["easy"] + g_["hard"], g_["junk"]),
+                 "hard": lambda g_: (g_["hard"], g_["junk"] + g_["easy"])}
+        monkeypatch.setenv("DB_ROOT", str(tmp_path))
+        from dirtorch import datasets as D
+        rox = D.create("ROxford5K")
+        for mode, split in modes.items():
+            o_aps = [O.eval_query_ap(sc[q], *split(g_)) if split(g_)[0] else -1 for q, g_ in enumerate(gnd_r)]
+            p_aps = [rox.eval_query_AP(q, sc[q])[mode] for q in range(len(qn))]
+            np.testing.assert_allclose(o_aps, p_aps, rtol=0, atol=1e-12)
+            m_mode = float(np.mean([a for a in o_aps if a >= 0]))
+            assert abs(m_mode - float(g["rox_" + mode])) < 1e-12, mode
+        assert [str(l) for l in g["rox_console"]] == [" * mAP-%s = %g" % (m_, float(g["rox_" + m_])) for m_ in ("easy", "medium", "hard")]
         # multi-scale protocol: --trfs "Scale(0.7)" "" "Scale(1.4)" --pooling gem --gemp 3.  The transform chains are
         # built by the product's host code (loader.create_transforms), PIL does the resizing as in the reference.
         from PIL import Image
