@@ -100,3 +100,63 @@ def test_resize_tables_reproduce_pil_for_any_size(h, w, oh, ow, seed):
     horiz = apply(img.transpose(1, 0, 2), w, ow).transpose(1, 0, 2)              # PIL: horizontal pass first
     got = apply(horiz, h, oh)
     assert np.array_equal(got, ref)
+
+
+@settings(max_examples=60, **COMMON)
+@given(dim=st.sampled_from([64, 128, 512, 1024, 2048]), seed=st.integers(0, 10**6),
+       kind=st.sampled_from(["gauss", "const", "sparse", "signed_const", "heavy", "tiny_tail"]))
+def test_fp16_score_error_stays_inside_the_search_band(dim, seed, kind):
+    """The exactness argument of the top-k search (search.cu) needs |fp16-path score - exact score| <= eps16 = 1.2e-3
+    for unit-norm rows: operands rounded to fp16 (relative 2^-11 each, 2^-25 absolute in the subnormal range), products
+    and sums in fp32.  Bound: (2*2^-11 + 2^-22) * sum|q_i d_i| <= 9.8e-4, + D * 2^-24 accumulation <= 1.2e-4 at D = 2048,
+    + subnormal term <= 2^-25 * sqrt(D).  Checked here on adversarial families (constant vectors sit on one rounding
+    error for every element; sparse and heavy-tailed vectors; rows whose tail is subnormal in fp16)."""
+    r = np.random.RandomState(seed)
+    n = 64
+
+    def family(rows):
+        if kind == "gauss":
+            x = r.standard_normal((rows, dim))
+        elif kind == "const":
+            x = np.ones((rows, dim)) * r.uniform(0.5, 2.0, (rows, 1))
+        elif kind == "signed_const":
+            x = np.sign(r.standard_normal((rows, dim))) * r.uniform(0.5, 2.0, (rows, 1))
+        elif kind == "sparse":
+            x = r.standard_normal((rows, dim)) * (r.uniform(size=(rows, dim)) < 8.0 / dim)
+            x[:, 0] += 1e-3
+        elif kind == "heavy":
+            x = r.standard_cauchy((rows, dim))
+        else:                                                     # one dominant entry, the rest far below fp16's normal range
+            x = r.standard_normal((rows, dim)) * 1e-6
+            x[:, 0] = 1.0
+        x = x.astype(np.float32)
+        return x / np.linalg.norm(x.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+
+    q, d = family(n), family(n)
+    exact = q.astype(np.float64) @ d.astype(np.float64).T
+    q16, d16 = q.astype(np.float16).astype(np.float32), d.astype(np.float16).astype(np.float32)
+    fast = np.zeros((n, n), np.float32)
+    for c in range(0, dim, 16):                                   # K = 16 slices accumulated in fp32, like the MMA
+        fast += q16[:, c:c + 16] @ d16[:, c:c + 16].T
+    err = np.abs(fast.astype(np.float64) - exact).max()
+    assert err <= 1.2e-3, (kind, dim, err)
+    if kind in ("const", "signed_const") and dim == 2048:
+        assert err > 1e-5                                         # the family does exercise the rounding term
+
+
+def test_fp16_score_error_bound_is_nearly_attained():
+    """Worst case of the bound above: every entry sits just below an fp16 rounding midpoint (relative error 2^-11, all
+    of one sign), q = d.  The error reaches ~9.8e-4 - eps16 = 1.2e-3 is neither loose by much nor too small."""
+    dim = 1024
+    v = np.float32(2.0 ** -5 + 2.0 ** -16 - 2.0 ** -24)           # rounds DOWN to 2^-5 in fp16
+    x = np.full(dim, v, np.float32)
+    x[-1] = np.float32(np.sqrt(max(0.0, 1.0 - float((x[:-1].astype(np.float64) ** 2).sum()))))
+    assert abs(np.linalg.norm(x.astype(np.float64)) - 1.0) < 1e-6
+    assert float(np.float16(v)) == 2.0 ** -5
+    exact = float(x.astype(np.float64) @ x.astype(np.float64))
+    x16 = x.astype(np.float16).astype(np.float32)
+    fast = np.float32(0)
+    for c in range(0, dim, 16):
+        fast = np.float32(fast + np.float32(x16[c:c + 16] @ x16[c:c + 16]))
+    err = abs(float(fast) - exact)
+    assert 9.0e-4 < err <= 1.2e-3, err
