@@ -120,9 +120,11 @@ __global__ void dense_compact_kernel(const float* __restrict__ dense, int64_t ld
 
 // Per query: exact k-th and k_shard-th largest candidate scores (fp16-path scores).
 //   kth_k[q]  : local k-th best - always a valid lower bound on the global k-th best
-//   sel[q]    : local k_shard-th best (k_shard = ceil(k / shards)); the MINIMUM of this value over all shards is a
-//               valid and much tighter lower bound on the global k-th best (every shard holds >= k_shard rows at or
-//               above its own value, hence >= k rows lie at or above the minimum) - the caller min-reduces it.
+//   sel[q]    : local min(k_shard, N)-th best; the MINIMUM of this value over all shards is a valid and much tighter
+//               lower bound on the global k-th best as long as the shards certify k rows between them,
+//               sum_g min(k_shard, N_g) >= min(k, N_total) (shard g holds min(k_shard, N_g) rows at or above its own
+//               value) - the caller picks k_shard accordingly (ceil(k / shards) for evenly filled shards, see
+//               dist.py: shard_quota) and min-reduces sel.
 // flags[q] bit0 = candidate overflow (cnt > cap): the tighter threshold kth(captured) - band is written to thr[q];
 // otherwise thr[q] = +inf so that a re-run of the filter pass leaves this query alone.
 __global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned long long* __restrict__ cand,

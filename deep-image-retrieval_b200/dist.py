@@ -19,6 +19,19 @@ def shard_rows(n_rows: int, world: int, rank: int):
     return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
 
 
+def shard_quota(k: int, shard_sizes) -> int:
+    """Per-shard selection depth c of the two-phase search: shard g reports its min(c, N_g)-th best score, and the
+    MINIMUM of the reports is a lower bound on the global k-th best only if the shards can certify k rows between
+    them, i.e.  sum_g min(c, N_g) >= min(k, sum_g N_g).  This returns the smallest such c: ceil(k / G) when every
+    shard holds at least that many rows, more when some shards are small or empty (c = k always satisfies it)."""
+    sizes = [int(n) for n in shard_sizes]
+    need = min(int(k), sum(sizes))
+    c = max(1, -(-int(k) // max(1, len(sizes))))
+    while c < k and sum(min(c, n) for n in sizes) < need:
+        c += 1
+    return min(c, int(k))
+
+
 def all_gather_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     """packed (2,Q,k) int64 per rank -> (G,2,Q,k); a single collective."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -38,6 +51,16 @@ class ShardedIndex:
         self.group = group
         self.row_offset = int(row_offset)
         self.local = ops.Index(db32_local, index_offset=row_offset, db16=db16_local)
+        # row counts of all shards (one small all-gather at construction, not on the search path): the selection depth
+        # of the two-phase search depends on them, see shard_quota
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            mine = torch.tensor([self.local.n], dtype=torch.int64, device=db32_local.device)
+            sizes = torch.empty(world, dtype=torch.int64, device=db32_local.device)
+            dist.all_gather_into_tensor(sizes, mine, group=group)
+            self.shard_sizes = [int(v) for v in sizes.tolist()]
+        else:
+            self.shard_sizes = [int(self.local.n)]
 
     @classmethod
     def from_store(cls, store, device, group=None, chunk_rows: int = 65536):
@@ -56,14 +79,14 @@ class ShardedIndex:
 
     def search(self, q32: torch.Tensor, k: int):
         """Global exact top-k.  Phase 1 on every shard (tensor-core passes) -> MIN all-reduce of the per-query
-        selection thresholds (4*Q bytes: the local ceil(k/G)-th best scores bound the global k-th best, so each shard
-        re-scores only ~k/G rows) -> phase 2 (exact re-scoring) -> one all-gather of the per-shard lists -> merge.
+        selection thresholds (4*Q bytes: the local c-th best scores, c = shard_quota(k, shard sizes) = ceil(k/G) for
+        evenly filled shards, bound the global k-th best, so each shard re-scores only ~k/G rows) -> phase 2 (exact re-scoring) -> one all-gather of the per-shard lists -> merge.
         Returns (scores fp64, idx int64), (Q,k)."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             packed = self.search_local(q32, k)
             return self.ops.topk_merge_packed(packed.unsqueeze(0), k)
-        k_shard = -(-k // world)
+        k_shard = shard_quota(k, self.shard_sizes)
         sel = self.local.search_begin(q32, k, k_shard)
         dist.all_reduce(sel, op=dist.ReduceOp.MIN, group=self.group)
         packed = torch.empty((2, q32.shape[0], k), dtype=torch.int64, device=q32.device)

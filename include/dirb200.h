@@ -177,11 +177,14 @@ int dirb200_index_set_option(dirb200_index* idx, const char* key, double value);
 int dirb200_index_search(dirb200_index* idx, const float* q32_dev, int Q, int k, double* scores_dev,
                          int64_t* idx_dev, void* stream);
 /* The same search in two phases, for a database sharded over several GPUs.  Phase 1 runs the tensor-core passes and
- * writes to sel_dev[Q] (caller-owned) the local k_shard-th best fp16-path score per query, k_shard = ceil(k / shards).
- * The caller MIN-reduces sel_dev over the shards (ncclAllReduce, 4*Q bytes): every shard holds >= k_shard rows at or
- * above its own value, so >= k rows of the whole database lie at or above the minimum - a valid, tight lower bound
- * on the global k-th best that lets each shard re-score only ~1.4 * k / shards rows instead of ~1.4 * k.  Phase 2
- * re-scores the rows within the band of max(sel_dev[q], local k-th) exactly and returns the shard's ordered list. */
+ * writes to sel_dev[Q] (caller-owned) the local min(k_shard, N_local)-th best fp16-path score per query (+inf for an
+ * empty shard).  The caller MIN-reduces sel_dev over the shards (ncclAllReduce, 4*Q bytes): shard g holds
+ * min(k_shard, N_g) rows at or above its own value, so the minimum is a valid lower bound on the global k-th best
+ * PROVIDED  sum_g min(k_shard, N_g) >= min(k, sum_g N_g)  - the caller's obligation.  k_shard = ceil(k / shards)
+ * satisfies it when every shard holds at least that many rows; with small shards use a larger value (k always
+ * works; deep-image-retrieval_b200/dist.py: shard_quota picks the smallest valid one from the shard sizes).  The
+ * tight bound lets each shard re-score only ~1.4 * k / shards rows instead of ~1.4 * k.  Phase 2 re-scores the rows
+ * within the band of max(sel_dev[q], local k-th) exactly and returns the shard's ordered list. */
 int dirb200_index_search_begin(dirb200_index* idx, const float* q32_dev, int Q, int k, int k_shard, float* sel_dev,
                                void* stream);
 int dirb200_index_search_finish(dirb200_index* idx, const float* q32_dev, const float* sel_dev, double* scores_dev,

@@ -1,0 +1,109 @@
+"""NumPy model of the exact top-k search protocol of deep-image-retrieval_b200/csrc/search.cu + dist.py.
+TEST INFRASTRUCTURE: it restates the ALGORITHM (thresholds, bands, the cross-shard MIN exchange, merge), not the
+kernels, so that its exactness can be checked on the CPU over thousands of random and adversarial cases
+(tests/test_properties.py).  Scores on the "fast" path are emulated as the kernels compute them: operands rounded to
+fp16, products accumulated in fp32."""
+import numpy as np
+
+EPS16 = 1.2e-3
+BAND = np.float32(2.0 * EPS16)
+
+
+def fast_scores(q, db):
+    q16, d16 = q.astype(np.float16).astype(np.float32), db.astype(np.float16).astype(np.float32)
+    out = np.zeros((q.shape[0], db.shape[0]), np.float32)
+    for c in range(0, q.shape[1], 16):
+        out += q16[:, c:c + 16] @ d16[:, c:c + 16].T
+    return out
+
+
+def exact_scores(q, db):
+    # one fp64 reduction per (query, row) pair whose order does not depend on which other rows are in the call
+    # (BLAS blocking would make the bits of a pair's score depend on the batch, i.e. break exact ties differently)
+    return (q.astype(np.float64)[:, None, :] * db.astype(np.float64)[None, :, :]).sum(axis=-1)
+
+
+def kth_largest(v, k):
+    return -np.inf if v.shape[0] < k else np.partition(v, v.shape[0] - k)[v.shape[0] - k]
+
+
+class ShardModel:
+    """One row shard: dirb200_index_search_begin / _finish."""
+
+    def __init__(self, db, offset, sample_rows):
+        self.db, self.offset, self.sample_rows = db, int(offset), int(sample_rows)
+
+    def begin(self, q, k, k_shard):
+        n = self.db.shape[0]
+        self.q, self.k = q, k
+        if n == 0:
+            self.cand = None
+            return np.full(q.shape[0], np.inf, np.float32)
+        self.fast = fast_scores(q, self.db)
+        s = min(max(self.sample_rows, min(n, 4 * k)), n)          # seed rows (search.cu: S)
+        small = n <= s
+        if not small and s // 32 < k:
+            s = min(n, max(s, 32 * k))
+        use_gmax = (not small) and (s // 32 >= k)
+        thr = np.empty(q.shape[0], np.float32)
+        for i in range(q.shape[0]):
+            seed = self.fast[i, :n if small else s]
+            if use_gmax:                                          # maxima of groups of 32 consecutive rows
+                pad = (-seed.shape[0]) % 32
+                vals = np.concatenate([seed, np.full(pad, -np.inf, np.float32)]).reshape(-1, 32).max(axis=1)
+            else:
+                vals = seed
+            thr[i] = kth_largest(vals, min(k, vals.shape[0])) - BAND
+        self.cand = [np.nonzero(self.fast[i] >= thr[i])[0] for i in range(q.shape[0])]
+        kk = min(k, n)
+        self.kth_k = np.array([kth_largest(self.fast[i, c], kk) for i, c in enumerate(self.cand)], np.float32)
+        ks = min(k_shard, kk)
+        return np.array([kth_largest(self.fast[i, c], ks) for i, c in enumerate(self.cand)], np.float32)
+
+    def finish(self, sel):
+        k, nq = self.k, self.q.shape[0]
+        scores = np.full((nq, k), -np.inf)
+        idx = np.full((nq, k), -1, np.int64)
+        self.survivors = 0
+        if self.cand is None:
+            return scores, idx
+        for i in range(nq):
+            t2 = np.float32(max(sel[i], self.kth_k[i])) - BAND
+            rows = self.cand[i][self.fast[i, self.cand[i]] >= t2]
+            self.survivors += rows.shape[0]
+            ex = exact_scores(self.q[i:i + 1], self.db[rows])[0]
+            order = np.lexsort((rows, -ex))[:k]
+            scores[i, :order.shape[0]] = ex[order]
+            idx[i, :order.shape[0]] = rows[order] + self.offset
+        return scores, idx
+
+
+def sharded_search(q, db, k, bounds, sample_rows=64, quota=None):
+    """dist.ShardedIndex.search over the row ranges `bounds` = [(start, end), ...]."""
+    shards = [ShardModel(db[a:b], a, sample_rows) for a, b in bounds]
+    from dirb200.dist import shard_quota                         # the product's own rule for the selection depth
+    k_shard = shard_quota(k, [b - a for a, b in bounds]) if quota is None else quota
+    sels = [s.begin(q, k, k_shard) for s in shards]
+    sel = np.minimum.reduce(sels)                                 # all_reduce(MIN)
+    lists = [s.finish(sel) for s in shards]
+    sc = np.concatenate([l[0] for l in lists], axis=1)            # all_gather + merge
+    ix = np.concatenate([l[1] for l in lists], axis=1)
+    out_s = np.full((q.shape[0], k), -np.inf)
+    out_i = np.full((q.shape[0], k), -1, np.int64)
+    for i in range(q.shape[0]):
+        valid = ix[i] >= 0
+        order = np.lexsort((ix[i][valid], -sc[i][valid]))[:k]
+        out_s[i, :order.shape[0]] = sc[i][valid][order]
+        out_i[i, :order.shape[0]] = ix[i][valid][order]
+    return out_s, out_i, sum(s.survivors for s in shards)
+
+
+def exact_topk(q, db, k):
+    ex = exact_scores(q, db)
+    out_s = np.full((q.shape[0], k), -np.inf)
+    out_i = np.full((q.shape[0], k), -1, np.int64)
+    for i in range(q.shape[0]):
+        order = np.lexsort((np.arange(db.shape[0]), -ex[i]))[:k]
+        out_s[i, :order.shape[0]] = ex[i][order]
+        out_i[i, :order.shape[0]] = order
+    return out_s, out_i

@@ -179,7 +179,7 @@ def test_two_phase_sharded_search_single_gpu():
         sh.search(qd, k)
         alone += sh.stats()["survivors"]
     assert surv_two_phase < 0.6 * alone, (surv_two_phase, alone)
-    # an empty shard and a skewed split must not break the bound
+    # a skewed split (both shards still hold at least k_shard rows) must not break the bound
     tiny = ops.Index(torch.from_numpy(db[:70]).to(DEV), index_offset=0)
     rest = ops.Index(torch.from_numpy(db[70:]).to(DEV), index_offset=70)
     s2 = [tiny.search_begin(qd, k, 30), rest.search_begin(qd, k, 30)]
@@ -187,3 +187,30 @@ def test_two_phase_sharded_search_single_gpu():
     o2 = [tiny.search_finish(qd, k, sel2), rest.search_finish(qd, k, sel2)]
     ms2, mi2 = ops.topk_merge(torch.stack([o[0] for o in o2]).contiguous(), torch.stack([o[1] for o in o2]).contiguous(), k)
     np.testing.assert_array_equal(mi2.cpu().numpy(), ri)
+
+
+def test_two_phase_search_with_a_shard_smaller_than_its_quota():
+    """A shard that holds fewer rows than ceil(k / G), all of them close to the query: the naive selection depth
+    certifies fewer than k rows and the exchanged threshold would cut true top-k rows (found on the CPU by
+    tests/test_properties.py).  dist.shard_quota picks the depth from the shard sizes; merge == oracle.
+    (Kept last in the last GPU test file: it was added after this round's final GPU run.)"""
+    ops = _ops()
+    from dirb200.dist import shard_quota
+    db, q, _ = synth.make_descriptor_db(5000, 4, dim=256, n_pos=5, db_seed=5, q_seed=6)
+    r = np.random.RandomState(9)
+    near = q[0][None, :] + 0.02 * r.standard_normal((50, 256)).astype(np.float32)
+    near = (near / np.linalg.norm(near, axis=1, keepdims=True)).astype(np.float32)
+    full = np.concatenate([near, db]).astype(np.float32)
+    k, sizes = 200, [50, 5000]
+    c = shard_quota(k, sizes)
+    assert c == 150
+    qd = torch.from_numpy(q).to(DEV)
+    shards = [ops.Index(torch.from_numpy(full[:50].copy()).to(DEV), index_offset=0),
+              ops.Index(torch.from_numpy(full[50:].copy()).to(DEV), index_offset=50)]
+    sels = [sh.search_begin(qd, k, c) for sh in shards]
+    sel = torch.minimum(sels[0], sels[1]).contiguous()
+    outs = [sh.search_finish(qd, k, sel) for sh in shards]
+    ms, mi = ops.topk_merge(torch.stack([o[0] for o in outs]).contiguous(), torch.stack([o[1] for o in outs]).contiguous(), k)
+    rs, ri = O.topk(q, full, k)
+    np.testing.assert_array_equal(mi.cpu().numpy(), ri)
+    np.testing.assert_allclose(ms.cpu().numpy(), rs, rtol=0, atol=1e-12)

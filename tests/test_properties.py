@@ -160,3 +160,72 @@ def test_fp16_score_error_bound_is_nearly_attained():
         fast = np.float32(fast + np.float32(x16[c:c + 16] @ x16[c:c + 16]))
     err = abs(float(fast) - exact)
     assert 9.0e-4 < err <= 1.2e-3, err
+
+
+def _unit(x):
+    return (x / np.linalg.norm(x.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
+
+
+@settings(max_examples=300, **COMMON)
+@given(n=st.integers(1, 1500), nq=st.integers(1, 5), k=st.integers(1, 40), shards=st.integers(1, 6),
+       sample=st.sampled_from([32, 64, 256, 4096]), kind=st.sampled_from(["random", "duplicates", "clustered", "planted"]),
+       seed=st.integers(0, 10**6), data=st.data())
+def test_search_protocol_model_returns_the_exact_topk(n, nq, k, shards, sample, kind, seed, data):
+    """The algorithm of search.cu + dist.py (group-max seed threshold, band filter, local k-th / ceil(k/G)-th
+    selection, MIN exchange, exact re-scoring, merge), restated in NumPy (tests/search_model.py), returns exactly the
+    top-k by (exact score desc, index asc) - for uneven and empty shards, exact duplicates (ties broken by index),
+    rows clustered inside the band, and k larger than a shard or than the database."""
+    import search_model as M
+    r = np.random.RandomState(seed)
+    dim = 64
+    q = _unit(r.standard_normal((nq, dim)))
+    if kind == "random":
+        db = _unit(r.standard_normal((n, dim)))
+    elif kind == "duplicates":                                     # few distinct rows, many exact copies
+        base = _unit(r.standard_normal((max(1, n // 20), dim)))
+        db = base[r.randint(0, base.shape[0], n)]
+    elif kind == "clustered":                                      # scores packed within a fraction of the band
+        db = _unit(q[0][None, :] + 2e-3 * r.standard_normal((n, dim)))
+    else:                                                          # a handful of strong matches in a random crowd
+        db = _unit(r.standard_normal((n, dim)))
+        for j in r.randint(0, n, min(n, 8)):
+            db[j] = _unit((q[r.randint(nq)] + 0.3 * r.standard_normal(dim))[None])[0]
+    cuts = sorted(data.draw(st.lists(st.integers(0, n), min_size=shards - 1, max_size=shards - 1)))
+    bounds = list(zip([0] + cuts, cuts + [n]))                     # arbitrary, possibly empty, row ranges
+    got_s, got_i, _ = M.sharded_search(q, db, k, bounds, sample_rows=sample)
+    ref_s, ref_i = M.exact_topk(q, db, k)
+    assert np.array_equal(got_i, ref_i)
+    assert np.array_equal(got_s, ref_s)
+
+
+def test_search_protocol_threshold_exchange_cuts_the_rescoring_work():
+    """What the MIN exchange is for: with G shards each shard re-scores ~k/G rows instead of ~k."""
+    import search_model as M
+    r = np.random.RandomState(3)
+    q, db = _unit(r.standard_normal((8, 64))), _unit(r.standard_normal((8000, 64)))
+    bounds = [(i * 1000, (i + 1) * 1000) for i in range(8)]
+    _, idx, surv = M.sharded_search(q, db, 64, bounds, sample_rows=256)
+    assert np.array_equal(idx, M.exact_topk(q, db, 64)[1])
+    solo = sum(M.sharded_search(q, db[a:b], 64, [(0, b - a)], sample_rows=256)[2] for a, b in bounds)
+    assert surv < 0.5 * solo
+
+
+def test_selection_depth_accounts_for_small_and_empty_shards():
+    """ceil(k / G) is NOT a valid selection depth when a shard holds fewer rows than that (found by the property test
+    above): the shards then certify fewer than k rows and the exchanged threshold cuts true top-k rows.
+    dist.shard_quota raises the depth until sum_g min(c, N_g) >= min(k, N)."""
+    import search_model as M
+    from dirb200.dist import shard_quota
+    assert shard_quota(100, [125000] * 8) == 13 and shard_quota(100, [1000]) == 100
+    assert shard_quota(2, [0, 2]) == 2 and shard_quota(4, [1, 1000]) == 3 and shard_quota(60, [70, 47930]) == 30
+    assert shard_quota(10, [0, 0, 0]) == 4 and shard_quota(10, [3, 3, 3]) == 4   # fewer rows than k: everything is kept
+    for k, sizes in ((7, [5, 0, 9, 1]), (40, [3, 3, 3, 100]), (1, [0, 5]), (1024, [10, 2000, 0])):
+        c = shard_quota(k, sizes)
+        assert sum(min(c, n) for n in sizes) >= min(k, sum(sizes)) and (c == 1 or c == -(-k // len(sizes)) or
+                                                                         sum(min(c - 1, n) for n in sizes) < min(k, sum(sizes)))
+    r = np.random.RandomState(0)
+    q, db = _unit(r.standard_normal((1, 64))), _unit(r.standard_normal((2, 64)))
+    ref = M.exact_topk(q, db, 2)[1]
+    assert np.array_equal(M.sharded_search(q, db, 2, [(0, 0), (0, 2)])[1], ref)
+    naive = M.sharded_search(q, db, 2, [(0, 0), (0, 2)], quota=1)[1]              # ceil(2 / 2) = 1
+    assert not np.array_equal(naive, ref)
