@@ -27,11 +27,19 @@ def kth_largest(v, k):
     return -np.inf if v.shape[0] < k else np.partition(v, v.shape[0] - k)[v.shape[0] - k]
 
 
-class ShardModel:
-    """One row shard: dirb200_index_search_begin / _finish."""
+class Overflow(Exception):
+    """DIRB200_EOVERFLOW: candidate / survivor buffers could not hold the rows inside the band."""
 
-    def __init__(self, db, offset, sample_rows):
+
+class ShardModel:
+    """One row shard: dirb200_index_search_begin / _finish.  cand_cap / surv_cap model the fixed-size candidate and
+    survivor buffers: an overflowing candidate list keeps an ARBITRARY subset of `cand_cap` entries (the kernels
+    append with atomics), its k-th best gives a tighter threshold and the pass is re-run (at most 4 times)."""
+
+    def __init__(self, db, offset, sample_rows, cand_cap=None, surv_cap=None, rng=None):
         self.db, self.offset, self.sample_rows = db, int(offset), int(sample_rows)
+        self.cand_cap, self.surv_cap, self.rng = cand_cap, surv_cap, rng or np.random.RandomState(0)
+        self.retries = 0
 
     def begin(self, q, k, k_shard):
         n = self.db.shape[0]
@@ -56,6 +64,19 @@ class ShardModel:
             thr[i] = kth_largest(vals, min(k, vals.shape[0])) - BAND
         self.cand = [np.nonzero(self.fast[i] >= thr[i])[0] for i in range(q.shape[0])]
         kk = min(k, n)
+        if self.cand_cap is not None:
+            cap = max(self.cand_cap, 2 * k)
+            for _ in range(5):
+                over = [i for i, c in enumerate(self.cand) if c.shape[0] > cap]
+                if not over:
+                    break
+                if self.retries == 4:
+                    raise Overflow("candidates")
+                self.retries += 1
+                for i in over:                                    # what was captured: any `cap` of the matching rows
+                    kept = self.rng.choice(self.cand[i], cap, replace=False)
+                    thr[i] = kth_largest(self.fast[i, kept], kk) - BAND
+                    self.cand[i] = np.nonzero(self.fast[i] >= thr[i])[0]
         self.kth_k = np.array([kth_largest(self.fast[i, c], kk) for i, c in enumerate(self.cand)], np.float32)
         ks = min(k_shard, kk)
         return np.array([kth_largest(self.fast[i, c], ks) for i, c in enumerate(self.cand)], np.float32)
@@ -70,6 +91,8 @@ class ShardModel:
         for i in range(nq):
             t2 = np.float32(max(sel[i], self.kth_k[i])) - BAND
             rows = self.cand[i][self.fast[i, self.cand[i]] >= t2]
+            if self.surv_cap is not None and rows.shape[0] > self.surv_cap:
+                raise Overflow("survivors")
             self.survivors += rows.shape[0]
             ex = exact_scores(self.q[i:i + 1], self.db[rows])[0]
             order = np.lexsort((rows, -ex))[:k]
@@ -78,9 +101,10 @@ class ShardModel:
         return scores, idx
 
 
-def sharded_search(q, db, k, bounds, sample_rows=64, quota=None):
+def sharded_search(q, db, k, bounds, sample_rows=64, quota=None, cand_cap=None, surv_cap=None, seed=0):
     """dist.ShardedIndex.search over the row ranges `bounds` = [(start, end), ...]."""
-    shards = [ShardModel(db[a:b], a, sample_rows) for a, b in bounds]
+    shards = [ShardModel(db[a:b], a, sample_rows, cand_cap, surv_cap, np.random.RandomState(seed + j))
+              for j, (a, b) in enumerate(bounds)]
     from dirb200.dist import shard_quota                         # the product's own rule for the selection depth
     k_shard = shard_quota(k, [b - a for a, b in bounds]) if quota is None else quota
     sels = [s.begin(q, k, k_shard) for s in shards]

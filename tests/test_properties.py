@@ -229,3 +229,30 @@ def test_selection_depth_accounts_for_small_and_empty_shards():
     assert np.array_equal(M.sharded_search(q, db, 2, [(0, 0), (0, 2)])[1], ref)
     naive = M.sharded_search(q, db, 2, [(0, 0), (0, 2)], quota=1)[1]              # ceil(2 / 2) = 1
     assert not np.array_equal(naive, ref)
+
+
+@settings(max_examples=120, **COMMON)
+@given(n=st.integers(200, 2500), k=st.integers(1, 30), shards=st.integers(1, 3), cap=st.sampled_from([64, 128, 512]),
+       kind=st.sampled_from(["random", "clustered", "planted"]), seed=st.integers(0, 10**6))
+def test_search_protocol_model_with_bounded_buffers_is_exact_or_fails_loudly(n, k, shards, cap, kind, seed):
+    """With small candidate buffers the overflow -> tightened threshold -> re-run loop either converges to the exact
+    top-k or ends in the overflow error (rows packed inside the band) - it never returns a different list."""
+    import search_model as M
+    r = np.random.RandomState(seed)
+    q = _unit(r.standard_normal((3, 64)))
+    if kind == "clustered":
+        db = _unit(q[0][None, :] + 2e-3 * r.standard_normal((n, 64)))
+    else:
+        db = _unit(r.standard_normal((n, 64)))
+        if kind == "planted":
+            for j in r.randint(0, n, 8):
+                db[j] = _unit((q[r.randint(3)] + 0.3 * r.standard_normal(64))[None])[0]
+    cuts = [n * (j + 1) // shards for j in range(shards - 1)]
+    bounds = list(zip([0] + cuts, cuts + [n]))
+    try:
+        got_s, got_i, _ = M.sharded_search(q, db, k, bounds, sample_rows=32, cand_cap=cap, surv_cap=1024, seed=seed)
+    except M.Overflow:
+        assert kind == "clustered"                                 # only rows packed inside the band may overflow
+        return
+    ref_s, ref_i = M.exact_topk(q, db, k)
+    assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)
