@@ -36,6 +36,18 @@ def _dev_f32(x):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))).cuda()
 
 
+def _drop_self(scores, idx, own_rows, k):
+    """Neighbour lists (best first, one more entry than needed) of database rows queried against their own
+    database -> the first k entries that are not the row itself, order preserved.  A row need not be in its own
+    list (exact duplicates with a lower index rank before it); then the list is just cut to k."""
+    own = np.asarray(own_rows)[:, None]
+    keep = np.argsort(idx == own, axis=1, kind="stable")[:, :k]                              # non-self entries first
+    s, i = np.take_along_axis(scores, keep, 1).copy(), np.take_along_axis(idx, keep, 1).copy()
+    left = i == own                                   # only when the database has no more than k rows: no neighbour
+    i[left], s[left] = -1, 0.0                        # (index -1 = skipped by dirb200_aqe_expand)
+    return s, i
+
+
 def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096):
     """alpha query expansion (db given) / database augmentation (db=None): test_dir.py:24-44.
     q' = normalize(mean([q] + [db_j * sim_ij^alpha for the k nearest j])).  Returns a host ndarray.
@@ -63,11 +75,8 @@ def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096):
             # the reference zeroes the diagonal of the self-similarity (test_dir.py:33-34): drop each row from its
             # own neighbour list
             s1, i1 = index.search(qc, min(k + 1, d.shape[0]))
-            s1, i1 = s1.cpu().numpy(), i1.cpu().numpy()
-            rows = np.arange(c0, c0 + qc.shape[0])[:, None]
-            keep = np.argsort(i1 == rows, axis=1, kind="stable")[:, :k]   # non-self entries first, order preserved
-            s = torch.from_numpy(np.take_along_axis(s1, keep, 1).copy()).cuda()
-            i = torch.from_numpy(np.take_along_axis(i1, keep, 1).copy()).cuda()
+            s1, i1 = _drop_self(s1.cpu().numpy(), i1.cpu().numpy(), np.arange(c0, c0 + qc.shape[0]), k)
+            s, i = torch.from_numpy(s1).cuda(), torch.from_numpy(i1).cuda()
         out[c0:c0 + qc.shape[0]] = ops.aqe_expand(qc, d, i.contiguous(), s.contiguous(), float(alpha))
     return out[:, :dim].cpu().numpy()
 

@@ -256,3 +256,26 @@ def test_search_protocol_model_with_bounded_buffers_is_exact_or_fails_loudly(n, 
         return
     ref_s, ref_i = M.exact_topk(q, db, k)
     assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)
+
+
+@settings(max_examples=100, **COMMON)
+@given(n=st.integers(2, 60), k=st.integers(1, 8), seed=st.integers(0, 10**6), dup=st.booleans())
+def test_dba_neighbour_lists_drop_exactly_the_row_itself(n, k, seed, dup):
+    """pipeline._drop_self (database-side augmentation, test_dir.py:33-34: the diagonal of the self-similarity is
+    zeroed): from the exact top-(k+1) of row i against its own database, the k best rows other than i, best first."""
+    from dirb200.pipeline import _drop_self
+    import search_model as M
+    r = np.random.RandomState(seed)
+    db = _unit(r.standard_normal((n, 16)))
+    if dup:
+        db[r.randint(n)] = db[r.randint(n)]                       # an exact duplicate pair (may be the same row)
+    kk = min(k + 1, n)
+    s1, i1 = M.exact_topk(db, db, kk)
+    s, i = _drop_self(s1, i1, np.arange(n), k)
+    ex = M.exact_scores(db, db)
+    for row in range(n):
+        others = [j for j in np.lexsort((np.arange(n), -ex[row])) if j != row][:k]
+        assert list(i[row][:len(others)]) == others[:i.shape[1]]
+        assert row not in i[row]
+        assert (i[row][len(others):] == -1).all() and (s[row][len(others):] == 0).all()      # fewer than k other rows
+    assert i.shape[1] == min(k, kk)
