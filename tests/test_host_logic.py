@@ -210,6 +210,40 @@ def test_topk_exchange_gloo_world2(tmp_path):
     assert open(tmp_path / "ok0").read() == "1" and open(tmp_path / "ok1").read() == "1"
 
 
+def _shard_sizes_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    import dirb200  # noqa: F401
+    from dirb200 import dist as ddist
+    from dirb200 import ops
+
+    class _NoGpuIndex:                                     # the real one uploads to the GPU
+        def __init__(self, db32, index_offset=0, db16=None):
+            self.db32, self.n, self.dim = db32, db32.shape[0], db32.shape[1]
+    ops.Index = _NoGpuIndex
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = ddist.ShardedIndex(torch.zeros(([3, 1000, 0][rank], 64)), row_offset=0)
+    ok = sh.shard_sizes == [3, 1000, 0] and ddist.shard_quota(100, sh.shard_sizes) == 97
+    with open(os.path.join(tmp, "ok%d" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_sharded_index_learns_all_shard_sizes_gloo_world3(tmp_path):
+    """ShardedIndex gathers the row counts of all shards at construction (they set the selection depth of the two-phase
+    search, dist.shard_quota); exchange plumbing under gloo with a stand-in for the GPU index."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_shard_sizes_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert all(open(tmp_path / ("ok%d" % r)).read() == "1" for r in range(3))
+
+
 class _FakeNet:
     """Stands in for the GPU network in host-plumbing tests: descriptor = per-channel mean / std of the image."""
     iscuda = False
