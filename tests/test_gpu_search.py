@@ -192,8 +192,7 @@ def test_two_phase_sharded_search_single_gpu():
 def test_two_phase_search_with_a_shard_smaller_than_its_quota():
     """A shard that holds fewer rows than ceil(k / G), all of them close to the query: the naive selection depth
     certifies fewer than k rows and the exchanged threshold would cut true top-k rows (found on the CPU by
-    tests/test_properties.py).  dist.shard_quota picks the depth from the shard sizes; merge == oracle.
-    (Kept last in the last GPU test file: it was added after this round's final GPU run.)"""
+    tests/test_properties.py).  dist.shard_quota picks the depth from the shard sizes; merge == oracle."""
     ops = _ops()
     from dirb200.dist import shard_quota
     db, q, _ = synth.make_descriptor_db(5000, 4, dim=256, n_pos=5, db_seed=5, q_seed=6)
