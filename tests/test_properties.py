@@ -10,10 +10,14 @@ from hypothesis import strategies as st
 from dirb200 import dist as ddist
 from dirb200 import store as S
 
-COMMON = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+# derandomize: the same examples on every run (a red CPU suite must mean a code change, not a new random draw);
+# explore with HYP_RANDOM=1 (fresh random draws) and HYP_SCALE=n (n times more examples)
+COMMON = dict(deadline=None, derandomize=os.environ.get("HYP_RANDOM", "") == "", database=None,
+              suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+_SCALE = int(os.environ.get("HYP_SCALE", "1"))        # HYP_RANDOM=1 HYP_SCALE=20: a long exploratory run
 
 
-@settings(max_examples=200, **COMMON)
+@settings(max_examples=200 * _SCALE, **COMMON)
 @given(n=st.integers(0, 10**7), world=st.integers(1, 64))
 def test_shard_rows_partitions_the_rows(n, world):
     rs = [ddist.shard_rows(n, world, r) for r in range(world)]
@@ -23,7 +27,7 @@ def test_shard_rows_partitions_the_rows(n, world):
     assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1                      # balanced to within one row
 
 
-@settings(max_examples=40, **COMMON)
+@settings(max_examples=40 * _SCALE, **COMMON)
 @given(n=st.integers(0, 300), dim=st.sampled_from([1, 8, 64]), per=st.integers(1, 128), world=st.integers(1, 9),
        f16=st.booleans(), data=st.data())
 def test_store_reads_equal_slices(tmp_path_factory, n, dim, per, world, f16, data):
@@ -48,7 +52,7 @@ def _relevants_dataset(tmp, n, gnd):
     return ImageListRelevants(os.path.join(tmp, "gnd.pkl"), root=tmp)
 
 
-@settings(max_examples=60, **COMMON)
+@settings(max_examples=60 * _SCALE, **COMMON)
 @given(n=st.integers(8, 120), seed=st.integers(0, 10**6), revisited=st.booleans(), data=st.data())
 def test_ap_from_full_ranking_equals_ap_from_scores(tmp_path_factory, n, seed, revisited, data):
     """eval_query_AP_from_ranking over the COMPLETE ranking == eval_query_AP on the score row (distinct scores), and a
@@ -78,7 +82,7 @@ def test_ap_from_full_ranking_equals_ap_from_scores(tmp_path_factory, n, seed, r
         assert part is None or abs(part - full) < 1e-12
 
 
-@settings(max_examples=25, **COMMON)
+@settings(max_examples=25 * _SCALE, **COMMON)
 @given(h=st.integers(2, 40), w=st.integers(2, 40), oh=st.integers(1, 60), ow=st.integers(1, 60), seed=st.integers(0, 999))
 def test_resize_tables_reproduce_pil_for_any_size(h, w, oh, ow, seed):
     """The coefficient tables the GPU resize uses (dirb200_resize_coeffs, a host function of the library), applied
@@ -102,7 +106,7 @@ def test_resize_tables_reproduce_pil_for_any_size(h, w, oh, ow, seed):
     assert np.array_equal(got, ref)
 
 
-@settings(max_examples=60, **COMMON)
+@settings(max_examples=60 * _SCALE, **COMMON)
 @given(dim=st.sampled_from([64, 128, 512, 1024, 2048]), seed=st.integers(0, 10**6),
        kind=st.sampled_from(["gauss", "const", "sparse", "signed_const", "heavy", "tiny_tail"]))
 def test_fp16_score_error_stays_inside_the_search_band(dim, seed, kind):
@@ -166,7 +170,7 @@ def _unit(x):
     return (x / np.linalg.norm(x.astype(np.float64), axis=1, keepdims=True)).astype(np.float32)
 
 
-@settings(max_examples=300, **COMMON)
+@settings(max_examples=300 * _SCALE, **COMMON)
 @given(n=st.integers(1, 1500), nq=st.integers(1, 5), k=st.integers(1, 40), shards=st.integers(1, 6),
        sample=st.sampled_from([32, 64, 256, 4096]), kind=st.sampled_from(["random", "duplicates", "clustered", "planted"]),
        seed=st.integers(0, 10**6), data=st.data())
@@ -231,7 +235,7 @@ def test_selection_depth_accounts_for_small_and_empty_shards():
     assert not np.array_equal(naive, ref)
 
 
-@settings(max_examples=120, **COMMON)
+@settings(max_examples=120 * _SCALE, **COMMON)
 @given(n=st.integers(200, 2500), k=st.integers(1, 30), shards=st.integers(1, 3), cap=st.sampled_from([64, 128, 512]),
        kind=st.sampled_from(["random", "clustered", "planted"]), seed=st.integers(0, 10**6))
 def test_search_protocol_model_with_bounded_buffers_is_exact_or_fails_loudly(n, k, shards, cap, kind, seed):
@@ -258,7 +262,7 @@ def test_search_protocol_model_with_bounded_buffers_is_exact_or_fails_loudly(n, 
     assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)
 
 
-@settings(max_examples=100, **COMMON)
+@settings(max_examples=100 * _SCALE, **COMMON)
 @given(n=st.integers(2, 60), k=st.integers(1, 8), seed=st.integers(0, 10**6), dup=st.booleans())
 def test_dba_neighbour_lists_drop_exactly_the_row_itself(n, k, seed, dup):
     """pipeline._drop_self (database-side augmentation, test_dir.py:33-34: the diagonal of the self-similarity is
@@ -308,7 +312,7 @@ def _row_rel(got, ref):
     return float((np.linalg.norm(got.astype(np.float64) - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
 
 
-@settings(max_examples=30, **COMMON)
+@settings(max_examples=30 * _SCALE, **COMMON)
 @given(dim=st.sampled_from([64, 256, 2048]), spread=st.sampled_from([1.0, 0.5, 0.25]), seed=st.integers(0, 10**6))
 def test_split_fp16_whitening_error_in_the_operating_regime(dim, spread, seed):
     """Unit-norm descriptors at distance >= 0.25 from their mean (trained descriptors: 0.5-0.9) projected on unit-norm
