@@ -87,6 +87,28 @@ def torch_set_seed(seed, cuda, randomize=True):
             torch.cuda.manual_seed(seed)
 
 
+def save_checkpoint(state, is_best, filename):
+    """common.py:100-112: write the checkpoint dict ({state_dict, model_options, preprocess?, pca?, ...}); a copy named
+    ``<filename>.best`` when is_best.  Errors are reported, not raised, like the reference."""
+    import shutil
+    try:
+        folder = os.path.split(filename)[0]
+        if folder and not os.path.isdir(folder):
+            os.makedirs(folder)
+        torch.save(state, filename)
+        if is_best:
+            shutil.copyfile(filename, filename + ".best")
+            filename += ".best"
+        print("saving to " + filename)
+    except Exception:
+        print("Error: Could not save checkpoint at %s, skipping" % filename)
+
+
+def model_size(model):
+    """common.py:178-184: number of parameters (all state-dict tensors)."""
+    return int(sum(int(np.prod(tuple(w.shape))) for w in model.state_dict().values()))
+
+
 def load_checkpoint(filename, iscuda=False):
     """common.py:117-147: torch.load of {state_dict, model_options, preprocess?, pca?}, 'module.' stripped."""
     if not filename:

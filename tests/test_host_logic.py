@@ -149,6 +149,24 @@ def test_cli_surface_and_no_cpu_path():
         extract_features.extract_features_main(["--dataset", "x"])   # --checkpoint is required
 
 
+def test_checkpoint_round_trip_and_model_size(tmp_path, capsys):
+    """save_checkpoint / load_checkpoint / model_size (common.py:100-147,178-184) on the duck-typed model."""
+    from dirtorch import nets
+    from dirtorch.utils import common, evaluation
+    net = nets.create_model("resnet50_rmac")
+    assert common.model_size(net) == 27757558 and len(net.state_dict()) == 321      # = the reference's own count
+    f = str(tmp_path / "sub" / "ck.pt")
+    state = {"state_dict": {"module." + k: v for k, v in net.state_dict().items()},
+             "model_options": dict(arch="resnet50_rmac", out_dim=2048, pooling="gem", gemp=3), "epoch": 3}
+    common.save_checkpoint(state, True, f)
+    assert os.path.isfile(f) and os.path.isfile(f + ".best") and "saving to" in capsys.readouterr().out
+    ck = common.load_checkpoint(f + ".best")
+    assert "(epoch 3)" in capsys.readouterr().out
+    assert list(ck["state_dict"]) == list(net.state_dict())                          # 'module.' stripped
+    assert all(torch.equal(ck["state_dict"][k], v) for k, v in net.state_dict().items())
+    assert abs(evaluation.compute_AP([1, 0, 1, 0], [0.9, 0.8, 0.7, 0.1]) - 5.0 / 6.0) < 1e-12
+
+
 def test_shard_rows_cover():
     from dirb200.dist import shard_rows
     for n, w in ((1_000_000, 8), (100, 8), (7, 3), (5, 8)):
