@@ -60,10 +60,19 @@ def arch_to_trunk(arch: str) -> str:
     return trunk
 
 
+BASIC_BLOCKS = {"resnet18": [2, 2, 2, 2]}
+
+
 def make_state_dict(arch: str = "resnet50_rmac", seed: int = 0, out_dim: int = 2048,
                     gemp: float = 3.0, res_gamma: float = 0.3) -> dict:
-    """Reference-keyed state dict for a Bottleneck ResNet + GeM(p) + FC head."""
-    blocks = BLOCKS[arch_to_trunk(arch)]
+    """Reference-keyed state dict: Bottleneck (resnet50/101/152) or BasicBlock (resnet18) trunk + GeM(p) + FC head;
+    ``*_fpn_rmac`` / ``*_fpn0_rmac`` names add the FPN head tensors (rmac_resnet_fpn.py:27-46)."""
+    name = arch.split("_")[0]
+    fpn = "_fpn" in arch
+    if name in BASIC_BLOCKS:
+        blocks, exp = BASIC_BLOCKS[name], 1
+    else:
+        blocks, exp = BLOCKS[arch_to_trunk(arch)], 4
     sd = {}
     sd["conv1.weight"] = _conv(seed, "conv1.weight", 64, 3, 7)
     sd.update(_bn(seed, "bn1", 64))
@@ -71,19 +80,34 @@ def make_state_dict(arch: str = "resnet50_rmac", seed: int = 0, out_dim: int = 2
     for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], blocks), start=1):
         for b in range(nblk):
             p = "layer%d.%d." % (li, b)
-            sd[p + "conv1.weight"] = _conv(seed, p + "conv1.weight", planes, inplanes, 1)
-            sd.update(_bn(seed, p + "bn1", planes))
-            sd[p + "conv2.weight"] = _conv(seed, p + "conv2.weight", planes, planes, 3)
-            sd.update(_bn(seed, p + "bn2", planes))
-            sd[p + "conv3.weight"] = _conv(seed, p + "conv3.weight", planes * 4, planes, 1)
-            sd.update(_bn(seed, p + "bn3", planes * 4, gamma_scale=res_gamma))
-            if b == 0:
-                sd[p + "downsample.0.weight"] = _conv(seed, p + "downsample.0.weight", planes * 4, inplanes, 1)
-                sd.update(_bn(seed, p + "downsample.1", planes * 4, gamma_scale=0.7))
-            inplanes = planes * 4
-    sd["adpool.p"] = torch.ones(1) * float(gemp)
+            stride = 2 if (li > 1 and b == 0) else 1
+            if exp == 4:
+                sd[p + "conv1.weight"] = _conv(seed, p + "conv1.weight", planes, inplanes, 1)
+                sd.update(_bn(seed, p + "bn1", planes))
+                sd[p + "conv2.weight"] = _conv(seed, p + "conv2.weight", planes, planes, 3)
+                sd.update(_bn(seed, p + "bn2", planes))
+                sd[p + "conv3.weight"] = _conv(seed, p + "conv3.weight", planes * 4, planes, 1)
+                sd.update(_bn(seed, p + "bn3", planes * 4, gamma_scale=res_gamma))
+            else:
+                sd[p + "conv1.weight"] = _conv(seed, p + "conv1.weight", planes, inplanes, 3)
+                sd.update(_bn(seed, p + "bn1", planes))
+                sd[p + "conv2.weight"] = _conv(seed, p + "conv2.weight", planes, planes, 3)
+                sd.update(_bn(seed, p + "bn2", planes, gamma_scale=res_gamma))
+            if b == 0 and (stride != 1 or inplanes != planes * exp):          # resnet.py:136-141
+                sd[p + "downsample.0.weight"] = _conv(seed, p + "downsample.0.weight", planes * exp, inplanes, 1)
+                sd.update(_bn(seed, p + "downsample.1", planes * exp, gamma_scale=0.7))
+            inplanes = planes * exp
+    feat = 512 * exp
     r = _rs(seed, "fc")
-    sd["fc.weight"] = torch.from_numpy((r.standard_normal((out_dim, 2048)) / np.sqrt(2048.0)).astype(np.float32))
+    if fpn:
+        sd["conv1x5.weight"] = _conv(seed, "conv1x5.weight", 256 * exp, 512 * exp, 1)
+        sd["conv3c4.weight"] = _conv(seed, "conv3c4.weight", 256 * exp, 256 * exp, 3)
+        sd["adpoolx5.p"] = torch.ones(1) * float(gemp)
+        sd["adpoolc4.p"] = torch.ones(1) * float(gemp)
+        feat = 768 * exp
+    else:
+        sd["adpool.p"] = torch.ones(1) * float(gemp)
+    sd["fc.weight"] = torch.from_numpy((r.standard_normal((out_dim, feat)) / np.sqrt(float(feat))).astype(np.float32))
     sd["fc.bias"] = torch.from_numpy((0.01 * r.standard_normal(out_dim)).astype(np.float32))
     return sd
 

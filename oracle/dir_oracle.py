@@ -25,6 +25,7 @@ import torch
 import torch.nn.functional as F
 
 BLOCKS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3], "resnet152": [3, 8, 36, 3]}  # rmac_resnet.py:78-88
+BASIC_BLOCKS = {"resnet18": [2, 2, 2, 2]}   # rmac_resnet.py:74-76 (BasicBlock, expansion 1) - oracle only so far, see DESIGN.md
 BN_EPS = 1e-5  # torch.nn.BatchNorm2d default, used by resnet.py:57,60,63,117,140
 
 
@@ -53,15 +54,32 @@ def bottleneck(x, sd, prefix, stride, has_down):
     return F.relu(out + x)
 
 
+def basic_block(x, sd, prefix, stride, has_down):
+    """3x3(stride, pad 1) -> BN -> ReLU -> 3x3 -> BN, + (downsampled) x, ReLU.  resnet.py:14-43."""
+    out = F.relu(_bn(F.conv2d(x, sd[prefix + "conv1.weight"], None, stride=stride, padding=1), sd, prefix + "bn1"))
+    out = _bn(F.conv2d(out, sd[prefix + "conv2.weight"], None, padding=1), sd, prefix + "bn2")
+    if has_down:
+        x = _bn(F.conv2d(x, sd[prefix + "downsample.0.weight"], None, stride=stride), sd, prefix + "downsample.1")
+    return F.relu(out + x)
+
+
 def trunk(x, sd, arch="resnet50", return_stages=False):
-    """ResNet.forward without the classifier, resnet.py:157-168; layer strides 1,2,2,2 (resnet.py:120-123)."""
-    blocks = BLOCKS[arch.split("_")[0]]
+    """ResNet.forward without the classifier, resnet.py:157-168; layer strides 1,2,2,2 (resnet.py:120-123).
+    A projection shortcut exists where the stride or the width changes (resnet.py:136-141): block 0 of every layer
+    for Bottleneck trunks, block 0 of layers 2-4 for BasicBlock trunks."""
+    name = arch.split("_")[0]
+    basic = name in BASIC_BLOCKS
+    blocks = BASIC_BLOCKS[name] if basic else BLOCKS[name]
     stages = {}
     x = stem(x, sd)
     stages["stem"] = x
     for li, nblk in enumerate(blocks, start=1):
         for b in range(nblk):
-            x = bottleneck(x, sd, "layer%d.%d." % (li, b), stride=(2 if (li > 1 and b == 0) else 1), has_down=(b == 0))
+            stride = 2 if (li > 1 and b == 0) else 1
+            if basic:
+                x = basic_block(x, sd, "layer%d.%d." % (li, b), stride=stride, has_down=(b == 0 and li > 1))
+            else:
+                x = bottleneck(x, sd, "layer%d.%d." % (li, b), stride=stride, has_down=(b == 0))
         stages["layer%d" % li] = x
     return (x, stages) if return_stages else x
 
@@ -100,6 +118,26 @@ def head(feat, sd, pooling="gem", norm_features=False, without_fc=False, squeeze
     if squeeze and x.shape[0] == 1:  # x.squeeze_() drops the batch dim at B=1, rmac_resnet.py:64
         x = x[0]
     return x
+
+
+@torch.no_grad()
+def extract_fpn(x, sd, arch="resnet50_fpn_rmac", mode=1, norm_features=False, without_fc=False, squeeze=True):
+    """ResNet_RMAC_FPN.forward, rmac_resnet_fpn.py:52-90: (layer3, layer4) maps; mode 1 adds the 1x1-reduced,
+    nearest-upsampled layer4 map to layer3 and smooths with a 3x3 conv (no BN, ReLU after each); one GeM per map
+    (own p each), concatenation [x4 | x5], (L2), fc, L2.  Oracle only so far."""
+    _, stages = trunk(x, sd, arch.replace("_fpn0", "").replace("_fpn", ""), return_stages=True)
+    x4, x5 = stages["layer3"], stages["layer4"]
+    if mode == 1:
+        c5 = F.interpolate(x5, size=x4.shape[-2:], mode="nearest")
+        c5 = F.relu(F.conv2d(c5, sd["conv1x5.weight"]))
+        x4 = F.relu(F.conv2d(x4 + c5, sd["conv3c4.weight"], None, padding=1))
+    v = torch.cat([gem(x4, sd["adpoolc4.p"].item()), gem(x5, sd["adpoolx5.p"].item())], dim=1)
+    if norm_features:
+        v = F.normalize(v, p=2, dim=1)
+    if not without_fc:
+        v = F.linear(v, sd["fc.weight"], sd["fc.bias"])
+    v = F.normalize(v, p=2, dim=-1)
+    return v[0] if (squeeze and v.shape[0] == 1) else v
 
 
 @torch.no_grad()

@@ -48,7 +48,10 @@ def ref_model(arch, seed, **kw):
     net = nets.create_model(arch, pretrained="", **kw)
     sd = synth.make_state_dict(arch, seed=seed, out_dim=kw.get("out_dim", 2048), gemp=kw.get("gemp", 3))
     if not kw.get("pooling", "gem").startswith("gem"):
-        sd.pop("adpool.p")                      # max/avg pooling has no learnable p (rmac_resnet.py:24-31)
+        sd.pop("adpool.p", None)                # max/avg pooling has no learnable p (rmac_resnet.py:24-31)
+    if kw.get("mode", 1) == 0:                  # FPN mode 0 has no lateral / smoothing convs (rmac_resnet_fpn.py:27-30)
+        sd.pop("conv1x5.weight", None)
+        sd.pop("conv3c4.weight", None)
     net.load_state_dict(sd, strict=True)
     net.eval()
     return net
@@ -182,6 +185,20 @@ def gold_aqe():
     save("aqe.npz", **out)
 
 
+@torch.no_grad()
+def gold_variants():
+    """Model variants of SURVEY 8f-4 for which only the oracle exists so far: BasicBlock trunk (resnet18_rmac,
+    rmac_resnet.py:74-76) and the FPN head (rmac_resnet_fpn.py:52-90), modes 1 and 0."""
+    out = {}
+    x = synth.make_images(2, 128, 160, seed=61)
+    out["desc_r18"] = ref_model("resnet18_rmac", seed=5)(x).numpy()
+    out["desc_r18_b1"] = ref_model("resnet18_rmac", seed=5)(x[:1]).numpy()
+    out["desc_r50_fpn"] = ref_model("resnet50_fpn_rmac", seed=6, out_dim=2048)(x).numpy()
+    out["desc_r50_fpn0"] = ref_model("resnet50_fpn_rmac", seed=6, out_dim=2048, mode=0)(x).numpy()
+    out["desc_r18_fpn"] = ref_model("resnet18_fpn_rmac", seed=7, out_dim=512)(x).numpy()
+    save("extract_variants.npz", img_seed=61, img_shape=np.array([2, 128, 160]), r18_seed=5, fpn_seed=6, r18_fpn_seed=7, **out)
+
+
 def gold_labels():
     """Label-based AP of Dataset.eval_query_AP (dataset.py:83-92 -> sklearn, evaluation.py:41-43) on labelled image
     lists (generic.py:44-105): every image a query, and a separate query list."""
@@ -311,6 +328,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["cli"]:
         gold_cli()
         sys.exit(0)
+    if sys.argv[1:] == ["variants"]:
+        gold_variants()
+        sys.exit(0)
     if sys.argv[1:] == ["labels"]:
         gold_labels()
         sys.exit(0)
@@ -323,3 +343,4 @@ if __name__ == "__main__":
     gold_extract_extra()
     gold_cli()
     gold_labels()
+    gold_variants()

@@ -224,3 +224,28 @@ def test_precision_design_meets_the_descriptor_bar(golden, name, arch):
     for fused in (True, False):
         err = rel_l2(QM.extract(x, sd, arch, fuse_shortcut=fused).numpy(), g["desc"])
         assert 2e-4 < err < 6e-4, (arch, fused, err)          # measured here: 3.5e-4 - 3.9e-4
+
+
+def test_variants_basic_block_trunk_and_fpn_head(golden):
+    """BasicBlock trunk (resnet18_rmac) and the FPN head (modes 1 and 0) - the oracle restatement is
+    pinned here; the GPU path does not build these variants yet."""
+    g = golden("extract_variants.npz")
+    b, h, w = [int(v) for v in g["img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["img_seed"]))
+    sd = synth.make_state_dict("resnet18_rmac", seed=int(g["r18_seed"]))
+    assert sd["fc.weight"].shape == (2048, 512) and "layer1.0.downsample.0.weight" not in sd and "layer2.0.downsample.0.weight" in sd
+    assert rel_l2(O.extract(x, sd, "resnet18_rmac").numpy(), g["desc_r18"]) < 2e-5
+    d1 = O.extract(x[:1], sd, "resnet18_rmac").numpy()
+    assert d1.shape == (2048,) and rel_l2(d1, g["desc_r18_b1"]) < 2e-5
+    sd = synth.make_state_dict("resnet50_fpn_rmac", seed=int(g["fpn_seed"]))
+    assert sd["fc.weight"].shape == (2048, 3072) and sd["conv1x5.weight"].shape == (1024, 2048, 1, 1)
+    assert rel_l2(O.extract_fpn(x, sd, "resnet50_fpn_rmac").numpy(), g["desc_r50_fpn"]) < 2e-5
+    assert rel_l2(O.extract_fpn(x, sd, "resnet50_fpn_rmac", mode=0).numpy(), g["desc_r50_fpn0"]) < 2e-5
+    sd = synth.make_state_dict("resnet18_fpn_rmac", seed=int(g["r18_fpn_seed"]), out_dim=512)
+    assert sd["fc.weight"].shape == (512, 768)
+    assert rel_l2(O.extract_fpn(x, sd, "resnet18_fpn_rmac").numpy(), g["desc_r18_fpn"]) < 2e-5
+    # the product says so loudly instead of running something else
+    from dirb200 import nets
+    for arch in ("resnet18_rmac", "resnet50_fpn_rmac"):
+        with pytest.raises(NameError):
+            nets.create_model(arch)
