@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
 def cpu_extract_rate(n_img, size, repeats):
     """The reference's CPU path for extraction = oracle port of net(imgs) (torch CPU fp32)."""
     import torch
-    import dirb200.synth as synth
+    import synthdata as synth
     from oracle import dir_oracle as O
     torch.set_num_threads(min(CPU_THREADS, os.cpu_count() or 1))
     sd = synth.make_state_dict(ARCH, seed=0)
@@ -172,7 +172,7 @@ def main():
 
     import numpy as np
     import torch
-    import dirb200.synth as synth
+    import synthdata as synth
     from dirb200 import nets, ops
     from dirb200.dist import ShardedIndex, shard_rows
 

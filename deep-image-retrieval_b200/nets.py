@@ -19,7 +19,10 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import lib, synth
+from . import lib
+
+RGB_MEANS = [0.485, 0.456, 0.406]            # resnet.py:110-111
+RGB_STDS = [0.229, 0.224, 0.225]
 
 _ARCH_BLOCKS = {"resnet50_rmac": [3, 4, 6, 3], "resnet101_rmac": [3, 4, 23, 3],     # rmac_resnet.py:78-88
                 "resnet152_rmac": [3, 8, 36, 3]}
@@ -78,8 +81,8 @@ class ResNetRMAC:
             raise ValueError(pooling)                            # rmac_resnet.py:30-31
         self.arch = arch
         self.model_name = arch.split("_")[0]
-        self.rgb_means = list(synth.RGB_MEANS)                   # resnet.py:110-112
-        self.rgb_stds = list(synth.RGB_STDS)
+        self.rgb_means = list(RGB_MEANS)                   # resnet.py:110-112
+        self.rgb_stds = list(RGB_STDS)
         self.input_size = (3, 224, 224)
         self.norm_features = bool(norm_features)
         self.without_fc = bool(without_fc)

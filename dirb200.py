@@ -3,7 +3,7 @@
 The package directory name is fixed by the project layout and is not a valid
 Python identifier, so this one-file shim registers it under the importable name
 ``dirb200`` (sub-modules resolve through ``__path__`` as usual:
-``import dirb200.synth``, ``from dirb200 import lib`` ...).
+``import dirb200.nets``, ``from dirb200 import lib`` ...).
 """
 import importlib.util
 import os

@@ -5,7 +5,7 @@ import pickle
 import numpy as np
 import torch
 
-import dirb200.synth as synth
+import synthdata as synth
 
 
 def build(root, n_groups=8, n_extra=8, size=(160, 192), seed=3, arch="resnet50_rmac", hard=False,

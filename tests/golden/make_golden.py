@@ -6,7 +6,7 @@ Run in the build container only (``/root/reference`` does not exist on the GPU b
     python tests/golden/make_golden.py
 
 It imports naver/deep-image-retrieval from /root/reference (read-only, nothing is copied),
-feeds it the seeded synthetic inputs of ``deep-image-retrieval_b200/synth.py`` and stores the
+feeds it the seeded synthetic inputs of ``synthdata.py`` and stores the
 reference's outputs as small ``.npz`` files.  Inputs are NOT stored when they can be
 regenerated from a seed; the seeds/shapes are recorded in each file.
 """
@@ -31,7 +31,7 @@ import torch  # noqa: E402
 
 torch.set_num_threads(os.cpu_count())
 
-spec = importlib.util.spec_from_file_location("synth", os.path.join(REPO, "deep-image-retrieval_b200", "synth.py"))
+spec = importlib.util.spec_from_file_location("synth", os.path.join(REPO, "synthdata.py"))
 synth = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(synth)
 

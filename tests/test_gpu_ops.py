@@ -4,7 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-import dirb200.synth as synth
+import synthdata as synth
 from oracle import dir_oracle as O
 from conftest import rel_l2
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-import dirb200.synth as synth
+import synthdata as synth
 from conftest import REPO, rel_l2
 from oracle import dir_oracle as O
 

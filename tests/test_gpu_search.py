@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-import dirb200.synth as synth
+import synthdata as synth
 from oracle import dir_oracle as O
 from conftest import rel_l2
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-import dirb200.synth as synth
+import synthdata as synth
 from conftest import REPO
 from oracle import dir_oracle as O
 
@@ -181,7 +181,7 @@ def _gloo_worker(rank, world, port, tmp):
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, REPO)
     import torch.distributed as dist
-    import dirb200.synth as synth
+    import synthdata as synth
     from dirb200.dist import all_gather_packed, shard_rows
     from oracle import dir_oracle as O
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -1,7 +1,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import dirb200.synth as synth
+import synthdata as synth
 from oracle import dir_oracle as O
 print("cpu_count", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)), "torch threads default", torch.get_num_threads())
 sd = synth.make_state_dict("resnet101_rmac", seed=0)

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-import dirb200.synth as synth
+import synthdata as synth
 from dirb200.dist import ShardedIndex, shard_rows
 from oracle import dir_oracle as O
 

@@ -1,7 +1,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import dirb200.synth as synth
+import synthdata as synth
 from dirb200 import nets
 net = nets.create_model("resnet101_rmac"); net.load_state_dict(synth.make_state_dict("resnet101_rmac", seed=0))
 for (b, h, w) in ((1, 1024, 768), (1, 1024, 1024), (1, 512, 384), (4, 1024, 768), (8, 1024, 1024), (1, 224, 224), (16, 224, 224)):

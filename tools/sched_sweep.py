@@ -1,7 +1,7 @@
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import dirb200.synth as synth
+import synthdata as synth
 from dirb200 import nets
 B, S = 64, 1024
 net = nets.create_model("resnet101_rmac")

@@ -1,7 +1,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import dirb200.synth as synth
+import synthdata as synth
 from dirb200 import nets
 net = nets.create_model("resnet101_rmac"); net.load_state_dict(synth.make_state_dict("resnet101_rmac", seed=0))
 x = torch.randn((64, 3, 1024, 1024), device="cuda")
