@@ -4,6 +4,9 @@
 #include "conv_pers.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
+#include <mutex>
+
 namespace dirb {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -435,16 +438,109 @@ __global__ void __launch_bounds__(256) whiten_gemm_kernel(const float* __restric
 }
 }  // namespace
 
-// x - mean -> fp16 hi + fp16 lo (hi + lo reproduces the fp32 value to ~2^-22 relative)
+// ---- device scratch cache -------------------------------------------------------------------------------------
+// dirb200_whiten has no handle, and allocating ~1 GB of split buffers per call (cudaMallocAsync after every
+// synchronisation point, i.e. a driver-level allocation) serialises badly when 8 processes share a box.  One scratch
+// buffer per device is therefore kept for the life of the process (grown on demand).  Users on different streams are
+// ordered through an event: acquire makes the caller's stream wait for the previous user, release records it.
+namespace {
+struct DevScratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t last_use = nullptr;
+};
+DevScratch g_scratch[64];
+std::mutex g_scratch_mu;
+}  // namespace
+
+static int scratch_acquire(size_t bytes, cudaStream_t stream, void** out) {
+  int dev = 0;
+  DIRB_CUDA(cudaGetDevice(&dev));
+  DIRB_REQUIRE(dev >= 0 && dev < 64, DIRB200_ENOTSUP, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  DevScratch& s = g_scratch[dev];
+  if (!s.last_use) DIRB_CUDA(cudaEventCreateWithFlags(&s.last_use, cudaEventDisableTiming));
+  if (bytes > s.bytes) {
+    if (s.ptr) DIRB_CUDA(cudaFree(s.ptr));   // synchronises the device: no earlier user is still running
+    s.ptr = nullptr;
+    s.bytes = 0;
+    const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+    DIRB_CUDA(cudaMalloc(&s.ptr, want));
+    s.bytes = want;
+  } else {
+    DIRB_CUDA(cudaStreamWaitEvent(stream, s.last_use, 0));
+  }
+  *out = s.ptr;
+  return 0;
+}
+
+static int scratch_release(cudaStream_t stream) {
+  int dev = 0;
+  DIRB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  DIRB_CUDA(cudaEventRecord(g_scratch[dev].last_use, stream));
+  return 0;
+}
+
+// ---- fp16 hi/lo split with an adaptive power-of-two prescale --------------------------------------------------------
+// v = x - mean is written as hi + lo (two fp16 numbers; hi + lo reproduces v to ~2^-22 relative).  The LOW half is
+// ~ v * 2^-11: without a prescale it falls into fp16's subnormal range (< 6.1e-5, quantum 6e-8) as soon as |v| < ~0.1
+// and the scheme degrades towards a single fp16 pass (relative error ~ 1 / |x - mean|, tests/test_properties.py).  Both
+// operands are therefore multiplied by a power of two chosen from their largest magnitude (exact in fp32) so that
+// max |v| lands in [2^13, 2^14): the low halves of all values within 2^-12 of the maximum stay normal; the product of
+// the two scales is divided out in the column scale.
+//   ws[0] = bits of max |x - mean|, ws[1] = bits of max |comp|   (atomicMax on the bit pattern: values are >= 0)
+//   ws[2] = scale_x, ws[3] = scale_c, ws[4] = 1 / (scale_x * scale_c)
+__global__ void absmax_kernel(const float* __restrict__ x, const float* __restrict__ mean, int D, int64_t total,
+                              unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(x + i);
+    if (mean) {
+      const float4 mu = *reinterpret_cast<const float4*>(mean + (i % D));
+      v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
+    }
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out_bits, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float prescale_for(float absmax) {
+  if (!(absmax > 0.f)) return 1.0f;
+  int e;
+  frexpf(absmax, &e);                       // absmax = f * 2^e, f in [0.5, 1)
+  int sh = 14 - e;                          // absmax * 2^sh in [2^13, 2^14)
+  sh = sh > 40 ? 40 : (sh < -40 ? -40 : sh);
+  return ldexpf(1.0f, sh);
+}
+
+// ws[2..4] from ws[0..1]; cs[j] = (colscale ? colscale[j] : 1) / (scale_x * scale_c)
+__global__ void pick_prescale_kernel(float* __restrict__ ws, const float* __restrict__ colscale, float* __restrict__ cs,
+                                     int n) {
+  const float sx = prescale_for(__uint_as_float(reinterpret_cast<unsigned int*>(ws)[0]));
+  const float sc = prescale_for(__uint_as_float(reinterpret_cast<unsigned int*>(ws)[1]));
+  const float inv = 1.0f / (sx * sc);
+  if (threadIdx.x == 0) {
+    ws[2] = sx;
+    ws[3] = sc;
+    ws[4] = inv;
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) cs[j] = (colscale ? colscale[j] : 1.0f) * inv;
+}
+
 __global__ void split_f16_kernel(const float* __restrict__ x, const float* __restrict__ mean, int D, int64_t total,
-                                 __half* __restrict__ hi, __half* __restrict__ lo) {
+                                 const float* __restrict__ scale_ptr, __half* __restrict__ hi, __half* __restrict__ lo) {
   const int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
   if (i >= total) return;
+  const float sc = *scale_ptr;
   float4 v = *reinterpret_cast<const float4*>(x + i);
   if (mean) {
     const float4 m = *reinterpret_cast<const float4*>(mean + (i % D));
     v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
   }
+  v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;               // power of two: exact
   const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
   uint2 oh, ol;
   oh.x = pack_h2(__half2float(h0), __half2float(h1));
@@ -459,15 +555,28 @@ __global__ void split_f16_kernel(const float* __restrict__ x, const float* __res
 // (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) - fp32-level accuracy at tensor-core speed.
 static int whiten_tc(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale,
                      int Dout, float* y, cudaStream_t stream) {
-  __half *xh = nullptr, *xl = nullptr, *ch = nullptr, *cl = nullptr;
   const size_t xe = static_cast<size_t>(N) * D, ce = static_cast<size_t>(Dout) * D;
-  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xh), xe * 2, stream));
-  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&xl), xe * 2, stream));
-  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ch), ce * 2, stream));
-  DIRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&cl), ce * 2, stream));
-  split_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(xe, 4), 256)), 256, 0, stream>>>(x, mean, D, xe, xh, xl);
-  split_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(ce, 4), 256)), 256, 0, stream>>>(comp, nullptr, D, ce, ch, cl);
-  count_launch(2);
+  auto al = [](size_t b) { return (b + 1023) & ~size_t(1023); };
+  const size_t o_xh = 0, o_xl = o_xh + al(xe * 2), o_ch = o_xl + al(xe * 2), o_cl = o_ch + al(ce * 2);
+  const size_t o_ws = o_cl + al(ce * 2), o_cs = o_ws + 1024, total_bytes = o_cs + al(static_cast<size_t>(Dout) * 4);
+  void* base = nullptr;
+  DIRB_TRY(scratch_acquire(total_bytes, stream, &base));
+  uint8_t* b8 = static_cast<uint8_t*>(base);
+  __half* xh = reinterpret_cast<__half*>(b8 + o_xh);
+  __half* xl = reinterpret_cast<__half*>(b8 + o_xl);
+  __half* ch = reinterpret_cast<__half*>(b8 + o_ch);
+  __half* cl = reinterpret_cast<__half*>(b8 + o_cl);
+  float* ws = reinterpret_cast<float*>(b8 + o_ws);
+  float* cs = reinterpret_cast<float*>(b8 + o_cs);
+  DIRB_CUDA(cudaMemsetAsync(ws, 0, 32, stream));
+  const unsigned gx = static_cast<unsigned>(std::min<int64_t>(ceil_div(ceil_div(xe, 4), 256), 148 * 16));
+  const unsigned gc = static_cast<unsigned>(std::min<int64_t>(ceil_div(ceil_div(ce, 4), 256), 148 * 16));
+  absmax_kernel<<<gx, 256, 0, stream>>>(x, mean, D, xe, reinterpret_cast<unsigned int*>(ws));
+  absmax_kernel<<<gc, 256, 0, stream>>>(comp, nullptr, D, ce, reinterpret_cast<unsigned int*>(ws) + 1);
+  pick_prescale_kernel<<<1, 256, 0, stream>>>(ws, colscale, cs, Dout);
+  split_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(xe, 4), 256)), 256, 0, stream>>>(x, mean, D, xe, ws + 2, xh, xl);
+  split_f16_kernel<<<static_cast<unsigned>(ceil_div(ceil_div(ce, 4), 256)), 256, 0, stream>>>(comp, nullptr, D, ce, ws + 3, ch, cl);
+  count_launch(5);
   DIRB_CUDA(cudaGetLastError());
   constexpr int BN = 256;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
@@ -492,13 +601,9 @@ static int whiten_tc(const float* x, int64_t N, int D, const float* comp, const 
   p.total_tiles = static_cast<int>(total);
   p.dense = y;
   p.dense_ld = Dout;
-  p.scale = colscale;
+  p.scale = cs;
   DIRB_TRY((conv_pers_launch<BN, 4, PERS_EPI_F32>(tmAh, tmBh, tmAl, tmBl, p, num_sms(), stream)));
-  DIRB_CUDA(cudaFreeAsync(xh, stream));
-  DIRB_CUDA(cudaFreeAsync(xl, stream));
-  DIRB_CUDA(cudaFreeAsync(ch, stream));
-  DIRB_CUDA(cudaFreeAsync(cl, stream));
-  return 0;
+  return scratch_release(stream);
 }
 
 int whiten(const float* x, int64_t N, int D, const float* comp, const float* mean, const float* colscale, int Dout,

@@ -304,7 +304,8 @@ __global__ void aqe_kernel(const float* __restrict__ q, int D, const float* __re
   const int i = blockIdx.x;
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     int64_t r = nn[static_cast<int64_t>(i) * k + j];
-    if (r >= 0 && n_rows > 0) {                      // global index -> local row of this shard, or "not mine"
+    if (r >= 0 && (partial || n_rows > 0)) {         // sharded: global index -> local row of this shard, or "not mine"
+                                                     // (partial sums are per shard by definition, also for an EMPTY shard)
       r -= row_offset;
       if (r < 0 || r >= n_rows) r = -1;
     }
@@ -344,6 +345,7 @@ struct dirb200_index {
   const float* db32 = nullptr;
   const __half* db16 = nullptr;
   int64_t N = 0, offset = 0;
+  bool has_db = false;
   double eps16 = 1.2e-3;
   int64_t sample_rows = 0;
   int cand_cap = 0;          // 0 = auto
@@ -420,12 +422,13 @@ int dirb200_index_create(int device, int dim, dirb200_index** out) {
 
 int dirb200_index_set_db(dirb200_index* h, const float* db32_dev, const void* db16_dev, int64_t N,
                          int64_t index_offset) {
-  DIRB_REQUIRE(h && db32_dev && db16_dev && N >= 0, DIRB200_EINVAL, "bad db arguments");
+  DIRB_REQUIRE(h && N >= 0 && (N == 0 || (db32_dev && db16_dev)), DIRB200_EINVAL, "bad db arguments");   // an empty shard has no buffers
   DIRB_REQUIRE(N < (int64_t(1) << 31) - 256, DIRB200_ENOTSUP, "shard too large (%lld rows)", (long long)N);
   h->db32 = db32_dev;
   h->db16 = static_cast<const __half*>(db16_dev);
   h->N = N;
   h->offset = index_offset;
+  h->has_db = true;
   return 0;
 }
 
@@ -476,7 +479,7 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
                                void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DIRB_REQUIRE(h && q32 && sel_dev, DIRB200_EINVAL, "null argument");
-  DIRB_REQUIRE(h->db32 != nullptr, DIRB200_ESTATE, "index has no database attached");
+  DIRB_REQUIRE(h->has_db, DIRB200_ESTATE, "index has no database attached");
   DIRB_REQUIRE(Q > 0 && k > 0 && k <= 1024, DIRB200_ENOTSUP, "need 0 < Q and 0 < k <= 1024 (got Q=%d k=%d)", Q, k);
   DIRB_REQUIRE(k_shard >= 1 && k_shard <= k, DIRB200_EINVAL, "k_shard must be in [1, k]");
   DIRB_CUDA(cudaSetDevice(h->device));
@@ -722,7 +725,8 @@ int dirb200_aqe_expand(const float* q_dev, int Q, int D, const float* db32_dev, 
                        const double* nn_scores_dev, int k, double alpha, int partial, int64_t row_offset, int64_t n_rows,
                        float* out_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DIRB_REQUIRE(q_dev && db32_dev && nn_idx_dev && nn_scores_dev && out_dev, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(q_dev && nn_idx_dev && nn_scores_dev && out_dev && (db32_dev || (partial && n_rows == 0)), DIRB200_EINVAL,
+               "null argument");
   DIRB_REQUIRE(k >= 1 && alpha >= 0, DIRB200_EINVAL, "k and alpha must be non-negative (test_dir.py:25)");
   DIRB_REQUIRE(k <= 2048, DIRB200_ENOTSUP, "at most 2048 neighbours per query (got %d)", k);
   if (Q == 0) return 0;

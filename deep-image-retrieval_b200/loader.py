@@ -2,7 +2,8 @@
 
 Mirrors ``dirtorch/utils/pytorch_loader.get_loader`` (pytorch_loader.py:11-73) and the part of
 ``dirtorch/utils/transforms.create`` the evaluation CLIs use (transforms.py:11-37: the chain always ends in
-ToTensor + Normalize(mean, std); ``Scale`` transforms.py:133-185).  CPU-side I/O, not part of the GPU hot path.
+ToTensor + Normalize(mean, std); the deterministic test-time transforms ``Scale`` :133-185, ``Pad`` :47-77,
+``PadSquare`` :79-104, ``CenterCrop`` :309-322, ``Identity`` :40-44).  CPU-side I/O, not part of the GPU hot path.
 """
 from __future__ import annotations
 
@@ -44,6 +45,68 @@ class Scale:
         return img
 
 
+def _rgb_fill(color):
+    assert len(color) == 3
+    return tuple(color) if all(isinstance(c, int) for c in color) else tuple(int(255 * c) for c in color)
+
+
+class Identity:
+    """transforms.py:40-44."""
+
+    def __call__(self, img):
+        return img
+
+
+class Pad:
+    """Pad the SHORTEST side up to `size` with a constant colour, image centred (transforms.py:47-77)."""
+
+    def __init__(self, size, color=(127, 127, 127)):
+        self.size, self.color = size, _rgb_fill(color)
+
+    def __call__(self, img):
+        w, h = img.size
+        target = (w, max(h, self.size)) if w >= h else (max(w, self.size), h)
+        if target == img.size:
+            return img
+        canvas = Image.new("RGB", target, self.color)
+        canvas.paste(img, ((target[0] - w) // 2, (target[1] - h) // 2))
+        return canvas
+
+
+class PadSquare:
+    """Pad (or centre-crop, when `size` is smaller) to size x size; size=None -> the larger side (transforms.py:79-104)."""
+
+    def __init__(self, size=None, color=(127, 127, 127)):
+        self.size, self.color = size, _rgb_fill(color)
+
+    def __call__(self, img):
+        w, h = img.size
+        s = self.size or max(w, h)
+        if (s, s) == img.size:
+            return img
+        canvas = Image.new("RGB", (s, s), self.color)
+        canvas.paste(img, ((s - w) // 2, (s - h) // 2))
+        return canvas
+
+
+class CenterCrop:
+    """Crop `size` = int or (h, w) around the centre, offsets rounded as int(0.5 + d/2) (transforms.py:309-322);
+    `padding` > 0 first adds a black border (RandomCrop.__call__, transforms.py:286-305)."""
+
+    def __init__(self, size, padding=0):
+        self.size = (int(size), int(size)) if isinstance(size, int) else tuple(size)
+        self.padding = padding
+
+    def __call__(self, img):
+        if self.padding > 0:
+            from PIL import ImageOps
+            img = ImageOps.expand(img, border=self.padding, fill=0)
+        w, h = img.size
+        th, tw = self.size
+        x, y = int(0.5 + (w - tw) / 2.0), int(0.5 + (h - th) / 2.0)
+        return img.crop((x, y, x + tw, y + th))
+
+
 class ToTensor:
     def __call__(self, img):
         a = np.array(img, dtype=np.uint8)
@@ -77,8 +140,15 @@ def create_transforms(cmd_line, to_tensor=False, **vars):
         elif "ToTensor" not in cmd_line:
             cmd_line += ", ToTensor(), Normalize(mean=mean, std=std)"
     assert isinstance(cmd_line, str)
-    env = {"Scale": Scale, "ToTensor": ToTensor, "Normalize": Normalize, "Image": Image}
+    env = {"Scale": Scale, "Identity": Identity, "Pad": Pad, "PadSquare": PadSquare, "CenterCrop": CenterCrop,
+           "ToTensor": ToTensor, "Normalize": Normalize, "Image": Image}
     env.update(vars)
+    import re
+    unknown = [n for n in re.findall(r"([A-Za-z_][A-Za-z_0-9]*)\s*\(", cmd_line) if n not in env]
+    if unknown:
+        raise SyntaxError("Cannot interpret this transform list: %s\nReason: unsupported transform(s) %s - the evaluation "
+                          "path implements the deterministic test-time transforms %s (the reference's random training "
+                          "augmentations are out of scope)" % (cmd_line, sorted(set(unknown)), sorted(k for k in env if k[0].isupper() and k != "Image")))
     try:
         return Compose(eval("[%s]" % cmd_line, {"__builtins__": {}}, env))
     except Exception as e:

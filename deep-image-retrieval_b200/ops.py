@@ -182,8 +182,16 @@ def whiten(x, comp, mean=None, colscale=None, l2norm=True, want_f16=False):
 
 
 def scores_exact(q, db):
+    """Dense exact scores (Q,N) fp32 = q . db^T (fp64 accumulation).  Any D: the kernel reads rows as float4, so both
+    operands are zero-padded to a multiple of 4 columns (zero columns change no score)."""
     _chk(q, torch.float32, "q")
     _chk(db, torch.float32, "db")
+    if q.shape[1] != db.shape[1]:
+        raise ValueError("descriptor dimensions differ: %d vs %d" % (q.shape[1], db.shape[1]))
+    pad = (-q.shape[1]) % 4
+    if pad:
+        q = torch.nn.functional.pad(q, (0, pad)).contiguous()
+        db = torch.nn.functional.pad(db, (0, pad)).contiguous()
     out = torch.empty((q.shape[0], db.shape[0]), dtype=torch.float32, device=q.device)
     lib.call("dirb200_scores_exact", _ptr(q), q.shape[0], _ptr(db), db.shape[0], q.shape[1], _ptr(out), _stream())
     return out

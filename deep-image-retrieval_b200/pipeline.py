@@ -293,7 +293,10 @@ def extract_to_store(db, net, trfs, store_path, pooling="mean", gemp=3, whiten=N
         rows = tonumpy(_pool_and_normalize(descs, pooling, gemp))
         if whiten is not None:
             rows = common.whiten_features(rows, net.pca, **whiten)
-    else:                                                     # more ranks than images
+    else:                                                     # more ranks than images: an empty shard with the
+        if whiten is not None:                                # dimension the other ranks' rows have after whitening
+            ncomp = np.asarray(net.pca.components_).shape[0]
+            dim = min(ncomp, whiten.get("whitenv") or ncomp)
         rows = np.zeros((0, dim), np.float32)
     meta = dict(arch=getattr(net, "arch", ""), trfs=list(trfs_list), pooling=pooling, gemp=gemp, whiten=whiten or {},
                 n_images=len(db))

@@ -207,10 +207,11 @@ int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, 
 int dirb200_scores_exact(const float* q_dev, int Q, const float* db_dev, int64_t N, int D, float* out_dev,
                          void* stream);
 /* Alpha query expansion, test_dir.py:24-44:  out_i = normalize(mean([q_i] + [db_j * s_ij^alpha, j in topk(i)])).
- * nn_idx_dev/nn_scores_dev: [Q][k] neighbour indices (-1 = none) and their scores.  With n_rows > 0 the indices
- * are GLOBAL and db32_dev holds the rows [row_offset, row_offset+n_rows) of a sharded database: neighbours owned
- * by other shards are skipped; with n_rows <= 0 the indices are plain rows of db32_dev.
- * partial != 0 writes the un-normalised SUM over the (owned) neighbours only, for a cross-GPU all-reduce. */
+ * nn_idx_dev/nn_scores_dev: [Q][k] neighbour indices (-1 = none) and their scores.  Sharded mode (partial != 0, or
+ * n_rows > 0): the indices are GLOBAL and db32_dev holds the rows [row_offset, row_offset+n_rows) of a sharded
+ * database; neighbours owned by other shards are skipped (an EMPTY shard, n_rows == 0 with partial != 0, owns none and
+ * may pass db32_dev = NULL).  Otherwise (partial == 0 and n_rows <= 0) the indices are plain rows of db32_dev.
+ * partial != 0 writes the un-normalised SUM over the owned neighbours only, for a cross-GPU all-reduce. */
 int dirb200_aqe_expand(const float* q_dev, int Q, int D, const float* db32_dev, const int64_t* nn_idx_dev,
                        const double* nn_scores_dev, int k, double alpha, int partial, int64_t row_offset, int64_t n_rows,
                        float* out_dev, void* stream);

@@ -228,6 +228,49 @@ def gold_labels():
          qaps=np.array(qaps, dtype=np.float64), gt0=ds.get_query_groundtruth(0), nclass=ds.nclass, nclass_q=dsq.nclass)
 
 
+TRF_CHAINS = ["Pad(70)", "PadSquare()", "PadSquare(60)", "PadSquare(100)", "CenterCrop(32)", "CenterCrop((20,40))",
+              "Scale(48), CenterCrop(40)", "Scale(0.7), Pad(64, color=(0.5,0.5,0.5))", "Identity()",
+              "CenterCrop(30, padding=4)", "Scale(0.5)", "Scale(1.4)", "Scale(40, largest=True)", "Scale((50, 30))"]
+TRF_SIZES = [(50, 80), (80, 50), (64, 64), (33, 97)]
+
+
+@torch.no_grad()
+def gold_transforms():
+    """The deterministic test-time transforms of dirtorch/utils/transforms.py (Scale, Pad, PadSquare, CenterCrop,
+    Identity + the ToTensor/Normalize tail that transforms.create appends) on seeded images: a CRC of every output
+    tensor; and the BATCHED extraction path of test_dir.extract_image_features (same_size=True, batch_size=4,
+    test_dir.py:52-53,64-75) through a 'Scale(..), CenterCrop(..)' chain."""
+    import zlib
+    from PIL import Image
+    from dirtorch.utils import transforms as RT
+    r = np.random.RandomState(0)
+    crcs, shapes = [], []
+    for (h, w) in TRF_SIZES:
+        img = Image.fromarray(r.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        for chain in TRF_CHAINS:
+            t = RT.create(chain, to_tensor=True, mean=synth.RGB_MEANS, std=synth.RGB_STDS)(img).numpy()
+            crcs.append(zlib.crc32(np.ascontiguousarray(t).tobytes()))
+            shapes.append(t.shape)
+    sys.path.append(REPO)
+    sys.path.append(os.path.join(REPO, "tests"))
+    import e2e_data
+    from dirtorch.datasets.generic import ImageList
+    root = tempfile.mkdtemp(prefix="dbroot_trf_")
+    gnd, names, qn, sd = e2e_data.build(root)
+    with open(os.path.join(root, "list.txt"), "w") as f:
+        f.write("\n".join(names[:10]) + "\n")
+    ds = ImageList(os.path.join(root, "list.txt"), os.path.join(root, "oxford5k", "jpg"))
+    net = ref_model("resnet50_rmac", seed=0)
+    net.iscuda = False
+    net.preprocess = dict(mean=synth.RGB_MEANS, std=synth.RGB_STDS, input_size=224)
+    chain = "Scale(140), CenterCrop(128)"
+    d = ref_test_dir.extract_image_features(ds, chain, net, same_size=True, batch_size=4, iscuda=False, threads=2)
+    d1 = ref_test_dir.extract_image_features(ds, chain, net, same_size=False, batch_size=4, iscuda=False, threads=2)
+    print("batched vs batch-1 descriptors:", float((d - d1).abs().max()))
+    save("transforms.npz", crcs=np.array(crcs, dtype=np.uint32), shapes=np.array(shapes, dtype=np.int32),
+         batched_chain=np.array(chain), batched_desc=d.numpy(), n_images=10)
+
+
 def gold_cli():
     for hard in (False, True):
         _gold_cli(hard)
@@ -334,6 +377,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["labels"]:
         gold_labels()
         sys.exit(0)
+    if sys.argv[1:] == ["transforms"]:
+        gold_transforms()
+        sys.exit(0)
     gold_gem()
     gold_pool()
     gold_whiten()
@@ -343,4 +389,5 @@ if __name__ == "__main__":
     gold_extract_extra()
     gold_cli()
     gold_labels()
+    gold_transforms()
     gold_variants()

@@ -160,6 +160,24 @@ def test_whiten_tensor_core_path_large():
     assert rel_l2(y.cpu().numpy(), ref) < 2e-5
 
 
+@pytest.mark.parametrize("mag,spread", [(1.0, 1.0), (1.0, 0.1), (1.0, 0.01), (1.0, 1e-3), (1e-3, 1.0), (300.0, 0.05)])
+def test_whiten_tensor_core_path_is_scale_invariant(mag, spread):
+    """Rows tightly clustered around their mean and rows of unusual magnitude: the adaptive power-of-two prescale of
+    the hi/lo split keeps the fp32-grade accuracy (without it the error grows like 1 / |x - mean|)."""
+    ops = _ops()
+    r = np.random.RandomState(11)
+    centre = synth._unit_rows(r.standard_normal((1, 2048)))
+    X = (mag * synth._unit_rows(centre + spread * r.standard_normal((1000, 2048)) / np.sqrt(2048.0))).astype(np.float32)
+    mean = X.mean(0).astype(np.float32)
+    comp = synth._unit_rows(r.standard_normal((256, 2048))).astype(np.float32)
+    ref = (X.astype(np.float64) - mean.astype(np.float64)) @ comp.astype(np.float64).T
+    y = ops.whiten(torch.from_numpy(X).to(DEV), torch.from_numpy(comp).to(DEV), torch.from_numpy(mean).to(DEV), None,
+                   l2norm=False)
+    torch.cuda.synchronize()
+    err = np.linalg.norm(y.cpu().numpy().astype(np.float64) - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert err.max() < 5e-6, (mag, spread, err.max())
+
+
 def test_pool_scales_l2_whiten(golden):
     ops = _ops()
     g = golden("pool.npz")

@@ -154,6 +154,33 @@ def test_cli_end_to_end(tmp_path, monkeypatch, capsys):
     assert res2["mAP"] == ref2
 
 
+def test_batched_extraction_with_crop_chain(tmp_path, golden):
+    """test_dir.extract_image_features with same_size=True, batch_size=4 (the 'Pad'/'Crop' branch of test_dir.py:114)
+    through 'Scale(140), CenterCrop(128)' vs the reference's descriptors (tests/golden/transforms.npz)."""
+    _gpu()
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import e2e_data
+    from dirtorch import nets, test_dir
+    from dirtorch.datasets import ImageList
+    g = golden("transforms.npz")
+    root = str(tmp_path)
+    _, names, _, sd = e2e_data.build(root)
+    n = int(g["n_images"])
+    with open(os.path.join(root, "list.txt"), "w") as f:
+        f.write("\n".join(names[:n]) + "\n")
+    ds = ImageList(os.path.join(root, "list.txt"), os.path.join(root, "oxford5k", "jpg"))
+    net = nets.create_model("resnet50_rmac")
+    net.load_state_dict(sd)
+    net.cuda()
+    chain = str(g["batched_chain"])
+    assert "Crop" in chain
+    d = test_dir.extract_image_features(ds, chain, net, same_size=True, batch_size=4, threads=2)
+    assert tuple(d.shape) == (n, 2048)
+    assert rel_l2(d.cpu().numpy(), g["batched_desc"]) < 1e-3
+    d1 = test_dir.extract_image_features(ds, chain, net, same_size=False, batch_size=4, threads=2)
+    assert torch.equal(d, d1)                      # batch invariance
+
+
 def test_two_gpu_sharded_search(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

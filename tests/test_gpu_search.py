@@ -99,6 +99,20 @@ def test_scores_exact_and_map(golden):
         assert abs(O.eval_query_ap(sc[i], gnd[i]["ok"], gnd[i]["junk"]) - g["aps"][i]) < 1e-12
 
 
+def test_matmul_any_dimension():
+    """common.matmul / scores_exact with D not a multiple of 4 (e.g. --whitenv 127): np.dot accepts any D."""
+    ops = _ops()
+    from dirtorch.utils import common
+    r = np.random.RandomState(3)
+    for d in (127, 30, 1):
+        q = r.standard_normal((5, d)).astype(np.float32)
+        db = r.standard_normal((33, d)).astype(np.float32)
+        ref = q.astype(np.float64) @ db.astype(np.float64).T
+        np.testing.assert_allclose(common.matmul(q, db), ref, rtol=0, atol=1e-5)
+        np.testing.assert_allclose(ops.scores_exact(torch.from_numpy(q).to(DEV), torch.from_numpy(db).to(DEV)).cpu().numpy(),
+                                   ref, rtol=0, atol=1e-5)
+
+
 def test_aqe(golden):
     ops = _ops()
     g = golden("aqe.npz")

@@ -120,6 +120,31 @@ def test_transforms_and_loader(tmp_path):
         create_transforms("Bogus(3)", to_tensor=True, **pre)
 
 
+def test_test_time_transforms_match_reference(golden):
+    """Scale / Pad / PadSquare / CenterCrop / Identity (+ ToTensor, Normalize) against CRCs of the reference's
+    output tensors (tests/golden/make_golden.py: gold_transforms); unknown transforms fail with a clear message."""
+    import zlib
+    from PIL import Image
+    sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+    from dirb200 import loader
+    g = golden("transforms.npz")
+    chains = ["Pad(70)", "PadSquare()", "PadSquare(60)", "PadSquare(100)", "CenterCrop(32)", "CenterCrop((20,40))",
+              "Scale(48), CenterCrop(40)", "Scale(0.7), Pad(64, color=(0.5,0.5,0.5))", "Identity()",
+              "CenterCrop(30, padding=4)", "Scale(0.5)", "Scale(1.4)", "Scale(40, largest=True)", "Scale((50, 30))"]
+    r = np.random.RandomState(0)
+    i = 0
+    for (h, w) in [(50, 80), (80, 50), (64, 64), (33, 97)]:
+        img = Image.fromarray(r.randint(0, 256, (h, w, 3), dtype=np.uint8))
+        for chain in chains:
+            t = loader.create_transforms(chain, to_tensor=True, mean=synth.RGB_MEANS, std=synth.RGB_STDS)(img).numpy()
+            assert tuple(t.shape) == tuple(g["shapes"][i]), (chain, h, w)
+            assert zlib.crc32(np.ascontiguousarray(t).tobytes()) == int(g["crcs"][i]), (chain, h, w)
+            i += 1
+    assert i == len(g["crcs"])
+    with pytest.raises(SyntaxError, match="unsupported transform"):
+        loader.create_transforms("RandomCrop(32)", to_tensor=True, mean=0, std=1)
+
+
 def test_cli_surface_and_no_cpu_path():
     from dirtorch import extract_features, test_dir
     from dirtorch.utils import common

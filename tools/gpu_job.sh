@@ -1,0 +1,37 @@
+#!/bin/bash
+# One gpurun trip = a list of named tasks (arguments), run in order on the GPU box; everything lands in gpurun_out/.
+#   tests [pytest -k expr]   full -m gpu suite (or a selection)
+#   sanitize <tool>          compute-sanitizer over the small operator tests (tools/gpu_sanitize.sh)
+#   searchprof               phase profile + ncu launch list of the search at 1M / 125k / 100k rows
+#   bench [args]             python bench.py <args>
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+rc_all=0
+while [ $# -gt 0 ]; do
+  task=$1; shift
+  case $task in
+    tests)
+      sel=${1:-}; [ -n "$sel" ] && shift
+      if [ -n "$sel" ] && [ "$sel" != "-" ]; then
+        timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider -k "$sel" > gpurun_out/pytest.log 2>&1
+      else
+        timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest.log 2>&1
+      fi
+      rc=$?; echo "== tests rc=$rc"; tail -15 gpurun_out/pytest.log; [ $rc -ne 0 ] && rc_all=$rc ;;
+    sanitize)
+      tool=$1; shift
+      bash tools/gpu_sanitize.sh $tool; rc=$?; [ $rc -ne 0 ] && rc_all=$rc ;;
+    searchprof)
+      timeout 300 python tools/search_profile.py > gpurun_out/search_profile.log 2>&1; echo "== searchprof rc=$?"; cat gpurun_out/search_profile.log
+      timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/search_launches.csv \
+        python tools/search_profile.py one > gpurun_out/search_ncu.log 2>&1; echo "== search ncu rc=$?" ;;
+    bench)
+      args=${1:-}; shift
+      timeout 900 python bench.py $args > gpurun_out/bench.log 2> gpurun_out/bench.err; rc=$?; echo "== bench rc=$rc"; tail -c 6000 gpurun_out/bench.log; tail -5 gpurun_out/bench.err; [ $rc -ne 0 ] && rc_all=$rc ;;
+    py)
+      script=$1; shift
+      timeout 900 python $script > gpurun_out/$(basename $script .py).log 2>&1; rc=$?; echo "== py $script rc=$rc"; tail -40 gpurun_out/$(basename $script .py).log; [ $rc -ne 0 ] && rc_all=$rc ;;
+    *) echo "unknown task $task"; rc_all=2 ;;
+  esac
+done
+exit $rc_all
