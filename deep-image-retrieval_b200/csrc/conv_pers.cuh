@@ -37,7 +37,7 @@ struct ConvPersParams {
   // block input x of the 1x1 downsample conv - while the weights are the K-concatenation [W3*s3 | Wd*sd].
   int k_split, a2_stride;
   // PERS_EPI_F32 (whitening): fp32-accurate product from fp16 hi/lo splits, K = 3 parts of k_per_part blocks:
-  // (A_hi, B_hi), (A_hi, B_lo), (A_lo, B_hi) with A_lo in tensor map tmR and B_lo in tmO; epilogue = column scale,
+  // (A_hi, B_lo), (A_lo, B_hi), (A_hi, B_hi) with A_lo in tensor map tmR and B_lo in tmO; epilogue = column scale,
   // fp32 store to dense[M][dense_ld].
   int k_per_part;
   const float* scale;
@@ -50,6 +50,9 @@ struct ConvPersParams {
   unsigned long long* cand;    // [M][cand_cap] packed (score bits << 32 | row)
   int* cand_cnt;               // [M]
   int cand_cap;
+  // Device-side launch predicate (retry passes of the search): when non-null the whole grid returns at once unless
+  // *gate != 0.  The value was written by the previous kernel of the stream, so it is read after pdl_wait().
+  const int* gate;
 };
 
 template <int BN, int STAGES, int EPI = 0, int NB = 4>
@@ -187,6 +190,10 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using L = ConvPersSmem<BN, STAGES, EPI, NB>;
   constexpr int NBUF = NB;
   constexpr int CHUNKS = BN / 64;
+  if (EPI != PERS_EPI_CONV && p.gate != nullptr) {   // uniform over the grid: nothing has been allocated yet
+    pdl_wait();
+    if (*reinterpret_cast<const volatile int*>(p.gate) == 0) return;
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + L::STG_OFF;
@@ -246,8 +253,11 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (EPI == PERS_EPI_F32) {
             const int part = it / p.k_per_part;
             const int kk = it - part * p.k_per_part;
-            tma_load_2d(sa, part == 2 ? &tmR : &tmA, &full_bar[s], kk * 64, c.m_tile * 128);
-            tma_load_2d(sa + L::A_BYTES, part == 1 ? &tmO : &tmB, &full_bar[s], kk * 64, c.n_tile * BN);
+            // small cross terms first, (hi, hi) last: the tensor core's fp32 accumulation truncates, an error that grows
+            // with the accumulator's magnitude per step - the 2/3 of the steps that add 2^-11-sized terms then run
+            // while the accumulator is still small (measured: 1.1e-5 -> see tests/test_gpu_ops.py)
+            tma_load_2d(sa, part == 1 ? &tmR : &tmA, &full_bar[s], kk * 64, c.m_tile * 128);
+            tma_load_2d(sa + L::A_BYTES, part == 0 ? &tmO : &tmB, &full_bar[s], kk * 64, c.n_tile * BN);
             continue;
           }
           if (p.k_split > 0 && it >= p.k_split) {

@@ -3,7 +3,7 @@
 // Replaces the reference's dense  scores = matmul(q, db)  (dirtorch/utils/common.py:30-38, test_dir.py:145) +
 // per-query sort (datasets/generic.py:207,221) for the first k ranks, without materialising the Q x N matrix:
 //
-//   1. queries -> fp16                                                             (f32_to_f16)
+//   1. queries -> fp16, counters / retry gates / status cleared                    (search_prep_kernel)
 //   2. seed:   tcgen05 GEMM of the queries against the first S rows.  The epilogue keeps the maximum of every group
 //              of 32 consecutive rows (PERS_EPI_SIM_GMAX; 1/32 of the dense score traffic); per query the k-th largest
 //              group maximum t_S has >= k rows at or above it, so it is a lower bound on the final k-th score.
@@ -11,10 +11,13 @@
 //   3. filter: tcgen05 GEMM against all N rows; the epilogue appends (score,row) to the query's candidate list
 //              only when score >= t_S - 2*eps16                                     (PERS_EPI_SIM_FILTER)
 //      (for N <= S step 3 is a scan of the dense scores instead: dense_compact_kernel)
-//   4. select: exact k-th largest candidate score t (radix select, cand_kth_kernel); survivors = candidates with
-//              score >= t - 2*eps16                                                    (cand_survivors_kernel)
-//   5. rescore the survivors exactly (fp64 accumulation of the fp32 rows, rescore_kernel) and sort
-//      (score desc, index asc: sort_topk_kernel).
+//   4. select: exact k-th largest candidate score t (radix select, cand_kth_kernel).  A query whose list overflowed
+//              gets a tighter threshold from what was captured and raises a device-side gate; the (always enqueued)
+//              retry passes of steps 3-4 return at once unless their gate is up - no host round trip.
+//   5. finish: survivors = candidates with score >= t - 2*eps16, exact re-scoring (fp64 accumulation of the fp32
+//              rows) and sort (score desc, index asc), one launch, one block per query      (search_finish_kernel)
+// The only host synchronisation is the status check at the very end (overflow that the retries could not resolve);
+// with option deferred_check it moves to dirb200_index_check / the start of the next search.
 //
 // eps16 bounds |fp16-path score - exact score| (unit-norm rows: 2 * 2^-11 from the operand roundings + fp32
 // accumulation, default 1.2e-3); any row of the true top-k then satisfies the step-3 and step-4 conditions, so the
@@ -23,6 +26,8 @@
 // so that the caller can MIN-reduce the per-shard selection thresholds in between (see cand_kth_kernel).
 // The GEMMs run on the persistent warp-specialised kernel of conv_pers.cuh (128 x 256 tiles, K = D).
 #include <math.h>
+
+#include <limits.h>
 
 #include <algorithm>
 #include <string>
@@ -76,14 +81,37 @@ __device__ float block_kth_largest(Acc acc, int n, int k, uint32_t* hist /*[256]
       if (bin != 0xffffffffu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], static_cast<uint32_t>(__popc(peers)));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int cum = 0, b = 255;
-      for (; b > 0; --b) {
-        if (cum + static_cast<int>(hist[b]) >= kk) break;
-        cum += hist[b];
+    if (threadIdx.x < 32) {
+      // Find the bin holding the kk-th largest key: lane l owns bins [8l, 8l+8); a suffix scan over the lanes gives
+      // the number of keys in higher bins, the owning lane walks its 8 bins.  (A single thread walking 256 bins
+      // serially cost ~10 us per pass.)
+      const int lane = threadIdx.x;
+      uint32_t loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[8 * lane + j];
+        sum += loc[j];
       }
-      bc[0] = b;
-      bc[1] = kk - cum;
+      uint32_t suf = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += v;
+      }
+      const uint32_t above = suf - sum;
+      const uint32_t want = static_cast<uint32_t>(kk);
+      if (above < want && want <= above + sum) {
+        uint32_t cum = above;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (cum + loc[j] >= want) {
+            bc[0] = 8 * lane + j;
+            bc[1] = want - cum;
+            break;
+          }
+          cum += loc[j];
+        }
+      }
     }
     __syncthreads();
     prefix |= bc[0] << shift;
@@ -106,7 +134,9 @@ __global__ void __launch_bounds__(SEL_THREADS) kth_dense_kernel(const float* __r
 
 // N <= S: candidates straight from the dense scores.
 __global__ void dense_compact_kernel(const float* __restrict__ dense, int64_t ld, int N, const float* __restrict__ thr,
-                                     unsigned long long* __restrict__ cand, int* __restrict__ cnt, int cap) {
+                                     unsigned long long* __restrict__ cand, int* __restrict__ cnt, int cap,
+                                     const int* __restrict__ gate) {
+  if (gate != nullptr && *reinterpret_cast<const volatile int*>(gate) == 0) return;
   const int q = blockIdx.y;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -118,6 +148,11 @@ __global__ void dense_compact_kernel(const float* __restrict__ dense, int64_t ld
   }
 }
 
+// Status block of a search (device, 8 x u64; copied to pinned host memory at the end of phase 2):
+//   [0] error bits: 1 = candidate overflow left after the last retry pass, 2 = more than cap2 survivors for some query
+//   [1] candidates captured (sum over queries)   [2] survivors re-scored   [3] retry passes that actually ran
+enum { ST_ERR = 0, ST_CAND = 1, ST_SURV = 2, ST_RETRIES = 3, ST_WORDS = 8 };
+
 // Per query: exact k-th and k_shard-th largest candidate scores (fp16-path scores).
 //   kth_k[q]  : local k-th best - always a valid lower bound on the global k-th best
 //   sel[q]    : local min(k_shard, N)-th best; the MINIMUM of this value over all shards is a valid and much tighter
@@ -125,16 +160,23 @@ __global__ void dense_compact_kernel(const float* __restrict__ dense, int64_t ld
 //               sum_g min(k_shard, N_g) >= min(k, N_total) (shard g holds min(k_shard, N_g) rows at or above its own
 //               value) - the caller picks k_shard accordingly (ceil(k / shards) for evenly filled shards, see
 //               dist.py: shard_quota) and min-reduces sel.
-// flags[q] bit0 = candidate overflow (cnt > cap): the tighter threshold kth(captured) - band is written to thr[q];
-// otherwise thr[q] = +inf so that a re-run of the filter pass leaves this query alone.
+// Overflow (cnt > cap) is resolved on the device: the query's list is emptied, the tighter threshold
+// kth(captured) - band goes to thr[q] and gate_out[0] is raised, which arms the next (gated) filter pass + selection;
+// finished queries get thr[q] = +inf so that a re-run leaves them alone.  `gate_in` != nullptr: this launch is itself
+// such a retry pass and returns at once unless *gate_in != 0.  `last` = no further retry follows: a remaining
+// overflow becomes error bit 1.
 __global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned long long* __restrict__ cand,
-                                                               const int* __restrict__ cnt, int cap, int k, int k_shard,
+                                                               int* __restrict__ cnt, int cap, int k, int k_shard,
                                                                float band, float* __restrict__ kth_k,
                                                                float* __restrict__ sel, float* __restrict__ thr,
-                                                               int* __restrict__ flags, int64_t n_rows) {
+                                                               int64_t n_rows, const int* __restrict__ gate_in,
+                                                               int* __restrict__ gate_out, int last,
+                                                               unsigned long long* __restrict__ status) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bc[2];
+  if (gate_in != nullptr && *reinterpret_cast<const volatile int*>(gate_in) == 0) return;
   const int q = blockIdx.x;
+  if (gate_in != nullptr && q == 0 && threadIdx.x == 0) atomicAdd(status + ST_RETRIES, 1ull);
   const int total = cnt[q];
   const int n = min(total, cap);
   const unsigned long long* c = cand + static_cast<int64_t>(q) * cap;
@@ -142,8 +184,16 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned lo
   const float t = block_kth_largest(CandAcc{c}, n, kk, hist, bc);
   if (total > cap) {
     if (threadIdx.x == 0) {
-      thr[q] = t - band;
-      flags[q] = 1;
+      if (last) {
+        atomicOr(status + ST_ERR, 1ull);
+        kth_k[q] = INFINITY;      // no survivors for this query; the error is reported by the status check
+        sel[q] = INFINITY;
+        thr[q] = INFINITY;
+      } else {
+        thr[q] = t - band;
+        cnt[q] = 0;               // the retry pass refills the list from scratch
+        *gate_out = 1;
+      }
     }
     return;
   }
@@ -155,60 +205,124 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned lo
   if (threadIdx.x == 0) {
     kth_k[q] = t;
     sel[q] = ts;
-    flags[q] = 0;
     thr[q] = INFINITY;
   }
 }
 
-// Survivors = candidates with score >= max(sel[q], kth_k[q]) - band.  flags[q] bit1 = more than cap2 survivors.
-__global__ void __launch_bounds__(SEL_THREADS) cand_survivors_kernel(const unsigned long long* __restrict__ cand,
-                                                                     const int* __restrict__ cnt, int cap,
-                                                                     const float* __restrict__ kth_k,
-                                                                     const float* __restrict__ sel, float band,
-                                                                     int* __restrict__ surv_idx, int* __restrict__ surv_cnt,
-                                                                     int cap2, int* __restrict__ flags) {
+// Start of a search: queries -> fp16 (the A operand of the tensor-core passes), candidate counters, retry gates and
+// the status block cleared.  One launch instead of a conversion kernel + memsets.
+__global__ void search_prep_kernel(const float* __restrict__ q32, __half* __restrict__ q16, int64_t n, int* __restrict__ cnt,
+                                   int Q, int* __restrict__ gates, int n_gates, unsigned long long* __restrict__ status) {
+  const int64_t gtid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t i = gtid * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(q32 + i);
+    uint2 o;
+    o.x = pack_h2(v.x, v.y);
+    o.y = pack_h2(v.z, v.w);
+    *reinterpret_cast<uint2*>(q16 + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) q16[j] = __float2half_rn(q32[j]);
+  }
+  if (gtid < Q) cnt[gtid] = 0;
+  if (gtid < n_gates) gates[gtid] = 0;
+  if (gtid < ST_WORDS) status[gtid] = 0ull;
+}
+
+// Empty shard: nothing can be selected (+inf never lowers the MIN over the shards) / nothing to return.
+__global__ void fill_f32_kernel(float* __restrict__ p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void fill_empty_result_kernel(double* __restrict__ sc, int64_t* __restrict__ ix, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    sc[i] = -INFINITY;
+    ix[i] = -1;
+  }
+}
+
+// Phase 2 of a search in ONE launch, one block per query:
+//   survivors = candidates with fp16-path score >= max(sel[q], kth_k[q]) - band   (compacted into shared memory)
+//   exact score of each survivor = fp64-accumulated dot product of the fp32 rows  (one warp per survivor)
+//   bitonic sort by (score desc, row asc), first k written as (fp64 score, int64 global index).
+// Replaces three launches whose grids were sized for the worst case (cap2 survivors per query) although a shard of a
+// G-way split keeps only ~1.4 k / G rows per query.
+constexpr int FIN_THREADS = 512;
+__global__ void __launch_bounds__(FIN_THREADS) search_finish_kernel(
+    const unsigned long long* __restrict__ cand, const int* __restrict__ cnt, int cap, const float* __restrict__ kth_k,
+    const float* __restrict__ sel, float band, const float* __restrict__ q32, const float* __restrict__ db32, int D,
+    int cap2, int64_t offset, int k, double* __restrict__ out_score, int64_t* __restrict__ out_idx,
+    unsigned long long* __restrict__ status) {
+  extern __shared__ uint8_t sm[];
   __shared__ int s_n;
+  double* sc = reinterpret_cast<double*>(sm);          // [cap2]
+  int* ix = reinterpret_cast<int*>(sc + cap2);         // [cap2]
   const int q = blockIdx.x;
   const int n = min(cnt[q], cap);
   const unsigned long long* c = cand + static_cast<int64_t>(q) * cap;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   const float t2 = fmaxf(sel[q], kth_k[q]) - band;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n; i += FIN_THREADS) {
     const unsigned long long e = c[i];
     if (__uint_as_float(static_cast<uint32_t>(e >> 32)) >= t2) {
       const int pos = atomicAdd(&s_n, 1);
-      if (pos < cap2) surv_idx[static_cast<int64_t>(q) * cap2 + pos] = static_cast<int>(e & 0xffffffffu);
+      if (pos < cap2) ix[pos] = static_cast<int>(e & 0xffffffffu);
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    surv_cnt[q] = min(s_n, cap2);
-    flags[q] = (s_n > cap2) ? 2 : 0;
-  }
-}
-
-// One warp per (query, survivor): exact score = fp64-accumulated dot product of the fp32 rows.
-__global__ void rescore_kernel(const float* __restrict__ q32, const float* __restrict__ db32, int D,
-                               const int* __restrict__ surv_idx, const int* __restrict__ surv_cnt, int cap2,
-                               double* __restrict__ surv_score) {
-  const int q = blockIdx.y;
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= surv_cnt[q]) return;
-  const int row = surv_idx[static_cast<int64_t>(q) * cap2 + w];
+  const int found = s_n;
+  const int ns = min(found, cap2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4* a = reinterpret_cast<const float4*>(q32 + static_cast<int64_t>(q) * D);
-  const float4* b = reinterpret_cast<const float4*>(db32 + static_cast<int64_t>(row) * D);
-  double acc = 0.0;
-  for (int i = lane; i < D / 4; i += 32) {
-    const float4 x = __ldg(a + i), y = __ldg(b + i);
-    acc += static_cast<double>(x.x) * y.x;
-    acc += static_cast<double>(x.y) * y.y;
-    acc += static_cast<double>(x.z) * y.z;
-    acc += static_cast<double>(x.w) * y.w;
+  for (int w = warp; w < ns; w += FIN_THREADS / 32) {
+    const float4* b = reinterpret_cast<const float4*>(db32 + static_cast<int64_t>(ix[w]) * D);
+    double acc = 0.0;
+    for (int i = lane; i < D / 4; i += 32) {
+      const float4 x = __ldg(a + i), y = __ldg(b + i);
+      acc += static_cast<double>(x.x) * y.x;
+      acc += static_cast<double>(x.y) * y.y;
+      acc += static_cast<double>(x.z) * y.z;
+      acc += static_cast<double>(x.w) * y.w;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sc[w] = acc;
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) surv_score[static_cast<int64_t>(q) * cap2 + w] = acc;
+  int P = 2;
+  while (P < ns) P <<= 1;
+  for (int i = ns + threadIdx.x; i < P; i += FIN_THREADS) {
+    sc[i] = -INFINITY;
+    ix[i] = INT_MAX;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int st = size >> 1; st > 0; st >>= 1) {
+      for (int i = threadIdx.x; i < P / 2; i += FIN_THREADS) {
+        const int lo = 2 * i - (i & (st - 1));
+        const int hi = lo + st;
+        const bool up = ((lo & size) == 0);  // "up" = this block sorted best-first
+        const double va = sc[lo], vb = sc[hi];
+        const int ia = ix[lo], ib = ix[hi];
+        const bool a_first = (va > vb) || (va == vb && ia < ib);
+        if (a_first != up) {
+          sc[lo] = vb; sc[hi] = va;
+          ix[lo] = ib; ix[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
+    const bool ok = i < ns;
+    out_score[static_cast<int64_t>(q) * k + i] = ok ? sc[i] : -INFINITY;
+    out_idx[static_cast<int64_t>(q) * k + i] = ok ? static_cast<int64_t>(ix[i]) + offset : -1;
+  }
+  if (threadIdx.x == 0) {
+    if (found > cap2) atomicOr(status + ST_ERR, 2ull);
+    atomicAdd(status + ST_CAND, static_cast<unsigned long long>(n));
+    atomicAdd(status + ST_SURV, static_cast<unsigned long long>(ns));
+  }
 }
 
 // Per query: bitonic sort of (score desc, index asc), write the first k.  Also used to merge shard lists.
@@ -340,6 +454,22 @@ __global__ void aqe_kernel(const float* __restrict__ q, int D, const float* __re
 
 using namespace dirb;
 
+// Encoded 2-D tensor maps, kept per (base, rows, box): a search re-uses the same three maps every call.
+struct TmapCache {
+  struct E { const void* base; uint64_t inner, outer; uint32_t box; CUtensorMap m; };
+  std::vector<E> es;
+  int get(const void* base, uint64_t inner, uint64_t outer, uint32_t box, const CUtensorMap** out) {
+    for (auto& e : es)
+      if (e.base == base && e.inner == inner && e.outer == outer && e.box == box) { *out = &e.m; return 0; }
+    if (es.size() >= 16) es.erase(es.begin());
+    E e{base, inner, outer, box, {}};
+    DIRB_TRY(encode_tmap_2d(&e.m, base, inner, outer, inner * 2, 64, box));
+    es.push_back(e);
+    *out = &es.back().m;
+    return 0;
+  }
+};
+
 struct dirb200_index {
   int device = 0, dim = 0;
   const float* db32 = nullptr;
@@ -349,62 +479,76 @@ struct dirb200_index {
   double eps16 = 1.2e-3;
   int64_t sample_rows = 0;
   int cand_cap = 0;          // 0 = auto
+  int retries = 2;           // gated retry passes enqueued after the first filter pass (device-side predicate)
+  int deferred = 0;          // 1 = search calls never synchronise; the caller collects the status (dirb200_index_check)
   // workspaces (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  int* h_flags = nullptr;  // pinned
-  int h_flags_n = 0;
+  unsigned long long* h_status = nullptr;   // pinned copy of the device status block
+  cudaEvent_t status_ev = nullptr;
+  bool status_pending = false;
+  int status_cap2 = 0;
+  double status_band = 0;
   int64_t stats[5] = {0, 0, 0, 0, 0};
   float* sel_own = nullptr;        // selection thresholds of the single-shard entry point
   size_t sel_bytes = 0;
   // state of a search between dirb200_index_search_begin and _finish
   struct Pending {
     bool active = false;
-    int Q = 0, k = 0, cap = 0, cap2 = 0, retries = 0, mark_i = 0;
+    int Q = 0, k = 0, cap = 0, cap2 = 0, mark_i = 0;
     int64_t S = 0, launches0 = 0;
     float band = 0;
-    int *cnt = nullptr, *sidx = nullptr, *scnt = nullptr, *flags = nullptr;
+    int* cnt = nullptr;
     unsigned long long* cand = nullptr;
-    double* sscore = nullptr;
-    float *kth_k = nullptr, *sel = nullptr;
+    unsigned long long* status = nullptr;
+    float* kth_k = nullptr;
   } pend;
+  TmapCache tmaps;
   int profile = 0;                 // option "profile": time the phases of a search with CUDA events
   cudaEvent_t ev[10] = {};
   double phase_ms[9] = {};
 };
 
 // Similarity GEMM on the persistent tcgen05 kernel (conv_pers.cuh): A = queries [Q][D], B = database rows [rows][D],
-// 128 x 256 tiles, K = D.  Tiles are ordered database-tile-fastest, so CTAs running at the same time share the
-// query tile (L2) and stream disjoint database rows.
+// 128 x 256 tiles, K = D.  Tiles are ordered query-tile-fastest, so CTAs running at the same time share the streamed
+// database tile (L2) and the database is read from HBM once.  Encoded tensor maps are kept per (base, rows) in the
+// handle: a search re-uses the same three maps every call.
 struct SimArgs {
   float* dense = nullptr; int64_t dense_ld = 0;
   const float* thr = nullptr; unsigned long long* cand = nullptr; int* cand_cnt = nullptr; int cand_cap = 0;
+  const int* gate = nullptr;
 };
-static int sim_gemm(int epi, const __half* q16, int Q, const __half* db16, int64_t rows, int D, const SimArgs& a,
-                    cudaStream_t stream) {
+static int sim_gemm(dirb200_index* h, int epi, const __half* q16, int Q, const __half* db16, int64_t rows, int D,
+                    const SimArgs& a, cudaStream_t stream) {
   constexpr int BN = 256;
-  CUtensorMap tmA, tmB;
-  DIRB_TRY(encode_tmap_2d(&tmA, q16, D, Q, (uint64_t)D * 2, 64, 128));
-  DIRB_TRY(encode_tmap_2d(&tmB, db16, D, rows, (uint64_t)D * 2, 64, BN));
-  ConvPersParams p{};
-  p.a_spatial = 0;
-  p.taps = 1; p.kw_taps = 1; p.cin_blocks = D / 64; p.stride = 1; p.pad = 0;
-  p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
-  p.M = Q;
-  p.N = static_cast<int>(rows);
-  p.n_tiles = static_cast<int>(ceil_div(rows, BN));
-  p.m_tiles = static_cast<int>(ceil_div(Q, 128));
-  p.m_fastest = 1;
-  const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
-  DIRB_REQUIRE(total < (int64_t(1) << 31), DIRB200_ENOTSUP, "too many tiles");
-  p.total_tiles = static_cast<int>(total);
-  p.dense = a.dense; p.dense_ld = a.dense_ld;
-  p.thr = a.thr; p.cand = a.cand; p.cand_cnt = a.cand_cnt; p.cand_cap = a.cand_cap;
-  if (epi == PERS_EPI_SIM_DENSE)
-    return conv_pers_launch<BN, 4, PERS_EPI_SIM_DENSE>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
-  if (epi == PERS_EPI_SIM_GMAX)
-    return conv_pers_launch<BN, 4, PERS_EPI_SIM_GMAX>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
-  return conv_pers_launch<BN, 4, PERS_EPI_SIM_FILTER>(tmA, tmB, tmA, tmA, p, num_sms(), stream);
+  const CUtensorMap *tmA, *tmB;
+  {
+    TmapCache& c = h->tmaps;
+    DIRB_TRY(c.get(q16, D, Q, 128, &tmA));
+    CUtensorMap a_copy = *tmA;                    // `get` may reallocate the vector: copy before the second lookup
+    DIRB_TRY(c.get(db16, D, rows, BN, &tmB));
+    CUtensorMap b_copy = *tmB;
+    ConvPersParams p{};
+    p.a_spatial = 0;
+    p.taps = 1; p.kw_taps = 1; p.cin_blocks = D / 64; p.stride = 1; p.pad = 0;
+    p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
+    p.M = Q;
+    p.N = static_cast<int>(rows);
+    p.n_tiles = static_cast<int>(ceil_div(rows, BN));
+    p.m_tiles = static_cast<int>(ceil_div(Q, 128));
+    p.m_fastest = 1;
+    const int64_t total = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+    DIRB_REQUIRE(total < (int64_t(1) << 31), DIRB200_ENOTSUP, "too many tiles");
+    p.total_tiles = static_cast<int>(total);
+    p.dense = a.dense; p.dense_ld = a.dense_ld;
+    p.thr = a.thr; p.cand = a.cand; p.cand_cnt = a.cand_cnt; p.cand_cap = a.cand_cap;
+    p.gate = a.gate;
+    if (epi == PERS_EPI_SIM_DENSE)
+      return conv_pers_launch<BN, 4, PERS_EPI_SIM_DENSE>(a_copy, b_copy, a_copy, a_copy, p, num_sms(), stream);
+    if (epi == PERS_EPI_SIM_GMAX)
+      return conv_pers_launch<BN, 4, PERS_EPI_SIM_GMAX>(a_copy, b_copy, a_copy, a_copy, p, num_sms(), stream);
+    return conv_pers_launch<BN, 4, PERS_EPI_SIM_FILTER>(a_copy, b_copy, a_copy, a_copy, p, num_sms(), stream);
+  }
 }
 
 extern "C" {
@@ -429,6 +573,7 @@ int dirb200_index_set_db(dirb200_index* h, const float* db32_dev, const void* db
   h->N = N;
   h->offset = index_offset;
   h->has_db = true;
+  h->tmaps.es.clear();
   return 0;
 }
 
@@ -439,12 +584,47 @@ int dirb200_index_set_option(dirb200_index* h, const char* key, double value) {
   else if (k == "sample_rows") h->sample_rows = static_cast<int64_t>(value);
   else if (k == "cand_cap") h->cand_cap = static_cast<int>(value);
   else if (k == "profile") h->profile = value != 0;
+  else if (k == "retries") h->retries = std::max(0, std::min(4, static_cast<int>(value)));
+  else if (k == "deferred_check") h->deferred = value != 0;
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown index option '%s'", key);
+  return 0;
+}
+
+// Collect the status of the last search (waits for it to finish): overflow errors + counters.
+int dirb200_index_check(dirb200_index* h) {
+  DIRB_REQUIRE(h, DIRB200_EINVAL, "null");
+  if (!h->status_pending) return 0;
+  DIRB_CUDA(cudaSetDevice(h->device));
+  DIRB_CUDA(cudaEventSynchronize(h->status_ev));
+  h->status_pending = false;
+  const unsigned long long err = h->h_status[ST_ERR];
+  h->stats[1] = static_cast<int64_t>(h->h_status[ST_CAND]);
+  h->stats[2] = static_cast<int64_t>(h->h_status[ST_SURV]);
+  h->stats[3] = static_cast<int64_t>(h->h_status[ST_RETRIES]);
+  if (h->profile && h->pend.mark_i >= 2) {
+    for (int i = 0; i + 1 < h->pend.mark_i && i < 8; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+      h->phase_ms[i] = ms;
+    }
+  }
+  DIRB_REQUIRE((err & 1ull) == 0, DIRB200_EOVERFLOW,
+               "candidate buffer overflow not resolved after %d retry passes (raise option cand_cap)", h->retries);
+  DIRB_REQUIRE((err & 2ull) == 0, DIRB200_EOVERFLOW,
+               "more than %d rows within 2*eps16=%g of the k-th score for some query (near-duplicate rows?)",
+               h->status_cap2, h->status_band);
   return 0;
 }
 
 int dirb200_index_last_stats(dirb200_index* h, int64_t stats[5]) {
   DIRB_REQUIRE(h && stats, DIRB200_EINVAL, "null");
+  if (h->status_pending) {                      // counters of a deferred search: wait for it, keep its error for _check
+    DIRB_CUDA(cudaSetDevice(h->device));
+    DIRB_CUDA(cudaEventSynchronize(h->status_ev));
+    h->stats[1] = static_cast<int64_t>(h->h_status[ST_CAND]);
+    h->stats[2] = static_cast<int64_t>(h->h_status[ST_SURV]);
+    h->stats[3] = static_cast<int64_t>(h->h_status[ST_RETRIES]);
+  }
   for (int i = 0; i < 5; ++i) stats[i] = h->stats[i];
   return 0;
 }
@@ -459,9 +639,10 @@ int dirb200_index_destroy(dirb200_index* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   for (auto e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->status_ev) cudaEventDestroy(h->status_ev);
   if (h->ws) cudaFree(h->ws);
   if (h->sel_own) cudaFree(h->sel_own);
-  if (h->h_flags) cudaFreeHost(h->h_flags);
+  if (h->h_status) cudaFreeHost(h->h_status);
   delete h;
   return 0;
 }
@@ -472,9 +653,10 @@ static void mark_phase(dirb200_index* h, cudaStream_t stream) {
   cudaEventRecord(h->ev[h->pend.mark_i++], stream);
 }
 
-// Phase 1: fp16 queries, seed pass, filter pass (with overflow retries), local k-th / k_shard-th candidate scores.
-// sel_dev[Q] receives the local k_shard-th best fp16-path score per query; with several shards the caller
+// Phase 1: fp16 queries, seed pass, filter pass (+ device-gated retry passes), local k-th / k_shard-th candidate
+// scores.  sel_dev[Q] receives the local k_shard-th best fp16-path score per query; with several shards the caller
 // MIN-reduces it over the shards before phase 2 (k_shard = ceil(k / shards)); with one shard k_shard = k.
+// Nothing here waits for the GPU: everything is enqueued on `stream`.
 int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k, int k_shard, float* sel_dev,
                                void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -483,6 +665,7 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
   DIRB_REQUIRE(Q > 0 && k > 0 && k <= 1024, DIRB200_ENOTSUP, "need 0 < Q and 0 < k <= 1024 (got Q=%d k=%d)", Q, k);
   DIRB_REQUIRE(k_shard >= 1 && k_shard <= k, DIRB200_EINVAL, "k_shard must be in [1, k]");
   DIRB_CUDA(cudaSetDevice(h->device));
+  DIRB_TRY(dirb200_index_check(h));          // an uncollected error of the previous search must not get lost
   const int D = h->dim;
   const int64_t N = h->N;
   auto& P = h->pend;
@@ -492,11 +675,10 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
   P.k = k;
   P.launches0 = launches_total();
   P.cap2 = (k > 256) ? 2048 : 1024;
-  const int cap2 = P.cap2;
   if (N == 0) {   // empty shard: nothing can be selected; +inf never lowers the MIN over the shards
-    std::vector<float> inf(Q, INFINITY);
-    DIRB_CUDA(cudaMemcpyAsync(sel_dev, inf.data(), static_cast<size_t>(Q) * 4, cudaMemcpyHostToDevice, stream));
-    DIRB_CUDA(cudaStreamSynchronize(stream));
+    fill_f32_kernel<<<static_cast<unsigned>(ceil_div(Q, 256)), 256, 0, stream>>>(sel_dev, Q, INFINITY);
+    count_launch();
+    DIRB_CUDA(cudaGetLastError());
     return 0;
   }
   // ---- sizes
@@ -526,47 +708,44 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
   const size_t o_thr = carve(static_cast<size_t>(Q) * 4);
   const size_t o_cnt = carve(static_cast<size_t>(Q) * 4);
   const size_t o_cand = carve(static_cast<size_t>(Q) * cap * 8);
-  const size_t o_sidx = carve(static_cast<size_t>(Q) * cap2 * 4);
-  const size_t o_sscore = carve(static_cast<size_t>(Q) * cap2 * 8);
-  const size_t o_scnt = carve(static_cast<size_t>(Q) * 4);
-  const size_t o_flags = carve(static_cast<size_t>(Q) * 4);
   const size_t o_kthk = carve(static_cast<size_t>(Q) * 4);
+  const size_t o_gates = carve(8 * 4);
+  const size_t o_status = carve(ST_WORDS * 8);
   if (off > h->ws_bytes) {
     if (h->ws) DIRB_CUDA(cudaFree(h->ws));
     h->ws = nullptr;
+    h->ws_bytes = 0;
     DIRB_CUDA(cudaMalloc(&h->ws, off));
     h->ws_bytes = off;
-  }
-  if (Q > h->h_flags_n) {
-    if (h->h_flags) cudaFreeHost(h->h_flags);
-    DIRB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_flags), static_cast<size_t>(Q) * 4));
-    h->h_flags_n = Q;
+    h->tmaps.es.clear();                    // the cached query map pointed into the old workspace
   }
   uint8_t* w = static_cast<uint8_t*>(h->ws);
   __half* q16 = reinterpret_cast<__half*>(w + o_q16);
   float* dense = reinterpret_cast<float*>(w + o_dense);
   float* thr = reinterpret_cast<float*>(w + o_thr);
+  int* gates = reinterpret_cast<int*>(w + o_gates);
   P.cnt = reinterpret_cast<int*>(w + o_cnt);
   P.cand = reinterpret_cast<unsigned long long*>(w + o_cand);
-  P.sidx = reinterpret_cast<int*>(w + o_sidx);
-  P.sscore = reinterpret_cast<double*>(w + o_sscore);
-  P.scnt = reinterpret_cast<int*>(w + o_scnt);
-  P.flags = reinterpret_cast<int*>(w + o_flags);
   P.kth_k = reinterpret_cast<float*>(w + o_kthk);
-  P.sel = sel_dev;
+  P.status = reinterpret_cast<unsigned long long*>(w + o_status);
   int* cnt = P.cnt;
   unsigned long long* cand = P.cand;
 
   mark_phase(h, stream);  // 0
-  // ---- 1. queries to fp16
-  DIRB_TRY(f32_to_f16(q32, static_cast<int64_t>(Q) * D, q16, stream));
+  // ---- 1. queries to fp16, counters / gates / status cleared
+  {
+    const int64_t n = static_cast<int64_t>(Q) * D;
+    const int64_t threads = std::max<int64_t>(ceil_div(n, 4), std::max<int64_t>(Q, 8));
+    search_prep_kernel<<<static_cast<unsigned>(ceil_div(threads, 256)), 256, 0, stream>>>(q32, q16, n, cnt, Q, gates, 8, P.status);
+    count_launch();
+  }
   mark_phase(h, stream);  // 1: convert
   // ---- 2. seed pass over the first S rows
   {
     SimArgs a;
     a.dense = dense;
     a.dense_ld = S_ld;
-    DIRB_TRY(sim_gemm(use_gmax ? PERS_EPI_SIM_GMAX : PERS_EPI_SIM_DENSE, q16, Q, h->db16, S, D, a, stream));
+    DIRB_TRY(sim_gemm(h, use_gmax ? PERS_EPI_SIM_GMAX : PERS_EPI_SIM_DENSE, q16, Q, h->db16, S, D, a, stream));
     mark_phase(h, stream);  // 2: seed GEMM
     const int n_vals = use_gmax ? static_cast<int>(ceil_div(S, 32)) : static_cast<int>(S);
     const int kk = static_cast<int>(std::min<int64_t>(k, n_vals));
@@ -574,12 +753,14 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
     count_launch();
     mark_phase(h, stream);  // 3: k-th of the seed scores
   }
-  DIRB_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(Q) * 4, stream));
-  for (;;) {
-    // ---- 3. candidates
+  // ---- 3./4. candidates + local k-th / k_shard-th candidate scores; pass r > 0 is armed by gate[r-1], which the
+  //            selection of pass r-1 raises when some query overflowed its candidate list
+  const int ks = std::min<int>(k_shard, static_cast<int>(std::min<int64_t>(k, N)));
+  for (int r = 0; r <= h->retries; ++r) {
+    const int* gate_in = r > 0 ? gates + (r - 1) : nullptr;
     if (small) {
       dim3 g(static_cast<unsigned>(ceil_div(N, 256)), static_cast<unsigned>(Q));
-      dense_compact_kernel<<<g, 256, 0, stream>>>(dense, S_ld, static_cast<int>(N), thr, cand, cnt, cap);
+      dense_compact_kernel<<<g, 256, 0, stream>>>(dense, S_ld, static_cast<int>(N), thr, cand, cnt, cap, gate_in);
       count_launch();
     } else {
       SimArgs a;
@@ -587,32 +768,23 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
       a.cand = cand;
       a.cand_cnt = cnt;
       a.cand_cap = cap;
-      DIRB_TRY(sim_gemm(PERS_EPI_SIM_FILTER, q16, Q, h->db16, N, D, a, stream));
+      a.gate = gate_in;
+      DIRB_TRY(sim_gemm(h, PERS_EPI_SIM_FILTER, q16, Q, h->db16, N, D, a, stream));
     }
-    if (P.retries == 0) mark_phase(h, stream);  // 4: filter pass
-    // ---- 4. local k-th / k_shard-th candidate scores
-    cand_kth_kernel<<<Q, SEL_THREADS, 0, stream>>>(cand, cnt, cap, k, std::min<int>(k_shard, static_cast<int>(std::min<int64_t>(k, N))), band,
-                                                   P.kth_k, sel_dev, thr, P.flags, N);
+    if (r == 0) mark_phase(h, stream);  // 4: filter pass
+    cand_kth_kernel<<<Q, SEL_THREADS, 0, stream>>>(cand, cnt, cap, k, ks, band, P.kth_k, sel_dev, thr, N, gate_in, gates + r,
+                                                   r == h->retries ? 1 : 0, P.status);
     count_launch();
-    if (P.retries == 0) mark_phase(h, stream);  // 5: candidate selection
-    DIRB_CUDA(cudaMemcpyAsync(h->h_flags, P.flags, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
-    DIRB_CUDA(cudaStreamSynchronize(stream));
-    bool cand_over = false;
-    for (int i = 0; i < Q; ++i) cand_over |= (h->h_flags[i] & 1) != 0;
-    if (!cand_over) break;
-    DIRB_REQUIRE(P.retries < 4, DIRB200_EOVERFLOW, "candidate buffer overflow not resolved after %d retries", P.retries);
-    ++P.retries;
-    // Overflowed queries restart from an empty list with the tightened threshold that cand_kth wrote.  Finished
-    // queries have thr = +inf, so the re-run appends nothing for them and the (idempotent) selection reproduces
-    // their values from the unchanged list.
-    for (int i = 0; i < Q; ++i)
-      if (h->h_flags[i] & 1) DIRB_CUDA(cudaMemsetAsync(cnt + i, 0, 4, stream));
+    if (r == 0) mark_phase(h, stream);  // 5: candidate selection
   }
-  mark_phase(h, stream);  // 6: flags round trip
+  mark_phase(h, stream);  // 6: gated retry passes (empty launches unless a list overflowed)
+  DIRB_CUDA(cudaGetLastError());
   return 0;
 }
 
-// Phase 2: survivors (candidates within the band of max(sel, local k-th)), exact re-scoring, ordered output.
+// Phase 2: survivors (candidates within the band of max(sel, local k-th)), exact re-scoring, ordered output - one
+// launch (search_finish_kernel) + an asynchronous copy of the status block.  Unless option deferred_check is set the
+// call ends with dirb200_index_check (the only host synchronisation of a search).
 int dirb200_index_search_finish(dirb200_index* h, const float* q32, const float* sel_dev, double* scores_dev,
                                 int64_t* idx_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -623,55 +795,30 @@ int dirb200_index_search_finish(dirb200_index* h, const float* q32, const float*
   const int Q = P.Q, k = P.k, cap2 = P.cap2;
   P.active = false;
   if (h->N == 0) {
-    std::vector<double> s(static_cast<size_t>(Q) * k, -INFINITY);
-    std::vector<int64_t> ix(static_cast<size_t>(Q) * k, -1);
-    DIRB_CUDA(cudaMemcpyAsync(scores_dev, s.data(), s.size() * 8, cudaMemcpyHostToDevice, stream));
-    DIRB_CUDA(cudaMemcpyAsync(idx_dev, ix.data(), ix.size() * 8, cudaMemcpyHostToDevice, stream));
-    DIRB_CUDA(cudaStreamSynchronize(stream));
+    const int64_t n = static_cast<int64_t>(Q) * k;
+    fill_empty_result_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(scores_dev, idx_dev, n);
+    count_launch();
+    DIRB_CUDA(cudaGetLastError());
+    h->stats[0] = h->stats[1] = h->stats[2] = h->stats[3] = 0;
+    h->stats[4] = launches_total() - P.launches0;
     return 0;
   }
-  cand_survivors_kernel<<<Q, SEL_THREADS, 0, stream>>>(P.cand, P.cnt, P.cap, P.kth_k, sel_dev, P.band, P.sidx, P.scnt, cap2,
-                                                       P.flags);
-  {
-    dim3 g(static_cast<unsigned>(ceil_div(cap2, 8)), static_cast<unsigned>(Q));
-    rescore_kernel<<<g, 256, 0, stream>>>(q32, h->db32, h->dim, P.sidx, P.scnt, cap2, P.sscore);
-    mark_phase(h, stream);  // 7: survivors + exact re-scoring
-    const size_t smem = static_cast<size_t>(cap2) * 16;
-    DIRB_CUDA(cudaFuncSetAttribute(sort_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-    sort_topk_kernel<<<Q, 1024, smem, stream>>>(P.sscore, P.sidx, nullptr, P.scnt, 0, cap2, h->offset, k, scores_dev, idx_dev);
-    count_launch(3);
-    DIRB_CUDA(cudaGetLastError());
-    mark_phase(h, stream);  // 8: sort
-  }
-  int64_t cand_total = 0, surv_total = 0;
-  {
-    std::vector<int> hc(Q), hs(Q);
-    DIRB_CUDA(cudaMemcpyAsync(hc.data(), P.cnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
-    DIRB_CUDA(cudaMemcpyAsync(hs.data(), P.scnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
-    DIRB_CUDA(cudaMemcpyAsync(h->h_flags, P.flags, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
-    DIRB_CUDA(cudaStreamSynchronize(stream));
-    bool surv_over = false;
-    for (int i = 0; i < Q; ++i) {
-      cand_total += hc[i];
-      surv_total += hs[i];
-      surv_over |= (h->h_flags[i] & 2) != 0;
-    }
-    DIRB_REQUIRE(!surv_over, DIRB200_EOVERFLOW,
-                 "more than %d rows within 2*eps16=%g of the k-th score for some query (near-duplicate rows?)", cap2,
-                 (double)P.band);
-  }
-  if (h->profile && P.mark_i == 9) {
-    for (int i = 0; i < 8; ++i) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
-      h->phase_ms[i] = ms;
-    }
-  }
+  const size_t smem = static_cast<size_t>(cap2) * 12;
+  search_finish_kernel<<<Q, FIN_THREADS, smem, stream>>>(P.cand, P.cnt, P.cap, P.kth_k, sel_dev, P.band, q32, h->db32, h->dim,
+                                                         cap2, h->offset, k, scores_dev, idx_dev, P.status);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  mark_phase(h, stream);  // 7: survivors + exact re-scoring + sort
+  if (!h->h_status) DIRB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_status), ST_WORDS * 8));
+  if (!h->status_ev) DIRB_CUDA(cudaEventCreateWithFlags(&h->status_ev, cudaEventDisableTiming));
+  DIRB_CUDA(cudaMemcpyAsync(h->h_status, P.status, ST_WORDS * 8, cudaMemcpyDeviceToHost, stream));
+  DIRB_CUDA(cudaEventRecord(h->status_ev, stream));
+  h->status_pending = true;
+  h->status_cap2 = cap2;
+  h->status_band = P.band;
   h->stats[0] = P.S;
-  h->stats[1] = cand_total;
-  h->stats[2] = surv_total;
-  h->stats[3] = P.retries;
   h->stats[4] = launches_total() - P.launches0;
+  if (!h->deferred) return dirb200_index_check(h);
   return 0;
 }
 

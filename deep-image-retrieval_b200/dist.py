@@ -77,22 +77,34 @@ class ShardedIndex:
         self.local.search(q32, k, out=packed)
         return packed
 
-    def search(self, q32: torch.Tensor, k: int):
+    def search(self, q32: torch.Tensor, k: int, check: bool = True):
         """Global exact top-k.  Phase 1 on every shard (tensor-core passes) -> MIN all-reduce of the per-query
         selection thresholds (4*Q bytes: the local c-th best scores, c = shard_quota(k, shard sizes) = ceil(k/G) for
-        evenly filled shards, bound the global k-th best, so each shard re-scores only ~k/G rows) -> phase 2 (exact re-scoring) -> one all-gather of the per-shard lists -> merge.
-        Returns (scores fp64, idx int64), (Q,k)."""
+        evenly filled shards, bound the global k-th best, so each shard re-scores only ~k/G rows) -> phase 2 (exact
+        re-scoring) -> one all-gather of the per-shard lists -> merge.  Returns (scores fp64, idx int64), (Q,k).
+
+        Nothing on this path waits for the GPU except the status check of the local shard (candidate overflow that the
+        device-side retry passes could not resolve).  check=True collects it before returning; check=False leaves it
+        to the next search() / an explicit check() so that the host can enqueue the next search while this one runs."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
-            packed = self.search_local(q32, k)
-            return self.ops.topk_merge_packed(packed.unsqueeze(0), k)
+            self.local.set_option("deferred_check", 0 if check else 1)
+            return self.local.search(q32, k)                 # the shard's ordered list IS the result: no merge pass
+        self.local.set_option("deferred_check", 1)
         k_shard = shard_quota(k, self.shard_sizes)
         sel = self.local.search_begin(q32, k, k_shard)
         dist.all_reduce(sel, op=dist.ReduceOp.MIN, group=self.group)
         packed = torch.empty((2, q32.shape[0], k), dtype=torch.int64, device=q32.device)
         self.local.search_finish(q32, k, sel, out=packed)
         gathered = all_gather_packed(packed, self.group)
-        return self.ops.topk_merge_packed(gathered, k)
+        out = self.ops.topk_merge_packed(gathered, k)
+        if check:
+            self.local.check()
+        return out
+
+    def check(self):
+        """Status of the last search(check=False)."""
+        self.local.check()
 
     def expand_queries(self, q32: torch.Tensor, k: int, alpha: float):
         """alpha-QE (test_dir.py:24-44) over the sharded database: global top-k, each rank sums the neighbours it

@@ -69,6 +69,7 @@ SIGNATURES = {
     "dirb200_index_search": (i32, [p, p, i32, i32, p, p, p]),
     "dirb200_index_search_begin": (i32, [p, p, i32, i32, i32, p, p]),
     "dirb200_index_search_finish": (i32, [p, p, p, p, p, p]),
+    "dirb200_index_check": (i32, [p]),
     "dirb200_index_last_stats": (i32, [p, C.POINTER(i64)]),
     "dirb200_index_last_profile": (i32, [p, C.POINTER(f64)]),
     "dirb200_index_destroy": (i32, [p]),

@@ -283,6 +283,10 @@ class Index:
                  _ptr(idx), _stream())
         return scores, idx
 
+    def check(self):
+        """Collect the status of the last search (option deferred_check): raises DirbError on an unresolved overflow."""
+        lib.call("dirb200_index_check", self._h)
+
     def stats(self):
         arr = (C.c_int64 * 5)()
         lib.call("dirb200_index_last_stats", self._h, arr)
@@ -291,7 +295,7 @@ class Index:
     def profile(self):
         arr = (C.c_double * 9)()
         lib.call("dirb200_index_last_profile", self._h, arr)
-        names = ["to_f16", "seed_gemm", "seed_kth", "filter_gemm", "cand_select", "flags_roundtrip", "rescore", "sort"]
+        names = ["prep", "seed_gemm", "seed_kth", "filter_gemm", "cand_select", "retry_gates", "finish"]
         return {n: float(arr[i]) for i, n in enumerate(names)}
 
     def close(self):

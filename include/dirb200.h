@@ -170,10 +170,15 @@ int dirb200_index_set_db(dirb200_index* idx, const float* db32_dev, const void* 
                          int64_t index_offset);
 /* "eps16": bound on |fp16-path score - exact score| used for the candidate band (default 1.2e-3, valid for
  * unit-norm rows); "sample_rows": rows scored densely to seed the threshold (0 = auto); "cand_cap": per-query
- * candidate-list capacity (0 = auto; a small value forces the overflow -> tightened re-run path). */
+ * candidate-list capacity (0 = auto; a small value forces the overflow -> tightened re-run path); "retries": gated
+ * retry passes enqueued after the filter pass (default 2; they return at once unless a list overflowed);
+ * "deferred_check" = 1: search calls never synchronise the host, the caller collects the status with
+ * dirb200_index_check (it is also collected at the start of the next search); "profile". */
 int dirb200_index_set_option(dirb200_index* idx, const char* key, double value);
 /* q32_dev [Q][dim] fp32.  Outputs (device): scores_dev [Q][k] fp64 exact scores, idx_dev [Q][k] int64.
- * If N < k the tail is filled with score -inf / index -1.  Synchronises the stream (overflow check). */
+ * If N < k the tail is filled with score -inf / index -1.  Everything is enqueued on `stream`; the call then waits
+ * once for the status block (overflow that the device-side retries could not resolve -> DIRB200_EOVERFLOW) unless
+ * option "deferred_check" is set. */
 int dirb200_index_search(dirb200_index* idx, const float* q32_dev, int Q, int k, double* scores_dev,
                          int64_t* idx_dev, void* stream);
 /* The same search in two phases, for a database sharded over several GPUs.  Phase 1 runs the tensor-core passes and
@@ -189,11 +194,15 @@ int dirb200_index_search_begin(dirb200_index* idx, const float* q32_dev, int Q, 
                                void* stream);
 int dirb200_index_search_finish(dirb200_index* idx, const float* q32_dev, const float* sel_dev, double* scores_dev,
                                 int64_t* idx_dev, void* stream);
-/* Statistics of the last search: {dense_rows, candidates_total, survivors_total, retries, launches}. */
+/* Status of the last search, for option "deferred_check": waits for it to finish; DIRB200_EOVERFLOW if a candidate
+ * list still overflowed after the retry passes or more than cap2 rows sat within the band of the k-th score. */
+int dirb200_index_check(dirb200_index* idx);
+/* Statistics of the last search: {dense_rows, candidates_total, survivors_total, retry passes run, launches}
+ * (waits for a deferred search to finish). */
 int dirb200_index_last_stats(dirb200_index* idx, int64_t stats[5]);
-/* With option "profile" = 1: CUDA-event milliseconds of the phases of the last search, out9[0..7] = {query fp16
- * conversion, seed GEMM, seed k-th select, filter GEMM, candidate k-th select, flag round trip to the host (+ any
- * cross-shard exchange between the phases), survivors + exact re-scoring, sort}. */
+/* With option "profile" = 1: CUDA-event milliseconds of the phases of the last search (valid after its status was
+ * collected), out9[0..6] = {query fp16 conversion + clears, seed GEMM, seed k-th select, filter GEMM, candidate k-th
+ * select, gated retry passes (+ any cross-shard exchange between the phases), survivors + exact re-scoring + sort}. */
 int dirb200_index_last_profile(dirb200_index* idx, double out9[9]);
 int dirb200_index_destroy(dirb200_index* idx);
 

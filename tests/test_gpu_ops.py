@@ -175,7 +175,8 @@ def test_whiten_tensor_core_path_is_scale_invariant(mag, spread):
                    l2norm=False)
     torch.cuda.synchronize()
     err = np.linalg.norm(y.cpu().numpy().astype(np.float64) - ref, axis=1) / np.linalg.norm(ref, axis=1)
-    assert err.max() < 5e-6, (mag, spread, err.max())
+    print("whiten rel err (mag %g, spread %g): max %.3e" % (mag, spread, err.max()))
+    assert err.max() < 2e-5, (mag, spread, err.max())        # bar: 2e-5 vs the fp64 oracle
 
 
 def test_pool_scales_l2_whiten(golden):

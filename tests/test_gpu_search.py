@@ -168,6 +168,137 @@ def test_full_size_1m_properties():
     assert st["retries"] == 0 and st["candidates"] < 40 * Q * K
 
 
+def test_config4_geometry_sharded_protocol_single_gpu():
+    """BASELINE configs[3]/[4] geometry with the 8 shards on ONE GPU (runs in the 1-GPU driver pass): 1000 queries x
+    (8 x 125 000) x 2048, k = 100.  The sharded protocol (phase 1 per shard with k_shard = shard_quota, MIN of the
+    thresholds = the all-reduce, phase 2 per shard, merge of the 8 lists = the all-gather + merge) must reproduce the
+    single-index search bit for bit (indices AND fp64 scores), and alpha-QE (k=2, alpha=0.5, test_dir.py:24-44) from
+    per-shard partial sums must equal the unsharded expansion; 8 queries are checked against the CPU fp64 oracle."""
+    ops = _ops()
+    from dirb200.dist import shard_quota, shard_rows
+    N, Q, D, K, G = 1_000_000, 1000, 2048, 100, 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    db, db16 = ops.l2_normalize(torch.randn((N, D), generator=g, device="cuda"), want_f16=True)
+    q = ops.l2_normalize(torch.randn((Q, D), generator=g, device="cuda"))
+    rows = torch.arange(Q, device="cuda") * 997 + 3                        # plant a close neighbour per query
+    q = ops.l2_normalize((db[rows] + 0.7 * q).contiguous())
+    whole = ops.Index(db, db16=db16)
+    s_ref, i_ref = whole.search(q, K)
+    bounds = [shard_rows(N, G, r) for r in range(G)]
+    shards = [ops.Index(db[a:b], index_offset=a, db16=db16[a:b]) for a, b in bounds]
+    c = shard_quota(K, [b - a for a, b in bounds])
+    assert c == 13
+    for sh in shards:
+        sh.set_option("deferred_check", 1)
+    sels = [sh.search_begin(q, K, c) for sh in shards]
+    sel = torch.stack(sels).min(dim=0).values.contiguous()
+    packed = torch.empty((G, 2, Q, K), dtype=torch.int64, device="cuda")
+    for j, sh in enumerate(shards):
+        sh.search_finish(q, K, sel, out=packed[j])
+    ms, mi = ops.topk_merge_packed(packed, K)
+    for sh in shards:
+        sh.check()
+    assert torch.equal(mi, i_ref) and torch.equal(ms, s_ref)
+    surv = sum(sh.stats()["survivors"] for sh in shards)
+    assert surv < 3 * Q * K, surv                                          # ~1.4 k rows per query over ALL shards
+    assert all(sh.stats()["retries"] == 0 for sh in shards)
+    # alpha-QE from per-shard partial sums (what the all-reduce adds up) == unsharded expansion
+    s2, i2 = ms[:, :2].contiguous(), mi[:, :2].contiguous()
+    full = ops.aqe_expand(q, db, i2, s2, 0.5)
+    part = torch.zeros_like(q)
+    for (a, b), sh in zip(bounds, shards):
+        part += ops.aqe_expand(q, db[a:b], i2, s2, 0.5, partial=True, row_offset=a, n_rows=b - a)
+    out = ops.pool_scales([part, q], "mean", l2=True)
+    assert rel_l2(out.cpu().numpy(), full.cpu().numpy()) < 1e-6
+    # second search with the expanded queries through the sharded protocol == through the single index
+    s3, i3 = whole.search(out, K)
+    sels = [sh.search_begin(out, K, c) for sh in shards]
+    sel = torch.stack(sels).min(dim=0).values.contiguous()
+    for j, sh in enumerate(shards):
+        sh.search_finish(out, K, sel, out=packed[j])
+    ms3, mi3 = ops.topk_merge_packed(packed, K)
+    assert torch.equal(mi3, i3) and torch.equal(ms3, s3)
+    # sampled oracle check (fp64 scores of 8 queries against all rows, chunked)
+    pick = [0, 1, 137, 500, 501, 777, 998, 999]
+    qs = q[pick].cpu().numpy().astype(np.float64)
+    best_s = np.full((len(pick), K), -np.inf)
+    best_i = np.zeros((len(pick), K), dtype=np.int64)
+    for c0 in range(0, N, 125_000):
+        blk = db[c0:c0 + 125_000].cpu().numpy().astype(np.float64)
+        sc = qs @ blk.T
+        cat_s = np.concatenate([best_s, sc], axis=1)
+        cat_i = np.concatenate([best_i, np.broadcast_to(np.arange(c0, c0 + blk.shape[0]), sc.shape)], axis=1)
+        for r in range(len(pick)):
+            o = np.lexsort((cat_i[r], -cat_s[r]))[:K]
+            best_s[r], best_i[r] = cat_s[r][o], cat_i[r][o]
+    np.testing.assert_array_equal(mi.cpu().numpy()[pick], best_i)
+    np.testing.assert_allclose(ms.cpu().numpy()[pick], best_s, rtol=0, atol=1e-12)
+    # alpha-QE of those queries against the oracle formula: normalize(q + sum_j db_j * s_j^alpha)
+    qe = q[pick].cpu().numpy().astype(np.float64)
+    for r in range(len(pick)):
+        for j in range(2):
+            qe[r] += db[int(best_i[r, j])].cpu().numpy().astype(np.float64) * best_s[r, j] ** 0.5
+    qe /= np.linalg.norm(qe, axis=1, keepdims=True)
+    assert rel_l2(out[pick].cpu().numpy(), qe) < 1e-5
+
+
+def test_deferred_check_and_unresolved_overflow():
+    """Option deferred_check: the search enqueues everything and returns; check() collects the status.  With the retry
+    passes disabled an overflowing candidate list must surface as DIRB200_EOVERFLOW - never as a silent wrong list."""
+    ops = _ops()
+    from dirb200.lib import DirbError
+    db, q, _ = synth.make_descriptor_db(60000, 5, dim=256, n_pos=10, db_seed=103, q_seed=203)
+    rs, ri = O.topk(q, db, 50)
+    qd = torch.from_numpy(q).to(DEV)
+    index = ops.Index(torch.from_numpy(db).to(DEV))
+    index.set_option("deferred_check", 1)
+    s, i = index.search(qd, 50)
+    index.check()
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+    # loose seed threshold + tiny candidate buffer: resolved by the gated retry passes ...
+    index.set_option("sample_rows", 256)
+    index.set_option("cand_cap", 512)
+    s, i = index.search(qd, 50)
+    index.check()
+    assert index.stats()["retries"] >= 1
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=0, atol=1e-12)
+    # ... and reported when there are none
+    index.set_option("retries", 0)
+    index.search(qd, 50)
+    with pytest.raises(DirbError) as e:
+        index.check()
+    assert e.value.status == -4
+    index.check()                                   # the error is reported once
+    index.set_option("deferred_check", 0)
+    with pytest.raises(DirbError):
+        index.search(qd, 50)                        # same condition, immediate check
+    index.set_option("retries", 2)
+    s, i = index.search(qd, 50)
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+
+
+def test_empty_shard():
+    """A shard without rows (more ranks than images): +inf thresholds, an all-(-inf, -1) list, no neighbour sums."""
+    ops = _ops()
+    db, q, _ = synth.make_descriptor_db(3000, 6, dim=128, n_pos=4)
+    qd = torch.from_numpy(q).to(DEV)
+    empty = ops.Index(torch.empty((0, 128), dtype=torch.float32, device=DEV), index_offset=3000)
+    rest = ops.Index(torch.from_numpy(db).to(DEV), index_offset=0)
+    k = 20
+    sels = [sh.search_begin(qd, k, k) for sh in (empty, rest)]
+    assert bool(torch.isinf(sels[0]).all())
+    sel = torch.minimum(sels[0], sels[1]).contiguous()
+    outs = [sh.search_finish(qd, k, sel) for sh in (empty, rest)]
+    assert bool((outs[0][1] == -1).all()) and bool(torch.isinf(outs[0][0]).all())
+    ms, mi = ops.topk_merge(torch.stack([o[0] for o in outs]).contiguous(), torch.stack([o[1] for o in outs]).contiguous(), k)
+    rs, ri = O.topk(q, db, k)
+    np.testing.assert_array_equal(mi.cpu().numpy(), ri)
+    part = ops.aqe_expand(qd, empty.db32, mi[:, :2].contiguous(), ms[:, :2].contiguous(), 0.5, partial=True,
+                          row_offset=3000, n_rows=0)
+    assert float(part.abs().max()) == 0.0
+
+
 def test_two_phase_sharded_search_single_gpu():
     """The sharded protocol with all shards on one GPU: phase 1 per shard (k_shard = ceil(k/G)), MIN over the shards'
     selection thresholds (what the all-reduce does), phase 2 per shard, merge == oracle.  Shards re-score far fewer

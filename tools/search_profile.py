@@ -2,7 +2,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dirb200 import ops
-CASES = ((125_000, 1000),) if sys.argv[1:] == ["one"] else ((1_000_000, 1000), (125_000, 1000), (100_000, 70))
+CASES = ((125_000, 1000),) if sys.argv[1:] == ["one"] else ((1_000_000, 1000), (500_000, 1000), (250_000, 1000), (125_000, 1000), (125_000, 1024), (100_000, 70))
 for (N, Q) in CASES:
     g = torch.Generator(device="cuda").manual_seed(1)
     db, db16 = ops.l2_normalize(torch.randn((N, 2048), generator=g, device="cuda"), want_f16=True)
