@@ -41,6 +41,25 @@ namespace {
 
 constexpr int SEL_THREADS = 512;
 
+// Exact score of one (query, row) pair by one warp: fp64 accumulation of the fp32 products, fixed summation order
+// (lane-strided float4 loads, xor-shuffle tree).  Every exact score of the library comes from this function, so two
+// evaluations of the same pair - or of two identical rows - are bit-identical wherever they are computed.
+__device__ __forceinline__ double exact_dot_warp(const float* __restrict__ qrow, const float* __restrict__ dbrow, int D,
+                                                 int lane) {
+  const float4* a = reinterpret_cast<const float4*>(qrow);
+  const float4* b = reinterpret_cast<const float4*>(dbrow);
+  double acc = 0.0;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 x = __ldg(a + i), y = __ldg(b + i);
+    acc += static_cast<double>(x.x) * y.x;
+    acc += static_cast<double>(x.y) * y.y;
+    acc += static_cast<double>(x.z) * y.z;
+    acc += static_cast<double>(x.w) * y.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 __device__ __forceinline__ uint32_t f2key(float f) {  // monotone increasing map float -> uint32
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -275,18 +294,8 @@ __global__ void __launch_bounds__(FIN_THREADS) search_finish_kernel(
   const int found = s_n;
   const int ns = min(found, cap2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float4* a = reinterpret_cast<const float4*>(q32 + static_cast<int64_t>(q) * D);
   for (int w = warp; w < ns; w += FIN_THREADS / 32) {
-    const float4* b = reinterpret_cast<const float4*>(db32 + static_cast<int64_t>(ix[w]) * D);
-    double acc = 0.0;
-    for (int i = lane; i < D / 4; i += 32) {
-      const float4 x = __ldg(a + i), y = __ldg(b + i);
-      acc += static_cast<double>(x.x) * y.x;
-      acc += static_cast<double>(x.y) * y.y;
-      acc += static_cast<double>(x.z) * y.z;
-      acc += static_cast<double>(x.w) * y.w;
-    }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double acc = exact_dot_warp(q32 + static_cast<int64_t>(q) * D, db32 + static_cast<int64_t>(ix[w]) * D, D, lane);
     if (lane == 0) sc[w] = acc;
   }
   int P = 2;
@@ -449,6 +458,133 @@ __global__ void aqe_kernel(const float* __restrict__ q, int D, const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ rank counting
+// AP needs, per query, only the RANKS of the labelled rows (generic.py:196-224: full argsort, junk dropped, positions
+// of the positives) - not the Q x N score matrix.  For each (query, target row) the kernels below return the exact
+// score s_t and above_t = the number of database rows that rank before the target under the library's order (exact
+// score descending, ties -> lower index first):
+//   1. exact scores of the targets                                                          (target_scores_kernel)
+//   2. per query thr = min over the counted targets of s_t - eps16                          (count_thr_kernel)
+//   3. tcgen05 filter pass: rows with fp16-path score >= thr go to the query's candidate list (PERS_EPI_SIM_FILTER);
+//      every row NOT captured has exact score < s_t for every counted target
+//   4. per (query, target): candidates with fp16-path score > s_t + eps16 rank before it for certain, those within
+//      +-eps16 are re-scored exactly and compared (score, index)                            (rank_count_kernel)
+// A query whose list overflows (a positive buried in the bulk of the score distribution) or whose band overflows is
+// flagged and counted exactly from the fp32 rows instead                                    (rank_count_exact_kernel)
+
+// one warp per target: score[t] = <q[t_q[t]], db[row - offset]> if this shard owns the row, else 0 (summed over shards)
+__global__ void target_scores_kernel(const float* __restrict__ q32, const float* __restrict__ db32, int D,
+                                     const int* __restrict__ t_q, const int64_t* __restrict__ t_rows, int T,
+                                     int64_t offset, int64_t n_rows, double* __restrict__ t_score) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const int64_t r = t_rows[t] - offset;
+  double v = 0.0;
+  if (r >= 0 && r < n_rows) v = exact_dot_warp(q32 + static_cast<int64_t>(t_q[t]) * D, db32 + r * D, D, lane);
+  if (lane == 0) t_score[t] = v;
+}
+
+// thr[q] = (float, rounded down) min over counted targets of s_t - eps; +inf when the query counts nothing
+__global__ void count_thr_kernel(const int* __restrict__ t_off, const unsigned char* __restrict__ t_flags,
+                                 const double* __restrict__ t_score, int Q, double eps, float* __restrict__ thr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  double m = INFINITY;
+  for (int t = t_off[q]; t < t_off[q + 1]; ++t)
+    if (t_flags[t]) m = fmin(m, t_score[t]);
+  thr[q] = (m == INFINITY) ? INFINITY : __double2float_rd(m - eps);
+}
+
+constexpr int RC_THREADS = 512;
+constexpr int RC_BAND = 2048;
+__global__ void __launch_bounds__(RC_THREADS) rank_count_kernel(
+    const unsigned long long* __restrict__ cand, const int* __restrict__ cnt, int cap, const float* __restrict__ q32,
+    const float* __restrict__ db32, int D, int64_t offset, double eps, const int* __restrict__ t_off,
+    const int64_t* __restrict__ t_rows, const unsigned char* __restrict__ t_flags, const double* __restrict__ t_score,
+    long long* __restrict__ above, int* __restrict__ q_over) {
+  __shared__ int band[RC_BAND];
+  __shared__ int s_band;
+  __shared__ unsigned long long s_count;
+  const int q = blockIdx.x;
+  const int total = cnt[q];
+  if (total > cap) {                      // uniform over the block
+    if (threadIdx.x == 0) q_over[q] = 1;
+    return;
+  }
+  const unsigned long long* c = cand + static_cast<int64_t>(q) * cap;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = t_off[q]; t < t_off[q + 1]; ++t) {
+    if (!t_flags[t]) continue;            // uniform
+    const double s = t_score[t];
+    const int64_t trow = t_rows[t];
+    const double hi = s + eps, lo = s - eps;
+    if (threadIdx.x == 0) {
+      s_band = 0;
+      s_count = 0ull;
+    }
+    __syncthreads();
+    unsigned int mine = 0;
+    for (int i = threadIdx.x; i < total; i += RC_THREADS) {
+      const unsigned long long e = c[i];
+      const double sh = static_cast<double>(__uint_as_float(static_cast<uint32_t>(e >> 32)));
+      if (sh > hi) {
+        ++mine;
+      } else if (sh >= lo) {
+        const int pos = atomicAdd(&s_band, 1);
+        if (pos < RC_BAND) band[pos] = static_cast<int>(e & 0xffffffffu);
+      }
+    }
+    __syncthreads();
+    const int nb = s_band;
+    if (nb > RC_BAND) {                   // uniform: too many near-ties for the shared-memory band
+      if (threadIdx.x == 0) q_over[q] = 1;
+      return;
+    }
+    for (int w = warp; w < nb; w += RC_THREADS / 32) {
+      const int row = band[w];
+      const double sc = exact_dot_warp(q32 + static_cast<int64_t>(q) * D, db32 + static_cast<int64_t>(row) * D, D, lane);
+      const int64_t g = static_cast<int64_t>(row) + offset;
+      if (lane == 0 && g != trow && (sc > s || (sc == s && g < trow))) ++mine;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicAdd(&s_count, static_cast<unsigned long long>(mine));
+    __syncthreads();
+    if (threadIdx.x == 0) above[t] = static_cast<long long>(s_count);
+    __syncthreads();
+  }
+}
+
+// Exact fallback, one query per blockIdx.y: every database row is scored exactly (warp per row, fp64) and compared
+// with the query's counted targets.  Reads the whole fp32 shard once per query.
+constexpr int RCE_THREADS = 256;
+__global__ void __launch_bounds__(RCE_THREADS) rank_count_exact_kernel(
+    const float* __restrict__ q32, const float* __restrict__ db32, int D, int64_t n_rows, int64_t offset,
+    const int* __restrict__ q_list, const int* __restrict__ t_off, const int64_t* __restrict__ t_rows,
+    const unsigned char* __restrict__ t_flags, const double* __restrict__ t_score, unsigned long long* __restrict__ above) {
+  extern __shared__ unsigned int cnts[];                   // [max targets per query of this launch]
+  const int q = q_list[blockIdx.y];
+  const int t0 = t_off[q], nt = t_off[q + 1] - t0;
+  for (int i = threadIdx.x; i < nt; i += RCE_THREADS) cnts[i] = 0u;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t wstride = static_cast<int64_t>(gridDim.x) * (RCE_THREADS / 32);
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * (RCE_THREADS / 32) + warp; r < n_rows; r += wstride) {
+    const double sc = exact_dot_warp(q32 + static_cast<int64_t>(q) * D, db32 + r * D, D, lane);
+    const int64_t g = r + offset;
+    for (int i = lane; i < nt; i += 32) {
+      if (!t_flags[t0 + i]) continue;
+      const double s = t_score[t0 + i];
+      const int64_t trow = t_rows[t0 + i];
+      if (g != trow && (sc > s || (sc == s && g < trow))) atomicAdd(&cnts[i], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nt; i += RCE_THREADS)
+    if (cnts[i]) atomicAdd(above + t0 + i, static_cast<unsigned long long>(cnts[i]));
+}
+
 }  // namespace
 }  // namespace dirb
 
@@ -479,6 +615,7 @@ struct dirb200_index {
   double eps16 = 1.2e-3;
   int64_t sample_rows = 0;
   int cand_cap = 0;          // 0 = auto
+  int count_cap = 0;         // candidate capacity per query of dirb200_index_rank_count (0 = 32768)
   int retries = 2;           // gated retry passes enqueued after the first filter pass (device-side predicate)
   int deferred = 0;          // 1 = search calls never synchronise; the caller collects the status (dirb200_index_check)
   // workspaces (grown on demand)
@@ -584,6 +721,7 @@ int dirb200_index_set_option(dirb200_index* h, const char* key, double value) {
   else if (k == "sample_rows") h->sample_rows = static_cast<int64_t>(value);
   else if (k == "cand_cap") h->cand_cap = static_cast<int>(value);
   else if (k == "profile") h->profile = value != 0;
+  else if (k == "count_cap") h->count_cap = static_cast<int>(value);
   else if (k == "retries") h->retries = std::max(0, std::min(4, static_cast<int>(value)));
   else if (k == "deferred_check") h->deferred = value != 0;
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown index option '%s'", key);
@@ -835,6 +973,131 @@ int dirb200_index_search(dirb200_index* h, const float* q32, int Q, int k, doubl
   }
   DIRB_TRY(dirb200_index_search_begin(h, q32, Q, k, k, h->sel_own, stream_));
   return dirb200_index_search_finish(h, q32, h->sel_own, scores_dev, idx_dev, stream_);
+}
+
+// ---- rank counting (see the kernels above): exact scores of the labelled rows + number of rows ranking before them
+int dirb200_index_target_scores(dirb200_index* h, const float* q32, int Q, const int* t_q_dev, const int64_t* t_rows_dev,
+                                int T, double* t_score_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(h && q32 && Q > 0 && T >= 0, DIRB200_EINVAL, "bad arguments");
+  DIRB_REQUIRE(h->has_db, DIRB200_ESTATE, "index has no database attached");
+  if (T == 0) return 0;
+  DIRB_REQUIRE(t_q_dev && t_rows_dev && t_score_dev, DIRB200_EINVAL, "null argument");
+  DIRB_CUDA(cudaSetDevice(h->device));
+  target_scores_kernel<<<static_cast<unsigned>(ceil_div(T, 8)), 256, 0, stream>>>(q32, h->db32, h->dim, t_q_dev, t_rows_dev, T,
+                                                                                  h->offset, h->N, t_score_dev);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dirb200_index_rank_count(dirb200_index* h, const float* q32, int Q, const int* t_off_host, const int* t_off_dev,
+                             const int64_t* t_rows_dev, const unsigned char* t_flags_dev, const double* t_score_dev,
+                             int T, int64_t* above_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(h && q32 && Q > 0 && T >= 0 && t_off_host, DIRB200_EINVAL, "bad arguments");
+  DIRB_REQUIRE(h->has_db, DIRB200_ESTATE, "index has no database attached");
+  if (T == 0) return 0;
+  DIRB_REQUIRE(t_off_dev && t_rows_dev && t_flags_dev && t_score_dev && above_dev, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(t_off_host[0] == 0 && t_off_host[Q] == T, DIRB200_EINVAL, "target offsets must run from 0 to T");
+  DIRB_CUDA(cudaSetDevice(h->device));
+  DIRB_TRY(dirb200_index_check(h));
+  h->pend.active = false;                        // shares the search workspace
+  const int64_t launches0 = launches_total();
+  DIRB_CUDA(cudaMemsetAsync(above_dev, 0, static_cast<size_t>(T) * 8, stream));
+  h->stats[0] = h->stats[1] = h->stats[2] = h->stats[3] = 0;
+  if (h->N == 0) {
+    h->stats[4] = launches_total() - launches0;
+    return 0;
+  }
+  const int D = h->dim;
+  const int64_t N = h->N;
+  int cap = h->count_cap > 0 ? h->count_cap : 32768;
+  cap = std::max(1024, (cap + 255) / 256 * 256);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_q16 = carve(static_cast<size_t>(Q) * D * 2);
+  const size_t o_thr = carve(static_cast<size_t>(Q) * 4);
+  const size_t o_cnt = carve(static_cast<size_t>(Q) * 4);
+  const size_t o_cand = carve(static_cast<size_t>(Q) * cap * 8);
+  const size_t o_gates = carve(8 * 4);
+  const size_t o_status = carve(ST_WORDS * 8);
+  const size_t o_over = carve(static_cast<size_t>(Q) * 4);
+  const size_t o_qlist = carve(static_cast<size_t>(Q) * 4);
+  if (off > h->ws_bytes) {
+    if (h->ws) DIRB_CUDA(cudaFree(h->ws));
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    DIRB_CUDA(cudaMalloc(&h->ws, off));
+    h->ws_bytes = off;
+    h->tmaps.es.clear();
+  }
+  uint8_t* w = static_cast<uint8_t*>(h->ws);
+  __half* q16 = reinterpret_cast<__half*>(w + o_q16);
+  float* thr = reinterpret_cast<float*>(w + o_thr);
+  int* cnt = reinterpret_cast<int*>(w + o_cnt);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(w + o_cand);
+  int* gates = reinterpret_cast<int*>(w + o_gates);
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(w + o_status);
+  int* q_over = reinterpret_cast<int*>(w + o_over);
+  int* q_list = reinterpret_cast<int*>(w + o_qlist);
+  {
+    const int64_t n = static_cast<int64_t>(Q) * D;
+    const int64_t threads = std::max<int64_t>(ceil_div(n, 4), std::max<int64_t>(Q, 8));
+    search_prep_kernel<<<static_cast<unsigned>(ceil_div(threads, 256)), 256, 0, stream>>>(q32, q16, n, cnt, Q, gates, 8, status);
+    count_launch();
+  }
+  DIRB_CUDA(cudaMemsetAsync(q_over, 0, static_cast<size_t>(Q) * 4, stream));
+  count_thr_kernel<<<static_cast<unsigned>(ceil_div(Q, 128)), 128, 0, stream>>>(t_off_dev, t_flags_dev, t_score_dev, Q, h->eps16, thr);
+  count_launch();
+  {
+    SimArgs a;
+    a.thr = thr;
+    a.cand = cand;
+    a.cand_cnt = cnt;
+    a.cand_cap = cap;
+    DIRB_TRY(sim_gemm(h, PERS_EPI_SIM_FILTER, q16, Q, h->db16, N, D, a, stream));
+  }
+  rank_count_kernel<<<Q, RC_THREADS, 0, stream>>>(cand, cnt, cap, q32, h->db32, D, h->offset, h->eps16, t_off_dev, t_rows_dev,
+                                                  t_flags_dev, t_score_dev, reinterpret_cast<long long*>(above_dev), q_over);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  std::vector<int> over(Q), hcnt(Q);
+  DIRB_CUDA(cudaMemcpyAsync(over.data(), q_over, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
+  DIRB_CUDA(cudaMemcpyAsync(hcnt.data(), cnt, static_cast<size_t>(Q) * 4, cudaMemcpyDeviceToHost, stream));
+  DIRB_CUDA(cudaStreamSynchronize(stream));
+  std::vector<int> list;
+  int max_nt = 0;
+  int64_t cand_total = 0;
+  for (int q = 0; q < Q; ++q) {
+    cand_total += std::min(hcnt[q], cap);
+    if (!over[q]) continue;
+    list.push_back(q);
+    max_nt = std::max(max_nt, t_off_host[q + 1] - t_off_host[q]);
+    // a band overflow may have left partial counts behind
+    DIRB_CUDA(cudaMemsetAsync(above_dev + t_off_host[q], 0, static_cast<size_t>(t_off_host[q + 1] - t_off_host[q]) * 8, stream));
+  }
+  if (!list.empty()) {
+    DIRB_REQUIRE(static_cast<size_t>(max_nt) * 4 <= 200 * 1024, DIRB200_ENOTSUP, "more than 51200 labelled rows for one query");
+    DIRB_CUDA(cudaMemcpyAsync(q_list, list.data(), list.size() * 4, cudaMemcpyHostToDevice, stream));
+    const size_t smem = static_cast<size_t>(std::max(max_nt, 1)) * 4;
+    DIRB_CUDA(cudaFuncSetAttribute(rank_count_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const int gx = static_cast<int>(std::min<int64_t>(ceil_div(N, RCE_THREADS / 32), 4 * static_cast<int64_t>(num_sms())));
+    // a few queries per launch: each grid row re-reads the whole fp32 shard
+    for (size_t i0 = 0; i0 < list.size(); i0 += 4096) {
+      const unsigned ny = static_cast<unsigned>(std::min<size_t>(4096, list.size() - i0));
+      rank_count_exact_kernel<<<dim3(gx, ny), RCE_THREADS, smem, stream>>>(
+          q32, h->db32, D, N, h->offset, q_list + i0, t_off_dev, t_rows_dev, t_flags_dev, t_score_dev,
+          reinterpret_cast<unsigned long long*>(above_dev));
+      count_launch();
+    }
+    DIRB_CUDA(cudaGetLastError());
+    DIRB_CUDA(cudaStreamSynchronize(stream));    // `list` is read by the async copy above
+  }
+  h->stats[1] = cand_total;
+  h->stats[3] = static_cast<int64_t>(list.size());
+  h->stats[4] = launches_total() - launches0;
+  return 0;
 }
 
 int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, int64_t shard_stride,

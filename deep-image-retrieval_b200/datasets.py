@@ -276,6 +276,44 @@ class ImageListRelevants(Dataset):
         return {m: self._ap_from_ranking(query_idx, ranked_idx, m) for m in ("easy", "medium", "hard")}
 
 
+    # ---- the same AP from rank COUNTS of the labelled rows (dirb200_index_rank_count) instead of a full score row
+    def rank_targets(self, q):
+        """Labelled rows of query q for the counting kernel: (rows int64 sorted, flags uint8); flag 1 = the row is a
+        positive in some evaluation mode (its rank is needed), 0 = junk only (its score suffices)."""
+        if self.relevants:
+            pos, junk = set(int(i) for i in self.relevants[q]), set(int(i) for i in self.junk[q])
+        else:
+            pos = set(int(i) for i in self.easy[q]) | set(int(i) for i in self.hard[q])
+            junk = set(int(i) for i in self.junk[q])
+        rows = np.array(sorted(pos | junk), dtype=np.int64)
+        flags = np.array([1 if int(r) in pos else 0 for r in rows], dtype=np.uint8)
+        return rows, flags
+
+    def _ap_from_counts(self, q, rows, scores, above, mode):
+        rel = set(int(i) for i in self.get_relevants(q, mode))
+        junk = set(int(i) for i in self.get_junk(q, mode))
+        rel -= junk                                  # a label set to 0 (junk) after 1 wins, as in get_query_groundtruth
+        if mode != "classic" and not rel:
+            return -1
+        at = {int(r): i for i, r in enumerate(rows)}
+        jidx = np.array(sorted(junk), dtype=np.int64)
+        js = np.array([scores[at[int(j)]] for j in jidx], dtype=np.float64)
+        ranks = []
+        for p in rel:
+            sp = scores[at[p]]
+            before = int(((js > sp) | ((js == sp) & (jidx < p))).sum()) if len(jidx) else 0   # junk rows ranked before p
+            ranks.append(int(above[at[p]]) - before)
+        return compute_average_precision(np.sort(np.array(ranks, dtype=np.int64)))
+
+    def eval_query_AP_from_counts(self, query_idx, rows, scores, above):
+        """AP of `eval_query_AP` from the exact scores of the labelled rows and, for each positive, the number of
+        database rows ranking before it (score desc, ties -> lower index): position among the non-junk rows =
+        that count minus the junk rows that rank before it."""
+        if self.relevants:
+            return self._ap_from_counts(query_idx, rows, scores, above, "classic")
+        return {m: self._ap_from_counts(query_idx, rows, scores, above, m) for m in ("easy", "medium", "hard")}
+
+
 def _db_root():
     return os.environ["DB_ROOT"]
 

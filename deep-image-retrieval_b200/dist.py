@@ -106,6 +106,25 @@ class ShardedIndex:
         """Status of the last search(check=False)."""
         self.local.check()
 
+    def rank_counts(self, q32: torch.Tensor, t_off, t_rows, t_flags):
+        """Exact scores of the labelled rows and the number of database rows ranking before each flagged one, over the
+        WHOLE sharded database: each shard scores the targets it owns (one SUM all-reduce of T doubles), counts its own
+        rows that rank before each target (one SUM all-reduce of T int64) - SURVEY 8e.  Returns CUDA tensors."""
+        import numpy as np
+        off = np.ascontiguousarray(t_off, dtype=np.int32)
+        dev = q32.device
+        t_q = torch.from_numpy(np.repeat(np.arange(q32.shape[0], dtype=np.int32), np.diff(off))).to(dev)
+        rows = torch.as_tensor(np.ascontiguousarray(t_rows, dtype=np.int64)).to(dev)
+        flags = torch.as_tensor(np.ascontiguousarray(t_flags, dtype=np.uint8)).to(dev)
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        sc = self.local.target_scores(q32, t_q, rows)
+        if multi:
+            dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=self.group)      # exactly one shard contributes a non-zero
+        above = self.local.rank_count(q32, off, rows, flags, sc)
+        if multi:
+            dist.all_reduce(above, op=dist.ReduceOp.SUM, group=self.group)
+        return sc, above
+
     def expand_queries(self, q32: torch.Tensor, k: int, alpha: float):
         """alpha-QE (test_dir.py:24-44) over the sharded database: global top-k, each rank sums the neighbours it
         owns, one all-reduce, add the query, normalise."""

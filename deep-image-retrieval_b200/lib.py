@@ -72,6 +72,8 @@ SIGNATURES = {
     "dirb200_index_check": (i32, [p]),
     "dirb200_index_last_stats": (i32, [p, C.POINTER(i64)]),
     "dirb200_index_last_profile": (i32, [p, C.POINTER(f64)]),
+    "dirb200_index_target_scores": (i32, [p, p, i32, p, p, i32, p, p]),
+    "dirb200_index_rank_count": (i32, [p, p, i32, p, p, p, p, p, i32, p, p]),
     "dirb200_index_destroy": (i32, [p]),
     "dirb200_topk_merge": (i32, [p, p, i32, i32, i32, i64, p, p, p]),
     "dirb200_scores_exact": (i32, [p, i32, p, i64, i32, p, p]),

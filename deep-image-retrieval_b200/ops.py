@@ -239,8 +239,10 @@ class Index:
     def __init__(self, db32: torch.Tensor, index_offset: int = 0, db16: torch.Tensor = None):
         _chk(db32, torch.float32, "db32")
         self.db32 = db32
-        self.db16 = db16 if db16 is not None else f32_to_f16(db32)
         self.n, self.dim = db32.shape
+        if db16 is None:                      # an empty shard (more ranks than rows) has nothing to convert
+            db16 = f32_to_f16(db32) if self.n else torch.empty((0, self.dim), dtype=torch.float16, device=db32.device)
+        self.db16 = db16
         self.offset = int(index_offset)
         self._h = C.c_void_p()
         lib.call("dirb200_index_create", db32.device.index or 0, self.dim, C.byref(self._h))
@@ -282,6 +284,42 @@ class Index:
         lib.call("dirb200_index_search_finish", self._h, _ptr(q32), _ptr(_chk(sel, torch.float32, "sel")), _ptr(scores),
                  _ptr(idx), _stream())
         return scores, idx
+
+    def target_scores(self, q32, t_q, t_rows):
+        """Exact scores <q32[t_q[t]], db[t_rows[t]]> (fp64) of the target rows this shard owns, 0 for the others.
+        t_q int32 (T,), t_rows int64 (T,) global indices - CUDA tensors."""
+        _chk(q32, torch.float32, "q32")
+        _chk(t_q, torch.int32, "t_q")
+        _chk(t_rows, torch.int64, "t_rows")
+        out = torch.zeros(t_rows.shape[0], dtype=torch.float64, device=q32.device)
+        lib.call("dirb200_index_target_scores", self._h, _ptr(q32), q32.shape[0], _ptr(t_q), _ptr(t_rows), t_rows.shape[0],
+                 _ptr(out), _stream())
+        return out
+
+    def rank_count(self, q32, t_off, t_rows, t_flags, t_score):
+        """above[t] = number of rows of this shard ranking before target t (exact score desc, ties -> lower index) for
+        the flagged targets of each query.  t_off: host int32 ndarray (Q+1,), the CSR offsets of the targets; t_rows
+        int64 / t_flags uint8 / t_score fp64 CUDA tensors (T,)."""
+        _chk(q32, torch.float32, "q32")
+        _chk(t_rows, torch.int64, "t_rows")
+        _chk(t_flags, torch.uint8, "t_flags")
+        _chk(t_score, torch.float64, "t_score")
+        off_h = np.ascontiguousarray(t_off, dtype=np.int32)
+        assert off_h.shape[0] == q32.shape[0] + 1
+        off_d = torch.from_numpy(off_h).to(q32.device)
+        above = torch.zeros(t_rows.shape[0], dtype=torch.int64, device=q32.device)
+        lib.call("dirb200_index_rank_count", self._h, _ptr(q32), q32.shape[0], off_h.ctypes.data_as(C.c_void_p), _ptr(off_d),
+                 _ptr(t_rows), _ptr(t_flags), _ptr(t_score), t_rows.shape[0], _ptr(above), _stream())
+        return above
+
+    def rank_counts(self, q32, t_off, t_rows, t_flags):
+        """Single-shard convenience: (exact scores fp64 (T,), rows ranking before each flagged target int64 (T,))."""
+        off = np.ascontiguousarray(t_off, dtype=np.int32)
+        t_q = torch.from_numpy(np.repeat(np.arange(q32.shape[0], dtype=np.int32), np.diff(off))).to(q32.device)
+        rows = torch.as_tensor(np.ascontiguousarray(t_rows, dtype=np.int64)).to(q32.device)
+        flags = torch.as_tensor(np.ascontiguousarray(t_flags, dtype=np.uint8)).to(q32.device)
+        sc = self.target_scores(q32, t_q, rows)
+        return sc, self.rank_count(q32, off, rows, flags, sc)
 
     def check(self):
         """Collect the status of the last search (option deferred_check): raises DirbError on an unresolved overflow."""

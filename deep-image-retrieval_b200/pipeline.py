@@ -141,10 +141,34 @@ def _aps_from_topk(db, qdescs, bdescs, k):
     return aps
 
 
+def _aps_from_counts(db, qdescs, bdescs):
+    """Per-query AP without the Q x N score matrix and without any host-side ranking: the GPU returns the exact scores
+    of the labelled rows and, for every positive, the number of database rows ranking before it
+    (dirb200_index_rank_count); datasets.eval_query_AP_from_counts turns that into the AP of generic.py:196-224."""
+    dim = qdescs.shape[1]
+    pad = (-dim) % 64
+    f = lambda a: torch.nn.functional.pad(_dev_f32(a), (0, pad)).contiguous() if pad else _dev_f32(a)
+    qd, bd = f(qdescs), f(bdescs)
+    offs, rows, flags = [0], [], []
+    for q in range(qd.shape[0]):
+        r, fl = db.rank_targets(q)
+        rows.append(r)
+        flags.append(fl)
+        offs.append(offs[-1] + len(r))
+    rows = np.concatenate(rows) if rows else np.zeros(0, np.int64)
+    flags = np.concatenate(flags) if flags else np.zeros(0, np.uint8)
+    sc, above = ops.Index(bd).rank_counts(qd, np.array(offs, np.int32), rows, flags)
+    sc, above = sc.cpu().numpy(), above.cpu().numpy()
+    return [db.eval_query_AP_from_counts(q, rows[offs[q]:offs[q + 1]], sc[offs[q]:offs[q + 1]], above[offs[q]:offs[q + 1]])
+            for q in range(qd.shape[0])]
+
+
 def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=None, aqe=None, adba=None, threads=8,
-               batch_size=16, save_feats=None, load_feats=None, dbg=(), rank_topk=0):
+               batch_size=16, save_feats=None, load_feats=None, dbg=(), rank_topk=0, dense_scores=False):
     """Evaluate a network on a retrieval dataset (test_dir.py:97-180).  aqe / adba: dict(k=..., alpha=...).
-    rank_topk > 0 (extension): rank with the exact top-k search instead of the dense Q x N score matrix."""
+    Ranking: datasets with relevance lists (Oxford/Paris style) are graded from GPU rank counts - no Q x N score
+    matrix, no host argsort; dense_scores=True (extension) forces the literal matmul + per-query sort of the
+    reference, which label datasets always use; rank_topk > 0 (extension) grades from the exact top-k lists."""
     print("\n>> Evaluation...")
     query_db = db.get_query_db()
     bdescs, qdescs = [], []
@@ -178,10 +202,16 @@ def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=Non
         qdescs = expand_descriptors(qdescs, db=bdescs, **aqe)
     res = {}
     qn, bn = tonumpy(qdescs), tonumpy(bdescs)
+    unit = bool(np.abs(np.linalg.norm(qn, axis=1) - 1).max() < 1e-3 and np.abs(np.linalg.norm(bn, axis=1) - 1).max() < 1e-3)
     if rank_topk and hasattr(db, "eval_query_AP_from_ranking"):
         # Large databases: rank with the exact top-k engine instead of materialising the Q x N score matrix; a
         # query whose positives are not all inside the top-k falls back to its exact dense score row.
         aps = _aps_from_topk(db, qn, bn, int(rank_topk))
+        scores = None
+    elif not dense_scores and unit and hasattr(db, "eval_query_AP_from_counts"):
+        # default for relevance-list datasets: exact rank counts of the labelled rows from one tensor-core pass
+        # (the error bound of the fp16 pass assumes unit-norm rows, which pooling / whitening / QE all produce)
+        aps = _aps_from_counts(db, qn, bn)
         scores = None
     else:
         scores = matmul(qn, bn)
@@ -351,6 +381,8 @@ def test_dir_main(argv=None):
     parser.add_argument("--adba", type=float, nargs="+", help="alpha-database augmentation parameters: k alpha")
     parser.add_argument("--rank-topk", type=int, default=0,
                         help="(extension) rank with the exact top-k search (k <= 1024) instead of the dense score matrix")
+    parser.add_argument("--dense-scores", action="store_true",
+                        help="(extension) force the reference's literal matmul + per-query sort instead of GPU rank counts")
     args = parser.parse_args(argv)
     args.iscuda = common.torch_set_gpu(args.gpu)
     aqe = {"k": int(args.aqe[0]), "alpha": args.aqe[1]} if args.aqe is not None else None
@@ -361,7 +393,8 @@ def test_dir_main(argv=None):
     whiten = _select_pca(net, args)
     res = eval_model(dataset, net, args.trfs, pooling=args.pooling, gemp=args.gemp, detailed=args.detailed,
                      threads=args.threads, dbg=args.dbg, whiten=whiten, aqe=aqe, adba=adba,
-                     save_feats=args.save_feats, load_feats=args.load_feats, rank_topk=args.rank_topk)
+                     save_feats=args.save_feats, load_feats=args.load_feats, rank_topk=args.rank_topk,
+                     dense_scores=args.dense_scores)
     # (the reference's '%s = %g' line raises on the list-valued entries that --detailed adds; print scalars only)
     print(" * " + "\n * ".join(["%s = %g" % p for p in res.items() if isinstance(p[1], (int, float))]))
     if args.out_json:

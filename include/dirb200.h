@@ -206,6 +206,25 @@ int dirb200_index_last_stats(dirb200_index* idx, int64_t stats[5]);
 int dirb200_index_last_profile(dirb200_index* idx, double out9[9]);
 int dirb200_index_destroy(dirb200_index* idx);
 
+/* Rank statistics for AP without the Q x N score matrix (replaces the per-query np.argsort of generic.py:207,221 +
+ * junk removal :204-206,216-221 as far as the positions of the labelled rows are concerned).  Targets = the labelled
+ * rows of each query, grouped by query: t_off[Q+1] (CSR), t_q[T] (query of target t), t_rows[T] GLOBAL database
+ * indices, t_flags[T] (1 = count the rows ranking before this target - the positives; 0 = score only - junk rows).
+ *   dirb200_index_target_scores: t_score_dev[t] = exact score <q, db[row]> for rows this shard owns, 0 otherwise
+ *                                (several shards: SUM all-reduce of t_score_dev, 8*T bytes).
+ *   dirb200_index_rank_count:    above_dev[t] = number of rows OF THIS SHARD that rank before target t under the
+ *                                order of dirb200_index_search (exact score desc, ties -> lower global index), for
+ *                                flagged targets (several shards: SUM all-reduce of above_dev).  t_score_dev must hold
+ *                                the complete scores.  One tensor-core pass; queries whose candidate list overflows
+ *                                ("count_cap", default 32768 rows scoring above their lowest positive) are counted
+ *                                exactly from the fp32 rows instead (last_stats[3] = number of such queries).
+ *                                Synchronises the stream.  Rows are assumed unit-norm (option "eps16"). */
+int dirb200_index_target_scores(dirb200_index* idx, const float* q32_dev, int Q, const int* t_q_dev,
+                                const int64_t* t_rows_dev, int T, double* t_score_dev, void* stream);
+int dirb200_index_rank_count(dirb200_index* idx, const float* q32_dev, int Q, const int* t_off_host, const int* t_off_dev,
+                             const int64_t* t_rows_dev, const unsigned char* t_flags_dev, const double* t_score_dev,
+                             int T, int64_t* above_dev, void* stream);
+
 /* Merge G per-shard top-k lists (scores fp64 + global indices int64, as produced by an all-gather of
  * dirb200_index_search outputs) into the global top-k with the same ordering rule.  Shard g's [Q][k] block starts
  * shard_stride elements after shard g-1's (0 = dense [G][Q][k]); a packed all-gather buffer [G][2][Q][k] uses

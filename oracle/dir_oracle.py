@@ -281,6 +281,21 @@ def ap_from_positive_ranks(pos_ranks_with_junk_removed):
     return average_precision(np.sort(np.asarray(pos_ranks_with_junk_removed)))
 
 
+def rank_counts(Q, DB, t_off, t_rows):
+    """What the ranking of generic.py:207,221 says about the labelled rows only: for target t of query q the exact
+    score and the number of database rows that come before it in rank_desc (score desc, ties -> lower index)."""
+    sc_out = np.zeros(len(t_rows), dtype=np.float64)
+    above = np.zeros(len(t_rows), dtype=np.int64)
+    for q in range(len(t_off) - 1):
+        row = scores_exact(np.asarray(Q)[q:q + 1], DB)[0]
+        for t in range(t_off[q], t_off[q + 1]):
+            r = int(t_rows[t])
+            s = row[r]
+            sc_out[t] = s
+            above[t] = int((row > s).sum() + (row[:r] == s).sum())
+    return sc_out, above
+
+
 def mean_ap(scores, gnd):
     """test_dir.py:153-159: mean over queries with AP >= 0."""
     aps = [eval_query_ap(scores[q], g["ok"], g["junk"]) for q, g in enumerate(gnd)]

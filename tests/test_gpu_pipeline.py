@@ -154,6 +154,65 @@ def test_cli_end_to_end(tmp_path, monkeypatch, capsys):
     assert res2["mAP"] == ref2
 
 
+def test_cli_hard_variant_matches_reference_command_lines(tmp_path, monkeypatch, capsys, golden):
+    """The HARD synthetic dataset (mAP 0.78: negatives outrank positives, a ranking that can differ) through the GPU
+    command lines, against what the reference's OWN command lines printed (tests/golden/cli_hard.npz): plain, dense
+    scores, --aqe, --adba, the revisited protocol (--dataset ROxford5K) and the three-scale protocol."""
+    _gpu()
+    import pickle
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import e2e_data
+    g = golden("cli_hard.npz")
+    root = str(tmp_path)
+    gnd, names, qn, sd = e2e_data.build(root, hard=True)
+    assert len(names) == int(g["n_images"])
+    xs = e2e_data.load_normalised(root, names)
+    with torch.no_grad():
+        D = np.stack([O.extract(x, sd, "resnet50_rmac").numpy() for x in xs])
+    mean = D.astype(np.float64).mean(0)       # the reference run's fitted PCA, rebuilt as in tests/test_oracle_golden.py
+    pca = SimpleNamespace(mean_=mean.astype(np.float32), whiten=True, explained_variance_=g["pca_var"],
+                          components_=(g["pca_coeff"] @ (D.astype(np.float64) - mean)).astype(np.float32))
+    ckpt = os.path.join(root, "ckpt.pt")
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()},
+                "model_options": dict(arch="resnet50_rmac", out_dim=2048, pooling="gem", gemp=3),
+                "pca": {"Landmarks_clean": pca}}, ckpt)
+    gnd_r = [{"bbx": g_["bbx"], "easy": [g_["ok"][0], g_["ok"][2]], "hard": [g_["ok"][1]], "junk": g_["junk"]} for g_ in gnd]
+    gnd_r[3]["easy"], gnd_r[3]["hard"] = gnd[3]["ok"], []
+    with open(os.path.join(root, "oxford5k", "gnd_roxford5k.pkl"), "wb") as f:
+        pickle.dump({"imlist": names, "qimlist": [names[i] for i in qn], "gnd": gnd_r}, f)
+    monkeypatch.setenv("DB_ROOT", root)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    from dirtorch import test_dir
+    common_args = ["--checkpoint", ckpt, "--whiten", "Landmarks_clean", "--whitenp", "0.25", "--gpu", "0", "--threads", "2"]
+    saved = os.path.join(root, "saved")
+    res = test_dir.test_dir_main(["--dataset", "Oxford5K"] + common_args + ["--save-feats", saved, "--detailed"])
+    np.testing.assert_allclose(res["APs"], g["APs"], rtol=0, atol=1e-12)             # GPU rank counts (default path)
+    assert abs(res["mAP"] - float(g["mAP"])) < 1e-12
+    assert str(g["console"][0]) in capsys.readouterr().out                          # the reference's literal line
+    assert rel_l2(np.load(os.path.join(saved, "feats.bdescs.npy"))[:3], g["desc_head"]) < 1e-3
+    res_d = test_dir.test_dir_main(["--dataset", "Oxford5K"] + common_args + ["--load-feats", saved, "--detailed", "--dense-scores"])
+    np.testing.assert_allclose(res_d["APs"], g["APs"], rtol=0, atol=1e-12)           # literal matmul + sort
+    res_k = test_dir.test_dir_main(["--dataset", "Oxford5K"] + common_args + ["--load-feats", saved, "--rank-topk", "8"])
+    assert abs(res_k["mAP"] - float(g["mAP"])) < 1e-12
+    res_a = test_dir.test_dir_main(["--dataset", "Oxford5K"] + common_args + ["--load-feats", saved, "--aqe", "2", "1"])
+    assert abs(res_a["mAP"] - float(g["mAP_aqe_k2_a1"])) < 1e-12
+    res_b = test_dir.test_dir_main(["--dataset", "Oxford5K"] + common_args + ["--load-feats", saved, "--adba", "2", "1"])
+    assert abs(res_b["mAP"] - float(g["mAP_adba_k2_a1"])) < 1e-12
+    capsys.readouterr()
+    res_r = test_dir.test_dir_main(["--dataset", "ROxford5K"] + common_args + ["--load-feats", saved])
+    for mode in ("easy", "medium", "hard"):
+        assert abs(res_r["mAP-" + mode] - float(g["rox_" + mode])) < 1e-12, mode
+    out = capsys.readouterr().out
+    assert all(str(l) in out for l in g["rox_console"])
+    res_m = test_dir.test_dir_main(["--dataset", "Oxford5K"] + common_args +
+                                   ["--trfs", "Scale(0.7)", "", "Scale(1.4)", "--pooling", "gem", "--gemp", "3",
+                                    "--save-feats", os.path.join(root, "saved_ms"), "--detailed"])
+    np.testing.assert_allclose(res_m["APs"], g["ms_APs"], rtol=0, atol=1e-12)
+    assert abs(res_m["mAP"] - float(g["ms_mAP"])) < 1e-12
+    assert rel_l2(np.load(os.path.join(root, "saved_ms", "feats.bdescs.npy"))[:3], g["ms_desc_head"]) < 1e-3
+
+
 def test_batched_extraction_with_crop_chain(tmp_path, golden):
     """test_dir.extract_image_features with same_size=True, batch_size=4 (the 'Pad'/'Crop' branch of test_dir.py:114)
     through 'Scale(140), CenterCrop(128)' vs the reference's descriptors (tests/golden/transforms.npz)."""

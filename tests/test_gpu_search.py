@@ -358,3 +358,102 @@ def test_two_phase_search_with_a_shard_smaller_than_its_quota():
     rs, ri = O.topk(q, full, k)
     np.testing.assert_array_equal(mi.cpu().numpy(), ri)
     np.testing.assert_allclose(ms.cpu().numpy(), rs, rtol=0, atol=1e-12)
+
+
+def _targets(pos, n_db, n_junk, seed):
+    gnd = synth.oxford_gt(pos, n_junk=n_junk, n_db=n_db, seed=seed)
+    offs, rows, flags = [0], [], []
+    for g in gnd:
+        r = sorted(set(g["ok"]) | set(g["junk"]))
+        rows += r
+        flags += [1 if x in set(g["ok"]) else 0 for x in r]
+        offs.append(len(rows))
+    return gnd, np.array(offs, np.int32), np.array(rows, np.int64), np.array(flags, np.uint8)
+
+
+def test_rank_counts_match_oracle():
+    """dirb200_index_rank_count: exact score and number of rows ranking before every positive == the oracle's reading
+    of the full ranking, with exact ties (duplicated rows), through the tensor-core pass, through the exact fallback
+    (tiny count_cap) and summed over shards; AP from the counts == AP from the score rows."""
+    ops = _ops()
+    db, q, pos = synth.make_descriptor_db(20000, 9, dim=256, n_pos=8, db_seed=41, q_seed=42)
+    db[15000] = db[pos[0, 2]]                      # a duplicate of a positive AFTER it: ranks behind it
+    db[3] = db[pos[1, 4]]                          # and one BEFORE a positive (lower index wins the tie)
+    gnd, offs, rows, flags = _targets(pos, 20000, 5, 7)
+    ref_s, ref_a = O.rank_counts(q, db, offs, rows)
+    qd = torch.from_numpy(q).to(DEV)
+    index = ops.Index(torch.from_numpy(db).to(DEV))
+    sc, above = index.rank_counts(qd, offs, rows, flags)
+    m = flags == 1
+    np.testing.assert_allclose(sc.cpu().numpy(), ref_s, rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(above.cpu().numpy()[m], ref_a[m])
+    assert index.stats()["retries"] == 0           # no query needed the exact fallback
+    # exact fallback: a candidate capacity far below the depth of the deepest positive (cos 0.15 of 20000 rows)
+    index.set_option("count_cap", 1024)
+    deep = q.copy()
+    deep_db = db.copy()
+    deep_db[pos[2, 7]] = db[11]                    # a 'positive' that is just a random row: ~half the database outranks it
+    idx2 = ops.Index(torch.from_numpy(deep_db).to(DEV))
+    idx2.set_option("count_cap", 1024)
+    sc2, above2 = idx2.rank_counts(qd, offs, rows, flags)
+    r2s, r2a = O.rank_counts(deep, deep_db, offs, rows)
+    np.testing.assert_array_equal(above2.cpu().numpy()[m], r2a[m])
+    assert idx2.stats()["retries"] >= 1 and int(r2a[m].max()) > 5000
+    # two shards: scores from the owning shard, counts add up
+    a_idx = ops.Index(torch.from_numpy(db[:7000]).to(DEV), index_offset=0)
+    b_idx = ops.Index(torch.from_numpy(db[7000:]).to(DEV), index_offset=7000)
+    t_q = torch.from_numpy(np.repeat(np.arange(9, dtype=np.int32), np.diff(offs))).to(DEV)
+    rows_d, flags_d = torch.from_numpy(rows).to(DEV), torch.from_numpy(flags).to(DEV)
+    s_sum = a_idx.target_scores(qd, t_q, rows_d) + b_idx.target_scores(qd, t_q, rows_d)
+    assert torch.equal(s_sum, sc)
+    ab = a_idx.rank_count(qd, offs, rows_d, flags_d, s_sum) + b_idx.rank_count(qd, offs, rows_d, flags_d, s_sum)
+    np.testing.assert_array_equal(ab.cpu().numpy()[m], ref_a[m])
+    # AP from the counts == AP from the exact score row (generic.py:196-224)
+    for i, g in enumerate(gnd):
+        sl = slice(offs[i], offs[i + 1])
+        at = {int(r): j for j, r in enumerate(rows[sl])}
+        js = np.array([ref_s[sl][at[j]] for j in g["junk"]])
+        ranks = []
+        for p in g["ok"]:
+            sp = ref_s[sl][at[p]]
+            before = int(((js > sp) | ((js == sp) & (np.array(g["junk"]) < p))).sum())
+            ranks.append(int(above.cpu().numpy()[sl][at[p]]) - before)
+        ap = O.average_precision(np.sort(np.array(ranks)))
+        assert abs(ap - O.eval_query_ap(O.scores_exact(q[i:i + 1], db)[0], g["ok"], g["junk"])) < 1e-12
+
+
+def test_rank_counts_1m_rows():
+    """1M x 2048 synthetic database with planted positives (cosines 0.8 .. 0.15): counts for 16 queries vs the CPU
+    oracle (chunked fp64 scores), without any Q x N matrix on either side."""
+    ops = _ops()
+    N, Q, D, P = 1_000_000, 16, 2048, 10
+    g = torch.Generator(device="cuda").manual_seed(21)
+    db = ops.l2_normalize(torch.randn((N, D), generator=g, device="cuda"))
+    q = ops.l2_normalize(torch.randn((Q, D), generator=g, device="cuda"))
+    rows = (torch.arange(Q * P, device="cuda") * 6151 + 17) % N
+    cos = torch.linspace(0.8, 0.15, P, device="cuda").repeat(Q)
+    noise = torch.randn((Q * P, D), generator=g, device="cuda")
+    qq = q.repeat_interleave(P, dim=0)
+    noise = noise - (noise * qq).sum(1, keepdim=True) * qq
+    noise = noise / noise.norm(dim=1, keepdim=True)
+    db[rows] = ops.l2_normalize((cos[:, None] * qq + torch.sqrt(1 - cos * cos)[:, None] * noise).contiguous())
+    offs = np.arange(Q + 1, dtype=np.int32) * P
+    rows_h = rows.cpu().numpy().astype(np.int64)
+    order = np.concatenate([np.argsort(rows_h[i * P:(i + 1) * P]) + i * P for i in range(Q)])
+    rows_h = rows_h[order]
+    index = ops.Index(db)
+    sc, above = index.rank_counts(q, offs, rows_h, np.ones(Q * P, np.uint8))
+    assert index.stats()["retries"] == 0
+    # oracle: chunked fp64 scores, counts per target
+    qs = q.cpu().numpy().astype(np.float64)
+    ts = np.array([qs[t // P] @ db[int(rows_h[t])].cpu().numpy().astype(np.float64) for t in range(Q * P)])
+    np.testing.assert_allclose(sc.cpu().numpy(), ts, rtol=0, atol=1e-12)
+    cnt = np.zeros(Q * P, dtype=np.int64)
+    for c0 in range(0, N, 125_000):
+        blk = db[c0:c0 + 125_000].cpu().numpy().astype(np.float64)
+        s_blk = qs @ blk.T
+        idx_blk = np.arange(c0, c0 + blk.shape[0])
+        for t in range(Q * P):
+            row = s_blk[t // P]
+            cnt[t] += int((row > ts[t]).sum() + ((row == ts[t]) & (idx_blk < rows_h[t])).sum())
+    np.testing.assert_array_equal(above.cpu().numpy(), cnt)

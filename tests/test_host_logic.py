@@ -63,6 +63,31 @@ def test_ap_from_ranked_prefix_equals_ap_from_scores(golden, tmp_path):
             assert short is None or (isinstance(short, dict) and any(v is None for v in short.values())) or worst == 0
 
 
+def test_ap_from_rank_counts_equals_ap_from_scores(golden, tmp_path):
+    """eval_query_AP_from_counts (what the GPU counting kernel feeds) == eval_query_AP on the golden score rows, classic
+    and revisited protocols; the counts come from the oracle's restatement of the ranking (O.rank_counts)."""
+    g = golden("rank_ap.npz")
+    for revisited in (False, True):
+        ds, db, q = _gt_dataset(tmp_path, g, revisited=revisited)
+        offs, rows, flags = [0], [], []
+        for i in range(6):
+            r, f = ds.rank_targets(i)
+            rows.append(r)
+            flags.append(f)
+            offs.append(offs[-1] + len(r))
+        rows = np.concatenate(rows)
+        sc, above = O.rank_counts(q, db, offs, rows)
+        for i in range(6):
+            sl = slice(offs[i], offs[i + 1])
+            ap = ds.eval_query_AP_from_counts(i, rows[sl], sc[sl], above[sl])
+            ref = ds.eval_query_AP(i, O.scores_exact(q[i:i + 1], db)[0])
+            if revisited:
+                assert ap.keys() == ref.keys() and all(abs(ap[m] - ref[m]) < 1e-12 for m in ap)
+                assert abs(ap["easy"] - g["aps_easy"][i]) < 1e-12
+            else:
+                assert abs(ap - ref) < 1e-12 and abs(ap - g["aps"][i]) < 1e-12
+
+
 def test_label_datasets_ap_matches_reference(golden, tmp_path):
     """Label-based AP / top-k (dataset.py:69-101) on labelled image lists (generic.py:44-105) vs the reference."""
     from dirtorch import datasets as D
