@@ -226,7 +226,7 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
   DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
                "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
   DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
-  if (g_conv_halo && s.KH == 3 && s.KW == 3 && s.stride == 1 && s.pad == 1 && s.H >= 16 && s.W >= 8 && res == nullptr) {
+  if (g_conv_halo && s.KH == 3 && s.KW == 3 && s.stride == 1 && s.pad == 1 && s.H >= 16 && s.W >= 8) {
     // halo slots (input prefetch depth): short tiles need more patches in flight to cover the HBM latency
     if (s.Cout == 64 && s.Cin == 64) return conv_halo_bn<64, 9, true, 4>(s, in, w, scale, shift, res, relu, out, stream);
     if (s.Cout % 256 == 0) return conv_halo_bn<256, 4, false, 2>(s, in, w, scale, shift, res, relu, out, stream);

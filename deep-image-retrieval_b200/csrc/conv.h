@@ -47,6 +47,16 @@ int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float
                     const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
                     cudaStream_t stream);
 
+// The pieces of head_pool_fc_l2, for heads that pool several maps side by side (FPN): see ops.cu.
+int head_pool(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features, float* partial,
+              float* g, int g_ld, int col_off, cudaStream_t stream);
+int head_fc_l2(const float* g, int B, int C, const float* fc_w, const float* fc_b, int out_dim, float* y, float* desc,
+               __half* desc16, cudaStream_t stream);
+size_t head_partial_floats(int B, int HW, int C);
+// x4 += nearest-upsampled t (FPN lateral connection, rmac_resnet_fpn.py:56-60); NHWC fp16, out may alias x4.
+int upsample_add(const __half* x4, const __half* t, __half* out, int B, int H, int W, int h, int w, int C,
+                 cudaStream_t stream);
+
 int pool_scales(const float* xs, int S, int64_t N, int D, int mode, float gemp, int l2, float* out,
                 cudaStream_t stream);
 int l2_normalize(const float* x, int64_t N, int D, float eps, float* out, __half* out16, cudaStream_t stream);

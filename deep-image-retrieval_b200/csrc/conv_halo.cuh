@@ -71,6 +71,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
+    if (p.has_res) tma_prefetch_desc(&tmR);
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], PersThreads<0>::EPI_WARPS); }
@@ -118,6 +119,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&a_empty[sa], ((ga / NA) & 1) ^ 1);
           mbar_expect_tx(&a_full[sa], L::HALO_DATA);
           tma_load_4d(smem + sa * L::HALO_SLOT, &tmA, &a_full[sa], kc * 64, c.wo0 - 1, c.ho0 - 1, c.n0);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0 && p.has_res) {
+      // ------------------------------------------------------------ residual producer (BasicBlock conv2: 3x3 + BN +
+      // residual, resnet.py:27-41): the same protocol as warp 2 of conv_pers_kernel, run by the otherwise idle
+      // TMEM-allocator warp
+      constexpr int CHUNKS = BN / 64;
+      uint32_t cc = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t);
+        for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
+          const int b = cc % NB;
+          mbar_wait(&res_empty[b], ((cc / NB) & 1) ^ 1);
+          mbar_expect_tx(&res_full[b], L::STG_BYTES);
+          tma_load_4d(stg + b * L::STG_BYTES, &tmR, &res_full[b], c.n_tile * BN + ch * 64, c.wo0, c.ho0, c.n0);
         }
       }
     }

@@ -103,6 +103,16 @@ struct dirb200_net {
   Profiler prof;
   float mean_std[6] = {0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f};   // preprocess of resnet.py:110-111
   int fuse_ds = 1;                // fuse the projection shortcut into conv3 of block 0 (tcgen05 path only)
+  // trunk / head variants (rmac_resnet.py:74-88, rmac_resnet_fpn.py:92-110)
+  bool basic = false;             // BasicBlock trunk (resnet18): two 3x3 convolutions per block, expansion 1
+  int expansion = 4;
+  int stage_ch[5] = {64, 256, 512, 1024, 2048};   // channels of the output of stage 0..4
+  int fpn = 0;                    // FPN head: GeM of layer3 (after the lateral merge in mode 1) and of layer4, concatenated
+  int fpn_mode = 1;               // rmac_resnet_fpn.py:27-30,55-62: 1 = lateral 1x1 + upsample-add + 3x3 smoothing, 0 = none
+  float gem_p4 = 3.0f;            // adpoolc4.p (layer3 map); gem_p holds adpoolx5.p (layer4 map) for FPN heads
+  ConvLayer fpn_lat, fpn_smooth;  // conv1x5 (1x1, C4 -> C3), conv3c4 (3x3, C3 -> C3): no BN, ReLU after each
+  int feat_in() const { return fpn ? stage_ch[3] + stage_ch[4] : stage_ch[4]; }     // fc.in_features
+  int desc_dim() const { return without_fc ? feat_in() : out_dim; }
   int sub[5] = {0, 0, 0, 0, 0};   // images per sub-chunk of stage 0..4 (0 = auto)
   int stage_sched = 0;            // 0 = every stage over the whole chunk (fastest measured), 1 = per-stage sub-chunks
   // pipelined host entry point
@@ -190,6 +200,31 @@ static int pack_conv(dirb200_net* n, ConvLayer& L) {
   return 0;
 }
 
+// Convolution without BatchNorm (FPN lateral / smoothing convs): scale = 1, shift = 0.
+static int pack_conv_plain(dirb200_net* n, ConvLayer& L) {
+  const HostTensor* w;
+  const size_t kk = static_cast<size_t>(L.K) * L.K;
+  DIRB_TRY(get_tensor(n, L.conv + ".weight", &w, static_cast<size_t>(L.Cout) * L.Cin * kk));
+  L.CinPad = L.Cin;
+  const int Ktot = L.K * L.K * L.CinPad;
+  L.Kpad = (Ktot + 31) / 32 * 32;
+  std::vector<__half> hw(static_cast<size_t>(L.Cout) * L.Kpad, __float2half(0.f));
+  for (int o = 0; o < L.Cout; ++o)
+    for (int c = 0; c < L.Cin; ++c)
+      for (int kh = 0; kh < L.K; ++kh)
+        for (int kw = 0; kw < L.K; ++kw)
+          hw[static_cast<size_t>(o) * L.Kpad + (static_cast<size_t>(kh) * L.K + kw) * L.CinPad + c] =
+              __float2half_rn(w->data[((static_cast<size_t>(o) * L.Cin + c) * L.K + kh) * L.K + kw]);
+  std::vector<float> sc(L.Cout, 1.0f), sh(L.Cout, 0.0f);
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&L.w), hw.size() * sizeof(__half)));
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&L.scale), L.Cout * sizeof(float)));
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&L.shift), L.Cout * sizeof(float)));
+  DIRB_CUDA(cudaMemcpy(L.w, hw.data(), hw.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  DIRB_CUDA(cudaMemcpy(L.scale, sc.data(), L.Cout * sizeof(float), cudaMemcpyHostToDevice));
+  DIRB_CUDA(cudaMemcpy(L.shift, sh.data(), L.Cout * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 static ConvLayer make_layer(const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride,
                             int pad) {
   ConvLayer L;
@@ -222,13 +257,32 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out) {
   auto* n = new dirb200_net();
   n->device = device;
   n->arch = arch;
-  if (n->arch == "resnet50_rmac") n->nblocks = {3, 4, 6, 3};          // rmac_resnet.py:80
-  else if (n->arch == "resnet101_rmac") n->nblocks = {3, 4, 23, 3};   // rmac_resnet.py:84
-  else if (n->arch == "resnet152_rmac") n->nblocks = {3, 8, 36, 3};   // rmac_resnet.py:88
-  else {
-    delete n;
-    DIRB_REQUIRE(false, DIRB200_ENOTSUP, "unknown model architecture '%s' (supported: resnet50_rmac, resnet101_rmac, resnet152_rmac)", arch);
+  // "<trunk>_rmac" (rmac_resnet.py:74-88), "<trunk>_fpn_rmac" / "resnet101_fpn0_rmac" (rmac_resnet_fpn.py:92-110)
+  std::string trunk = n->arch;
+  const char* suffixes[3] = {"_fpn0_rmac", "_fpn_rmac", "_rmac"};
+  int which = -1;
+  for (int i = 0; i < 3 && which < 0; ++i) {
+    const std::string suf(suffixes[i]);
+    if (trunk.size() > suf.size() && trunk.compare(trunk.size() - suf.size(), suf.size(), suf) == 0) {
+      trunk = trunk.substr(0, trunk.size() - suf.size());
+      which = i;
+    }
   }
+  n->fpn = (which == 0 || which == 1) ? 1 : 0;
+  n->fpn_mode = (which == 0) ? 0 : 1;
+  if (trunk == "resnet18") { n->nblocks = {2, 2, 2, 2}; n->basic = true; }        // rmac_resnet.py:76
+  else if (trunk == "resnet50") n->nblocks = {3, 4, 6, 3};                         // rmac_resnet.py:80
+  else if (trunk == "resnet101") n->nblocks = {3, 4, 23, 3};                       // rmac_resnet.py:84
+  else if (trunk == "resnet152") n->nblocks = {3, 8, 36, 3};                       // rmac_resnet.py:88
+  const bool known = which >= 0 && !n->nblocks.empty() && !(which == 0 && trunk != "resnet101");
+  if (!known) {
+    delete n;
+    DIRB_REQUIRE(false, DIRB200_ENOTSUP,
+                 "unknown model architecture '%s' (supported: resnet{18,50,101,152}_rmac, resnet{18,50,101,152}_fpn_rmac, "
+                 "resnet101_fpn0_rmac)", arch);
+  }
+  n->expansion = n->basic ? 1 : 4;
+  for (int s = 1; s < 5; ++s) n->stage_ch[s] = (64 << (s - 1)) * n->expansion;
   *out = n;
   return 0;
 }
@@ -237,12 +291,16 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   DIRB_REQUIRE(n && key, DIRB200_EINVAL, "null argument");
   const std::string k(key);
   // options that decide which tensors dirb200_net_finalize reads / packs cannot change afterwards
-  const bool structural = (k == "pooling" || k == "without_fc" || k == "out_dim");
+  const bool structural = (k == "pooling" || k == "without_fc" || k == "out_dim" || k == "fpn_mode");
   DIRB_REQUIRE(!(structural && n->finalized), DIRB200_ESTATE, "option '%s' must be set before dirb200_net_finalize", key);
   if (k == "pooling") n->pooling = static_cast<int>(value);
   else if (k == "norm_features") n->norm_features = value != 0;
   else if (k == "without_fc") n->without_fc = value != 0;
   else if (k == "out_dim") n->out_dim = static_cast<int>(value);
+  else if (k == "fpn_mode") {
+    DIRB_REQUIRE(n->fpn && (value == 0 || value == 1), DIRB200_EINVAL, "fpn_mode is 0 or 1 and only applies to *_fpn_rmac networks");
+    n->fpn_mode = static_cast<int>(value);
+  }
   else if (k == "chunk") n->chunk = static_cast<int>(value);
   else if (k == "conv_impl") n->conv_impl = static_cast<int>(value);
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
@@ -302,6 +360,21 @@ int dirb200_net_finalize(dirb200_net* n) {
       const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(b) + ".";
       const int stride = (li > 0 && b == 0) ? 2 : 1;
       Block blk;
+      const int cout = planes * n->expansion;
+      if (n->basic) {                                                              // resnet.py:15-44
+        blk.c1 = make_layer(p + "conv1", p + "bn1", inplanes, planes, 3, stride, 1);
+        blk.c2 = make_layer(p + "conv2", p + "bn2", planes, planes, 3, 1, 1);
+        blk.has_down = (b == 0) && (stride != 1 || inplanes != cout);              // resnet.py:136-141
+        DIRB_TRY(pack_conv(n, blk.c1));
+        DIRB_TRY(pack_conv(n, blk.c2));
+        if (blk.has_down) {
+          blk.down = make_layer(p + "downsample.0", p + "downsample.1", inplanes, cout, 1, stride, 0);
+          DIRB_TRY(pack_conv(n, blk.down));
+        }
+        n->blocks.push_back(blk);
+        inplanes = cout;
+        continue;
+      }
       blk.c1 = make_layer(p + "conv1", p + "bn1", inplanes, planes, 1, 1, 0);
       blk.c2 = make_layer(p + "conv2", p + "bn2", planes, planes, 3, stride, 1);     // stride on conv2, resnet.py:58
       blk.c3 = make_layer(p + "conv3", p + "bn3", planes, planes * 4, 1, 1, 0);
@@ -314,7 +387,7 @@ int dirb200_net_finalize(dirb200_net* n) {
         DIRB_TRY(pack_conv(n, blk.down));
         // K-concatenated, BN-scaled weights for the fused conv3 + shortcut
         const HostTensor *w3, *wd;
-        const int cout = planes * 4, kcat = planes + inplanes;
+        const int kcat = planes + inplanes;
         DIRB_TRY(get_tensor(n, p + "conv3.weight", &w3, static_cast<size_t>(cout) * planes));
         DIRB_TRY(get_tensor(n, p + "downsample.0.weight", &wd, static_cast<size_t>(cout) * inplanes));
         std::vector<float> s3(cout), sh3(cout), sd(cout), shd(cout);
@@ -341,7 +414,22 @@ int dirb200_net_finalize(dirb200_net* n) {
     }
     n->layer_end.push_back(static_cast<int>(n->blocks.size()));
   }
-  if (n->pooling == 0) {
+  if (n->fpn) {
+    // rmac_resnet_fpn.py:36-43: only the 'gem' branch creates the two pooling layers forward() uses
+    DIRB_REQUIRE(n->pooling == 0, DIRB200_ENOTSUP, "FPN heads support pooling='gem' only (rmac_resnet_fpn.py:36-43,76-77)");
+    const HostTensor *p5, *p4;
+    DIRB_TRY(get_tensor(n, "adpoolx5.p", &p5, 1));
+    DIRB_TRY(get_tensor(n, "adpoolc4.p", &p4, 1));
+    n->gem_p = p5->data[0];
+    n->gem_p4 = p4->data[0];
+    DIRB_REQUIRE(n->gem_p > 0 && n->gem_p4 > 0, DIRB200_EINVAL, "GeM p must be positive");
+    if (n->fpn_mode == 1) {                                                       // rmac_resnet_fpn.py:27-30
+      n->fpn_lat = make_layer("conv1x5", "", n->stage_ch[4], n->stage_ch[3], 1, 1, 0);
+      n->fpn_smooth = make_layer("conv3c4", "", n->stage_ch[3], n->stage_ch[3], 3, 1, 1);
+      DIRB_TRY(pack_conv_plain(n, n->fpn_lat));
+      DIRB_TRY(pack_conv_plain(n, n->fpn_smooth));
+    }
+  } else if (n->pooling == 0) {
     const HostTensor* p;
     DIRB_TRY(get_tensor(n, "adpool.p", &p, 1));                  // pooling.py:54
     n->gem_p = p->data[0];
@@ -349,7 +437,7 @@ int dirb200_net_finalize(dirb200_net* n) {
   }
   if (!n->without_fc) {
     const HostTensor *w, *b;
-    DIRB_TRY(get_tensor(n, "fc.weight", &w, static_cast<size_t>(n->out_dim) * 2048));   // rmac_resnet.py:34
+    DIRB_TRY(get_tensor(n, "fc.weight", &w, static_cast<size_t>(n->out_dim) * n->feat_in()));   // rmac_resnet.py:34, rmac_resnet_fpn.py:46
     DIRB_TRY(get_tensor(n, "fc.bias", &b, n->out_dim));
     DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&n->fc_w), w->data.size() * 4));
     DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&n->fc_b), b->data.size() * 4));
@@ -386,8 +474,6 @@ struct Workspace {
   int h[5], w[5];         // spatial size of the output of stage 0..4
   int sub[5];
 };
-
-const int kStageCh[5] = {64, 256, 512, 1024, 2048};
 }  // namespace
 
 static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w) {
@@ -416,15 +502,23 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
   const size_t o_sws = carve(std::max(static_cast<size_t>(w->sub[0]) * H * W * 8 * 2, stem_workspace_bytes(w->sub[0], H, W)));
   const size_t o_stem = carve(static_cast<size_t>(w->sub[0]) * w->H1 * w->W1 * 64 * 2);
   size_t o_stage[4], o_scr[4];
-  for (int s = 0; s < 4; ++s) o_stage[s] = carve(static_cast<size_t>(chunk) * w->h[s] * w->w[s] * kStageCh[s] * 2);
+  for (int s = 0; s < 4; ++s) o_stage[s] = carve(static_cast<size_t>(chunk) * w->h[s] * w->w[s] * n->stage_ch[s] * 2);
   size_t scr = 0;   // largest tensor inside any stage = the stage's sub-chunk at the stage's INPUT resolution x output channels / or input
   for (int s = 1; s < 5; ++s) {
     const size_t in_px = static_cast<size_t>(w->h[s - 1]) * w->w[s - 1];
-    scr = std::max(scr, static_cast<size_t>(w->sub[s]) * in_px * (kStageCh[s] / 4) * 2);          // conv1 output at input resolution
-    scr = std::max(scr, static_cast<size_t>(w->sub[s]) * w->h[s] * w->w[s] * kStageCh[s] * 2);    // block output
+    scr = std::max(scr, static_cast<size_t>(w->sub[s]) * in_px * (n->stage_ch[s] / 4) * 2);          // conv1 output at input resolution
+    scr = std::max(scr, static_cast<size_t>(w->sub[s]) * w->h[s] * w->w[s] * n->stage_ch[s] * 2);    // block output
   }
+  if (n->fpn)   // the merged / smoothed layer3 map of a stage-4 sub-chunk lives in a scratch tensor
+    scr = std::max(scr, static_cast<size_t>(w->sub[4]) * w->h[3] * w->w[3] * n->stage_ch[3] * 2);
   for (int i = 0; i < 4; ++i) o_scr[i] = carve(scr);
-  const size_t o_head = carve(head_workspace_floats(w->sub[4], w->h[4] * w->w[4], 2048, n->out_dim) * 4);
+  size_t head_floats = head_workspace_floats(w->sub[4], w->h[4] * w->w[4], n->stage_ch[4], n->out_dim);
+  if (n->fpn) {
+    const size_t partial = std::max(head_partial_floats(w->sub[4], w->h[3] * w->w[3], n->stage_ch[3]),
+                                    head_partial_floats(w->sub[4], w->h[4] * w->w[4], n->stage_ch[4]));
+    head_floats = partial + static_cast<size_t>(w->sub[4]) * (n->feat_in() + std::max(n->out_dim, n->feat_in()));
+  }
+  const size_t o_head = carve(head_floats * 4);
   if (off > n->ws_bytes) {
     if (n->ws) DIRB_CUDA(cudaFree(n->ws));
     n->ws = nullptr;
@@ -443,7 +537,7 @@ static int setup_workspace(dirb200_net* n, int chunk, int H, int W, Workspace* w
 // One pass of the network over `cb` images (NCHW fp32 on the device) -> cb descriptors.
 static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, int cb, int H, int W, float* desc_dev,
                      __half* desc16_dev, cudaStream_t stream, const uint8_t* imgs_u8 = nullptr) {
-  const int D = n->without_fc ? 2048 : n->out_dim;
+  const int D = n->desc_dim();
   // ---------------------------------------------------------------- stage 0: stem + maxpool
   for (int b0 = 0; b0 < cb; b0 += w.sub[0]) {
     const int sb = std::min(w.sub[0], cb - b0);
@@ -476,7 +570,7 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
     const __half* stage_in = w.stage_out[s - 1];
     for (int b0 = 0; b0 < cb; b0 += w.sub[s]) {
       const int sb = std::min(w.sub[s], cb - b0);
-      const __half* x = stage_in + static_cast<size_t>(b0) * hi * wi * kStageCh[s - 1];
+      const __half* x = stage_in + static_cast<size_t>(b0) * hi * wi * n->stage_ch[s - 1];
       int h = hi, wd = wi;
       for (int bi = first; bi < last; ++bi) {
         const Block& blk = n->blocks[bi];
@@ -485,7 +579,23 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
         __half* t2 = w.scratch[1];
         __half* rs = w.scratch[2];
         __half* y = (j % 2 == 0) ? w.scratch[3] : w.scratch[2];
-        if (bi == last - 1 && s < 4) y = w.stage_out[s] + static_cast<size_t>(b0) * ho * wo * kStageCh[s];
+        if (bi == last - 1 && s < 4) y = w.stage_out[s] + static_cast<size_t>(b0) * ho * wo * n->stage_ch[s];
+        if (n->basic) {
+          // BasicBlock, resnet.py:27-44: 3x3(stride) + BN + ReLU -> 3x3 + BN -> + (projected) x -> ReLU
+          const int st = blk.c1.stride;
+          const int h2 = (h + 2 - 3) / st + 1, w2 = (wd + 2 - 3) / st + 1;
+          DIRB_TRY(run_conv(n, blk.c1, x, sb, h, wd, nullptr, 1, t1, stream));
+          const __half* res = x;
+          if (blk.has_down) {
+            DIRB_TRY(run_conv(n, blk.down, x, sb, h, wd, nullptr, 0, rs, stream));
+            res = rs;
+          }
+          DIRB_TRY(run_conv(n, blk.c2, t1, sb, h2, w2, res, 1, y, stream));
+          x = y;
+          h = h2;
+          wd = w2;
+          continue;
+        }
         const int st = blk.c2.stride;
         const int h2 = (h + 2 - 3) / st + 1, w2 = (wd + 2 - 3) / st + 1;
         DIRB_TRY(run_conv(n, blk.c1, x, sb, h, wd, nullptr, 1, t1, stream));
@@ -515,18 +625,52 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
         wd = w2;
       }
       if (s == 4) {
-        if (b0 + sb >= cb) DIRB_TRY(record_tap(n, "layer4", x, sb, ho, wo, 2048, stream));
-        ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * 2048.0 * n->out_dim, 2.0 * sb * ho * wo * 2048.0);
+        const int C4 = n->stage_ch[4];
+        if (b0 + sb >= cb) DIRB_TRY(record_tap(n, "layer4", x, sb, ho, wo, C4, stream));
+        if (n->fpn) {
+          // ---- FPN head, rmac_resnet_fpn.py:52-90
+          const int C3 = n->stage_ch[3], h3 = w.h[3], w3 = w.w[3], Ct = C3 + C4;
+          const __half* x4 = w.stage_out[3] + static_cast<size_t>(b0) * h3 * w3 * C3;
+          if (n->fpn_mode == 1) {
+            // relu(conv1x5(upsample(x5))) == upsample(relu(conv1x5(x5))): the 1x1 convolution runs on the small map.
+            // x (layer4 output) sits in scratch[2] or [3]; scratch[0] / [1] are free after the last block.
+            __half* tbuf = w.scratch[0];
+            __half* x4p = w.scratch[1];
+            DIRB_TRY(run_conv(n, n->fpn_lat, x, sb, ho, wo, nullptr, 1, tbuf, stream));
+            {
+              ProfScope ps(n, stream, 2, 0, 2.0 * sb * (2.0 * h3 * w3 + static_cast<double>(ho) * wo) * C3);
+              DIRB_TRY(upsample_add(x4, tbuf, x4p, sb, h3, w3, ho, wo, C3, stream));
+            }
+            DIRB_TRY(run_conv(n, n->fpn_smooth, x4p, sb, h3, w3, nullptr, 1, tbuf, stream));
+            x4 = tbuf;
+            if (b0 + sb >= cb) DIRB_TRY(record_tap(n, "fpn_c4", x4, sb, h3, w3, C3, stream));
+          }
+          ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * static_cast<double>(Ct) * n->out_dim,
+                       2.0 * sb * (static_cast<double>(ho) * wo * C4 + static_cast<double>(h3) * w3 * C3));
+          const size_t partial_floats = std::max(head_partial_floats(w.sub[4], h3 * w3, C3), head_partial_floats(w.sub[4], ho * wo, C4));
+          float* partial = w.head_ws;
+          float* g = partial + partial_floats;
+          float* yv = g + static_cast<size_t>(w.sub[4]) * Ct;
+          DIRB_TRY(head_pool(x4, sb, h3 * w3, C3, 0, n->gem_p4, n->gem_eps, 0, partial, g, Ct, 0, stream));    // torch.cat((x4, x5), 1)
+          DIRB_TRY(head_pool(x, sb, ho * wo, C4, 0, n->gem_p, n->gem_eps, 0, partial, g, Ct, C3, stream));
+          if (n->norm_features) DIRB_TRY(l2_normalize(g, sb, Ct, 1e-12f, g, nullptr, stream));
+          DIRB_TRY(head_fc_l2(g, sb, Ct, n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, yv,
+                              desc_dev + static_cast<size_t>(b0) * D,
+                              desc16_dev ? desc16_dev + static_cast<size_t>(b0) * D : nullptr, stream));
+          if (!n->without_fc) n->last_flops += 2.0 * sb * static_cast<double>(Ct) * n->out_dim;
+          continue;
+        }
+        ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * static_cast<double>(C4) * n->out_dim, 2.0 * sb * ho * wo * static_cast<double>(C4));
         if (n->center_bias > 0.0f)   // x is a scratch buffer whose only remaining reader is the pooling below
-          DIRB_TRY(center_bias(const_cast<__half*>(x), sb, ho, wo, 2048, n->center_bias, stream));
-        DIRB_TRY(head_pool_fc_l2(x, sb, ho * wo, 2048, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
+          DIRB_TRY(center_bias(const_cast<__half*>(x), sb, ho, wo, C4, n->center_bias, stream));
+        DIRB_TRY(head_pool_fc_l2(x, sb, ho * wo, C4, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
                                  n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, w.head_ws,
                                  desc_dev + static_cast<size_t>(b0) * D,
                                  desc16_dev ? desc16_dev + static_cast<size_t>(b0) * D : nullptr, stream));
-        if (!n->without_fc) n->last_flops += 2.0 * sb * 2048.0 * n->out_dim;
+        if (!n->without_fc) n->last_flops += 2.0 * sb * static_cast<double>(C4) * n->out_dim;
       }
     }
-    if (s < 4) DIRB_TRY(record_tap(n, "layer" + std::to_string(s), w.stage_out[s], cb, ho, wo, kStageCh[s], stream));
+    if (s < 4) DIRB_TRY(record_tap(n, "layer" + std::to_string(s), w.stage_out[s], cb, ho, wo, n->stage_ch[s], stream));
     first = last;
   }
   return 0;
@@ -548,7 +692,7 @@ int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int
   n->last_flops = 0;
   n->prof.reset();
   const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
-  const int D = n->without_fc ? 2048 : n->out_dim;
+  const int D = n->desc_dim();
   Workspace w;
   DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
   for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -583,7 +727,7 @@ int dirb200_net_forward_u8(dirb200_net* n, const uint8_t* imgs_dev, int B, int H
   n->last_flops = 0;
   n->prof.reset();
   const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
-  const int D = n->without_fc ? 2048 : n->out_dim;
+  const int D = n->desc_dim();
   Workspace w;
   DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
   for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -626,7 +770,7 @@ static int forward_host_impl(dirb200_net* n, const void* imgs_host_, int is_u8, 
   const int chunk = *std::max_element(sizes.begin(), sizes.end());
   const size_t img_bytes = static_cast<size_t>(3) * H * W * (is_u8 ? 1 : 4);
   const size_t in_bytes = 2 * static_cast<size_t>(chunk) * img_bytes;
-  const int D = n->without_fc ? 2048 : n->out_dim;
+  const int D = n->desc_dim();
   const size_t out_bytes = static_cast<size_t>(B) * D * 4;
   if (in_bytes > n->h2d_bytes) {
     if (n->h2d) DIRB_CUDA(cudaFree(n->h2d));

@@ -142,11 +142,13 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return t;
 }
 
-// one block per image: finish the pooling, optional L2 over channels.
+// one block per image: finish the pooling, optional L2 over channels.  The pooled vector goes to columns
+// [col_off, col_off + C) of row b of g (row length g_ld): two feature maps can be pooled side by side (FPN head).
 __global__ void head_pool_final_kernel(const float* __restrict__ partial, float* __restrict__ g, int HW, int C, int S,
-                                       int pooling, float p, int norm_features) {
+                                       int pooling, float p, int norm_features, int g_ld, int col_off) {
   __shared__ float sh[32];
   const int b = blockIdx.x;
+  float* grow = g + static_cast<int64_t>(b) * g_ld + col_off;
   float ss = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float r = partial[(static_cast<int64_t>(b) * S) * C + c];
@@ -156,13 +158,13 @@ __global__ void head_pool_final_kernel(const float* __restrict__ partial, float*
     }
     if (pooling == 0) r = powf(r / static_cast<float>(HW), 1.0f / p);
     else if (pooling == 2) r = r / static_cast<float>(HW);
-    g[static_cast<int64_t>(b) * C + c] = r;
+    grow[c] = r;
     ss += r * r;
   }
   if (norm_features) {
     const float tot = block_sum(ss, sh);
     const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) g[static_cast<int64_t>(b) * C + c] *= inv;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) grow[c] *= inv;
   }
 }
 
@@ -225,23 +227,31 @@ static int head_splits(int B, int HW, int C) {
   return max(1, min(16, HW / 64));
 }
 
+size_t head_partial_floats(int B, int HW, int C) { return static_cast<size_t>(B) * head_splits(B, HW, C) * C; }
+
 size_t head_workspace_floats(int B, int HW, int C, int out_dim) {
   return static_cast<size_t>(B) * head_splits(B, HW, C) * C + static_cast<size_t>(B) * C +
          static_cast<size_t>(B) * (out_dim > C ? out_dim : C);
 }
 
-int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features,
-                    const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
-                    cudaStream_t stream) {
+// Global pooling of one NHWC map into g[b][col_off .. col_off + C) (rows of g_ld floats); `partial` = B * S * C floats.
+int head_pool(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features, float* partial,
+              float* g, int g_ld, int col_off, cudaStream_t stream) {
   DIRB_REQUIRE(C % 8 == 0 && C % 4 == 0, DIRB200_ENOTSUP, "head needs C %% 8 == 0");
   DIRB_REQUIRE(pooling >= 0 && pooling <= 2, DIRB200_EINVAL, "pooling mode %d", pooling);
   const int S = head_splits(B, HW, C);
-  float* partial = ws;
-  float* g = partial + static_cast<size_t>(B) * S * C;
-  float* y = g + static_cast<size_t>(B) * C;
   dim3 g1((unsigned)ceil_div(C, 256), (unsigned)S, (unsigned)B);
   head_pool_partial_kernel<<<g1, 256, 0, stream>>>(feat, partial, HW, C, S, pooling, p, eps);
-  head_pool_final_kernel<<<B, 256, 0, stream>>>(partial, g, HW, C, S, pooling, p, norm_features);
+  head_pool_final_kernel<<<B, 256, 0, stream>>>(partial, g, HW, C, S, pooling, p, norm_features, g_ld, col_off);
+  count_launch(2);
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Pooled features g [B][C] -> (fc + bias) -> L2 -> desc [B][D] (+ fp16 copy); y = B * out_dim floats of scratch.
+int head_fc_l2(const float* g, int B, int C, const float* fc_w, const float* fc_b, int out_dim, float* y, float* desc,
+               __half* desc16, cudaStream_t stream) {
+  DIRB_REQUIRE(C % 4 == 0, DIRB200_ENOTSUP, "head needs C %% 4 == 0");
   const float* pre = g;
   int D = C;
   if (fc_w != nullptr) {
@@ -252,7 +262,60 @@ int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float
     D = out_dim;
   }
   l2_rows_kernel<<<B, 256, 0, stream>>>(pre, desc, desc16, D, 1e-12f);
-  count_launch(3);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features,
+                    const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
+                    cudaStream_t stream) {
+  const int S = head_splits(B, HW, C);
+  float* partial = ws;
+  float* g = partial + static_cast<size_t>(B) * S * C;
+  float* y = g + static_cast<size_t>(B) * C;
+  DIRB_TRY(head_pool(feat, B, HW, C, pooling, p, eps, norm_features, partial, g, C, 0, stream));
+  return head_fc_l2(g, B, C, fc_w, fc_b, out_dim, y, desc, desc16, stream);
+}
+
+// FPN lateral connection (rmac_resnet_fpn.py:56-60): x4[b][y][x][:] += t[b][sy][sx][:], (sy, sx) = nearest-neighbour
+// source of (y, x) as F.interpolate(mode='nearest', size=(H,W)) picks it: min(floor(dst * in / out), in - 1) with the
+// ratio in fp32.  t is the 1x1-reduced, ReLU-ed layer4 map: the 1x1 convolution commutes with the upsampling, so it
+// runs on the small map.  out may alias x4.  8 channels per thread.
+__global__ void upsample_add_kernel(const __half* __restrict__ x4, const __half* __restrict__ t, __half* __restrict__ out,
+                                    int H, int W, int h, int w, int C8, float sy, float sx, int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % C8);
+  int64_t r = i / C8;
+  const int x = static_cast<int>(r % W);
+  r /= W;
+  const int y = static_cast<int>(r % H);
+  const int64_t b = r / H;
+  const int yy = min(static_cast<int>(floorf(static_cast<float>(y) * sy)), h - 1);
+  const int xx = min(static_cast<int>(floorf(static_cast<float>(x) * sx)), w - 1);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(x4) + i);
+  const uint4 bv = __ldg(reinterpret_cast<const uint4*>(t) + ((b * h + yy) * w + xx) * C8 + c8);
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&bv);
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+    ho[e] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+  }
+  reinterpret_cast<uint4*>(out)[i] = o;
+}
+
+int upsample_add(const __half* x4, const __half* t, __half* out, int B, int H, int W, int h, int w, int C,
+                 cudaStream_t stream) {
+  DIRB_REQUIRE(C % 8 == 0, DIRB200_ENOTSUP, "upsample_add needs C %% 8 == 0 (got %d)", C);
+  const int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  if (total == 0) return 0;
+  upsample_add_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, stream>>>(
+      x4, t, out, H, W, h, w, C / 8, static_cast<float>(h) / static_cast<float>(H), static_cast<float>(w) / static_cast<float>(W), total);
+  count_launch();
   DIRB_CUDA(cudaGetLastError());
   return 0;
 }

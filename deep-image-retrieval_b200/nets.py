@@ -24,16 +24,24 @@ from . import lib
 RGB_MEANS = [0.485, 0.456, 0.406]            # resnet.py:110-111
 RGB_STDS = [0.229, 0.224, 0.225]
 
-_ARCH_BLOCKS = {"resnet50_rmac": [3, 4, 6, 3], "resnet101_rmac": [3, 4, 23, 3],     # rmac_resnet.py:78-88
-                "resnet152_rmac": [3, 8, 36, 3]}
-model_names = set(_ARCH_BLOCKS)
+_TRUNKS = {"resnet18": ([2, 2, 2, 2], 1), "resnet50": ([3, 4, 6, 3], 4), "resnet101": ([3, 4, 23, 3], 4),
+           "resnet152": ([3, 8, 36, 3], 4)}                       # (blocks per layer, block.expansion): resnet.py:15,47
+# rmac_resnet.py:74-88 and rmac_resnet_fpn.py:92-110 (the trunk-only classifiers resnet18/50/101/152 of
+# nets/__init__.py:14 are ImageNet classifiers, not descriptor networks: not on this path)
+_ARCH = {t + "_rmac": (t, False, 1) for t in _TRUNKS}
+_ARCH.update({t + "_fpn_rmac": (t, True, 1) for t in _TRUNKS})
+_ARCH["resnet101_fpn0_rmac"] = ("resnet101", True, 0)
+_ARCH_BLOCKS = {a: _TRUNKS[t][0] for a, (t, _f, _m) in _ARCH.items()}
+model_names = set(_ARCH)
 
 
-def _reference_style_init(arch, out_dim, seed_gen=None):
+def _reference_style_init(arch, out_dim, seed_gen=None, fpn_mode=1):
     """Fresh weights with the statistics of the reference's constructor: conv ~ N(0, sqrt(2/(k*k*Cout)))
     and BN weight 1 / bias 0 (resnet.py:92-99), identity running stats, Linear default init."""
     g = seed_gen or torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
     sd = OrderedDict()
+    trunk, fpn, _ = _ARCH[arch]
+    blocks, exp = _TRUNKS[trunk]
 
     def conv(name, cout, cin, k):
         sd[name] = torch.randn((cout, cin, k, k), generator=g) * math.sqrt(2.0 / (k * k * cout))
@@ -48,39 +56,68 @@ def _reference_style_init(arch, out_dim, seed_gen=None):
     conv("conv1.weight", 64, 3, 7)
     bn("bn1", 64)
     inplanes = 64
-    for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], _ARCH_BLOCKS[arch]), start=1):
+    for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], blocks), start=1):
         for b in range(nblk):
             p = "layer%d.%d." % (li, b)
-            conv(p + "conv1.weight", planes, inplanes, 1)
-            bn(p + "bn1", planes)
-            conv(p + "conv2.weight", planes, planes, 3)
-            bn(p + "bn2", planes)
-            conv(p + "conv3.weight", planes * 4, planes, 1)
-            bn(p + "bn3", planes * 4)
-            if b == 0:
-                conv(p + "downsample.0.weight", planes * 4, inplanes, 1)
-                bn(p + "downsample.1", planes * 4)
-            inplanes = planes * 4
-    bound = 1.0 / math.sqrt(2048)
-    sd["fc.weight"] = (torch.rand((out_dim, 2048), generator=g) * 2 - 1) * bound
+            stride = 2 if (li > 1 and b == 0) else 1
+            if exp == 4:                                          # Bottleneck, resnet.py:54-65
+                conv(p + "conv1.weight", planes, inplanes, 1)
+                bn(p + "bn1", planes)
+                conv(p + "conv2.weight", planes, planes, 3)
+                bn(p + "bn2", planes)
+                conv(p + "conv3.weight", planes * 4, planes, 1)
+                bn(p + "bn3", planes * 4)
+            else:                                                 # BasicBlock, resnet.py:18-25
+                conv(p + "conv1.weight", planes, inplanes, 3)
+                bn(p + "bn1", planes)
+                conv(p + "conv2.weight", planes, planes, 3)
+                bn(p + "bn2", planes)
+            if b == 0 and (stride != 1 or inplanes != planes * exp):          # resnet.py:136-141
+                conv(p + "downsample.0.weight", planes * exp, inplanes, 1)
+                bn(p + "downsample.1", planes * exp)
+            inplanes = planes * exp
+    feat = 512 * exp
+    if fpn:
+        if fpn_mode == 1:                                         # rmac_resnet_fpn.py:27-30
+            conv("conv1x5.weight", 256 * exp, 512 * exp, 1)
+            conv("conv3c4.weight", 256 * exp, 256 * exp, 3)
+        feat = 768 * exp                                          # rmac_resnet_fpn.py:46
+    bound = 1.0 / math.sqrt(feat)
+    sd["fc.weight"] = (torch.rand((out_dim, feat), generator=g) * 2 - 1) * bound
     sd["fc.bias"] = (torch.rand(out_dim, generator=g) * 2 - 1) * bound
     return sd
 
 
 class ResNetRMAC:
-    """ResNet-50/101 trunk + global pooling + FC + L2 (``ResNet_RMAC``, rmac_resnet.py:12-69)."""
+    """ResNet-18/50/101/152 trunk + global pooling + FC + L2 (``ResNet_RMAC``, rmac_resnet.py:12-69), or the FPN head
+    over the layer3 and layer4 maps (``ResNet_RMAC_FPN``, rmac_resnet_fpn.py:11-90)."""
 
-    def __init__(self, arch, out_dim=2048, norm_features=False, pooling="gem", gemp=3, center_bias=0,
-                 dropout_p=None, without_fc=False, **kwargs):
+    def __init__(self, arch, out_dim=None, norm_features=False, pooling="gem", gemp=3, center_bias=0,
+                 dropout_p=None, without_fc=False, mode=None, **kwargs):
         kwargs.pop("scales", None)                              # rmac_resnet.py:75,79,83
         if kwargs:
             raise TypeError("unexpected model options: %s" % sorted(kwargs))
-        if arch not in _ARCH_BLOCKS:
+        if arch not in _ARCH:
             raise NameError("unknown model architecture '%s'\nSelect one in %s" % (arch, ",".join(sorted(model_names))))
-        if not (pooling in ("max", "avg") or pooling.startswith("gem")):
-            raise ValueError(pooling)                            # rmac_resnet.py:30-31
+        trunk, self.fpn, default_mode = _ARCH[arch]
+        exp = _TRUNKS[trunk][1]
+        if mode is not None and not self.fpn:
+            raise TypeError("unexpected model options: ['mode']")          # ResNet_RMAC has no `mode` (rmac_resnet.py:15-17)
+        self.mode = default_mode if mode is None else int(mode)
+        if self.fpn:
+            if pooling != "gem":
+                # rmac_resnet_fpn.py:36-43,76-77: forward() uses adpoolx5 / adpoolc4, which only pooling='gem' creates
+                raise ValueError("the FPN head supports pooling='gem' only (got %r)" % (pooling,))
+            if out_dim is None:
+                out_dim = 768 * exp                             # rmac_resnet_fpn.py:25
+        else:
+            if not (pooling in ("max", "avg") or pooling.startswith("gem")):
+                raise ValueError(pooling)                        # rmac_resnet.py:30-31
+            if out_dim is None:
+                out_dim = 2048                                  # rmac_resnet.py:15
         self.arch = arch
-        self.model_name = arch.split("_")[0]
+        self.model_name = trunk
+        self.trunk_dim = (768 if self.fpn else 512) * exp       # fc.in_features
         self.rgb_means = list(RGB_MEANS)                   # resnet.py:110-112
         self.rgb_stds = list(RGB_STDS)
         self.input_size = (3, 224, 224)
@@ -96,8 +133,11 @@ class ResNetRMAC:
         self.iscuda = False
         self.training = False
         self.preprocess = dict(mean=self.rgb_means, std=self.rgb_stds, input_size=max(self.input_size))
-        self._sd = _reference_style_init(arch, out_dim)
-        if pooling.startswith("gem"):
+        self._sd = _reference_style_init(arch, out_dim, fpn_mode=self.mode)
+        if self.fpn:
+            self._sd["adpoolx5.p"] = torch.ones(1) * float(gemp)   # rmac_resnet_fpn.py:41-42
+            self._sd["adpoolc4.p"] = torch.ones(1) * float(gemp)
+        elif pooling.startswith("gem"):
             self._sd["adpool.p"] = torch.ones(1) * float(gemp)   # pooling.py:54
         self._handle = None
         self._handle_device = None
@@ -172,8 +212,11 @@ class ResNetRMAC:
         lib.call("dirb200_net_create", self.arch.encode(), int(device_index), C.byref(h))
         try:
             mode = 0 if self.pooling.startswith("gem") else (1 if self.pooling == "max" else 2)
-            for k, v in [("pooling", mode), ("norm_features", self.norm_features), ("without_fc", self.without_fc),
-                         ("out_dim", self.out_dim), ("center_bias", max(0.0, float(self.center_bias)))] + list(self._opts.items()):
+            base = [("pooling", mode), ("norm_features", self.norm_features), ("without_fc", self.without_fc),
+                    ("out_dim", self.out_dim), ("center_bias", max(0.0, float(self.center_bias)))]
+            if self.fpn:
+                base.append(("fpn_mode", self.mode))
+            for k, v in base + list(self._opts.items()):
                 lib.call("dirb200_net_set_option", h, k.encode(), float(v))
             for name, t in self._sd.items():
                 if name.endswith("num_batches_tracked"):
@@ -191,7 +234,7 @@ class ResNetRMAC:
     # ------------------------------------------------------------------ forward
     @property
     def descriptor_dim(self):
-        return 2048 if self.without_fc else self.out_dim
+        return self.trunk_dim if self.without_fc else self.out_dim
 
     def forward(self, x, want_f16=False):
         if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
@@ -296,16 +339,15 @@ class ResNetRMAC:
         return int(n.value), float(f.value)
 
 
-def resnet50_rmac(**kwargs):
-    return ResNetRMAC("resnet50_rmac", **kwargs)
+def _factory(arch):
+    def make(**kwargs):
+        return ResNetRMAC(arch, **kwargs)
+    make.__name__ = arch
+    return make
 
 
-def resnet101_rmac(**kwargs):
-    return ResNetRMAC("resnet101_rmac", **kwargs)
-
-
-def resnet152_rmac(**kwargs):
-    return ResNetRMAC("resnet152_rmac", **kwargs)
+for _a in _ARCH:                                    # resnet18_rmac ... resnet152_fpn_rmac, as nets/__init__.py:14-16 lists them
+    globals()[_a] = _factory(_a)
 
 
 def create_model(arch, pretrained="", delete_fc=False, *args, **kwargs):

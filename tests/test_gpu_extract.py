@@ -83,6 +83,58 @@ def test_extract_r152_and_center_bias_golden(golden):
         assert rel_l2(net(x).cpu().numpy(), g["desc_" + tag]) < TOL, tag
 
 
+def _variant_net(arch, seed, **kw):
+    from dirb200 import nets, ops
+    ops.require_gpu(0)
+    net = nets.create_model(arch, **kw)
+    sd = synth.make_state_dict(arch, seed=seed, out_dim=net.out_dim)
+    if net.fpn and net.mode == 0:
+        sd.pop("conv1x5.weight")
+        sd.pop("conv3c4.weight")
+    net.load_state_dict(sd)
+    return net.eval(), sd
+
+
+def test_extract_variants_golden(golden):
+    """BasicBlock trunk (resnet18_rmac, resnet.py:15-44) and the FPN head (rmac_resnet_fpn.py:52-90,
+    modes 1 and 0) against the unmodified reference's descriptors."""
+    g = golden("extract_variants.npz")
+    b, h, w = [int(v) for v in g["img_shape"]]
+    x = synth.make_images(b, h, w, seed=int(g["img_seed"])).cuda()
+    net, _ = _variant_net("resnet18_rmac", int(g["r18_seed"]))
+    assert rel_l2(net(x).cpu().numpy(), g["desc_r18"]) < TOL
+    d1 = net(x[:1])
+    assert tuple(d1.shape) == (2048,) and rel_l2(d1.cpu().numpy(), g["desc_r18_b1"]) < TOL
+    net, _ = _variant_net("resnet50_fpn_rmac", int(g["fpn_seed"]), out_dim=2048)
+    assert rel_l2(net(x).cpu().numpy(), g["desc_r50_fpn"]) < TOL
+    net, _ = _variant_net("resnet50_fpn_rmac", int(g["fpn_seed"]), out_dim=2048, mode=0)
+    assert rel_l2(net(x).cpu().numpy(), g["desc_r50_fpn0"]) < TOL
+    net, _ = _variant_net("resnet18_fpn_rmac", int(g["r18_fpn_seed"]), out_dim=512)
+    d = net(x)
+    assert tuple(d.shape) == (2, 512) and rel_l2(d.cpu().numpy(), g["desc_r18_fpn"]) < TOL
+
+
+@pytest.mark.parametrize("arch,kw", [("resnet18_rmac", {}), ("resnet18_fpn_rmac", {}), ("resnet50_fpn_rmac", {}),
+                                      ("resnet101_fpn0_rmac", {}), ("resnet50_fpn_rmac", dict(norm_features=True, without_fc=True))],
+                         ids=["r18", "r18_fpn", "r50_fpn", "r101_fpn0", "r50_fpn_nofc_norm"])
+def test_variants_larger_images_vs_oracle(arch, kw):
+    """Same variants at sizes that reach the halo 3x3 kernel with a residual (BasicBlock conv2), the stride-2 3x3
+    convolutions, odd map sizes in the nearest upsampling (layer3 25x19 <- layer4 13x10) and batch / chunk invariance."""
+    net, sd = _variant_net(arch, 9, **kw)
+    x = synth.make_images(3, 400, 300, seed=17)
+    d = net(x.cuda())
+    if "_fpn" in arch:
+        ref = O.extract_fpn(x, sd, arch, mode=net.mode, norm_features=bool(kw.get("norm_features")),
+                            without_fc=bool(kw.get("without_fc"))).numpy()
+    else:
+        ref = O.extract(x, sd, arch).numpy()
+    assert d.shape == ref.shape and rel_l2(d.cpu().numpy(), ref) < TOL
+    one = net(x[1:2].cuda())
+    assert torch.equal(one, d[1])                                       # batch invariance, B=1 squeeze
+    net.set_backend_option("chunk", 2)
+    assert torch.equal(net(x.cuda()), d)
+
+
 def test_extract_r101_large_image_vs_oracle():
     # one 512x384 image against the CPU oracle, plus batch-composition invariance at that size
     net, sd = _net("resnet101_rmac", 2)

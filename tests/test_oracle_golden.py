@@ -228,7 +228,7 @@ def test_precision_design_meets_the_descriptor_bar(golden, name, arch):
 
 def test_variants_basic_block_trunk_and_fpn_head(golden):
     """BasicBlock trunk (resnet18_rmac) and the FPN head (modes 1 and 0) - the oracle restatement is
-    pinned here; the GPU path does not build these variants yet."""
+    pinned here; the GPU path is checked against the same goldens in tests/test_gpu_extract.py."""
     g = golden("extract_variants.npz")
     b, h, w = [int(v) for v in g["img_shape"]]
     x = synth.make_images(b, h, w, seed=int(g["img_seed"]))
@@ -244,8 +244,16 @@ def test_variants_basic_block_trunk_and_fpn_head(golden):
     sd = synth.make_state_dict("resnet18_fpn_rmac", seed=int(g["r18_fpn_seed"]), out_dim=512)
     assert sd["fc.weight"].shape == (512, 768)
     assert rel_l2(O.extract_fpn(x, sd, "resnet18_fpn_rmac").numpy(), g["desc_r18_fpn"]) < 2e-5
-    # the product says so loudly instead of running something else
+    # the product's model list is the reference's (nets/__init__.py:14-16), its state dicts load strictly, and the
+    # option errors follow the reference's constructors
     from dirb200 import nets
-    for arch in ("resnet18_rmac", "resnet50_fpn_rmac"):
-        with pytest.raises(NameError):
-            nets.create_model(arch)
+    assert {"resnet18_rmac", "resnet18_fpn_rmac", "resnet50_fpn_rmac", "resnet101_fpn_rmac", "resnet101_fpn0_rmac",
+            "resnet152_fpn_rmac"} <= set(nets.model_names)
+    net = nets.create_model("resnet18_fpn_rmac", out_dim=512)
+    net.load_state_dict(sd)
+    assert net.descriptor_dim == 512 and nets.create_model("resnet50_fpn_rmac").out_dim == 3072       # rmac_resnet_fpn.py:25
+    nets.create_model("resnet18_rmac").load_state_dict(synth.make_state_dict("resnet18_rmac", seed=1))
+    with pytest.raises(ValueError):
+        nets.create_model("resnet50_fpn_rmac", pooling="max")
+    with pytest.raises(TypeError):
+        nets.create_model("resnet50_rmac", mode=0)
