@@ -7,6 +7,7 @@
 // with the residual add and ReLU; head weights fp32.  A batch is processed in chunks of `chunk` images so that
 // the activations of consecutive layers stay L2-resident.
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -49,7 +50,7 @@ struct Block {
 // Per-launch CUDA-event timing of one forward (option "profile"): class 0 = tcgen05 conv, 1 = stem conv (mma.sync),
 // 2 = layout/maxpool, 3 = head.  Events sit on the launch stream, so they time exactly the kernels between them.
 struct Profiler {
-  struct Rec { cudaEvent_t a, b; int cls; double flops, bytes; };
+  struct Rec { cudaEvent_t a, b; int cls; double flops, bytes; std::string tag; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
@@ -123,9 +124,10 @@ struct dirb200_net {
 
 struct ProfScope {
   dirb200_net* n; cudaStream_t st; bool on;
-  ProfScope(dirb200_net* n_, cudaStream_t st_, int cls, double flops, double bytes) : n(n_), st(st_), on(n_->profile != 0) {
+  ProfScope(dirb200_net* n_, cudaStream_t st_, int cls, double flops, double bytes, const std::string& tag = std::string())
+      : n(n_), st(st_), on(n_->profile != 0) {
     if (on) {
-      Profiler::Rec r{n->prof.get(), n->prof.get(), cls, flops, bytes};
+      Profiler::Rec r{n->prof.get(), n->prof.get(), cls, flops, bytes, tag};
       cudaEventRecord(r.a, st);
       n->prof.recs.push_back(r);
     }
@@ -242,7 +244,13 @@ static int run_conv(dirb200_net* n, const ConvLayer& L, const __half* in, int B,
                               static_cast<double>(L.Cout) * L.K * L.K * L.CinPad);
   n->last_flops += flops;
   const bool mma = force_mma || n->conv_impl == 1 || L.CinPad % 64 != 0;
-  ProfScope ps(n, stream, mma ? 1 : 0, flops, bytes);
+  std::string tag;
+  if (n->profile) {
+    char buf[96];
+    snprintf(buf, sizeof(buf), "%dx%d%s %d->%d%s @%dx%d", L.K, L.K, L.stride == 2 ? "/s2" : "", L.Cin, L.Cout, res ? " +res" : "", s.Ho(), s.Wo());
+    tag = buf;
+  }
+  ProfScope ps(n, stream, mma ? 1 : 0, flops, bytes, tag);
   if (mma)
     return conv_mma(s, in, L.w, L.Kpad, L.scale, L.shift, res, relu, out, stream);
   if (n->conv_impl == 2) return conv_tc_np(s, in, L.w, L.scale, L.shift, res, relu, out, stream);
@@ -306,7 +314,10 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "gem_eps") n->gem_eps = static_cast<float>(value);
   else if (k == "center_bias") n->center_bias = static_cast<float>(value);
   else if (k == "debug_taps") n->debug_taps = value != 0;
-  else if (k == "profile") n->profile = value != 0;
+  else if (k == "profile") {             // 1 = time every launch of the NEXT forward; 2 = accumulate over forwards
+    n->profile = static_cast<int>(value);
+    n->prof.reset();
+  }
   else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "fuse_ds") n->fuse_ds = value != 0;
   else if (k == "pdl") g_use_pdl = value != 0;
@@ -553,11 +564,11 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
     } else {
       const double flops = 2.0 * sb * w.H1 * w.W1 * 64.0 * 147.0;
       n->last_flops += flops;
-      ProfScope ps(n, stream, 1, flops, static_cast<double>(sb) * (12.0 * H * W + 2.0 * stem_workspace_bytes(1, H, W) + 128.0 * w.H1 * w.W1));
+      ProfScope ps(n, stream, 1, flops, static_cast<double>(sb) * (12.0 * H * W + 2.0 * stem_workspace_bytes(1, H, W) + 128.0 * w.H1 * w.W1), "stem s2d + 7x7/s2 3->64");
       DIRB_TRY(stem_tc(img, sb, H, W, n->stem_w2, n->stem.scale, n->stem.shift, w.stem_ws, w.stem_out, stream, img8,
                        n->mean_std));
     }
-    ProfScope ps(n, stream, 2, 0, 2.0 * sb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.h[0]) * w.w[0]));
+    ProfScope ps(n, stream, 2, 0, 2.0 * sb * 64 * (static_cast<double>(w.H1) * w.W1 + static_cast<double>(w.h[0]) * w.w[0]), "maxpool 3x3/s2");
     DIRB_TRY(maxpool_3x3s2(w.stem_out, sb, w.H1, w.W1, 64,
                            w.stage_out[0] + static_cast<size_t>(b0) * w.h[0] * w.w[0] * 64, stream));
   }
@@ -607,7 +618,9 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
                                       static_cast<double>(sb) * h * wd * blk.down.Cin +
                                       static_cast<double>(blk.c3.Cout) * (blk.c3.Cin + blk.down.Cin));
           n->last_flops += flops;
-          ProfScope ps(n, stream, 0, flops, bytes);
+          char tbuf_[96];
+          snprintf(tbuf_, sizeof(tbuf_), "1x1 [%d|%d%s]->%d fused-shortcut @%dx%d", blk.c3.Cin, blk.down.Cin, st == 2 ? "/s2" : "", blk.c3.Cout, h2, w2);
+          ProfScope ps(n, stream, 0, flops, bytes, tbuf_);
           DIRB_TRY(conv_fused_ds(sb, h2, w2, blk.c3.Cin, t2, h, wd, blk.down.Cin, st, x, blk.wcat, blk.c3.Cout, blk.ones,
                                  blk.cat_shift, y, stream));
           x = y;
@@ -660,7 +673,7 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
           if (!n->without_fc) n->last_flops += 2.0 * sb * static_cast<double>(Ct) * n->out_dim;
           continue;
         }
-        ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * static_cast<double>(C4) * n->out_dim, 2.0 * sb * ho * wo * static_cast<double>(C4));
+        ProfScope ps(n, stream, 3, n->without_fc ? 0.0 : 2.0 * sb * static_cast<double>(C4) * n->out_dim, 2.0 * sb * ho * wo * static_cast<double>(C4), "head pool+fc+l2");
         if (n->center_bias > 0.0f)   // x is a scratch buffer whose only remaining reader is the pooling below
           DIRB_TRY(center_bias(const_cast<__half*>(x), sb, ho, wo, C4, n->center_bias, stream));
         DIRB_TRY(head_pool_fc_l2(x, sb, ho * wo, C4, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
@@ -690,7 +703,7 @@ int dirb200_net_forward(dirb200_net* n, const float* imgs_dev, int B, int H, int
   DIRB_CUDA(cudaSetDevice(n->device));
   const int64_t launches0 = launches_total();
   n->last_flops = 0;
-  n->prof.reset();
+  if (n->profile != 2) n->prof.reset();
   const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
   const int D = n->desc_dim();
   Workspace w;
@@ -725,7 +738,7 @@ int dirb200_net_forward_u8(dirb200_net* n, const uint8_t* imgs_dev, int B, int H
   DIRB_CUDA(cudaSetDevice(n->device));
   const int64_t launches0 = launches_total();
   n->last_flops = 0;
-  n->prof.reset();
+  if (n->profile != 2) n->prof.reset();
   const int chunk = n->chunk > 0 ? std::min(n->chunk, B) : auto_chunk(B, H, W);
   const int D = n->desc_dim();
   Workspace w;
@@ -791,7 +804,7 @@ static int forward_host_impl(dirb200_net* n, const void* imgs_host_, int is_u8, 
   }
   const int64_t launches0 = launches_total();
   n->last_flops = 0;
-  n->prof.reset();
+  if (n->profile != 2) n->prof.reset();
   Workspace w;
   DIRB_TRY(setup_workspace(n, chunk, H, W, &w));
   int b0 = 0;
@@ -827,6 +840,40 @@ int dirb200_net_profile(dirb200_net* n, double* out16) {
     double* o = out16 + 4 * r.cls;
     o[0] += 1; o[1] += ms; o[2] += r.flops; o[3] += r.bytes;
   }
+  return 0;
+}
+
+// Per launch-type timing of the profiled forward(s) as JSON text: [{"tag","cls","launches","ms","flops","bytes"}, ...]
+// in first-launch order.  Returns the number of bytes needed (incl. the terminator) through *needed when buf is too
+// small or NULL.  Synchronises the device.
+int dirb200_net_profile_table(dirb200_net* n, char* buf, size_t cap, size_t* needed) {
+  DIRB_REQUIRE(n, DIRB200_EINVAL, "null argument");
+  DIRB_CUDA(cudaDeviceSynchronize());
+  struct Row { std::string tag; int cls; double launches, ms, flops, bytes; };
+  std::vector<Row> rows;
+  std::map<std::string, size_t> at;
+  for (auto& r : n->prof.recs) {
+    float ms = 0;
+    DIRB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    auto it = at.find(r.tag);
+    if (it == at.end()) {
+      at[r.tag] = rows.size();
+      rows.push_back(Row{r.tag, r.cls, 0, 0, 0, 0});
+      it = at.find(r.tag);
+    }
+    Row& row = rows[it->second];
+    row.launches += 1; row.ms += ms; row.flops += r.flops; row.bytes += r.bytes;
+  }
+  std::string out = "[";
+  for (size_t i = 0; i < rows.size(); ++i) {
+    char line[320];
+    snprintf(line, sizeof(line), "%s{\"tag\": \"%s\", \"cls\": %d, \"launches\": %.0f, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             i ? ", " : "", rows[i].tag.c_str(), rows[i].cls, rows[i].launches, rows[i].ms, rows[i].flops, rows[i].bytes);
+    out += line;
+  }
+  out += "]";
+  if (needed) *needed = out.size() + 1;
+  if (buf && cap >= out.size() + 1) memcpy(buf, out.c_str(), out.size() + 1);
   return 0;
 }
 

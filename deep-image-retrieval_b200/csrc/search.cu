@@ -616,7 +616,7 @@ struct dirb200_index {
   int64_t sample_rows = 0;
   int cand_cap = 0;          // 0 = auto
   int count_cap = 0;         // candidate capacity per query of dirb200_index_rank_count (0 = 32768)
-  int retries = 2;           // gated retry passes enqueued after the first filter pass (device-side predicate)
+  int retries = 1;           // gated retry passes enqueued after the first filter pass (device-side predicate)
   int deferred = 0;          // 1 = search calls never synchronise; the caller collects the status (dirb200_index_check)
   // workspaces (grown on demand)
   void* ws = nullptr;

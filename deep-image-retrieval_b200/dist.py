@@ -125,10 +125,10 @@ class ShardedIndex:
             dist.all_reduce(above, op=dist.ReduceOp.SUM, group=self.group)
         return sc, above
 
-    def expand_queries(self, q32: torch.Tensor, k: int, alpha: float):
+    def expand_queries(self, q32: torch.Tensor, k: int, alpha: float, check: bool = True):
         """alpha-QE (test_dir.py:24-44) over the sharded database: global top-k, each rank sums the neighbours it
         owns, one all-reduce, add the query, normalise."""
-        scores, idx = self.search(q32, k)
+        scores, idx = self.search(q32, k, check=check)
         partial = self.ops.aqe_expand(q32, self.local.db32, idx, scores, alpha, partial=True,
                                       row_offset=self.row_offset, n_rows=self.local.n)
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:

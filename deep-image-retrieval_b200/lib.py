@@ -48,6 +48,7 @@ SIGNATURES = {
     "dirb200_resize_coeffs": (i32, [i32, i32, p, p, C.POINTER(i32)]),
     "dirb200_net_debug_stage": (i32, [p, C.c_char_p, p, C.c_size_t, C.POINTER(i32), p]),
     "dirb200_net_profile": (i32, [p, C.POINTER(f64)]),
+    "dirb200_net_profile_table": (i32, [p, p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dirb200_net_last_launches": (i32, [p, C.POINTER(i64), C.POINTER(f64)]),
     "dirb200_net_destroy": (i32, [p]),
     "dirb200_nchw_to_nhwc8": (i32, [p, i32, i32, i32, p, p]),

@@ -333,6 +333,15 @@ class ResNetRMAC:
         return {nm: dict(launches=int(arr[4 * i]), ms=arr[4 * i + 1], flops=arr[4 * i + 2], bytes=arr[4 * i + 3])
                 for i, nm in enumerate(names)}
 
+    def profile_table(self):
+        """Per launch type of the profiled forward(s): list of dict(tag, cls, launches, ms, flops, bytes)."""
+        import json
+        need = C.c_size_t()
+        lib.call("dirb200_net_profile_table", self._handle, C.c_void_p(0), 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        lib.call("dirb200_net_profile_table", self._handle, buf, need.value, C.byref(need))
+        return json.loads(buf.value.decode())
+
     def last_launch_stats(self):
         n, f = C.c_int64(), C.c_double()
         lib.call("dirb200_net_last_launches", self._handle, C.byref(n), C.byref(f))

@@ -103,6 +103,10 @@ int dirb200_net_debug_stage(dirb200_net* net, const char* what, void* dst_dev, s
  * {launches, milliseconds, algorithmic FLOPs, algorithmic bytes} for 0 tcgen05 convolutions, 1 stem convolution,
  * 2 layout + maxpool, 3 head.  Synchronises the device. */
 int dirb200_net_profile(dirb200_net* net, double* out16);
+/* Option "profile" = 1 (next forward) or 2 (accumulate over forwards until the option is set again): per launch TYPE
+ * (e.g. "1x1 256->1024 +res @64x64") the launches, CUDA-event milliseconds, algorithmic FLOPs and bytes, as JSON text.
+ * Two-call protocol: buf = NULL returns the size through *needed. */
+int dirb200_net_profile_table(dirb200_net* net, char* buf, size_t cap, size_t* needed);
 /* Number of kernels the last forward launched / algorithmic conv+fc FLOPs of the last forward. */
 int dirb200_net_last_launches(dirb200_net* net, int64_t* launches, double* flops);
 int dirb200_net_destroy(dirb200_net* net);
@@ -171,7 +175,7 @@ int dirb200_index_set_db(dirb200_index* idx, const float* db32_dev, const void* 
 /* "eps16": bound on |fp16-path score - exact score| used for the candidate band (default 1.2e-3, valid for
  * unit-norm rows); "sample_rows": rows scored densely to seed the threshold (0 = auto); "cand_cap": per-query
  * candidate-list capacity (0 = auto; a small value forces the overflow -> tightened re-run path); "retries": gated
- * retry passes enqueued after the filter pass (default 2; they return at once unless a list overflowed);
+ * retry passes enqueued after the filter pass (default 1; they return at once unless a list overflowed);
  * "deferred_check" = 1: search calls never synchronise the host, the caller collects the status with
  * dirb200_index_check (it is also collected at the start of the next search); "profile". */
 int dirb200_index_set_option(dirb200_index* idx, const char* key, double value);

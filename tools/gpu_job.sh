@@ -28,6 +28,17 @@ while [ $# -gt 0 ]; do
     bench)
       args=${1:-}; shift
       timeout 900 python bench.py $args > gpurun_out/bench.log 2> gpurun_out/bench.err; rc=$?; echo "== bench rc=$rc"; tail -c 6000 gpurun_out/bench.log; tail -5 gpurun_out/bench.err; [ $rc -ne 0 ] && rc_all=$rc ;;
+    traffic)
+      # measured DRAM bytes per launch (metrics-only ncu passes; numbers printed under ncu are never bench values)
+      M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
+      timeout 600 ncu --metrics $M --clock-control none -k regex:"conv_|stem_|maxpool|head_|s2d" -s 330 -c 240 --csv --log-file gpurun_out/traffic_conv.csv \
+        python bench.py --steps 1 --warmup 3 --no-search --no-cpu-baseline --no-latency > gpurun_out/traffic_conv.log 2>&1; echo "== traffic conv rc=$?"
+      timeout 300 ncu --metrics $M --clock-control none -k regex:"conv_pers" -s 6 -c 4 --csv --log-file gpurun_out/traffic_search_1000q_1000k.csv \
+        python tools/search_profile.py c4 > gpurun_out/traffic_s4.log 2>&1; echo "== traffic c4 rc=$?"
+      timeout 300 ncu --metrics $M --clock-control none -k regex:"conv_pers" -s 6 -c 4 --csv --log-file gpurun_out/traffic_search_70q_100k.csv \
+        python tools/search_profile.py c3 > gpurun_out/traffic_s3.log 2>&1; echo "== traffic c3 rc=$?"
+      timeout 300 ncu --metrics $M --clock-control none -k regex:"conv_pers" -s 6 -c 4 --csv --log-file gpurun_out/traffic_search_1000q_125k.csv \
+        python tools/search_profile.py one > gpurun_out/traffic_s8.log 2>&1; echo "== traffic shard rc=$?" ;;
     py)
       script=$1; shift
       timeout 900 python $script > gpurun_out/$(basename $script .py).log 2>&1; rc=$?; echo "== py $script rc=$rc"; tail -40 gpurun_out/$(basename $script .py).log; [ $rc -ne 0 ] && rc_all=$rc ;;

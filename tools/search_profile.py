@@ -4,7 +4,7 @@ import torch
 from dirb200 import ops
 # (rows, queries, options): eps16 = -1 puts the filter threshold above every score (no candidate appends: isolates the
 # cost of the epilogue's atomics), sample_rows trades seed-pass time for a tighter threshold (fewer candidates)
-CASES = ((125_000, 1000, {}),) if sys.argv[1:] == ["one"] else (
+CASES = ((125_000, 1000, {}),) if sys.argv[1:] == ["one"] else ((1_000_000, 1000, {}),) if sys.argv[1:] == ["c4"] else ((100_000, 70, {}),) if sys.argv[1:] == ["c3"] else (
     (1_000_000, 1000, {}), (125_000, 1000, {}), (125_000, 1000, {"eps16": -1.0}), (125_000, 1000, {"sample_rows": 32768}),
     (1_000_000, 1000, {"eps16": -1.0}), (100_000, 70, {}))
 for (N, Q, OPT) in CASES:
