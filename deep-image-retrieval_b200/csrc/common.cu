@@ -3,6 +3,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
 
 namespace dirb {
 
@@ -41,8 +44,50 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Encoded maps are pure functions of their arguments; a forward pass re-encodes the same ~400 maps every call
+// (same workspace pointers, same shapes), which is a visible share of the launch overhead at batch 1.  Per-thread
+// cache keyed by the raw argument bytes (handles are single-threaded by contract, so no lock is needed).
+namespace {
+struct TmapKey {
+  int kind;
+  const void* base;
+  uint64_t a[6];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> t_tmaps;
+
+bool tmap_lookup(const TmapKey& k, CUtensorMap* m) {
+  auto it = t_tmaps.find(k);
+  if (it == t_tmaps.end()) return false;
+  *m = it->second;
+  return true;
+}
+void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  if (t_tmaps.size() > 8192) t_tmaps.clear();
+  t_tmaps.emplace(k, m);
+}
+TmapKey make_key(int kind, const void* base, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t a4, uint64_t a5) {
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.kind = kind;
+  k.base = base;
+  k.a[0] = a0; k.a[1] = a1; k.a[2] = a2; k.a[3] = a3; k.a[4] = a4; k.a[5] = a5;
+  return k;
+}
+}  // namespace
+
 int encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                    uint32_t box_inner, uint32_t box_outer) {
+  const TmapKey key = make_key(1, base, inner, outer, row_stride_bytes, box_inner, box_outer, 0);
+  if (tmap_lookup(key, m)) return 0;
   EncodeTiledFn enc = get_encode();
   DIRB_REQUIRE(enc != nullptr, DIRB200_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {inner, outer};
@@ -56,10 +101,13 @@ int encode_tmap_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t ou
                "cuTensorMapEncodeTiled(2d) failed: %d (inner=%llu outer=%llu stride=%llu box=%u,%u base=%p)", (int)r,
                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
                box_outer, base);
+  tmap_store(key, *m);
   return 0;
 }
 
 int encode_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int tw, int th, int nb, int es) {
+  const TmapKey key = make_key(2, base, (uint64_t)B << 32 | (uint32_t)H, (uint64_t)W << 32 | (uint32_t)C, tw, th, nb, es);
+  if (tmap_lookup(key, m)) return 0;
   EncodeTiledFn enc = get_encode();
   DIRB_REQUIRE(enc != nullptr, DIRB200_EDRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -72,6 +120,7 @@ int encode_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int 
   DIRB_REQUIRE(r == CUDA_SUCCESS, DIRB200_EDRIVER,
                "cuTensorMapEncodeTiled(nhwc) failed: %d (B=%d H=%d W=%d C=%d box=%d,%d,%d es=%d base=%p)", (int)r, B, H,
                W, C, tw, th, nb, es, base);
+  tmap_store(key, *m);
   return 0;
 }
 

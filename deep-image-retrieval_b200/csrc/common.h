@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/dirb200.h"
 
 namespace dirb {
@@ -65,6 +67,17 @@ inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+// cudaFuncSetAttribute is per (function, device) and costs ~1-2 us of host time: do it once per device, not per launch.
+// `mask` is a function-local static of the launcher template instantiation.
+inline bool first_launch_on_device(std::atomic<uint64_t>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask.load(std::memory_order_relaxed) & bit) return false;
+  mask.fetch_or(bit, std::memory_order_relaxed);
+  return true;
 }
 
 // Launch counter (the "gpu_launches" the benchmark reports): every kernel launch of this library bumps it.

@@ -6,6 +6,7 @@
 // :115-118 (stem).  BatchNorm (eval) is folded by the caller into scale = gamma/sqrt(var+eps), shift = beta-mean*scale.
 #include "conv.h"
 
+#include "conv_c23.cuh"
 #include "conv_halo.cuh"
 #include "conv_pers.cuh"
 #include "gemm_tc.cuh"
@@ -187,6 +188,43 @@ int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int
   return conv_fused_ds_bn<256, 4>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
 }
 
+// Bottleneck conv2 (3x3/s1/p1) + BN + ReLU + conv3 (1x1, x4) + BN + residual + ReLU in one kernel (conv_c23.cuh).
+// t1: (B,H,W,Cm); w2: [Cm][9*Cm]; w3: [4*Cm][Cm]; res / out: (B,H,W,4*Cm).
+bool conv_c23_supported(int H, int W, int Cm) { return (Cm == 128 || Cm == 256) && H >= 16 && W >= 8; }
+
+int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, const float* scale2, const float* shift2,
+             const __half* w3, const float* scale3, const float* shift3, const __half* res, __half* out,
+             cudaStream_t stream) {
+  DIRB_REQUIRE(conv_c23_supported(H, W, Cm), DIRB200_ENOTSUP, "fused conv2+conv3 needs Cm in {128, 256}, H >= 16, W >= 8 (got %d, %d, %d)", Cm, H, W);
+  DIRB_REQUIRE(t1 && w2 && w3 && res && out, DIRB200_EINVAL, "null argument");
+  ConvPersParams p{};
+  p.a_spatial = 1;
+  p.taps = 9; p.kw_taps = 3;
+  p.cin_blocks = Cm / 64;
+  p.stride = 1; p.pad = 1;
+  p.tw = 8; p.th = 16; p.nb = 1;
+  p.tiles_w = (int)ceil_div(W, 8);
+  p.tiles_h = (int)ceil_div(H, 16);
+  p.n_tiles = 1;
+  p.has_res = 1;
+  p.relu = 1;
+  p.scale = scale3;
+  p.shift = shift3;
+  p.scale2 = scale2;
+  p.shift2 = shift2;
+  const int64_t total = (int64_t)p.tiles_w * p.tiles_h * B;
+  DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
+  p.total_tiles = static_cast<int>(total);
+  CUtensorMap tmA, tmB2, tmB3, tmR, tmO;
+  DIRB_TRY(encode_tmap_nhwc(&tmA, t1, B, H, W, Cm, 10, 18, 1, 1));
+  DIRB_TRY(encode_tmap_2d(&tmB2, w2, 9 * Cm, Cm, (uint64_t)9 * Cm * 2, 64, 128));
+  DIRB_TRY(encode_tmap_2d(&tmB3, w3, Cm, 4 * Cm, (uint64_t)Cm * 2, 64, 128));
+  DIRB_TRY(encode_tmap_nhwc(&tmR, res, B, H, W, 4 * Cm, 8, 16, 1, 1));
+  DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, H, W, 4 * Cm, 8, 16, 1, 1));
+  if (Cm == 256) return conv_c23_launch<256>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
+  return conv_c23_launch<128>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
+}
+
 static int g_conv_halo = 1;
 void set_conv_halo(int on) { g_conv_halo = on; }
 static int g_res_variant = 0;   // tuning knob: shared-memory split of the residual (conv3) kernel, see conv_tc
@@ -366,7 +404,9 @@ int stem_tc(const float* imgs, int B, int H, int W, const __half* w2, const floa
   DIRB_TRY(encode_tmap_nhwc16(&tmS, s2d_ws, B, Hs, Ws, 11, 19, 1));
   DIRB_TRY(encode_tmap_2d_sw32(&tmW, w2, 256, 64, 512, 64));
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, 64, p.tw, p.th, p.nb, 1));
-  DIRB_CUDA(cudaFuncSetAttribute(stem_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::TOTAL));
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_launch_on_device(attr_done))
+    DIRB_CUDA(cudaFuncSetAttribute(stem_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::TOTAL));
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   DIRB_CUDA(launch_pdl(stem_pers_kernel, dim3(grid), dim3(256), StemSmem::TOTAL, stream, tmS, tmW, tmO, p));
   count_launch();

@@ -237,7 +237,9 @@ int conv_halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   using L = ConvHaloSmem<BN, BSTAGES, NB, NA_>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   auto kern = conv_halo_kernel<BN, BSTAGES, NB, BRES, NA_>;
-  DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_launch_on_device(attr_done))
+    DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   DIRB_CUDA(launch_pdl(kern, dim3(grid), dim3(PersThreads<0>::THREADS), L::TOTAL, stream, tmA, tmB, tmR, tmO, p));
   count_launch();

@@ -42,6 +42,8 @@ struct ConvPersParams {
   int k_per_part;
   const float* scale;
   const float* shift;
+  const float* scale2;         // conv_c23.cuh: BN of the first (3x3) convolution of the fused pair
+  const float* shift2;
   // similarity epilogues (search.cu): D[q][n] = <query q, database row n>
   int M, N;                    // valid queries / database rows of this launch
   float* dense;                // [M][dense_ld] fp32 scores                     (PERS_EPI_SIM_DENSE)
@@ -451,7 +453,9 @@ int conv_pers_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   using L = ConvPersSmem<BN, STAGES, EPI, NB>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   auto kern = conv_pers_kernel<BN, STAGES, EPI, NB>;
-  DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_launch_on_device(attr_done))
+    DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   DIRB_CUDA(launch_pdl(kern, dim3(grid), dim3(PersThreads<EPI>::THREADS), L::TOTAL, stream, tmA, tmB, tmR, tmO, p));
   count_launch();

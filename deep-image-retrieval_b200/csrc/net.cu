@@ -104,6 +104,7 @@ struct dirb200_net {
   Profiler prof;
   float mean_std[6] = {0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f};   // preprocess of resnet.py:110-111
   int fuse_ds = 1;                // fuse the projection shortcut into conv3 of block 0 (tcgen05 path only)
+  int fuse_c23 = 1;               // conv2 + conv3 (+ residual) of the identity blocks as one kernel (conv_c23.cuh)
   // trunk / head variants (rmac_resnet.py:74-88, rmac_resnet_fpn.py:92-110)
   bool basic = false;             // BasicBlock trunk (resnet18): two 3x3 convolutions per block, expansion 1
   int expansion = 4;
@@ -320,6 +321,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   }
   else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "fuse_ds") n->fuse_ds = value != 0;
+  else if (k == "fuse_c23") n->fuse_c23 = value != 0;
   else if (k == "pdl") g_use_pdl = value != 0;
   else if (k == "res_variant") set_res_variant(static_cast<int>(value));
   else if (k.size() == 5 && k.compare(0, 4, "mean") == 0 && k[4] >= '0' && k[4] <= '2') n->mean_std[k[4] - '0'] = static_cast<float>(value);
@@ -610,6 +612,20 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
         const int st = blk.c2.stride;
         const int h2 = (h + 2 - 3) / st + 1, w2 = (wd + 2 - 3) / st + 1;
         DIRB_TRY(run_conv(n, blk.c1, x, sb, h, wd, nullptr, 1, t1, stream));
+        if (!blk.has_down && n->fuse_c23 && n->conv_impl == 0 && st == 1 && conv_c23_supported(h, wd, blk.c2.Cin)) {
+          // identity block: conv2 -> conv3 (+ x) in one kernel, the conv2 output stays in shared memory
+          const int Cm = blk.c2.Cin;
+          const double flops = 2.0 * sb * h * wd * (9.0 * Cm * Cm + 4.0 * Cm * Cm);
+          const double bytes = 2.0 * (static_cast<double>(sb) * h * wd * (Cm + 8.0 * Cm) + 13.0 * Cm * Cm);   // t1 + residual + output, weights
+          n->last_flops += flops;
+          char tg[96];
+          snprintf(tg, sizeof(tg), "3x3 %d->%d + 1x1 ->%d +res fused @%dx%d", Cm, Cm, 4 * Cm, h, wd);
+          ProfScope ps(n, stream, 0, flops, bytes, tg);
+          DIRB_TRY(conv_c23(sb, h, wd, Cm, t1, blk.c2.w, blk.c2.scale, blk.c2.shift, blk.c3.w, blk.c3.scale, blk.c3.shift, x, y,
+                            stream));
+          x = y;
+          continue;
+        }
         DIRB_TRY(run_conv(n, blk.c2, t1, sb, h, wd, nullptr, 1, t2, stream));
         const __half* res = x;
         if (blk.has_down && n->fuse_ds && n->conv_impl == 0 && blk.c3.Cout % 256 == 0) {

@@ -59,7 +59,8 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out);
  * images per sub-chunk of stem / layer1..4), 0 (default, faster as measured) = whole chunk per stage.
  * Implementation A/B switches: "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit
  * GEMM (validation path), 2 = one-tile-per-CTA tcgen05 kernel (baseline); "fuse_ds" 1 (default) = projection
- * shortcut fused into conv3 as a K-concatenated GEMM.  PROCESS-WIDE (they select kernels, not handle state; set
+ * shortcut fused into conv3 as a K-concatenated GEMM; "fuse_c23" 1 (default) = conv2 + conv3 (+ residual) of the
+ * identity blocks with 128 / 256 mid channels as one kernel (dirb200_conv_c23).  PROCESS-WIDE (they select kernels, not handle state; set
  * them once, not concurrently with a running forward): "halo" 1 (default) / 0 = 3x3 stride-1 convolutions load
  * their input patch once per tile (conv_halo.cuh) or tap by tap; "pdl" 1 (default) = programmatic dependent
  * launch between consecutive kernels; "res_variant" tile-variant selector of the residual 1x1 convolutions.
@@ -123,6 +124,13 @@ int dirb200_nchw_to_nhwc8(const float* in_dev, int B, int H, int W, void* out_de
 int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const void* w_dev, int Cout, int KH,
                         int KW, int stride, int pad, const float* scale_dev, const float* shift_dev,
                         const void* res_dev, int relu, int impl, void* out_dev, void* stream);
+/* conv2 + conv3 of a Bottleneck in one kernel (resnet.py:75-85): out = relu(bn3(conv1x1(relu(bn2(conv3x3(t1))))) + res).
+ * t1 NHWC fp16 (B,H,W,Cm), w2 [Cm][3][3][Cm] fp16, w3 [4*Cm][Cm] fp16 (the layouts of dirb200_conv_bn_act), res / out
+ * NHWC fp16 (B,H,W,4*Cm).  Cm in {128, 256}, H >= 16, W >= 8, stride 1.  The conv2 output stays in shared memory as the
+ * A operand of conv3 (fp16, the same rounding as the two-kernel path). */
+int dirb200_conv_c23(const void* t1_dev, int B, int H, int W, int Cm, const void* w2_dev, const float* scale2_dev,
+                     const float* shift2_dev, const void* w3_dev, const float* scale3_dev, const float* shift3_dev,
+                     const void* res_dev, void* out_dev, void* stream);
 /* The stem on tensor cores: Conv2d(3, 64, 7, stride 2, pad 3, bias=False) + folded BN + ReLU, resnet.py:115-118.
  * imgs_dev NCHW fp32 (B,3,H,W); w2_dev = the [64][256] fp16 weight layout produced (on the host) by
  * dirb200_stem_pack_weight from the OIHW fp32 [64][3][7][7] tensor; ws_dev scratch of

@@ -135,6 +135,21 @@ def test_variants_larger_images_vs_oracle(arch, kw):
     assert torch.equal(net(x.cuda()), d)
 
 
+def test_fused_c23_network_equals_two_kernel_path():
+    """Option fuse_c23 (conv2 + conv3 + residual of the identity blocks as one kernel) does not change a single bit
+    of the descriptors."""
+    net, sd = _net("resnet101_rmac", 3)
+    x = synth.make_images(3, 320, 272, seed=8).cuda()
+    net.set_backend_option("fuse_c23", 1)
+    a = net(x)
+    n_fused = net.last_launch_stats()[0]
+    net.set_backend_option("fuse_c23", 0)
+    b = net(x)
+    assert net.last_launch_stats()[0] > n_fused          # fewer launches with the fused blocks
+    assert torch.equal(a, b)
+    assert rel_l2(a.cpu().numpy(), O.extract(x.cpu(), sd, "resnet101_rmac").numpy()) < TOL
+
+
 def test_extract_r101_large_image_vs_oracle():
     # one 512x384 image against the CPU oracle, plus batch-composition invariance at that size
     net, sd = _net("resnet101_rmac", 2)

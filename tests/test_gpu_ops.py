@@ -160,6 +160,36 @@ def test_whiten_tensor_core_path_large():
     assert rel_l2(y.cpu().numpy(), ref) < 2e-5
 
 
+@pytest.mark.parametrize("cm,b,h,w", [(256, 2, 64, 64), (128, 1, 48, 40), (256, 1, 17, 23), (128, 3, 16, 8), (256, 5, 72, 56)])
+def test_conv_c23_fused_bottleneck_tail(cm, b, h, w):
+    """conv2 (3x3) + BN + ReLU + conv3 (1x1) + BN + residual + ReLU in ONE kernel (resnet.py:75-85) == the two-kernel
+    path bit for bit (same fp16 rounding of the intermediate, same K order), and within fp16 tolerance of the oracle;
+    ragged tiles (sizes that are not multiples of the 8 x 16 patch) and many tiles per CTA."""
+    ops = _ops()
+    r = np.random.RandomState(cm + h)
+    t1 = torch.from_numpy(np.maximum(r.standard_normal((b, h, w, cm)), 0).astype(np.float16)).to(DEV)
+    res = torch.from_numpy(r.standard_normal((b, h, w, 4 * cm)).astype(np.float16)).to(DEV)
+    w2 = torch.from_numpy((r.standard_normal((cm, cm, 3, 3)) * np.sqrt(2.0 / (9 * cm))).astype(np.float32))
+    w3 = torch.from_numpy((r.standard_normal((4 * cm, cm, 1, 1)) * np.sqrt(2.0 / cm)).astype(np.float32))
+    s2 = torch.from_numpy(r.uniform(0.7, 1.3, cm).astype(np.float32)).to(DEV)
+    h2 = torch.from_numpy((0.1 * r.standard_normal(cm)).astype(np.float32)).to(DEV)
+    s3 = torch.from_numpy(r.uniform(0.2, 0.4, 4 * cm).astype(np.float32)).to(DEV)
+    h3 = torch.from_numpy((0.1 * r.standard_normal(4 * cm)).astype(np.float32)).to(DEV)
+    w2p, w3p = ops.pack_conv_weight(w2).to(DEV), ops.pack_conv_weight(w3).to(DEV)
+    fused = ops.conv_c23(t1, w2p, s2, h2, w3p, s3, h3, res)
+    t2 = ops.conv_bn_act(t1, w2p, cm, 3, 3, 1, 1, s2, h2, None, True)
+    two = ops.conv_bn_act(t2, w3p, 4 * cm, 1, 1, 1, 0, s3, h3, res, True)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, two)
+    # oracle: fp32 convolutions on the fp16-rounded operands
+    x = t1.float().cpu().permute(0, 3, 1, 2)
+    mid = torch.relu(torch.nn.functional.conv2d(x, w2.half().float(), padding=1) * s2.cpu().view(1, -1, 1, 1) + h2.cpu().view(1, -1, 1, 1))
+    out = torch.nn.functional.conv2d(mid.half().float(), w3.half().float()) * s3.cpu().view(1, -1, 1, 1) + h3.cpu().view(1, -1, 1, 1)
+    out = torch.relu(out + res.float().cpu().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    err = (fused.float().cpu() - out).abs().max().item()
+    assert err < 2e-3 * max(1.0, out.abs().max().item()), err
+
+
 @pytest.mark.parametrize("mag,spread", [(1.0, 1.0), (1.0, 0.1), (1.0, 0.01), (1.0, 1e-3), (1e-3, 1.0), (300.0, 0.05)])
 def test_whiten_tensor_core_path_is_scale_invariant(mag, spread):
     """Rows tightly clustered around their mean and rows of unusual magnitude: the adaptive power-of-two prescale of
