@@ -190,12 +190,16 @@ int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int
 
 // Bottleneck conv2 (3x3/s1/p1) + BN + ReLU + conv3 (1x1, x4) + BN + residual + ReLU in one kernel (conv_c23.cuh).
 // t1: (B,H,W,Cm); w2: [Cm][9*Cm]; w3: [4*Cm][Cm]; res / out: (B,H,W,4*Cm).
-bool conv_c23_supported(int H, int W, int Cm) { return (Cm == 128 || Cm == 256) && H >= 16 && W >= 8; }
+bool conv_c23_supported(int H, int W, int Cm) { return (Cm == 64 || Cm == 128 || Cm == 256) && H >= 16 && W >= 8; }
+// worth it only when every SM gets several 128-pixel tiles (each tile walks ALL 4*Cm output channels)
+bool conv_c23_profitable(int B, int H, int W, int Cm) {
+  return conv_c23_supported(H, W, Cm) && ceil_div(W, 8) * ceil_div(H, 16) * B >= 2 * num_sms();
+}
 
 int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, const float* scale2, const float* shift2,
              const __half* w3, const float* scale3, const float* shift3, const __half* res, __half* out,
              cudaStream_t stream) {
-  DIRB_REQUIRE(conv_c23_supported(H, W, Cm), DIRB200_ENOTSUP, "fused conv2+conv3 needs Cm in {128, 256}, H >= 16, W >= 8 (got %d, %d, %d)", Cm, H, W);
+  DIRB_REQUIRE(conv_c23_supported(H, W, Cm), DIRB200_ENOTSUP, "fused conv2+conv3 needs Cm in {64, 128, 256}, H >= 16, W >= 8 (got %d, %d, %d)", Cm, H, W);
   DIRB_REQUIRE(t1 && w2 && w3 && res && out, DIRB200_EINVAL, "null argument");
   ConvPersParams p{};
   p.a_spatial = 1;
@@ -217,11 +221,12 @@ int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, co
   p.total_tiles = static_cast<int>(total);
   CUtensorMap tmA, tmB2, tmB3, tmR, tmO;
   DIRB_TRY(encode_tmap_nhwc(&tmA, t1, B, H, W, Cm, 10, 18, 1, 1));
-  DIRB_TRY(encode_tmap_2d(&tmB2, w2, 9 * Cm, Cm, (uint64_t)9 * Cm * 2, 64, 128));
+  DIRB_TRY(encode_tmap_2d(&tmB2, w2, 9 * Cm, Cm, (uint64_t)9 * Cm * 2, 64, Cm < 128 ? Cm : 128));
   DIRB_TRY(encode_tmap_2d(&tmB3, w3, Cm, 4 * Cm, (uint64_t)Cm * 2, 64, 128));
   DIRB_TRY(encode_tmap_nhwc(&tmR, res, B, H, W, 4 * Cm, 8, 16, 1, 1));
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, H, W, 4 * Cm, 8, 16, 1, 1));
   if (Cm == 256) return conv_c23_launch<256>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
+  if (Cm == 64) return conv_c23_launch<64>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
   return conv_c23_launch<128>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
 }
 
@@ -264,16 +269,24 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
   DIRB_REQUIRE(s.Cin % 64 == 0 && s.Cout % 64 == 0, DIRB200_ENOTSUP,
                "tcgen05 conv needs Cin %% 64 == 0 and Cout %% 64 == 0 (got %d, %d)", s.Cin, s.Cout);
   DIRB_REQUIRE(s.stride == 1 || s.stride == 2, DIRB200_ENOTSUP, "stride %d unsupported", s.stride);
+  // Tile width (output channels per tile): the widest one that still gives every SM a tile.  Large batches keep 256;
+  // at batch 1-8 a 256-wide tile would leave most of the 148 SMs idle (e.g. layer3 conv1 of ONE 1024x1024 image is 32
+  // tiles), so the tile narrows to 128 or 64 channels - the reference's default evaluation mode is batch 1
+  // (test_dir.py:52-53,114).
+  const int64_t m_tiles = ceil_div(static_cast<int64_t>(s.B) * s.Ho() * s.Wo(), 128);
+  int bn = 64;
+  if (s.Cout % 256 == 0 && m_tiles * (s.Cout / 256) >= num_sms()) bn = 256;
+  else if (s.Cout % 128 == 0 && m_tiles * (s.Cout / 128) >= num_sms()) bn = 128;
   if (g_conv_halo && s.KH == 3 && s.KW == 3 && s.stride == 1 && s.pad == 1 && s.H >= 16 && s.W >= 8) {
     // halo slots (input prefetch depth): short tiles need more patches in flight to cover the HBM latency
     if (s.Cout == 64 && s.Cin == 64) return conv_halo_bn<64, 9, true, 4>(s, in, w, scale, shift, res, relu, out, stream);
-    if (s.Cout % 256 == 0) return conv_halo_bn<256, 4, false, 2>(s, in, w, scale, shift, res, relu, out, stream);
-    if (s.Cout % 128 == 0) return conv_halo_bn<128, 6, false, 3>(s, in, w, scale, shift, res, relu, out, stream);
+    if (bn == 256) return conv_halo_bn<256, 4, false, 2>(s, in, w, scale, shift, res, relu, out, stream);
+    if (bn == 128) return conv_halo_bn<128, 6, false, 3>(s, in, w, scale, shift, res, relu, out, stream);
     return conv_halo_bn<64, 8, false, 4>(s, in, w, scale, shift, res, relu, out, stream);
   }
   // Shared memory split: convolutions with a residual keep 4 staging buffers (residual prefetch depth) and a
   // shorter operand ring; the others trade two staging buffers for one more ring slot (deeper TMA lookahead).
-  if (s.Cout % 256 == 0) {
+  if (bn == 256) {
     if (res) {
       if (g_res_variant == 1) return conv_pers_bn<256, 2, 6>(s, in, w, scale, shift, res, relu, out, stream);
       if (g_res_variant == 2) return conv_pers_bn<128, 4, 6>(s, in, w, scale, shift, res, relu, out, stream);
@@ -281,7 +294,7 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
     }
     return conv_pers_bn<256, 4, 2>(s, in, w, scale, shift, res, relu, out, stream);
   }
-  if (s.Cout % 128 == 0) {
+  if (bn == 128) {
     if (res) return conv_pers_bn<128, 5, 4>(s, in, w, scale, shift, res, relu, out, stream);
     return conv_pers_bn<128, 6, 2>(s, in, w, scale, shift, res, relu, out, stream);
   }

@@ -20,6 +20,7 @@ int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int
                   cudaStream_t stream);
 // conv2 (3x3/s1) + BN + ReLU + conv3 (1x1, x4) + BN + residual + ReLU of a Bottleneck in one kernel (conv_c23.cuh).
 bool conv_c23_supported(int H, int W, int Cm);
+bool conv_c23_profitable(int B, int H, int W, int Cm);
 int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, const float* scale2, const float* shift2,
              const __half* w3, const float* scale3, const float* shift3, const __half* res, __half* out,
              cudaStream_t stream);

@@ -40,13 +40,15 @@ struct ConvC23Smem {
   static constexpr int BAR_OFF = STG_OFF + NSTG * STG_BYTES;
   static constexpr int NUM_BARS = 2 * NA + 2 * NB2 + 2 * NB3 + 4 + 4 + 2 * NSTG;
   static constexpr int TOTAL = BAR_OFF + 8 * NUM_BARS + 16 + 1024;
-  static constexpr int HALVES = CM / 128;                          // N = 128 MMAs per K step of conv2
+  static constexpr int N2 = CM < 128 ? CM : 128;                   // N of the conv2 MMAs (one W2 tile = N2 rows x 64 K)
+  static constexpr int B2_TILE = N2 * 128;                         // bytes landed per W2 tile (slot stride stays B_BYTES)
+  static constexpr int HALVES = CM / N2;                           // conv2 MMAs per K step
   static constexpr int NT3 = 4 * CM / 128;                         // 128-channel slices of the conv3 output
   static constexpr int THREADS = 13 * 32;
 };
 
 // p: a_spatial = 1, tw = 8, th = 16, nb = 1, n_tiles = 1, cin_blocks = CM / 64; scale/shift = BN3, scale2/shift2 = BN2.
-// tmA: halo map over t1 (box 64 x 10 x 18 x 1); tmB2: W2 [CM][9*CM] (box 64 x 128); tmB3: W3 [4*CM][CM] (box 64 x 128);
+// tmA: halo map over t1 (box 64 x 10 x 18 x 1); tmB2: W2 [CM][9*CM] (box 64 x min(CM, 128)); tmB3: W3 [4*CM][CM] (box 64 x 128);
 // tmR / tmO: residual / output (B,H,W,4*CM), box 64 x 8 x 16 x 1.
 template <int CM>
 __global__ void __launch_bounds__(ConvC23Smem<CM>::THREADS, 1)
@@ -117,8 +119,8 @@ conv_c23_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int h = 0; h < HALVES; ++h, ++g) {
               const int s = g % NB2;
               mbar_wait(&b2_empty[s], ((g / NB2) & 1) ^ 1);
-              mbar_expect_tx(&b2_full[s], L::B_BYTES);
-              tma_load_2d(b2sm + s * L::B_BYTES, &tmB2, &b2_full[s], tap * cin + kc * 64, h * 128);
+              mbar_expect_tx(&b2_full[s], L::B2_TILE);
+              tma_load_2d(b2sm + s * L::B_BYTES, &tmB2, &b2_full[s], tap * cin + kc * 64, h * L::N2);
             }
       }
     }
@@ -168,6 +170,7 @@ conv_c23_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // -------------------------------------------------------------- MMA issuer (whole warp walks the loops, one elected
     // lane issues; see conv_pers.cuh)
     constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+    constexpr uint32_t idesc2 = umma_idesc_f16(128, L::N2);
     const uint64_t b2desc0 = umma_desc_sw128(smem_u32(b2sm));
     const uint64_t b3desc0 = umma_desc_sw128(smem_u32(b3sm));
     const uint64_t t2desc0 = umma_desc_sw128(smem_u32(t2));
@@ -240,7 +243,7 @@ conv_c23_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t bd = b2desc0 + static_cast<uint64_t>(s) * (L::B_BYTES >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(acc2 + h * 128, ad + 2 * k, bd + 2 * k, idesc, (kc | tap | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_f16(acc2 + h * L::N2, ad + 2 * k, bd + 2 * k, idesc2, (kc | tap | k) != 0);
               umma_commit(&b2_empty[s]);
               if (tap == 8 && h == HALVES - 1) {
                 umma_commit(&a_empty[sa]);
@@ -337,7 +340,7 @@ int conv_c23_launch(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUten
                     const CUtensorMap& tmO, const ConvPersParams& p, int num_sms, cudaStream_t stream) {
   using L = ConvC23Smem<CM>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  static_assert(CM == 128 || CM == 256, "TMEM budget: conv2 accumulator of CM <= 256 columns");
+  static_assert(CM == 64 || CM == 128 || CM == 256, "TMEM budget: conv2 accumulator of CM <= 256 columns");
   auto kern = conv_c23_kernel<CM>;
   static std::atomic<uint64_t> attr_done{0};
   if (first_launch_on_device(attr_done))

@@ -104,7 +104,8 @@ struct dirb200_net {
   Profiler prof;
   float mean_std[6] = {0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f};   // preprocess of resnet.py:110-111
   int fuse_ds = 1;                // fuse the projection shortcut into conv3 of block 0 (tcgen05 path only)
-  int fuse_c23 = 1;               // conv2 + conv3 (+ residual) of the identity blocks as one kernel (conv_c23.cuh)
+  int fuse_c23 = 0;               // conv2 + conv3 (+ residual) of the identity blocks as one kernel (conv_c23.cuh):
+                                  // 0 off, 1 where every SM gets several tiles, 2 wherever the kernel supports the shape
   // trunk / head variants (rmac_resnet.py:74-88, rmac_resnet_fpn.py:92-110)
   bool basic = false;             // BasicBlock trunk (resnet18): two 3x3 convolutions per block, expansion 1
   int expansion = 4;
@@ -321,7 +322,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   }
   else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "fuse_ds") n->fuse_ds = value != 0;
-  else if (k == "fuse_c23") n->fuse_c23 = value != 0;
+  else if (k == "fuse_c23") n->fuse_c23 = static_cast<int>(value);
   else if (k == "pdl") g_use_pdl = value != 0;
   else if (k == "res_variant") set_res_variant(static_cast<int>(value));
   else if (k.size() == 5 && k.compare(0, 4, "mean") == 0 && k[4] >= '0' && k[4] <= '2') n->mean_std[k[4] - '0'] = static_cast<float>(value);
@@ -612,7 +613,8 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
         const int st = blk.c2.stride;
         const int h2 = (h + 2 - 3) / st + 1, w2 = (wd + 2 - 3) / st + 1;
         DIRB_TRY(run_conv(n, blk.c1, x, sb, h, wd, nullptr, 1, t1, stream));
-        if (!blk.has_down && n->fuse_c23 && n->conv_impl == 0 && st == 1 && conv_c23_supported(h, wd, blk.c2.Cin)) {
+        if (!blk.has_down && n->fuse_c23 && n->conv_impl == 0 && st == 1 &&
+            (n->fuse_c23 == 2 ? conv_c23_supported(h, wd, blk.c2.Cin) : conv_c23_profitable(sb, h, wd, blk.c2.Cin))) {
           // identity block: conv2 -> conv3 (+ x) in one kernel, the conv2 output stays in shared memory
           const int Cm = blk.c2.Cin;
           const double flops = 2.0 * sb * h * wd * (9.0 * Cm * Cm + 4.0 * Cm * Cm);

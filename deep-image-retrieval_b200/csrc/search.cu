@@ -334,60 +334,6 @@ __global__ void __launch_bounds__(FIN_THREADS) search_finish_kernel(
   }
 }
 
-// Per query: bitonic sort of (score desc, index asc), write the first k.  Also used to merge shard lists.
-// in_idx is int32 local rows (+offset) when idx32 != nullptr, else int64 global indices from idx64.
-// With shard_k > 0 the input is G shard lists read in place: entry i of query q = element (i % shard_k) of shard
-// (i / shard_k), i.e. in[(i / shard_k) * shard_stride + q * shard_k + i % shard_k] (the all-gather buffer layout).
-__global__ void __launch_bounds__(1024) sort_topk_kernel(const double* __restrict__ in_score, const int* __restrict__ idx32,
-                                                         const int64_t* __restrict__ idx64, const int* __restrict__ cnts,
-                                                         int fixed_cnt, int stride, int64_t offset, int k,
-                                                         double* __restrict__ out_score, int64_t* __restrict__ out_idx,
-                                                         int shard_k = 0, int64_t shard_stride = 0) {
-  extern __shared__ uint8_t sm[];
-  const int q = blockIdx.x;
-  const int n = cnts ? cnts[q] : fixed_cnt;
-  int P = 1;
-  while (P < n) P <<= 1;
-  if (P < 2) P = 2;
-  double* sc = reinterpret_cast<double*>(sm);
-  int64_t* ix = reinterpret_cast<int64_t*>(sc + P);
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    if (i < n) {
-      const int64_t src = shard_k > 0 ? (static_cast<int64_t>(i / shard_k) * shard_stride + static_cast<int64_t>(q) * shard_k + i % shard_k)
-                                      : (static_cast<int64_t>(q) * stride + i);
-      sc[i] = in_score[src];
-      ix[i] = idx32 ? (static_cast<int64_t>(idx32[src]) + offset) : idx64[src];
-      if (ix[i] < 0) sc[i] = -INFINITY;  // empty slots of a shard list
-    } else {
-      sc[i] = -INFINITY;
-      ix[i] = INT64_MAX;
-    }
-  }
-  __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int st = size >> 1; st > 0; st >>= 1) {
-      for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
-        const int lo = 2 * i - (i & (st - 1));
-        const int hi = lo + st;
-        const bool up = ((lo & size) == 0);  // "up" = this block sorted best-first
-        const double a = sc[lo], b = sc[hi];
-        const int64_t ia = ix[lo], ib = ix[hi];
-        const bool a_first = (a > b) || (a == b && ia < ib);
-        if (a_first != up) {
-          sc[lo] = b; sc[hi] = a;
-          ix[lo] = ib; ix[hi] = ia;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const bool ok = (i < n) && (ix[i] >= 0) && (ix[i] != INT64_MAX);
-    out_score[static_cast<int64_t>(q) * k + i] = ok ? sc[i] : -INFINITY;
-    out_idx[static_cast<int64_t>(q) * k + i] = ok ? ix[i] : -1;
-  }
-}
-
 // Exact dense scores for small evaluation sets: grid (ceil(N/8), ceil(Q/4)), warp = one db row x 4 queries.
 __global__ void scores_exact_kernel(const float* __restrict__ q, int Q, const float* __restrict__ db, int64_t N, int D,
                                     float* __restrict__ out) {
@@ -583,6 +529,59 @@ __global__ void __launch_bounds__(RCE_THREADS) rank_count_exact_kernel(
   __syncthreads();
   for (int i = threadIdx.x; i < nt; i += RCE_THREADS)
     if (cnts[i]) atomicAdd(above + t0 + i, static_cast<unsigned long long>(cnts[i]));
+}
+
+
+// Merge G per-shard lists that are each already ordered (score desc, index asc; empty slots = index -1 at the tail):
+// the final position of an entry = its position in its own list + the number of entries of every other list that come
+// before it (binary search) - no sorting network, no barriers after the load.  One block per query.
+__global__ void __launch_bounds__(1024) merge_lists_kernel(const double* __restrict__ in_score, const int64_t* __restrict__ in_idx,
+                                                          int G, int k, int64_t shard_stride, double* __restrict__ out_score,
+                                                          int64_t* __restrict__ out_idx) {
+  extern __shared__ uint8_t sm[];
+  __shared__ int s_valid;
+  const int q = blockIdx.x;
+  const int n = G * k;
+  double* sc = reinterpret_cast<double*>(sm);
+  int64_t* ix = reinterpret_cast<int64_t*>(sc + n);
+  if (threadIdx.x == 0) s_valid = 0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int64_t src = static_cast<int64_t>(e / k) * shard_stride + static_cast<int64_t>(q) * k + e % k;
+    sc[e] = in_score[src];
+    ix[e] = in_idx[src];
+  }
+  __syncthreads();
+  int my_valid = 0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int g = e / k, j = e - g * k;
+    const double se = sc[e];
+    const int64_t ie = ix[e];
+    if (ie < 0) continue;
+    ++my_valid;
+    int rank = j;
+    for (int h = 0; h < G; ++h) {
+      if (h == g) continue;
+      const double* hs = sc + h * k;
+      const int64_t* hi = ix + h * k;
+      int lo = 0, hi_ = k;                      // first position of list h that does NOT come before (se, ie)
+      while (lo < hi_) {
+        const int mid = (lo + hi_) >> 1;
+        const bool before = hi[mid] >= 0 && (hs[mid] > se || (hs[mid] == se && hi[mid] < ie));
+        if (before) lo = mid + 1; else hi_ = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_score[static_cast<int64_t>(q) * k + rank] = se;
+      out_idx[static_cast<int64_t>(q) * k + rank] = ie;
+    }
+  }
+  if (my_valid) atomicAdd(&s_valid, my_valid);
+  __syncthreads();
+  for (int r = s_valid + threadIdx.x; r < k; r += blockDim.x) {      // fewer than k rows in the whole database
+    out_score[static_cast<int64_t>(q) * k + r] = -INFINITY;
+    out_idx[static_cast<int64_t>(q) * k + r] = -1;
+  }
 }
 
 }  // namespace
@@ -1106,14 +1105,12 @@ int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, 
   DIRB_REQUIRE(scores_dev && idx_dev && out_scores_dev && out_idx_dev, DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(G >= 1 && Q >= 1 && k >= 1 && static_cast<int64_t>(G) * k <= 4096, DIRB200_ENOTSUP,
                "merge supports G*k <= 4096 (got G=%d k=%d)", G, k);
-  // shard g holds [Q][k] at element offset g*shard_stride; the sort kernel gathers the G lists of a query in place
+  // shard g holds [Q][k] at element offset g*shard_stride, each list already ordered: rank-based merge, read in place
   if (shard_stride <= 0) shard_stride = static_cast<int64_t>(Q) * k;
   const int n = G * k;
-  int P = 2;
-  while (P < n) P <<= 1;
-  DIRB_CUDA(cudaFuncSetAttribute(sort_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-  sort_topk_kernel<<<Q, 1024, static_cast<size_t>(P) * 16, stream>>>(scores_dev, nullptr, idx_dev, nullptr, n, n, 0, k,
-                                                                    out_scores_dev, out_idx_dev, k, shard_stride);
+  const int threads = std::min(1024, (n + 31) / 32 * 32);
+  merge_lists_kernel<<<Q, threads, static_cast<size_t>(n) * 16, stream>>>(scores_dev, idx_dev, G, k, shard_stride, out_scores_dev,
+                                                                        out_idx_dev);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   return 0;

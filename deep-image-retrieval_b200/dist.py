@@ -51,6 +51,7 @@ class ShardedIndex:
         self.group = group
         self.row_offset = int(row_offset)
         self.local = ops.Index(db32_local, index_offset=row_offset, db16=db16_local)
+        self.local.set_option("retries", 2)      # a rank cannot re-run alone (collectives): one more gated retry pass up front
         # row counts of all shards (one small all-gather at construction, not on the search path): the selection depth
         # of the two-phase search depends on them, see shard_quota
         world = dist.get_world_size(group) if dist.is_initialized() else 1

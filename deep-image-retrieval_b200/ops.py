@@ -275,7 +275,21 @@ class Index:
         else:
             scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
             idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
-        lib.call("dirb200_index_search", self._h, _ptr(q32), nq, int(k), _ptr(scores), _ptr(idx), _stream())
+        try:
+            lib.call("dirb200_index_search", self._h, _ptr(q32), nq, int(k), _ptr(scores), _ptr(idx), _stream())
+        except lib.DirbError as e:
+            if e.status != -4:                      # DIRB200_EOVERFLOW: candidate lists did not fit after the retry passes
+                raise
+            # rare (clustered databases whose first rows are not a sample of the rest): run again with more gated
+            # retry passes and a larger candidate buffer, then restore the defaults
+            self.set_option("retries", 4)
+            self.set_option("cand_cap", 1 << 17)
+            try:
+                lib.call("dirb200_index_search", self._h, _ptr(q32), nq, int(k), _ptr(scores), _ptr(idx), _stream())
+                lib.call("dirb200_index_check", self._h)
+            finally:
+                self.set_option("retries", 1)
+                self.set_option("cand_cap", 0)
         return scores, idx
 
     def search_begin(self, q32: torch.Tensor, k: int, k_shard: int):

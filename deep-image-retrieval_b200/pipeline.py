@@ -48,10 +48,10 @@ def _drop_self(scores, idx, own_rows, k):
     return s, i
 
 
-def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096):
+def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096, to_numpy=True):
     """alpha query expansion (db given) / database augmentation (db=None): test_dir.py:24-44.
-    q' = normalize(mean([q] + [db_j * sim_ij^alpha for the k nearest j])).  Returns a host ndarray.
-    q_block (extension): queries searched per pass."""
+    q' = normalize(mean([q] + [db_j * sim_ij^alpha for the k nearest j])).  Returns a host ndarray like the
+    reference (to_numpy=False, extension: the device tensor).  q_block (extension): queries searched per pass."""
     assert k >= 0 and alpha >= 0, "k and alpha must be non-negative"
     if k == 0:
         return descs
@@ -78,18 +78,70 @@ def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096):
             s1, i1 = _drop_self(s1.cpu().numpy(), i1.cpu().numpy(), np.arange(c0, c0 + qc.shape[0]), k)
             s, i = torch.from_numpy(s1).cuda(), torch.from_numpy(i1).cuda()
         out[c0:c0 + qc.shape[0]] = ops.aqe_expand(qc, d, i.contiguous(), s.contiguous(), float(alpha))
-    return out[:, :dim].cpu().numpy()
+    out = out[:, :dim].contiguous()
+    return out.cpu().numpy() if to_numpy else out
+
+
+_GPU_CHAIN = None
+
+
+def _gpu_chain_scale(transforms):
+    """Transform chains the GPU preprocessing path reproduces bit for bit: '' (ToTensor + Normalize only) and
+    'Scale(<float>)' (transforms.py:133-185 with PIL bilinear) -> the scale factor (1.0 for ''), else None."""
+    import re
+    global _GPU_CHAIN
+    if _GPU_CHAIN is None:
+        _GPU_CHAIN = re.compile(r"^\s*(?:Scale\(\s*([0-9]*\.[0-9]+|[0-9]+\.[0-9]*)\s*\))?\s*$")
+    m = _GPU_CHAIN.match(transforms or "")
+    if not m:
+        return None
+    s = float(m.group(1)) if m.group(1) else 1.0
+    return s if 0 < s <= 4 else None
+
+
+class _RawImages(torch.utils.data.Dataset):
+    """Decoded images as uint8 HWC tensors (the decode stays on CPU workers; everything after it runs on the GPU)."""
+
+    def __init__(self, dataset):
+        self.dataset = dataset
+
+    def __len__(self):
+        return len(self.dataset)
+
+    def __getitem__(self, i):
+        return torch.from_numpy(np.array(self.dataset.get_image(i).convert("RGB"), dtype=np.uint8))
 
 
 def extract_image_features(dataset, transforms, net, ret_imgs=False, same_size=False, flip=None,
-                           desc="Extract feats...", iscuda=True, threads=8, batch_size=8):
-    """Descriptors of every image of `dataset`, (N, D) on the GPU (test_dir.py:47-94)."""
+                           desc="Extract feats...", iscuda=True, threads=8, batch_size=8, gpu_preprocess=True):
+    """Descriptors of every image of `dataset`, (N, D) on the GPU (test_dir.py:47-94).
+    gpu_preprocess (extension): when the chain is '' or 'Scale(<float>)' and images go through one by one, resize
+    (byte-identical to PIL bilinear), ToTensor and Normalize run on the GPU from the decoded uint8 pixels
+    (dirb200_resize_bilinear_u8 + dirb200_net_forward_u8) - bit-identical descriptors, no PIL resize / float
+    conversion on the host and 4x fewer bytes over PCIe."""
     if not same_size:
         batch_size = 1
-    loader = get_loader(dataset, trf_chain=transforms, preprocess=net.preprocess, iscuda=iscuda, output=["img"],
-                        batch_size=batch_size, threads=threads, shuffle=False)
+    scale = _gpu_chain_scale(transforms) if (gpu_preprocess and not same_size and not ret_imgs and hasattr(net, "forward_u8")) else None
     if hasattr(net, "eval"):
         net.eval()
+    if scale is not None:
+        loader = torch.utils.data.DataLoader(_RawImages(dataset), batch_size=None, shuffle=False,
+                                             num_workers=max(0, threads if threads > 1 else 0), pin_memory=True)
+        img_feats = []
+        for img in tqdm.tqdm(loader, desc, total=len(dataset)):
+            x = img.cuda(non_blocking=True)
+            if flip and flip.pop(0):
+                x = x.flip(1)                            # horizontal flip (imgs[i].flip(2) on CHW, test_dir.py:70-72)
+            h, w = int(x.shape[0]), int(x.shape[1])
+            oh, ow = int(0.5 + scale * h), int(0.5 + scale * w)          # Scale.get_params, transforms.py:168
+            x = x.unsqueeze(0).contiguous()
+            if (oh, ow) != (h, w) and min(oh, ow) != min(h, w):          # Scale.__call__: can_upscale / can_downscale
+                x = ops.resize_bilinear_u8(x, (oh, ow))
+            d = net.forward_u8(x)
+            img_feats.append(d.unsqueeze(0) if d.dim() == 1 else d)
+        return torch.cat(img_feats, dim=0)
+    loader = get_loader(dataset, trf_chain=transforms, preprocess=net.preprocess, iscuda=iscuda, output=["img"],
+                        batch_size=batch_size, threads=threads, shuffle=False)
     tocpu = (lambda x: x.cpu()) if ret_imgs == "cpu" else (lambda x: x)
     img_feats, trf_images = [], []
     for inputs in tqdm.tqdm(loader, desc, total=1 + (len(dataset) - 1) // batch_size):
@@ -193,16 +245,20 @@ def eval_model(db, net, trfs, pooling="mean", gemp=3, detailed=False, whiten=Non
         np.save(os.path.join(save_feats, "feats.bdescs.npy"), tonumpy(bdescs))
         if query_db is not db:
             np.save(os.path.join(save_feats, "feats.qdescs.npy"), tonumpy(qdescs))
+    # From here on the descriptors stay in HBM (the reference hops GPU -> numpy -> GPU -> numpy between the steps,
+    # test_dir.py:136-145): whitening, database augmentation, query expansion and the grading all take device tensors.
+    same = qdescs is bdescs
     if whiten is not None:
-        bdescs = common.whiten_features(tonumpy(bdescs), net.pca, **whiten)
-        qdescs = common.whiten_features(tonumpy(qdescs), net.pca, **whiten)
+        bdescs = common.whiten_features_gpu(bdescs, net.pca, **whiten)
+        qdescs = bdescs if same else common.whiten_features_gpu(qdescs, net.pca, **whiten)
     if adba is not None:
-        bdescs = expand_descriptors(bdescs, **adba)
+        # (the reference augments the database rows only: queries drawn from the database keep their un-augmented rows)
+        bdescs = expand_descriptors(bdescs, to_numpy=False, **adba)
     if aqe is not None:
-        qdescs = expand_descriptors(qdescs, db=bdescs, **aqe)
+        qdescs = expand_descriptors(qdescs, db=bdescs, to_numpy=False, **aqe)
     res = {}
-    qn, bn = tonumpy(qdescs), tonumpy(bdescs)
-    unit = bool(np.abs(np.linalg.norm(qn, axis=1) - 1).max() < 1e-3 and np.abs(np.linalg.norm(bn, axis=1) - 1).max() < 1e-3)
+    qn, bn = _dev_f32(qdescs), _dev_f32(bdescs)
+    unit = bool(float((qn.norm(dim=1) - 1).abs().max()) < 1e-3 and float((bn.norm(dim=1) - 1).abs().max()) < 1e-3)
     if rank_topk and hasattr(db, "eval_query_AP_from_ranking"):
         # Large databases: rank with the exact top-k engine instead of materialising the Q x N score matrix; a
         # query whose positives are not all inside the top-k falls back to its exact dense score row.

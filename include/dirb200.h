@@ -60,7 +60,7 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out);
  * Implementation A/B switches: "conv_impl" 0 = persistent tcgen05 implicit GEMM (default), 1 = mma.sync implicit
  * GEMM (validation path), 2 = one-tile-per-CTA tcgen05 kernel (baseline); "fuse_ds" 1 (default) = projection
  * shortcut fused into conv3 as a K-concatenated GEMM; "fuse_c23" 1 (default) = conv2 + conv3 (+ residual) of the
- * identity blocks with 128 / 256 mid channels as one kernel (dirb200_conv_c23).  PROCESS-WIDE (they select kernels, not handle state; set
+ * identity blocks with 64 / 128 / 256 mid channels as one kernel (dirb200_conv_c23).  PROCESS-WIDE (they select kernels, not handle state; set
  * them once, not concurrently with a running forward): "halo" 1 (default) / 0 = 3x3 stride-1 convolutions load
  * their input patch once per tile (conv_halo.cuh) or tap by tap; "pdl" 1 (default) = programmatic dependent
  * launch between consecutive kernels; "res_variant" tile-variant selector of the residual 1x1 convolutions.
@@ -126,7 +126,7 @@ int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const 
                         const void* res_dev, int relu, int impl, void* out_dev, void* stream);
 /* conv2 + conv3 of a Bottleneck in one kernel (resnet.py:75-85): out = relu(bn3(conv1x1(relu(bn2(conv3x3(t1))))) + res).
  * t1 NHWC fp16 (B,H,W,Cm), w2 [Cm][3][3][Cm] fp16, w3 [4*Cm][Cm] fp16 (the layouts of dirb200_conv_bn_act), res / out
- * NHWC fp16 (B,H,W,4*Cm).  Cm in {128, 256}, H >= 16, W >= 8, stride 1.  The conv2 output stays in shared memory as the
+ * NHWC fp16 (B,H,W,4*Cm).  Cm in {64, 128, 256}, H >= 16, W >= 8, stride 1.  The conv2 output stays in shared memory as the
  * A operand of conv3 (fp16, the same rounding as the two-kernel path). */
 int dirb200_conv_c23(const void* t1_dev, int B, int H, int W, int Cm, const void* w2_dev, const float* scale2_dev,
                      const float* shift2_dev, const void* w3_dev, const float* scale3_dev, const float* shift3_dev,
@@ -238,7 +238,8 @@ int dirb200_index_rank_count(dirb200_index* idx, const float* q32_dev, int Q, co
                              int T, int64_t* above_dev, void* stream);
 
 /* Merge G per-shard top-k lists (scores fp64 + global indices int64, as produced by an all-gather of
- * dirb200_index_search outputs) into the global top-k with the same ordering rule.  Shard g's [Q][k] block starts
+ * dirb200_index_search outputs: each list ordered best first, empty slots = index -1 at the tail, no row in two
+ * lists) into the global top-k with the same ordering rule.  Shard g's [Q][k] block starts
  * shard_stride elements after shard g-1's (0 = dense [G][Q][k]); a packed all-gather buffer [G][2][Q][k] uses
  * shard_stride = 2*Q*k with idx_dev = scores_dev + Q*k. */
 int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, int64_t shard_stride,

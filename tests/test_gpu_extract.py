@@ -140,7 +140,7 @@ def test_fused_c23_network_equals_two_kernel_path():
     of the descriptors."""
     net, sd = _net("resnet101_rmac", 3)
     x = synth.make_images(3, 320, 272, seed=8).cuda()
-    net.set_backend_option("fuse_c23", 1)
+    net.set_backend_option("fuse_c23", 2)
     a = net(x)
     n_fused = net.last_launch_stats()[0]
     net.set_backend_option("fuse_c23", 0)

@@ -226,6 +226,34 @@ def test_cli_hard_variant_matches_reference_command_lines(tmp_path, monkeypatch,
     assert abs(res_m["mAP"] - m_ref) < 1e-12
 
 
+def test_gpu_preprocessing_path_is_bit_identical_to_the_pil_path(tmp_path):
+    """extract_image_features: decoded uint8 pixels -> GPU resize (PIL-exact) -> ToTensor/Normalize fused into the stem
+    gives the SAME descriptors as PIL resize + host ToTensor/Normalize, for the three chains of the multi-scale
+    protocol, with horizontal flips, and falls back to the PIL path for other chains."""
+    _gpu()
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import e2e_data
+    from dirtorch import nets, test_dir
+    from dirtorch.datasets import ImageList
+    root = str(tmp_path)
+    _, names, _, sd = e2e_data.build(root)
+    with open(os.path.join(root, "list.txt"), "w") as f:
+        f.write("\n".join(names[:6]) + "\n")
+    ds = ImageList(os.path.join(root, "list.txt"), os.path.join(root, "oxford5k", "jpg"))
+    net = nets.create_model("resnet50_rmac")
+    net.load_state_dict(sd)
+    net.cuda()
+    from dirb200 import pipeline
+    assert pipeline._gpu_chain_scale("") == 1.0 and pipeline._gpu_chain_scale("Scale(0.7)") == 0.7
+    assert pipeline._gpu_chain_scale("Scale(256)") is None and pipeline._gpu_chain_scale("Scale(0.7), Pad(300)") is None
+    for chain in ("", "Scale(0.7)", "Scale(1.4)"):
+        a = test_dir.extract_image_features(ds, chain, net, threads=2, flip=[False, True, False, True, False, False])
+        b = test_dir.extract_image_features(ds, chain, net, threads=2, flip=[False, True, False, True, False, False],
+                                            gpu_preprocess=False)
+        assert torch.equal(a, b), chain
+    assert not torch.equal(a[1], test_dir.extract_image_features(ds, "Scale(1.4)", net, threads=2)[1])   # the flip mattered
+
+
 def test_batched_extraction_with_crop_chain(tmp_path, golden):
     """test_dir.extract_image_features with same_size=True, batch_size=4 (the 'Pad'/'Crop' branch of test_dir.py:114)
     through 'Scale(140), CenterCrop(128)' vs the reference's descriptors (tests/golden/transforms.npz)."""

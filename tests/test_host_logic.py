@@ -290,6 +290,9 @@ def _shard_sizes_worker(rank, world, port, tmp):
     class _NoGpuIndex:                                     # the real one uploads to the GPU
         def __init__(self, db32, index_offset=0, db16=None):
             self.db32, self.n, self.dim = db32, db32.shape[0], db32.shape[1]
+
+        def set_option(self, key, value):
+            pass
     ops.Index = _NoGpuIndex
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sh = ddist.ShardedIndex(torch.zeros(([3, 1000, 0][rank], 64)), row_offset=0)

@@ -31,6 +31,19 @@ out = index.expand_queries(qd, 2, 0.5)
 if rank == 0:
     ref = O.expand_descriptors(q, db=db, k=2, alpha=0.5)
     ok = ok and float(np.linalg.norm(out.cpu().numpy() - ref) / np.linalg.norm(ref)) < 1e-5
+# exact-mAP rank counting over the sharded database: scores from the owning shard, counts summed over shards
+gnd = synth.oxford_gt(pos, n_junk=3, n_db=db.shape[0], seed=5)
+offs, rows, flags = [0], [], []
+for g_ in gnd:
+    r_ = sorted(set(g_["ok"]) | set(g_["junk"]))
+    rows += r_
+    flags += [1 if x in set(g_["ok"]) else 0 for x in r_]
+    offs.append(len(rows))
+sc, above = index.rank_counts(qd, np.array(offs, np.int32), np.array(rows, np.int64), np.array(flags, np.uint8))
+if rank == 0:
+    rs_, ra_ = O.rank_counts(q, db, offs, np.array(rows))
+    m_ = np.array(flags) == 1
+    ok = ok and bool(np.abs(sc.cpu().numpy() - rs_).max() < 1e-12 and np.array_equal(above.cpu().numpy()[m_], ra_[m_]))
 # Persisted path (opt-in: DIST_CHECK_STORE=<directory on a filesystem all ranks see>): every rank writes its rows as a
 # shard of a descriptor store, the store is re-read under the current world size (row ranges come from the manifest)
 # and searched again.
