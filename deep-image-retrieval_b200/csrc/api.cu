@@ -31,12 +31,12 @@ int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const 
 
 int dirb200_conv_c23(const void* t1_dev, int B, int H, int W, int Cm, const void* w2_dev, const float* scale2_dev,
                      const float* shift2_dev, const void* w3_dev, const float* scale3_dev, const float* shift3_dev,
-                     const void* res_dev, void* out_dev, void* stream) {
+                     const void* res_dev, void* out_dev, int variant, void* stream) {
   DIRB_REQUIRE(t1_dev && w2_dev && w3_dev && scale2_dev && shift2_dev && scale3_dev && shift3_dev && res_dev && out_dev,
                DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(B > 0 && H > 0 && W > 0, DIRB200_EINVAL, "bad shape");
   return conv_c23(B, H, W, Cm, CH16(t1_dev), CH16(w2_dev), scale2_dev, shift2_dev, CH16(w3_dev), scale3_dev, shift3_dev,
-                  CH16(res_dev), H16(out_dev), ST(stream));
+                  CH16(res_dev), H16(out_dev), ST(stream), variant);
 }
 
 size_t dirb200_stem_workspace_bytes(int B, int H, int W) { return stem_workspace_bytes(B, H, W); }

@@ -7,6 +7,7 @@
 #include "conv.h"
 
 #include "conv_c23.cuh"
+#include "conv_c23p.cuh"
 #include "conv_halo.cuh"
 #include "conv_pers.cuh"
 #include "gemm_tc.cuh"
@@ -198,7 +199,7 @@ bool conv_c23_profitable(int B, int H, int W, int Cm) {
 
 int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, const float* scale2, const float* shift2,
              const __half* w3, const float* scale3, const float* shift3, const __half* res, __half* out,
-             cudaStream_t stream) {
+             cudaStream_t stream, int variant) {
   DIRB_REQUIRE(conv_c23_supported(H, W, Cm), DIRB200_ENOTSUP, "fused conv2+conv3 needs Cm in {64, 128, 256}, H >= 16, W >= 8 (got %d, %d, %d)", Cm, H, W);
   DIRB_REQUIRE(t1 && w2 && w3 && res && out, DIRB200_EINVAL, "null argument");
   ConvPersParams p{};
@@ -221,10 +222,16 @@ int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, co
   p.total_tiles = static_cast<int>(total);
   CUtensorMap tmA, tmB2, tmB3, tmR, tmO;
   DIRB_TRY(encode_tmap_nhwc(&tmA, t1, B, H, W, Cm, 10, 18, 1, 1));
-  DIRB_TRY(encode_tmap_2d(&tmB2, w2, 9 * Cm, Cm, (uint64_t)9 * Cm * 2, 64, Cm < 128 ? Cm : 128));
-  DIRB_TRY(encode_tmap_2d(&tmB3, w3, Cm, 4 * Cm, (uint64_t)Cm * 2, 64, 128));
+  const bool pair = variant != 0;      // CTA pairs (cta_group::2): each CTA loads half of every weight tile
+  DIRB_TRY(encode_tmap_2d(&tmB2, w2, 9 * Cm, Cm, (uint64_t)9 * Cm * 2, 64, pair ? Cm / 2 : (Cm < 128 ? Cm : 128)));
+  DIRB_TRY(encode_tmap_2d(&tmB3, w3, Cm, 4 * Cm, (uint64_t)Cm * 2, 64, pair ? 64 : 128));
   DIRB_TRY(encode_tmap_nhwc(&tmR, res, B, H, W, 4 * Cm, 8, 16, 1, 1));
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, H, W, 4 * Cm, 8, 16, 1, 1));
+  if (pair) {
+    if (Cm == 256) return conv_c23p_launch<256>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
+    if (Cm == 64) return conv_c23p_launch<64>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
+    return conv_c23p_launch<128>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
+  }
   if (Cm == 256) return conv_c23_launch<256>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
   if (Cm == 64) return conv_c23_launch<64>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);
   return conv_c23_launch<128>(tmA, tmB2, tmB3, tmR, tmO, p, num_sms(), stream);

@@ -23,7 +23,7 @@ bool conv_c23_supported(int H, int W, int Cm);
 bool conv_c23_profitable(int B, int H, int W, int Cm);
 int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, const float* scale2, const float* shift2,
              const __half* w3, const float* scale3, const float* shift3, const __half* res, __half* out,
-             cudaStream_t stream);
+             cudaStream_t stream, int variant = 1);   // variant 0: one CTA per tile (conv_c23.cuh), 1: CTA pairs (conv_c23p.cuh)
 // The earlier one-tile-per-CTA tcgen05 kernel (gemm_tc.cuh), kept as an A/B baseline (impl 2).
 int conv_tc_np(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
                const __half* res, int relu, __half* out, cudaStream_t stream);

@@ -104,6 +104,7 @@ struct dirb200_net {
   Profiler prof;
   float mean_std[6] = {0.485f, 0.456f, 0.406f, 0.229f, 0.224f, 0.225f};   // preprocess of resnet.py:110-111
   int fuse_ds = 1;                // fuse the projection shortcut into conv3 of block 0 (tcgen05 path only)
+  int c23_variant = 1;            // 1 = CTA pairs (cta_group::2), 0 = one CTA per tile
   int fuse_c23 = 0;               // conv2 + conv3 (+ residual) of the identity blocks as one kernel (conv_c23.cuh):
                                   // 0 off, 1 where every SM gets several tiles, 2 wherever the kernel supports the shape
   // trunk / head variants (rmac_resnet.py:74-88, rmac_resnet_fpn.py:92-110)
@@ -323,6 +324,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "fuse_ds") n->fuse_ds = value != 0;
   else if (k == "fuse_c23") n->fuse_c23 = static_cast<int>(value);
+  else if (k == "c23_variant") n->c23_variant = static_cast<int>(value);
   else if (k == "pdl") g_use_pdl = value != 0;
   else if (k == "res_variant") set_res_variant(static_cast<int>(value));
   else if (k.size() == 5 && k.compare(0, 4, "mean") == 0 && k[4] >= '0' && k[4] <= '2') n->mean_std[k[4] - '0'] = static_cast<float>(value);
@@ -624,7 +626,7 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
           snprintf(tg, sizeof(tg), "3x3 %d->%d + 1x1 ->%d +res fused @%dx%d", Cm, Cm, 4 * Cm, h, wd);
           ProfScope ps(n, stream, 0, flops, bytes, tg);
           DIRB_TRY(conv_c23(sb, h, wd, Cm, t1, blk.c2.w, blk.c2.scale, blk.c2.shift, blk.c3.w, blk.c3.scale, blk.c3.shift, x, y,
-                            stream));
+                            stream, n->c23_variant));
           x = y;
           continue;
         }

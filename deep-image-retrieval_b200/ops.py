@@ -72,7 +72,7 @@ def conv_bn_act(x, w_packed, cout, kh, kw, stride, pad, scale, shift, res=None, 
     return out
 
 
-def conv_c23(t1, w2_packed, scale2, shift2, w3_packed, scale3, shift3, res):
+def conv_c23(t1, w2_packed, scale2, shift2, w3_packed, scale3, shift3, res, variant=1):
     """Fused Bottleneck tail: relu(bn3(conv1x1(relu(bn2(conv3x3(t1))))) + res).  t1 NHWC fp16 (B,H,W,Cm) -> (B,H,W,4Cm)."""
     _chk(t1, torch.float16, "t1")
     _chk(res, torch.float16, "res")
@@ -80,7 +80,7 @@ def conv_c23(t1, w2_packed, scale2, shift2, w3_packed, scale3, shift3, res):
     assert tuple(res.shape) == (b, h, w, 4 * cm)
     out = torch.empty_like(res)
     lib.call("dirb200_conv_c23", _ptr(t1), b, h, w, cm, _ptr(_chk(w2_packed, torch.float16, "w2")), _ptr(scale2), _ptr(shift2),
-             _ptr(_chk(w3_packed, torch.float16, "w3")), _ptr(scale3), _ptr(shift3), _ptr(res), _ptr(out), _stream())
+             _ptr(_chk(w3_packed, torch.float16, "w3")), _ptr(scale3), _ptr(shift3), _ptr(res), _ptr(out), int(variant), _stream())
     return out
 
 

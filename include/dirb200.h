@@ -127,10 +127,11 @@ int dirb200_conv_bn_act(const void* in_dev, int B, int H, int W, int Cin, const 
 /* conv2 + conv3 of a Bottleneck in one kernel (resnet.py:75-85): out = relu(bn3(conv1x1(relu(bn2(conv3x3(t1))))) + res).
  * t1 NHWC fp16 (B,H,W,Cm), w2 [Cm][3][3][Cm] fp16, w3 [4*Cm][Cm] fp16 (the layouts of dirb200_conv_bn_act), res / out
  * NHWC fp16 (B,H,W,4*Cm).  Cm in {64, 128, 256}, H >= 16, W >= 8, stride 1.  The conv2 output stays in shared memory as the
- * A operand of conv3 (fp16, the same rounding as the two-kernel path). */
+ * A operand of conv3 (fp16, the same rounding as the two-kernel path).  variant 1: CTA pairs - every MMA spans two SMs
+ * (tcgen05 cta_group::2), each CTA loads half of every weight tile; variant 0: one CTA per tile. */
 int dirb200_conv_c23(const void* t1_dev, int B, int H, int W, int Cm, const void* w2_dev, const float* scale2_dev,
                      const float* shift2_dev, const void* w3_dev, const float* scale3_dev, const float* shift3_dev,
-                     const void* res_dev, void* out_dev, void* stream);
+                     const void* res_dev, void* out_dev, int variant, void* stream);
 /* The stem on tensor cores: Conv2d(3, 64, 7, stride 2, pad 3, bias=False) + folded BN + ReLU, resnet.py:115-118.
  * imgs_dev NCHW fp32 (B,3,H,W); w2_dev = the [64][256] fp16 weight layout produced (on the host) by
  * dirb200_stem_pack_weight from the OIHW fp32 [64][3][7][7] tensor; ws_dev scratch of

@@ -160,8 +160,9 @@ def test_whiten_tensor_core_path_large():
     assert rel_l2(y.cpu().numpy(), ref) < 2e-5
 
 
+@pytest.mark.parametrize("variant", [1, 0], ids=["pair", "single"])
 @pytest.mark.parametrize("cm,b,h,w", [(256, 2, 64, 64), (128, 1, 48, 40), (256, 1, 17, 23), (128, 3, 16, 8), (256, 5, 72, 56), (64, 2, 80, 72), (64, 1, 16, 9)])
-def test_conv_c23_fused_bottleneck_tail(cm, b, h, w):
+def test_conv_c23_fused_bottleneck_tail(cm, b, h, w, variant):
     """conv2 (3x3) + BN + ReLU + conv3 (1x1) + BN + residual + ReLU in ONE kernel (resnet.py:75-85) == the two-kernel
     path bit for bit (same fp16 rounding of the intermediate, same K order), and within fp16 tolerance of the oracle;
     ragged tiles (sizes that are not multiples of the 8 x 16 patch) and many tiles per CTA."""
@@ -176,7 +177,7 @@ def test_conv_c23_fused_bottleneck_tail(cm, b, h, w):
     s3 = torch.from_numpy(r.uniform(0.2, 0.4, 4 * cm).astype(np.float32)).to(DEV)
     h3 = torch.from_numpy((0.1 * r.standard_normal(4 * cm)).astype(np.float32)).to(DEV)
     w2p, w3p = ops.pack_conv_weight(w2).to(DEV), ops.pack_conv_weight(w3).to(DEV)
-    fused = ops.conv_c23(t1, w2p, s2, h2, w3p, s3, h3, res)
+    fused = ops.conv_c23(t1, w2p, s2, h2, w3p, s3, h3, res, variant=variant)
     t2 = ops.conv_bn_act(t1, w2p, cm, 3, 3, 1, 1, s2, h2, None, True)
     two = ops.conv_bn_act(t2, w3p, 4 * cm, 1, 1, 1, 0, s3, h3, res, True)
     torch.cuda.synchronize()

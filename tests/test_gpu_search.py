@@ -273,11 +273,19 @@ def test_deferred_check_and_unresolved_overflow():
     assert e.value.status == -4
     index.check()                                   # the error is reported once
     index.set_option("deferred_check", 0)
-    with pytest.raises(DirbError):
-        index.search(qd, 50)                        # same condition, immediate check
-    index.set_option("retries", 1)                  # Python front-end: re-runs once with more retry passes and a larger buffer
-    s, i = index.search(qd, 50)
-    np.testing.assert_array_equal(i.cpu().numpy(), ri)
+    s, i = index.search(qd, 50)                     # immediate check: the Python front-end catches the overflow and re-runs
+    np.testing.assert_array_equal(i.cpu().numpy(), ri)   # once with more retry passes and a larger candidate buffer
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=0, atol=1e-12)
+    from dirb200 import lib
+    import ctypes as C
+    sc = torch.empty((5, 50), dtype=torch.float64, device=DEV)
+    ix = torch.empty((5, 50), dtype=torch.int64, device=DEV)
+    index.set_option("sample_rows", 256)
+    index.set_option("cand_cap", 512)
+    index.set_option("retries", 0)
+    with pytest.raises(DirbError):                  # the C entry point itself reports it
+        lib.call("dirb200_index_search", index._h, C.c_void_p(qd.data_ptr()), 5, 50, C.c_void_p(sc.data_ptr()),
+                 C.c_void_p(ix.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
 
 def test_empty_shard():
