@@ -248,8 +248,17 @@ def aqe_expand(q, db32, nn_idx, nn_scores, alpha, partial=False, row_offset=0, n
 class Index:
     """One row shard of a descriptor database on one GPU (dirb200_index)."""
 
-    def __init__(self, db32: torch.Tensor, index_offset: int = 0, db16: torch.Tensor = None):
+    def __init__(self, db32: torch.Tensor, index_offset: int = 0, db16: torch.Tensor = None, check_norms: bool = True):
+        """check_norms: the exactness of the top-k rests on |fp16-path score - exact score| <= eps16 = 1.2e-3, which is
+        derived for UNIT-NORM rows and queries (what pooling / whitening / query expansion produce).  Rows with larger
+        norms are refused here instead of silently returning an inexact list; pass check_norms=False and set option
+        'eps16' to 1.2e-3 * max|q| * max|row| to search un-normalised data."""
         _chk(db32, torch.float32, "db32")
+        if check_norms and db32.shape[0]:
+            worst = float(torch.linalg.vector_norm(db32, dim=1).max())
+            if worst > 1.0 + 1e-3:
+                raise ValueError("database rows are not unit-norm (max norm %.4g): the exact-top-k error bound assumes |row| <= 1; "
+                                 "normalise them, or pass check_norms=False and set option 'eps16' accordingly" % worst)
         self.db32 = db32
         self.n, self.dim = db32.shape
         if db16 is None:                      # an empty shard (more ranks than rows) has nothing to convert
