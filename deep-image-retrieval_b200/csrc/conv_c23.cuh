@@ -155,9 +155,20 @@ conv_c23_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 3) {
     if (lane == 0) {
       // ------------------------------------------------------------ residual tiles, in the order E2 consumes them
+      // Only NSTG = 2 staging buffers exist (the conv3 operand occupies the shared memory a deeper residual ring would
+      // need), so a residual chunk cannot be requested more than ~one chunk ahead of its use and its HBM latency would
+      // sit on the epilogue's critical path (measured: 2.5 us per 16 KB chunk, 40 us per tile).  The residual of the
+      // NEXT tile is therefore prefetched into L2 while this tile is processed: 256 KB per CTA, 38 MB for the grid.
       uint32_t cc = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
+        if (t == static_cast<int>(blockIdx.x)) {
+          for (int ch = 0; ch < 4 * CM / 64; ++ch) tma_prefetch_4d(&tmR, ch * 64, c.wo0, c.ho0, c.n0);
+        }
+        if (t + static_cast<int>(gridDim.x) < p.total_tiles) {
+          const TileCoord cn = decode_tile(p, t + gridDim.x);
+          for (int ch = 0; ch < 4 * CM / 64; ++ch) tma_prefetch_4d(&tmR, ch * 64, cn.wo0, cn.ho0, cn.n0);
+        }
         for (int ch = 0; ch < 4 * CM / 64; ++ch, ++cc) {
           const int b = cc % NSTG;
           mbar_wait(&res_empty[b], ((cc / NSTG) & 1) ^ 1);

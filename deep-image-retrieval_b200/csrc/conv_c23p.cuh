@@ -230,9 +230,17 @@ conv_c23p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 3) {
     if (lane == 0) {
       // ------------------------------------------------------------ residual tiles (local barriers)
+      // (the residual of the NEXT tile is prefetched into L2 while this one is processed, see conv_c23.cuh)
       uint32_t cc = 0;
       for (int j = pair_id; j < pair_tiles; j += pairs) {
         const TileCoord c = decode_tile(p, my_tile(j));
+        if (j == pair_id) {
+          for (int ch = 0; ch < 4 * CM / 64; ++ch) tma_prefetch_4d(&tmR, ch * 64, c.wo0, c.ho0, c.n0);
+        }
+        if (j + pairs < pair_tiles) {
+          const TileCoord cn = decode_tile(p, my_tile(j + pairs));
+          for (int ch = 0; ch < 4 * CM / 64; ++ch) tma_prefetch_4d(&tmR, ch * 64, cn.wo0, cn.ho0, cn.n0);
+        }
         for (int ch = 0; ch < 4 * CM / 64; ++ch, ++cc) {
           const int b = cc % NSTG;
           mbar_wait(&res_empty[b], ((cc / NSTG) & 1) ^ 1);

@@ -10,7 +10,7 @@ DEV = "cuda:0"
 for (cm, b, h, w) in ((256, 64, 64, 64), (128, 64, 128, 128), (64, 64, 256, 256)):
     r = np.random.RandomState(cm)
     t1 = torch.relu(torch.randn((b, h, w, cm), device=DEV)).half()
-    res = torch.randn((b, h, w, 4 * cm), device=DEV).half()
+    res = torch.relu(torch.randn((b, h, w, 4 * cm), device=DEV)).half()
     w2 = torch.from_numpy((r.standard_normal((cm, cm, 3, 3)) * np.sqrt(2.0 / (9 * cm))).astype(np.float32))
     w3 = torch.from_numpy((r.standard_normal((4 * cm, cm, 1, 1)) * np.sqrt(2.0 / cm)).astype(np.float32))
     s2, h2 = torch.ones(cm, device=DEV), torch.zeros(cm, device=DEV)

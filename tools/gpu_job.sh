@@ -39,6 +39,12 @@ while [ $# -gt 0 ]; do
         python tools/search_profile.py c3 > gpurun_out/traffic_s3.log 2>&1; echo "== traffic c3 rc=$?"
       timeout 300 ncu --metrics $M --clock-control none -k regex:"conv_pers" -s 6 -c 4 --csv --log-file gpurun_out/traffic_search_1000q_125k.csv \
         python tools/search_profile.py one > gpurun_out/traffic_s8.log 2>&1; echo "== traffic shard rc=$?" ;;
+    dist)
+      # multi-GPU: NCCL parity (tools/dist_check.py) + bench lines under torchrun; $1 = number of GPUs, $2 = bench args
+      n=$1; shift; bargs=${1:-}; shift
+      TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533"
+      timeout 600 $TR tools/dist_check.py > gpurun_out/dist_check_$n.log 2>&1; rc=$?; echo "== dist_check x$n rc=$rc"; tail -3 gpurun_out/dist_check_$n.log; [ $rc -ne 0 ] && rc_all=$rc
+      timeout 900 $TR bench.py --gpus $n $bargs > gpurun_out/bench_${n}gpu.log 2> gpurun_out/bench_${n}gpu.err; rc=$?; echo "== bench x$n rc=$rc"; tail -c 3000 gpurun_out/bench_${n}gpu.log; tail -3 gpurun_out/bench_${n}gpu.err; [ $rc -ne 0 ] && rc_all=$rc ;;
     py)
       script=$1; shift
       timeout 900 python $script > gpurun_out/$(basename $script .py).log 2>&1; rc=$?; echo "== py $script rc=$rc"; tail -40 gpurun_out/$(basename $script .py).log; [ $rc -ne 0 ] && rc_all=$rc ;;
