@@ -39,6 +39,24 @@ while [ $# -gt 0 ]; do
         python tools/search_profile.py c3 > gpurun_out/traffic_s3.log 2>&1; echo "== traffic c3 rc=$?"
       timeout 300 ncu --metrics $M --clock-control none -k regex:"conv_pers" -s 6 -c 4 --csv --log-file gpurun_out/traffic_search_1000q_125k.csv \
         python tools/search_profile.py one > gpurun_out/traffic_s8.log 2>&1; echo "== traffic shard rc=$?" ;;
+    benchall)
+      # one JSON line per BASELINE configuration (1 GPU), kept for profiles/
+      for cfg in c2 c3 c4 c5; do
+        st=20; [ $cfg = c5 ] && st=5
+        timeout 900 python bench.py --config $cfg --steps $st --warmup 3 > gpurun_out/bench_$cfg.json 2> gpurun_out/bench_$cfg.err; rc=$?
+        echo "== bench $cfg rc=$rc"; python - <<PY
+import json
+try:
+    l = json.loads(open("gpurun_out/bench_$cfg.json").read().strip().splitlines()[-1])
+    r = l.get("roofline", {})
+    print("   ", l["metric"], round(l["value"], 1), l["unit"], "ms/step", round(l["ms_per_step"], 3), "e2e", round(l["e2e"]["value"], 1),
+          "| roofline", r.get("bound"), round(r.get("achieved", 0), 1), r.get("unit"), "frac", round(r.get("frac", 0), 3), "| clocks", l.get("clocks", {}).get("sm_mhz"), l.get("clocks", {}).get("reasons"))
+    if "search" in l: print("    search", round(l["search"]["value"], 1), "q/s", l["search"]["ms_per_step"], l["search"].get("phases_ms"))
+except Exception as e:
+    print("    (no line)", e); print(open("gpurun_out/bench_$cfg.err").read()[-1500:])
+PY
+        [ $rc -ne 0 ] && rc_all=$rc
+      done ;;
     dist)
       # multi-GPU: NCCL parity (tools/dist_check.py) + bench lines under torchrun; $1 = number of GPUs, $2 = bench args
       n=$1; shift; bargs=${1:-}; shift
