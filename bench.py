@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="c2: skip the small-batch latency table")
     ap.add_argument("--fuse-c23", type=int, default=-1, help="override the library default of option fuse_c23 (A/B runs)")
+    ap.add_argument("--opt", action="append", default=[], help="library option KEY=VALUE for the network handle (A/B runs)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--host-chunk", type=int, default=0)
     ap.add_argument("--search-n", type=int, default=SEARCH_N)
@@ -298,6 +299,9 @@ def make_net(args, ctx):
         net.set_backend_option("host_chunk", args.host_chunk)
     if args.fuse_c23 >= 0:
         net.set_backend_option("fuse_c23", args.fuse_c23)
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        net.set_backend_option(k_, float(v_))
     return net
 
 

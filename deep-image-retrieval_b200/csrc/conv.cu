@@ -105,6 +105,9 @@ int num_sms() {
   return n;
 }
 
+static int g_l2_prefetch = 0;    // tuning knob (option "l2_prefetch"): next-tile L2 prefetch in the 1x1 convolutions
+void set_l2_prefetch(int v) { g_l2_prefetch = v; }
+
 template <int BN, int STAGES, int NB>
 static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
                         const __half* res, int relu, __half* out, cudaStream_t stream) {
@@ -143,6 +146,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
     if (res) DIRB_TRY(encode_tmap_nhwc(&tmR, res, s.B, Ho, Wo, s.Cout, p.tw, p.th, p.nb, 1));
   }
   if (!res) tmR = tmO;
+  p.l2_prefetch = g_l2_prefetch;
   DIRB_TRY(encode_tmap_2d(&tmB, w, Ktot, s.Cout, (uint64_t)Ktot * 2, 64, BN));
   const int64_t total = m_tiles * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);

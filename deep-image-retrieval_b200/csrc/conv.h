@@ -35,6 +35,7 @@ int num_sms();
 // Process-wide switch (A/B testing): 3x3/s1 convolutions through conv_halo.cuh (1, default) or tap by tap (0).
 void set_conv_halo(int on);
 void set_res_variant(int v);
+void set_l2_prefetch(int v);
 int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_t stream);
 
 // Stem 7x7/s2/p3 (3 -> 64) + BN + ReLU on tensor cores (stem_pers.cuh).  imgs: NCHW fp32; w2: [64][256] fp16 in the

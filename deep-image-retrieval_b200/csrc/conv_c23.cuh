@@ -278,7 +278,8 @@ conv_c23_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quarter = warp & 3;
     const int hsel = (warp - 4) >> 2;
     const int row = quarter * 32 + lane;
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (threadIdx.x == 128u + 128u * hsel);       // first thread of this epilogue group (E2)
+    const bool leader0 = (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
@@ -322,8 +323,8 @@ conv_c23_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       fence_proxy_async_smem();                              // generic-proxy writes -> visible to the tensor core
-      named_bar_sync(3, EPI_THREADS);
-      if (leader) mbar_arrive(t2_full);
+      named_bar_sync(5, EPI_THREADS);                        // (ids 1-4 belong to the two groups of conv_epilogue_tile)
+      if (leader0) mbar_arrive(t2_full);
       // ---- E2: the NT3 output slices of conv3
 #pragma unroll 1
       for (int n3 = 0; n3 < NT3; ++n3, ++m3) {

@@ -207,7 +207,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const int hsel = (warp - 4) >> 2;
     const int row = quarter * 32 + lane;
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (threadIdx.x == 128u + 128u * hsel);       // first thread of this epilogue group
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t cc = 0, i = 0;

@@ -52,6 +52,10 @@ struct ConvPersParams {
   unsigned long long* cand;    // [M][cand_cap] packed (score bits << 32 | row)
   int* cand_cnt;               // [M]
   int cand_cap;
+  // HBM-bound 1x1 convolutions: the producers also request the NEXT tile's activation / residual boxes into L2
+  // (cp.async.bulk.prefetch.tensor) while the current tile streams, which deepens the HBM request queue beyond what the
+  // shared-memory rings can hold in flight.  0 = off.
+  int l2_prefetch;
   // Device-side launch predicate (retry passes of the search): when non-null the whole grid returns at once unless
   // *gate != 0.  The value was written by the previous kernel of the stream, so it is read after pdl_wait().
   const int* gate;
@@ -95,85 +99,109 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvPersParams& p, int t)
   return c;
 }
 
-// Convolution epilogue of one output tile: for each 64-channel chunk read the accumulator row of this thread from
-// TMEM, apply BN scale/shift (+ residual from the staging buffer) (+ ReLU), write fp16 in place into the swizzled
-// staging buffer and let the leader thread TMA-store it.  `cc` counts staging chunks across tiles.
+// Convolution epilogue of one output tile.  The 8 epilogue warps form TWO independent groups of 4 warps (one warp per
+// TMEM lane quarter); group g takes the 64-channel chunks whose running index has parity g, so two chunks are in
+// flight at any time.  Per chunk a thread reads its accumulator row (64 columns) from TMEM, applies BN scale/shift
+// (+ residual from the staging buffer) (+ ReLU), writes fp16 in place into the 128-byte-swizzled staging buffer, and the
+// group's leader TMA-stores it.  (Round 1 ran all 8 warps on ONE chunk at a time: two 256-thread barriers, a proxy fence
+// and the store hand-off made ~1.2 us per chunk the critical path of every 1x1 convolution with a residual - 4.9 us per
+// 128 x 256 tile where the MMAs need 1.5 us and HBM 3.3 us.)
+// `cc` counts staging chunks across tiles (same value in every thread); chunk i uses staging buffer i % NBUF, NBUF even,
+// so a buffer always belongs to the same group.  `g` = group of this thread, `leader` = first thread of its group.
 template <int BN, int NBUF, int EPI_THREADS>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
                                                    uint8_t* stg, uint64_t* res_full, uint64_t* res_empty,
                                                    uint64_t* acc_empty_a, uint32_t& cc, uint32_t row_off, uint32_t sw,
-                                                   int hsel, int lane, bool leader, const CUtensorMap& tmO) {
+                                                   int g, int lane, bool leader, const CUtensorMap& tmO) {
+  static_assert(NBUF % 2 == 0, "staging buffers are split between the two epilogue groups");
   constexpr int CHUNKS = BN / 64;
   constexpr int STG_BYTES = 128 * 128;
+  constexpr int GROUP_THREADS = 128;
+  int my_last = -1;                                         // last chunk of this tile that this group reads from TMEM
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch)
+    if (static_cast<int>((cc + ch) & 1u) == g) my_last = ch;
+  if (my_last < 0) {                                        // (BN = 64: one chunk per tile, the other group only releases)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty_a);
+  }
 #pragma unroll 1
-      for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
-        const int b = cc % NBUF;
-        uint8_t* buf = stg + b * STG_BYTES;
-        if (p.has_res) {
-          mbar_wait(&res_full[b], (cc / NBUF) & 1);       // residual chunk has landed in `buf`
-        } else {
-          if (leader) bulk_wait_read<NBUF - 1>();           // the store issued NBUF chunks ago has left `buf`
-          named_bar_sync(1, EPI_THREADS);
-        }
-        const int col0 = c.n_tile * BN + ch * 64;
-        {
-          const int half = hsel;
-          float v[32];
-          tmem_ld32(taddr + ch * 64 + half * 32, v);
-          tmem_ld_wait();
-          if (ch == CHUNKS - 1) {                          // last TMEM read of this tile: release the accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty_a);
-          }
-          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+  for (int ch = 0; ch < CHUNKS; ++ch) {
+    const uint32_t ccc = cc + ch;
+    if (static_cast<int>(ccc & 1u) != g) continue;
+    const int b = ccc % NBUF;
+    uint8_t* buf = stg + b * STG_BYTES;
+    if (p.has_res) {
+      mbar_wait(&res_full[b], (ccc / NBUF) & 1);            // residual chunk has landed in `buf`
+    } else {
+      if (leader) bulk_wait_read<NBUF / 2 - 1>();            // this group's store NBUF/2 chunks ago (same buffer) has left it
+      named_bar_sync(1 + 2 * g, GROUP_THREADS);
+    }
+    const int col0 = c.n_tile * BN + ch * 64;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
-            v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
-            v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
-            v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
-            v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {                    // 4 x 16-byte chunks (8 channels each) of this half
-            const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
-            uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
-            if (p.has_res) {
-              const uint4 r = *sp;
-              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_h2(rr[e]);
-                v[j * 8 + e * 2] += f.x;
-                v[j * 8 + e * 2 + 1] += f.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
-            }
-            uint4 o;
-            o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
-            o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
-            o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
-            o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
-            *sp = o;
-          }
-        }
-        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(2, EPI_THREADS);
-        if (leader) {
-          if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
-          else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
-          bulk_commit();
-          if (p.has_res && cc >= 1) {                       // the previous chunk's store has finished reading its
-            bulk_wait_read<1>();                            // buffer -> hand that buffer back to the residual producer
-            mbar_arrive(&res_empty[(cc - 1) % NBUF]);
-          }
-        }
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      tmem_ld32(taddr + ch * 64 + half * 32, v);
+      tmem_ld_wait();
+      if (ch == my_last && half == 1) {                     // last TMEM read of this warp for this tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty_a);
       }
+      const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
+      const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
+        v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+        v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+        v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+        v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                          // 4 x 16-byte chunks (8 channels each) of this half
+        const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+        uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
+        if (p.has_res) {
+          const uint4 r = *sp;
+          const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_h2(rr[e]);
+            v[j * 8 + e * 2] += f.x;
+            v[j * 8 + e * 2 + 1] += f.y;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
+        }
+        uint4 o;
+        o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
+        o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
+        o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
+        o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
+        *sp = o;
+      }
+    }
+    fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the TMA engine
+    named_bar_sync(2 + 2 * g, GROUP_THREADS);
+    if (leader) {
+      if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
+      else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
+      bulk_commit();
+      if (p.has_res) {
+        // hand a staging buffer back to the residual producer once its store has finished reading it: with NG buffers
+        // per group the group's stores older than the latest NG - 1 are complete, i.e. the one of chunk ccc - 2 (NG - 1)
+        // (NG = 1: this very chunk - the group's only buffer must be free before its next residual can land)
+        constexpr int NG = NBUF / 2;
+        bulk_wait_read<NG - 1>();
+        if (ccc >= 2u * (NG - 1)) mbar_arrive(&res_empty[(ccc - 2u * (NG - 1)) % NBUF]);
+      }
+    }
+  }
+  cc += CHUNKS;
 }
 
 // Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
@@ -245,6 +273,15 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t g = 0;  // ring slot counter, runs across tiles
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
+        if (EPI == PERS_EPI_CONV && p.l2_prefetch && p.taps == 1 && p.k_split == 0 && t + static_cast<int>(gridDim.x) < p.total_tiles) {
+          const TileCoord cn = decode_tile(p, t + gridDim.x);
+          if (cn.m_tile != c.m_tile) {                          // (n-tile-fastest order: same pixels, next channel slice)
+            for (int it = 0; it < k_iters; ++it) {
+              if (p.a_spatial) tma_prefetch_4d(&tmA, it * 64, cn.wo0 * p.stride - p.pad, cn.ho0 * p.stride - p.pad, cn.n0);
+              else tma_prefetch_2d(&tmA, it * 64, cn.m_tile * 128);
+            }
+          }
+        }
         for (int it = 0; it < k_iters; ++it, ++g) {
           const int s = g % STAGES;
           mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
@@ -309,6 +346,13 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t cc = 0;  // staging chunk counter, runs across tiles
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
+        if (p.l2_prefetch && t + static_cast<int>(gridDim.x) < p.total_tiles) {
+          const TileCoord cn = decode_tile(p, t + gridDim.x);
+          for (int ch = 0; ch < CHUNKS; ++ch) {
+            if (p.a_spatial) tma_prefetch_4d(&tmR, cn.n_tile * BN + ch * 64, cn.wo0, cn.ho0, cn.n0);
+            else tma_prefetch_2d(&tmR, cn.n_tile * BN + ch * 64, cn.m_tile * 128);
+          }
+        }
         for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
           const int b = cc % NBUF;
           mbar_wait(&res_empty[b], ((cc / NBUF) & 1) ^ 1);
@@ -324,9 +368,9 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // -------------------------------------------------------------- epilogue
     constexpr int EPI_THREADS = 32 * PersThreads<EPI>::EPI_WARPS;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
-    const int hsel = (warp - 4) >> 2;                  // conv epilogue: which 32-channel half of a chunk
+    const int hsel = (warp - 4) >> 2;                  // conv epilogue: group of 4 warps (takes every other chunk)
     const int row = quarter * 32 + lane;
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (EPI == PERS_EPI_CONV) ? (threadIdx.x == 128u + 128u * hsel) : (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t cc = 0, i = 0;

@@ -327,6 +327,7 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   else if (k == "c23_variant") n->c23_variant = static_cast<int>(value);
   else if (k == "pdl") g_use_pdl = value != 0;
   else if (k == "res_variant") set_res_variant(static_cast<int>(value));
+  else if (k == "l2_prefetch") set_l2_prefetch(static_cast<int>(value));
   else if (k.size() == 5 && k.compare(0, 4, "mean") == 0 && k[4] >= '0' && k[4] <= '2') n->mean_std[k[4] - '0'] = static_cast<float>(value);
   else if (k.size() == 4 && k.compare(0, 3, "std") == 0 && k[3] >= '0' && k[3] <= '2') n->mean_std[3 + k[3] - '0'] = static_cast<float>(value);
   else if (k == "stage_sched") n->stage_sched = static_cast<int>(value);
