@@ -107,6 +107,8 @@ int num_sms() {
 
 static int g_l2_prefetch = 0;    // tuning knob (option "l2_prefetch"): next-tile L2 prefetch in the 1x1 convolutions
 void set_l2_prefetch(int v) { g_l2_prefetch = v; }
+static int g_epi_mode = 1;       // tuning knob (option "epi_mode"): epilogue organisation, see ConvPersParams::epi_mode
+void set_epi_mode(int v) { g_epi_mode = v; }
 
 template <int BN, int STAGES, int NB>
 static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
@@ -147,6 +149,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
   }
   if (!res) tmR = tmO;
   p.l2_prefetch = g_l2_prefetch;
+  p.epi_mode = g_epi_mode;
   DIRB_TRY(encode_tmap_2d(&tmB, w, Ktot, s.Cout, (uint64_t)Ktot * 2, 64, BN));
   const int64_t total = m_tiles * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
@@ -175,6 +178,7 @@ static int conv_fused_ds_bn(int B, int Ho, int Wo, int Cmid, const __half* t2, i
   p.relu = 1;
   p.scale = scale;
   p.shift = shift;
+  p.epi_mode = g_epi_mode;
   const int64_t total = (int64_t)p.tiles_w * p.tiles_h * ceil_div(B, p.nb) * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
   p.total_tiles = static_cast<int>(total);
@@ -221,6 +225,7 @@ int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, co
   p.shift = shift3;
   p.scale2 = scale2;
   p.shift2 = shift2;
+  p.epi_mode = g_epi_mode;
   const int64_t total = (int64_t)p.tiles_w * p.tiles_h * B;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
   p.total_tiles = static_cast<int>(total);
@@ -263,6 +268,7 @@ static int conv_halo_bn(const ConvShape& s, const __half* in, const __half* w, c
   p.relu = relu;
   p.scale = scale;
   p.shift = shift;
+  p.epi_mode = g_epi_mode;
   const int64_t total = (int64_t)p.tiles_w * p.tiles_h * s.B * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
   p.total_tiles = static_cast<int>(total);
@@ -301,6 +307,7 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
     if (res) {
       if (g_res_variant == 1) return conv_pers_bn<256, 2, 6>(s, in, w, scale, shift, res, relu, out, stream);
       if (g_res_variant == 2) return conv_pers_bn<128, 4, 6>(s, in, w, scale, shift, res, relu, out, stream);
+      if (g_res_variant == 3) return conv_pers_bn<256, 2, 8>(s, in, w, scale, shift, res, relu, out, stream);
       return conv_pers_bn<256, 3, 4>(s, in, w, scale, shift, res, relu, out, stream);
     }
     return conv_pers_bn<256, 4, 2>(s, in, w, scale, shift, res, relu, out, stream);

@@ -36,6 +36,7 @@ int num_sms();
 void set_conv_halo(int on);
 void set_res_variant(int v);
 void set_l2_prefetch(int v);
+void set_epi_mode(int v);
 int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_t stream);
 
 // Stem 7x7/s2/p3 (3 -> 64) + BN + ReLU on tensor cores (stem_pers.cuh).  imgs: NCHW fp32; w2: [64][256] fp16 in the
@@ -52,7 +53,8 @@ int maxpool_3x3s2(const __half* in, int B, int H, int W, int C, __half* out, cud
 size_t head_workspace_floats(int B, int HW, int C, int out_dim);
 int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features,
                     const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
-                    cudaStream_t stream);
+                    cudaStream_t stream, unsigned int* bar = nullptr);
+void set_head_fused(int on);   // 1 (default) = the plain head is ONE persistent kernel, 0 = one kernel per phase
 
 // The pieces of head_pool_fc_l2, for heads that pool several maps side by side (FPN): see ops.cu.
 int head_pool(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features, float* partial,

@@ -56,6 +56,10 @@ struct ConvPersParams {
   // (cp.async.bulk.prefetch.tensor) while the current tile streams, which deepens the HBM request queue beyond what the
   // shared-memory rings can hold in flight.  0 = off.
   int l2_prefetch;
+  // Epilogue organisation of the convolution kernels (A/B knobs, option "epi_mode"): bit 0 = 1: two independent groups of
+  // 4 warps (two chunks in flight), 0: all 8 warps on one chunk; bit 1 = 1: a staging buffer goes back to the residual
+  // producer as soon as its own TMA store has finished reading it (earliest possible), 0: one store later.
+  int epi_mode;
   // Device-side launch predicate (retry passes of the search): when non-null the whole grid returns at once unless
   // *gate != 0.  The value was written by the previous kernel of the stream, so it is read after pdl_wait().
   const int* gate;
@@ -196,12 +200,101 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, cons
         // per group the group's stores older than the latest NG - 1 are complete, i.e. the one of chunk ccc - 2 (NG - 1)
         // (NG = 1: this very chunk - the group's only buffer must be free before its next residual can land)
         constexpr int NG = NBUF / 2;
-        bulk_wait_read<NG - 1>();
-        if (ccc >= 2u * (NG - 1)) mbar_arrive(&res_empty[(ccc - 2u * (NG - 1)) % NBUF]);
+        if (p.epi_mode & 2) {
+          bulk_wait_read<0>();                             // this very store has left `buf`: the residual of chunk ccc + NBUF may land
+          mbar_arrive(&res_empty[b]);
+        } else {
+          bulk_wait_read<NG - 1>();
+          if (ccc >= 2u * (NG - 1)) mbar_arrive(&res_empty[(ccc - 2u * (NG - 1)) % NBUF]);
+        }
       }
     }
   }
   cc += CHUNKS;
+}
+
+// One-group organisation (round 1): all 8 epilogue warps work on the same 64-channel chunk, warp group `hsel` taking one
+// 32-channel half of it; the staging buffer of chunk cc - 1 goes back to the residual producer after the store of chunk
+// cc (epi_mode bit 1: the buffer of chunk cc itself, after its own store has been read).
+template <int BN, int NBUF, int EPI_THREADS>
+__device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
+                                                      uint8_t* stg, uint64_t* res_full, uint64_t* res_empty,
+                                                      uint64_t* acc_empty_a, uint32_t& cc, uint32_t row_off, uint32_t sw,
+                                                      int hsel, int lane, bool leader, const CUtensorMap& tmO) {
+  constexpr int CHUNKS = BN / 64;
+  constexpr int STG_BYTES = 128 * 128;
+#pragma unroll 1
+  for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
+    const int b = cc % NBUF;
+    uint8_t* buf = stg + b * STG_BYTES;
+    if (p.has_res) {
+      mbar_wait(&res_full[b], (cc / NBUF) & 1);           // residual chunk has landed in `buf`
+    } else {
+      if (leader) bulk_wait_read<NBUF - 1>();               // the store issued NBUF chunks ago has left `buf`
+      named_bar_sync(1, EPI_THREADS);
+    }
+    const int col0 = c.n_tile * BN + ch * 64;
+    const int half = hsel;
+    float v[32];
+    tmem_ld32(taddr + ch * 64 + half * 32, v);
+    tmem_ld_wait();
+    if (ch == CHUNKS - 1) {                              // last TMEM read of this tile: release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_a);
+    }
+    const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
+    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
+      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                        // 4 x 16-byte chunks (8 channels each) of this half
+      const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+      uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
+      if (p.has_res) {
+        const uint4 r = *sp;
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_h2(rr[e]);
+          v[j * 8 + e * 2] += f.x;
+          v[j * 8 + e * 2 + 1] += f.y;
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
+      }
+      uint4 o;
+      o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
+      o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
+      o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
+      o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
+      *sp = o;
+    }
+    fence_proxy_async_smem();                            // generic-proxy smem writes -> visible to the TMA engine
+    named_bar_sync(2, EPI_THREADS);
+    if (leader) {
+      if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
+      else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
+      bulk_commit();
+      if (p.has_res) {
+        if (p.epi_mode & 2) {
+          bulk_wait_read<0>();
+          mbar_arrive(&res_empty[b]);
+        } else if (cc >= 1) {                             // the previous chunk's store has finished reading its
+          bulk_wait_read<1>();                            // buffer -> hand that buffer back to the residual producer
+          mbar_arrive(&res_empty[(cc - 1) % NBUF]);
+        }
+      }
+    }
+  }
 }
 
 // Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
@@ -370,7 +463,8 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
     const int hsel = (warp - 4) >> 2;                  // conv epilogue: group of 4 warps (takes every other chunk)
     const int row = quarter * 32 + lane;
-    const bool leader = (EPI == PERS_EPI_CONV) ? (threadIdx.x == 128u + 128u * hsel) : (threadIdx.x == 128);
+    const bool two_groups = (EPI == PERS_EPI_CONV) && (p.epi_mode & 1);
+    const bool leader = two_groups ? (threadIdx.x == 128u + 128u * hsel) : (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint32_t cc = 0, i = 0;
@@ -381,8 +475,12 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       if (EPI == PERS_EPI_CONV) {
-        conv_epilogue_tile<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off, sw,
-                                                  hsel, lane, leader, tmO);
+        if (two_groups)
+          conv_epilogue_tile<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off, sw,
+                                                    hsel, lane, leader, tmO);
+        else
+          conv_epilogue_tile_1g<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off,
+                                                       sw, hsel, lane, leader, tmO);
       } else {
         // ---------------------------------------------------------- similarity epilogues: row = query
         const int64_t qi = static_cast<int64_t>(c.m_tile) * 128 + row;

@@ -84,6 +84,7 @@ struct dirb200_net {
   std::vector<int> layer_end;     // index (exclusive) of the last block of each layer
   float* fc_w = nullptr;
   float* fc_b = nullptr;
+  unsigned int* head_bar = nullptr;   // grid-barrier words of the fused head kernel (zero once, self-resetting)
   std::vector<void*> owned;
   // workspace
   void* ws = nullptr;
@@ -298,6 +299,23 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out) {
   return 0;
 }
 
+static bool is_global_option(const std::string& k) {
+  return k == "halo" || k == "pdl" || k == "res_variant" || k == "head_fused" || k == "l2_prefetch" || k == "epi_mode";
+}
+
+int dirb200_set_global_option(const char* key, double value) {
+  DIRB_REQUIRE(key, DIRB200_EINVAL, "null argument");
+  const std::string k(key);
+  if (k == "halo") set_conv_halo(value != 0);
+  else if (k == "pdl") g_use_pdl = value != 0;
+  else if (k == "res_variant") set_res_variant(static_cast<int>(value));
+  else if (k == "head_fused") set_head_fused(static_cast<int>(value));
+  else if (k == "l2_prefetch") set_l2_prefetch(static_cast<int>(value));
+  else if (k == "epi_mode") set_epi_mode(static_cast<int>(value));
+  else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown global option '%s'", key);
+  return 0;
+}
+
 int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   DIRB_REQUIRE(n && key, DIRB200_EINVAL, "null argument");
   const std::string k(key);
@@ -321,13 +339,10 @@ int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
     n->profile = static_cast<int>(value);
     n->prof.reset();
   }
-  else if (k == "halo") set_conv_halo(value != 0);
   else if (k == "fuse_ds") n->fuse_ds = value != 0;
   else if (k == "fuse_c23") n->fuse_c23 = static_cast<int>(value);
   else if (k == "c23_variant") n->c23_variant = static_cast<int>(value);
-  else if (k == "pdl") g_use_pdl = value != 0;
-  else if (k == "res_variant") set_res_variant(static_cast<int>(value));
-  else if (k == "l2_prefetch") set_l2_prefetch(static_cast<int>(value));
+  else if (is_global_option(k)) return dirb200_set_global_option(key, value);   // process-wide kernel selectors
   else if (k.size() == 5 && k.compare(0, 4, "mean") == 0 && k[4] >= '0' && k[4] <= '2') n->mean_std[k[4] - '0'] = static_cast<float>(value);
   else if (k.size() == 4 && k.compare(0, 3, "std") == 0 && k[3] >= '0' && k[3] <= '2') n->mean_std[3 + k[3] - '0'] = static_cast<float>(value);
   else if (k == "stage_sched") n->stage_sched = static_cast<int>(value);
@@ -461,6 +476,8 @@ int dirb200_net_finalize(dirb200_net* n) {
     DIRB_CUDA(cudaMemcpy(n->fc_w, w->data.data(), w->data.size() * 4, cudaMemcpyHostToDevice));
     DIRB_CUDA(cudaMemcpy(n->fc_b, b->data.data(), b->data.size() * 4, cudaMemcpyHostToDevice));
   }
+  DIRB_TRY(dev_alloc(n, reinterpret_cast<void**>(&n->head_bar), 128));
+  DIRB_CUDA(cudaMemset(n->head_bar, 0, 128));
   n->sd.clear();
   n->finalized = true;
   return 0;
@@ -700,7 +717,7 @@ static int run_chunk(dirb200_net* n, const Workspace& w, const float* imgs_dev, 
         DIRB_TRY(head_pool_fc_l2(x, sb, ho * wo, C4, n->pooling, n->gem_p, n->gem_eps, n->norm_features,
                                  n->without_fc ? nullptr : n->fc_w, n->without_fc ? nullptr : n->fc_b, D, w.head_ws,
                                  desc_dev + static_cast<size_t>(b0) * D,
-                                 desc16_dev ? desc16_dev + static_cast<size_t>(b0) * D : nullptr, stream));
+                                 desc16_dev ? desc16_dev + static_cast<size_t>(b0) * D : nullptr, stream, n->head_bar));
         if (!n->without_fc) n->last_flops += 2.0 * sb * static_cast<double>(C4) * n->out_dim;
       }
     }

@@ -79,20 +79,32 @@ int maxpool_3x3s2(const __half* in, int B, int H, int W, int C, __half* out, cud
 
 // ---------------------------------------------------------------------------------------------------------------
 // Head: global pooling (GeM / max / avg) -> (L2 over C) -> FC + bias -> L2.      (rmac_resnet.py:59-68, pooling.py:38-40)
-// Stage 1 streams the NHWC feature map once (the only large read), stage 2..4 are tiny.
+// Four phases: 1 partial pooling (streams the NHWC feature map once - the only large read), 2 finish the pooling
+// (+ optional L2 over channels), 3 FC + bias, 4 L2 (+ fp16 copy).  Every phase is written as the body of one "virtual
+// block" (256 threads), used two ways with the SAME arithmetic in the same order, so the results are bit-identical:
+//   * head_fused_kernel: ONE persistent launch, every CTA loops over the virtual blocks of a phase and the phases are
+//     separated by a self-resetting grid barrier (default for the plain head);
+//   * one kernel per phase (FPN head, which pools two maps side by side; option head_fused = 0).
+// Buffers produced by one phase and consumed by the next (partial, g, y) are read with ld.global.cg / .ca, never
+// through the non-coherent path: in the fused kernel they were written by other CTAs of the same launch.
 namespace {
 
 constexpr int HEAD_PX_LANES = 8;
+constexpr int HEAD_THREADS = 256;
 
 __device__ __forceinline__ float gem_pow(float x, float p, int p_is3) { return p_is3 ? x * x * x : powf(x, p); }
 
-// grid (C/256, S, B), block 256: thread = (pixel lane 0..7, channel group 0..31 of 8 channels)
-__global__ void head_pool_partial_kernel(const __half* __restrict__ feat, float* __restrict__ partial, int HW, int C,
-                                         int S, int pooling, float p, float eps) {
-  __shared__ float red[HEAD_PX_LANES][256 + 8];
+struct HeadSmem {
+  float red[HEAD_PX_LANES][256 + 8];
+  float sh[32];
+};
+
+// phase 1, virtual grid (C/256, S, B): thread = (pixel lane 0..7, channel group 0..31 of 8 channels)
+__device__ __forceinline__ void head_pool_partial_body(HeadSmem& sm, int bx, int s, int b, const __half* __restrict__ feat,
+                                                       float* partial, int HW, int C, int S, int pooling, float p,
+                                                       float eps) {
   const int cg = threadIdx.x & 31, pl = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + cg * 8;
-  const int s = blockIdx.y, b = blockIdx.z;
+  const int c0 = bx * 256 + cg * 8;
   const int per = (HW + S - 1) / S;
   const int beg = s * per, end = min(HW, beg + per);
   const int p_is3 = (p == 3.0f);
@@ -120,15 +132,16 @@ __global__ void head_pool_partial_kernel(const __half* __restrict__ feat, float*
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[pl][cg * 8 + e] = acc[e];
+  for (int e = 0; e < 8; ++e) sm.red[pl][cg * 8 + e] = acc[e];
   __syncthreads();
   const int c = threadIdx.x;
-  if (blockIdx.x * 256 + c < C) {
-    float r = red[0][c];
+  if (bx * 256 + c < C) {
+    float r = sm.red[0][c];
 #pragma unroll
-    for (int l = 1; l < HEAD_PX_LANES; ++l) r = (pooling == 1) ? fmaxf(r, red[l][c]) : r + red[l][c];
-    partial[(static_cast<int64_t>(b) * S + s) * C + blockIdx.x * 256 + c] = r;
+    for (int l = 1; l < HEAD_PX_LANES; ++l) r = (pooling == 1) ? fmaxf(r, sm.red[l][c]) : r + sm.red[l][c];
+    partial[(static_cast<int64_t>(b) * S + s) * C + bx * 256 + c] = r;
   }
+  __syncthreads();                                          // sm.red is free for the caller's next virtual block
 }
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
@@ -142,18 +155,17 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return t;
 }
 
-// one block per image: finish the pooling, optional L2 over channels.  The pooled vector goes to columns
-// [col_off, col_off + C) of row b of g (row length g_ld): two feature maps can be pooled side by side (FPN head).
-__global__ void head_pool_final_kernel(const float* __restrict__ partial, float* __restrict__ g, int HW, int C, int S,
-                                       int pooling, float p, int norm_features, int g_ld, int col_off) {
-  __shared__ float sh[32];
-  const int b = blockIdx.x;
+// phase 2, one virtual block per image: finish the pooling, optional L2 over channels.  The pooled vector goes to
+// columns [col_off, col_off + C) of row b of g (row length g_ld): two feature maps can be pooled side by side (FPN).
+__device__ __forceinline__ void head_pool_final_body(HeadSmem& sm, int b, const float* partial, float* g, int HW, int C,
+                                                     int S, int pooling, float p, int norm_features, int g_ld,
+                                                     int col_off) {
   float* grow = g + static_cast<int64_t>(b) * g_ld + col_off;
   float ss = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float r = partial[(static_cast<int64_t>(b) * S) * C + c];
+    float r = __ldcg(partial + (static_cast<int64_t>(b) * S) * C + c);
     for (int s = 1; s < S; ++s) {
-      const float q = partial[(static_cast<int64_t>(b) * S + s) * C + c];
+      const float q = __ldcg(partial + (static_cast<int64_t>(b) * S + s) * C + c);
       r = (pooling == 1) ? fmaxf(r, q) : r + q;
     }
     if (pooling == 0) r = powf(r / static_cast<float>(HW), 1.0f / p);
@@ -162,19 +174,19 @@ __global__ void head_pool_final_kernel(const float* __restrict__ partial, float*
     ss += r * r;
   }
   if (norm_features) {
-    const float tot = block_sum(ss, sh);
+    const float tot = block_sum(ss, sm.sh);
     const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
     for (int c = threadIdx.x; c < C; c += blockDim.x) grow[c] *= inv;
   }
 }
 
-// y[b][o] = sum_c W[o][c] g[b][c] + bias[o]; grid (ceil(out/8), ceil(B/8)), block 256 = 8 warps, warp = one output row
-__global__ void head_fc_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ bias,
-                               float* __restrict__ y, int B, int C, int out_dim) {
+// phase 3, virtual grid (ceil(out/8), ceil(B/8)): y[b][o] = sum_c W[o][c] g[b][c] + bias[o]; warp = one output row
+__device__ __forceinline__ void head_fc_body(int bx, int by, const float* g, const float* __restrict__ w,
+                                             const float* __restrict__ bias, float* y, int B, int C, int out_dim) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 8 + warp;
-  const int b0 = blockIdx.y * 8;
-  if (o >= out_dim) return;
+  const int o = bx * 8 + warp;
+  const int b0 = by * 8;
+  if (o >= out_dim) return;                                 // (no block-wide synchronisation in this phase)
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -184,7 +196,7 @@ __global__ void head_fc_kernel(const float* __restrict__ g, const float* __restr
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (b0 + i < B) {
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + static_cast<int64_t>(b0 + i) * C) + c4);
+        const float4 gv = __ldca(reinterpret_cast<const float4*>(g + static_cast<int64_t>(b0 + i) * C) + c4);
         acc[i] = fmaf(wv.x, gv.x, acc[i]);
         acc[i] = fmaf(wv.y, gv.y, acc[i]);
         acc[i] = fmaf(wv.z, gv.z, acc[i]);
@@ -196,26 +208,110 @@ __global__ void head_fc_kernel(const float* __restrict__ g, const float* __restr
   for (int i = 0; i < 8; ++i) {
     float v = acc[i];
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    if (lane == 0 && b0 + i < B) y[static_cast<int64_t>(b0 + i) * out_dim + o] = v + (bias ? bias[o] : 0.f);
+    if (lane == 0 && b0 + i < B) y[static_cast<int64_t>(b0 + i) * out_dim + o] = v + (bias ? __ldg(bias + o) : 0.f);
   }
 }
 
-// one block per row: out = x / max(||x||, eps)
-__global__ void l2_rows_kernel(const float* __restrict__ x, float* __restrict__ out, __half* __restrict__ out16, int D,
-                               float eps) {
-  __shared__ float sh[32];
-  const int64_t r = blockIdx.x;
+// phase 4, one virtual block per row: out = x / max(||x||, eps)
+__device__ __forceinline__ void l2_row_body(HeadSmem& sm, int64_t r, const float* x, float* out, __half* out16, int D,
+                                            float eps) {
   const float* xr = x + r * D;
   float ss = 0.f;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) ss += xr[c] * xr[c];
-  const float tot = block_sum(ss, sh);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = __ldcg(xr + c);
+    ss += v * v;
+  }
+  const float tot = block_sum(ss, sm.sh);
   const float nrm = sqrtf(tot);
   const float inv = 1.0f / (eps > 0.f ? fmaxf(nrm, eps) : nrm);
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    const float v = xr[c] * inv;
+    const float v = __ldcg(xr + c) * inv;
     if (out) out[r * D + c] = v;
     if (out16) out16[r * D + c] = __float2half_rn(v);
   }
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_pool_partial_kernel(const __half* __restrict__ feat, float* partial,
+                                                                         int HW, int C, int S, int pooling, float p,
+                                                                         float eps) {
+  __shared__ HeadSmem sm;
+  head_pool_partial_body(sm, blockIdx.x, blockIdx.y, blockIdx.z, feat, partial, HW, C, S, pooling, p, eps);
+}
+__global__ void __launch_bounds__(HEAD_THREADS) head_pool_final_kernel(const float* partial, float* g, int HW, int C, int S,
+                                                                       int pooling, float p, int norm_features, int g_ld,
+                                                                       int col_off) {
+  __shared__ HeadSmem sm;
+  head_pool_final_body(sm, blockIdx.x, partial, g, HW, C, S, pooling, p, norm_features, g_ld, col_off);
+}
+__global__ void __launch_bounds__(HEAD_THREADS) head_fc_kernel(const float* g, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* y, int B, int C,
+                                                               int out_dim) {
+  head_fc_body(blockIdx.x, blockIdx.y, g, w, bias, y, B, C, out_dim);
+}
+__global__ void __launch_bounds__(HEAD_THREADS) l2_rows_kernel(const float* x, float* out, __half* out16, int D, float eps) {
+  __shared__ HeadSmem sm;
+  l2_row_body(sm, blockIdx.x, x, out, out16, D, eps);
+}
+
+// Grid barrier of a persistent launch whose CTAs are all co-resident (the launcher sizes the grid from the occupancy
+// calculator).  bar[0] = arrival counter, bar[1] = generation.  Self-resetting: the last arrival zeroes the counter and
+// bumps the generation, so the words only have to be zero once, at allocation, and survive CUDA-graph replays.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = bar + 1;
+    const unsigned int g0 = *gen;                           // cannot advance before this CTA has arrived
+    __threadfence();                                        // this CTA's writes (ordered by the bar.sync above) -> gpu scope
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*gen == g0) __nanosleep(32);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct HeadFusedParams {
+  const __half* feat;
+  const float* fc_w;
+  const float* fc_b;
+  float* partial;
+  float* g;
+  float* y;
+  float* desc;
+  __half* desc16;
+  unsigned int* bar;
+  int B, HW, C, S, pooling, norm_features, out_dim;
+  float p, eps;
+};
+
+__global__ void __launch_bounds__(HEAD_THREADS, 4) head_fused_kernel(const HeadFusedParams q) {
+  __shared__ HeadSmem sm;
+  const int nb = gridDim.x;
+  {  // ---- 1: partial pooling
+    const int gx = (q.C + 255) / 256;
+    const int total = gx * q.S * q.B;
+    for (int v = blockIdx.x; v < total; v += nb)
+      head_pool_partial_body(sm, v % gx, (v / gx) % q.S, v / (gx * q.S), q.feat, q.partial, q.HW, q.C, q.S, q.pooling, q.p, q.eps);
+  }
+  grid_barrier(q.bar, nb);
+  for (int b = blockIdx.x; b < q.B; b += nb)   // ---- 2: finish the pooling
+    head_pool_final_body(sm, b, q.partial, q.g, q.HW, q.C, q.S, q.pooling, q.p, q.norm_features, q.C, 0);
+  const float* pre = q.g;
+  int D = q.C;
+  if (q.fc_w != nullptr) {
+    grid_barrier(q.bar, nb);
+    const int gx = (q.out_dim + 7) / 8, gy = (q.B + 7) / 8;   // ---- 3: FC + bias
+    for (int v = blockIdx.x; v < gx * gy; v += nb) head_fc_body(v % gx, v / gx, q.g, q.fc_w, q.fc_b, q.y, q.B, q.C, q.out_dim);
+    pre = q.y;
+    D = q.out_dim;
+  }
+  grid_barrier(q.bar, nb);
+  for (int b = blockIdx.x; b < q.B; b += nb)   // ---- 4: L2 (+ fp16 copy)
+    l2_row_body(sm, b, pre, q.desc, q.desc16, D, 1e-12f);
 }
 
 }  // namespace
@@ -227,11 +323,13 @@ static int head_splits(int B, int HW, int C) {
   return max(1, min(16, HW / 64));
 }
 
-size_t head_partial_floats(int B, int HW, int C) { return static_cast<size_t>(B) * head_splits(B, HW, C) * C; }
+static size_t align32(size_t floats) { return (floats + 31) / 32 * 32; }   // 128-byte lines: no line shared by two buffers
+
+size_t head_partial_floats(int B, int HW, int C) { return align32(static_cast<size_t>(B) * head_splits(B, HW, C) * C); }
 
 size_t head_workspace_floats(int B, int HW, int C, int out_dim) {
-  return static_cast<size_t>(B) * head_splits(B, HW, C) * C + static_cast<size_t>(B) * C +
-         static_cast<size_t>(B) * (out_dim > C ? out_dim : C);
+  return head_partial_floats(B, HW, C) + align32(static_cast<size_t>(B) * C) +
+         align32(static_cast<size_t>(B) * (out_dim > C ? out_dim : C)) + 32;   // + barrier words of the fused kernel
 }
 
 // Global pooling of one NHWC map into g[b][col_off .. col_off + C) (rows of g_ld floats); `partial` = B * S * C floats.
@@ -241,8 +339,8 @@ int head_pool(const __half* feat, int B, int HW, int C, int pooling, float p, fl
   DIRB_REQUIRE(pooling >= 0 && pooling <= 2, DIRB200_EINVAL, "pooling mode %d", pooling);
   const int S = head_splits(B, HW, C);
   dim3 g1((unsigned)ceil_div(C, 256), (unsigned)S, (unsigned)B);
-  head_pool_partial_kernel<<<g1, 256, 0, stream>>>(feat, partial, HW, C, S, pooling, p, eps);
-  head_pool_final_kernel<<<B, 256, 0, stream>>>(partial, g, HW, C, S, pooling, p, norm_features, g_ld, col_off);
+  head_pool_partial_kernel<<<g1, HEAD_THREADS, 0, stream>>>(feat, partial, HW, C, S, pooling, p, eps);
+  head_pool_final_kernel<<<B, HEAD_THREADS, 0, stream>>>(partial, g, HW, C, S, pooling, p, norm_features, g_ld, col_off);
   count_launch(2);
   DIRB_CUDA(cudaGetLastError());
   return 0;
@@ -256,26 +354,52 @@ int head_fc_l2(const float* g, int B, int C, const float* fc_w, const float* fc_
   int D = C;
   if (fc_w != nullptr) {
     dim3 g3((unsigned)ceil_div(out_dim, 8), (unsigned)ceil_div(B, 8));
-    head_fc_kernel<<<g3, 256, 0, stream>>>(g, fc_w, fc_b, y, B, C, out_dim);
+    head_fc_kernel<<<g3, HEAD_THREADS, 0, stream>>>(g, fc_w, fc_b, y, B, C, out_dim);
     count_launch();
     pre = y;
     D = out_dim;
   }
-  l2_rows_kernel<<<B, 256, 0, stream>>>(pre, desc, desc16, D, 1e-12f);
+  l2_rows_kernel<<<B, HEAD_THREADS, 0, stream>>>(pre, desc, desc16, D, 1e-12f);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   return 0;
 }
 
+static int g_head_fused = 1;   // tuning knob (option "head_fused"): 0 = one kernel per phase
+void set_head_fused(int on) { g_head_fused = on; }
+
+// `bar`: two zero-initialised device words owned by the caller for the fused kernel's grid barrier (they return to a
+// reusable state after every launch); nullptr = use the tail of `ws` and clear it on the stream first.
 int head_pool_fc_l2(const __half* feat, int B, int HW, int C, int pooling, float p, float eps, int norm_features,
                     const float* fc_w, const float* fc_b, int out_dim, float* ws, float* desc, __half* desc16,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, unsigned int* bar) {
   const int S = head_splits(B, HW, C);
   float* partial = ws;
-  float* g = partial + static_cast<size_t>(B) * S * C;
-  float* y = g + static_cast<size_t>(B) * C;
-  DIRB_TRY(head_pool(feat, B, HW, C, pooling, p, eps, norm_features, partial, g, C, 0, stream));
-  return head_fc_l2(g, B, C, fc_w, fc_b, out_dim, y, desc, desc16, stream);
+  float* g = partial + head_partial_floats(B, HW, C);
+  float* y = g + align32(static_cast<size_t>(B) * C);
+  if (!g_head_fused) {
+    DIRB_TRY(head_pool(feat, B, HW, C, pooling, p, eps, norm_features, partial, g, C, 0, stream));
+    return head_fc_l2(g, B, C, fc_w, fc_b, out_dim, y, desc, desc16, stream);
+  }
+  DIRB_REQUIRE(C % 8 == 0, DIRB200_ENOTSUP, "head needs C %% 8 == 0");
+  DIRB_REQUIRE(pooling >= 0 && pooling <= 2, DIRB200_EINVAL, "pooling mode %d", pooling);
+  if (bar == nullptr) {
+    bar = reinterpret_cast<unsigned int*>(y + align32(static_cast<size_t>(B) * (out_dim > C ? out_dim : C)));
+    DIRB_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), stream));
+  }
+  // every CTA must be resident at once (spin barrier): grid = what the occupancy calculator guarantees, capped by the work
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    DIRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, head_fused_kernel, HEAD_THREADS, 0));
+    per_sm = std::max(1, std::min(per_sm, 4));
+  }
+  const int64_t work = std::max<int64_t>(ceil_div(C, 256) * S * B, fc_w ? ceil_div(out_dim, 8) * ceil_div(B, 8) : B);
+  const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(per_sm) * num_sms(), std::max<int64_t>(work, 1)));
+  HeadFusedParams q{feat, fc_w, fc_b, partial, g, y, desc, desc16, bar, B, HW, C, S, pooling, norm_features, out_dim, p, eps};
+  head_fused_kernel<<<grid, HEAD_THREADS, 0, stream>>>(q);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // FPN lateral connection (rmac_resnet_fpn.py:56-60): x4[b][y][x][:] += t[b][sy][sx][:], (sy, sx) = nearest-neighbour

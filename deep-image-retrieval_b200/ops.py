@@ -31,6 +31,11 @@ def require_gpu(device=0):
     lib.call("dirb200_device_check", int(device))
 
 
+def set_global_option(key, value):
+    """Process-wide kernel selectors ('halo', 'pdl', 'res_variant', 'l2_prefetch', 'head_fused'); include/dirb200.h."""
+    lib.call("dirb200_set_global_option", key.encode(), float(value))
+
+
 def nchw_to_nhwc8(x):
     _chk(x, torch.float32, "x")
     b, c, h, w = x.shape

@@ -47,6 +47,15 @@ int dirb200_device_check(int device);
  * dirtorch/nets/__init__.py:24-64, dirtorch/nets/rmac_resnet.py:12-69,
  * dirtorch/nets/backbones/resnet.py:46-87,102-174, dirtorch/nets/layers/pooling.py:38-54.   */
 
+/* Process-wide kernel selectors (they pick which kernel a launcher uses; no reference counterpart - the reference
+ * delegates kernel choice to torch.backends.cudnn, utils/common.py:74-75 cudnn.benchmark / cudnn.fastest).  Set them once,
+ * not concurrently with a running call: "halo" 1 (default) / 0 = 3x3 stride-1 convolutions load their input patch
+ * once per tile (conv_halo.cuh) or tap by tap; "pdl" 1 (default) = programmatic dependent launch between consecutive
+ * kernels; "res_variant" tile-variant selector of the residual 1x1 convolutions; "l2_prefetch" 1 = the 1x1
+ * convolutions request the next tile's activation / residual boxes into L2 ahead of time; "head_fused" 1 (default) =
+ * pooling + FC + L2 of the plain head as ONE persistent kernel, 0 = one kernel per phase (bit-identical results).
+ * dirb200_net_set_option forwards these keys here. */
+int dirb200_set_global_option(const char* key, double value);
 /* arch: "resnet50_rmac" | "resnet101_rmac" | "resnet152_rmac" (Bottleneck trunks, rmac_resnet.py:78-88). */
 int dirb200_net_create(const char* arch, int device, dirb200_net** out);
 /* Options.

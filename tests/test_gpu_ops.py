@@ -145,6 +145,36 @@ def test_head(shape, kw):
     assert rel_l2(out.cpu().numpy(), ref) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 32), (5, 7, 9), (19, 16, 12), (64, 8, 8)], ids=["1x32x32", "5x7x9", "19x16x12", "64x8x8"])
+@pytest.mark.parametrize("kw", [dict(pooling="gem", p=3.0), dict(pooling="gem", p=2.5, norm_features=True),
+                                dict(pooling="max", without_fc=True), dict(pooling="avg")],
+                         ids=["gem3", "gem2.5-normfeat", "max-nofc", "avg"])
+def test_head_single_kernel_is_bit_identical_to_the_phase_kernels(shape, kw):
+    """rmac_resnet.py:59-68 as ONE persistent launch (grid barrier between pooling / FC / L2) vs one kernel per phase:
+    the same virtual-block bodies in the same order, so fp32 and fp16 descriptors must agree bit for bit; repeated
+    launches check that the self-resetting barrier words are reusable."""
+    ops = _ops()
+    b, h, w = shape
+    r = np.random.RandomState(7)
+    feat = torch.from_numpy(np.abs(r.standard_normal((b, h, w, 2048))).astype(np.float32)).half().to(DEV)
+    without_fc = kw.get("without_fc", False)
+    fc_w = None if without_fc else torch.from_numpy((r.standard_normal((2048, 2048)) / 45.0).astype(np.float32)).to(DEV)
+    fc_b = None if without_fc else torch.from_numpy((0.01 * r.standard_normal(2048)).astype(np.float32)).to(DEV)
+    args = dict(pooling=kw["pooling"], p=kw.get("p", 3.0), eps=1e-6, norm_features=kw.get("norm_features", False),
+                fc_w=fc_w, fc_b=fc_b, want_f16=True)
+    try:
+        ops.set_global_option("head_fused", 0)
+        ref32, ref16 = ops.head_pool_fc_l2(feat, **args)
+        ops.set_global_option("head_fused", 1)
+        for _ in range(3):
+            out32, out16 = ops.head_pool_fc_l2(feat, **args)
+            torch.cuda.synchronize()
+            assert torch.equal(out32, ref32) and torch.equal(out16, ref16)
+    finally:
+        ops.set_global_option("head_fused", 1)
+    assert torch.isfinite(ref32).all() and abs(float(ref32[0].norm()) - 1.0) < 1e-5
+
+
 def test_whiten_tensor_core_path_large():
     """5000 x 2048 rows through the tcgen05 hi/lo-split whitening vs the fp64 oracle, ragged row count."""
     ops = _ops()
