@@ -107,8 +107,10 @@ int num_sms() {
 
 static int g_l2_prefetch = 0;    // tuning knob (option "l2_prefetch"): next-tile L2 prefetch in the 1x1 convolutions
 void set_l2_prefetch(int v) { g_l2_prefetch = v; }
-static int g_epi_mode = 1;       // tuning knob (option "epi_mode"): epilogue organisation, see ConvPersParams::epi_mode
+int get_l2_prefetch() { return g_l2_prefetch; }
+static int g_epi_mode = 0;       // tuning knob (option "epi_mode"): epilogue organisation, see ConvPersParams::epi_mode
 void set_epi_mode(int v) { g_epi_mode = v; }
+int get_epi_mode() { return g_epi_mode; }
 
 template <int BN, int STAGES, int NB>
 static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
@@ -135,7 +137,9 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
     p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
     m_tiles = ceil_div(M, 128);
     DIRB_TRY(encode_tmap_2d(&tmA, in, s.Cin, M, (uint64_t)s.Cin * 2, 64, 128));
-    DIRB_TRY(encode_tmap_2d(&tmO, out, s.Cout, M, (uint64_t)s.Cout * 2, 64, 128));
+    // warp-autonomous epilogue (epi_mode bit 2, kernels with a residual ring): every warp stores its own 32-row slab
+    const bool warp_store = (g_epi_mode & 4) && NB >= 4;
+    DIRB_TRY(encode_tmap_2d(&tmO, out, s.Cout, M, (uint64_t)s.Cout * 2, 64, warp_store ? 32 : 128));
     if (res) DIRB_TRY(encode_tmap_2d(&tmR, res, s.Cout, M, (uint64_t)s.Cout * 2, 64, 128));
   } else {
     p.a_spatial = 1;
@@ -147,7 +151,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
     DIRB_TRY(encode_tmap_nhwc(&tmO, out, s.B, Ho, Wo, s.Cout, p.tw, p.th, p.nb, 1));
     if (res) DIRB_TRY(encode_tmap_nhwc(&tmR, res, s.B, Ho, Wo, s.Cout, p.tw, p.th, p.nb, 1));
   }
-  if (!res) tmR = tmO;
+  if (!res) tmR = tmO;   // (never dereferenced without a residual)
   p.l2_prefetch = g_l2_prefetch;
   p.epi_mode = g_epi_mode;
   DIRB_TRY(encode_tmap_2d(&tmB, w, Ktot, s.Cout, (uint64_t)Ktot * 2, 64, BN));
@@ -248,8 +252,10 @@ int conv_c23(int B, int H, int W, int Cm, const __half* t1, const __half* w2, co
 
 static int g_conv_halo = 1;
 void set_conv_halo(int on) { g_conv_halo = on; }
+int get_conv_halo() { return g_conv_halo; }
 static int g_res_variant = 0;   // tuning knob: shared-memory split of the residual (conv3) kernel, see conv_tc
 void set_res_variant(int v) { g_res_variant = v; }
+int get_res_variant() { return g_res_variant; }
 
 // 3x3 / stride 1 / pad 1 with the halo patch loaded once per tile (conv_halo.cuh).
 template <int BN, int BSTAGES, bool BRES, int NA>

@@ -37,6 +37,11 @@ void set_conv_halo(int on);
 void set_res_variant(int v);
 void set_l2_prefetch(int v);
 void set_epi_mode(int v);
+int get_l2_prefetch();
+int get_epi_mode();
+int get_conv_halo();
+int get_res_variant();
+int get_head_fused();
 int nchw_to_nhwc8(const float* in, int B, int H, int W, __half* out, cudaStream_t stream);
 
 // Stem 7x7/s2/p3 (3 -> 64) + BN + ReLU on tensor cores (stem_pers.cuh).  imgs: NCHW fp32; w2: [64][256] fp16 in the

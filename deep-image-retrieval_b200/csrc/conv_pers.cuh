@@ -58,7 +58,9 @@ struct ConvPersParams {
   int l2_prefetch;
   // Epilogue organisation of the convolution kernels (A/B knobs, option "epi_mode"): bit 0 = 1: two independent groups of
   // 4 warps (two chunks in flight), 0: all 8 warps on one chunk; bit 1 = 1: a staging buffer goes back to the residual
-  // producer as soon as its own TMA store has finished reading it (earliest possible), 0: one store later.
+  // producer as soon as its own TMA store has finished reading it (earliest possible), 0: one store later; bit 2 = 1 (flat
+  // 1x1 convolutions only, whose output map has 32-row boxes): warp-autonomous epilogue - every warp stores its own
+  // 32-pixel slab, no CTA-wide barrier per chunk (conv_epilogue_tile_warp).
   int epi_mode;
   // Device-side launch predicate (retry passes of the search): when non-null the whole grid returns at once unless
   // *gate != 0.  The value was written by the previous kernel of the stream, so it is read after pdl_wait().
@@ -73,8 +75,14 @@ struct ConvPersSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 128 * 128;                      // 128 rows x 64 channels fp16
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = STG_OFF + NBUF * STG_BYTES;
+  // BN scale | shift of the current tile, double-buffered by tile parity: only where the epilogue is the bottleneck
+  // (configurations with a residual ring) and the budget allows it
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * (NB > 4 ? NB : 4);   // ring, accumulators, residual ring
+  static constexpr bool SS = (EPI == 0) && (NB >= 4) &&
+                             (STAGES * STAGE_BYTES + NB * STG_BYTES + 16 * BN + 8 * NUM_BARS + 16 + 1024 <= 232448);
+  static constexpr int SS_OFF = STG_OFF + NBUF * STG_BYTES;
+  static constexpr int SS_BYTES = SS ? 2 * 2 * BN * 4 : 0;
+  static constexpr int BAR_OFF = SS_OFF + SS_BYTES;
   static constexpr int TOTAL = BAR_OFF + 8 * NUM_BARS + 16 + 1024;  // + tmem slot + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                          // two accumulators
 };
@@ -136,6 +144,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, cons
     if (static_cast<int>(ccc & 1u) != g) continue;
     const int b = ccc % NBUF;
     uint8_t* buf = stg + b * STG_BYTES;
+    const uint32_t buf_addr = smem_u32(buf);
     if (p.has_res) {
       mbar_wait(&res_full[b], (ccc / NBUF) & 1);            // residual chunk has landed in `buf`
     } else {
@@ -166,9 +175,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, cons
 #pragma unroll
       for (int j = 0; j < 4; ++j) {                          // 4 x 16-byte chunks (8 channels each) of this half
         const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
-        uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
+        const uint32_t sp = buf_addr + row_off + ((chunk ^ sw) << 4);
         if (p.has_res) {
-          const uint4 r = *sp;
+          const uint4 r = lds128(sp);
           const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -186,7 +195,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, cons
         o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
         o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
         o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
-        *sp = o;
+        sts128(sp, o);
       }
     }
     fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the TMA engine
@@ -213,36 +222,35 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, cons
   cc += CHUNKS;
 }
 
-// One-group organisation (round 1): all 8 epilogue warps work on the same 64-channel chunk, warp group `hsel` taking one
-// 32-channel half of it; the staging buffer of chunk cc - 1 goes back to the residual producer after the store of chunk
-// cc (epi_mode bit 1: the buffer of chunk cc itself, after its own store has been read).
-template <int BN, int NBUF, int EPI_THREADS>
-__device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
-                                                      uint8_t* stg, uint64_t* res_full, uint64_t* res_empty,
-                                                      uint64_t* acc_empty_a, uint32_t& cc, uint32_t row_off, uint32_t sw,
-                                                      int hsel, int lane, bool leader, const CUtensorMap& tmO) {
-  constexpr int CHUNKS = BN / 64;
-  constexpr int STG_BYTES = 128 * 128;
-#pragma unroll 1
-  for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
-    const int b = cc % NBUF;
-    uint8_t* buf = stg + b * STG_BYTES;
-    if (p.has_res) {
-      mbar_wait(&res_full[b], (cc / NBUF) & 1);           // residual chunk has landed in `buf`
-    } else {
-      if (leader) bulk_wait_read<NBUF - 1>();               // the store issued NBUF chunks ago has left `buf`
-      named_bar_sync(1, EPI_THREADS);
+// One-group organisation: all 8 epilogue warps work on the same 64-channel chunk, warp group `hsel` taking one 32-channel
+// half of it.  The per-chunk dependency chain of a warp (TMEM read -> scale/shift -> residual read -> pack -> store ->
+// proxy fence -> barrier) is what bounds the 1x1 convolutions with a residual (ncu warp-state samples of round 2: the
+// MMA warp spends 57 % of its time waiting for a drained accumulator, the epilogue warps never wait for data), so the
+// long-latency links are kept out of it:
+//   * the accumulator columns of chunk ch + 1 are requested from TMEM (tcgen05.ld is asynchronous) before chunk ch is
+//     processed, two register arrays alternate;
+//   * BN scale / shift of the tile's BN channels are staged in shared memory once per tile (`ss_addr`, SS = true) and read
+//     back with broadcast LDS instead of 16 LDG.128 per chunk and thread;
+//   * staging-buffer accesses are explicit ld.shared / st.shared (see ptx.cuh: lds128).
+// The staging buffer of chunk cc - 1 goes back to the residual producer after the store of chunk cc (epi_mode bit 1: the
+// buffer of chunk cc itself, after its own store has been read).
+template <int BN, int NBUF, int EPI_THREADS, bool SS>
+__device__ __forceinline__ void conv_epilogue_chunk_1g(const ConvPersParams& p, const TileCoord& c, float (&v)[32], int ch,
+                                                       uint32_t buf_addr, int b, uint32_t cc, uint32_t ss_addr,
+                                                       uint64_t* res_empty, uint32_t row_off, uint32_t sw, int half,
+                                                       bool leader, const CUtensorMap& tmO) {
+  const int col0 = c.n_tile * BN + ch * 64;
+  if (SS) {
+    const uint32_t sa = ss_addr + static_cast<uint32_t>(ch * 64 + half * 32) * 4u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = lds128f(sa + q * 16), h = lds128f(sa + BN * 4 + q * 16);
+      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
     }
-    const int col0 = c.n_tile * BN + ch * 64;
-    const int half = hsel;
-    float v[32];
-    tmem_ld32(taddr + ch * 64 + half * 32, v);
-    tmem_ld_wait();
-    if (ch == CHUNKS - 1) {                              // last TMEM read of this tile: release the accumulator
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty_a);
-    }
+  } else {
     const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
     const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
 #pragma unroll
@@ -253,48 +261,222 @@ __device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, c
       v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
       v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {                        // 4 x 16-byte chunks (8 channels each) of this half
-      const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
-      uint4* sp = reinterpret_cast<uint4*>(buf + row_off + ((chunk ^ sw) << 4));
-      if (p.has_res) {
-        const uint4 r = *sp;
-        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  for (int j = 0; j < 4; ++j) {                          // 4 x 16-byte chunks (8 channels each) of this half
+    const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+    const uint32_t sp = buf_addr + row_off + ((chunk ^ sw) << 4);
+    if (p.has_res) {
+      const uint4 r = lds128(sp);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_h2(rr[e]);
-          v[j * 8 + e * 2] += f.x;
-          v[j * 8 + e * 2 + 1] += f.y;
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_h2(rr[e]);
+        v[j * 8 + e * 2] += f.x;
+        v[j * 8 + e * 2 + 1] += f.y;
       }
-      if (p.relu) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
-      }
-      uint4 o;
-      o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
-      o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
-      o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
-      o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
-      *sp = o;
     }
-    fence_proxy_async_smem();                            // generic-proxy smem writes -> visible to the TMA engine
-    named_bar_sync(2, EPI_THREADS);
-    if (leader) {
-      if (p.a_spatial) tma_store_4d(&tmO, buf, col0, c.wo0, c.ho0, c.n0);
-      else tma_store_2d(&tmO, buf, col0, c.m_tile * 128);
-      bulk_commit();
-      if (p.has_res) {
-        if (p.epi_mode & 2) {
-          bulk_wait_read<0>();
-          mbar_arrive(&res_empty[b]);
-        } else if (cc >= 1) {                             // the previous chunk's store has finished reading its
-          bulk_wait_read<1>();                            // buffer -> hand that buffer back to the residual producer
-          mbar_arrive(&res_empty[(cc - 1) % NBUF]);
-        }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
+    }
+    uint4 o;
+    o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
+    o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
+    o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
+    o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
+    sts128(sp, o);
+  }
+  fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the TMA engine
+  named_bar_sync(2, EPI_THREADS);
+  if (leader) {
+    if (p.a_spatial) tma_store_4d_addr(&tmO, buf_addr, col0, c.wo0, c.ho0, c.n0);
+    else tma_store_2d_addr(&tmO, buf_addr, col0, c.m_tile * 128);
+    bulk_commit();
+    if (p.has_res) {
+      if (p.epi_mode & 2) {
+        bulk_wait_read<0>();
+        mbar_arrive(&res_empty[b]);
+      } else if (cc >= 1) {                               // the previous chunk's store has finished reading its
+        bulk_wait_read<1>();                              // buffer -> hand that buffer back to the residual producer
+        mbar_arrive(&res_empty[(cc - 1) % NBUF]);
       }
     }
   }
+}
+
+template <int BN, int NBUF, int EPI_THREADS, bool SS>
+__device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
+                                                      uint32_t stg_addr, uint32_t ss_addr, uint64_t* res_full,
+                                                      uint64_t* res_empty, uint64_t* acc_empty_a, uint32_t& cc,
+                                                      uint32_t row_off, uint32_t sw, int hsel, int lane, bool leader,
+                                                      const CUtensorMap& tmO) {
+  constexpr int CHUNKS = BN / 64;
+  constexpr int STG_BYTES = 128 * 128;
+  const int half = hsel;
+  if (SS) {                                              // BN scale | shift of this tile's channels -> shared memory
+    const int j = static_cast<int>(threadIdx.x) - 128;
+    if (j < BN) {
+      sts32f(ss_addr + j * 4, __ldg(p.scale + c.n_tile * BN + j));
+      sts32f(ss_addr + (BN + j) * 4, __ldg(p.shift + c.n_tile * BN + j));
+    }
+    named_bar_sync(6, EPI_THREADS);
+  }
+  float va[32], vb[32];
+  tmem_ld32(taddr + half * 32, va);
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
+    const int b = cc % NBUF;
+    const uint32_t buf_addr = stg_addr + b * STG_BYTES;
+    if (p.has_res) {
+      mbar_wait(&res_full[b], (cc / NBUF) & 1);           // residual chunk has landed in the buffer
+    } else {
+      if (leader) bulk_wait_read<NBUF - 1>();               // the store issued NBUF chunks ago has left the buffer
+      named_bar_sync(1, EPI_THREADS);
+    }
+    tmem_ld_wait();                                        // this chunk's accumulator columns are in registers
+    if (ch + 1 < CHUNKS) {
+      tmem_ld32(taddr + (ch + 1) * 64 + half * 32, (ch & 1) ? va : vb);
+    } else {                                               // last TMEM read of this tile: release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_a);
+    }
+    conv_epilogue_chunk_1g<BN, NBUF, EPI_THREADS, SS>(p, c, (ch & 1) ? vb : va, ch, buf_addr, b, cc, ss_addr, res_empty,
+                                                      row_off, sw, half, leader, tmO);
+  }
+}
+
+// Warp-autonomous organisation (flat 1x1 convolutions: output rows = pixels, the output tensor map has 64 x 32 boxes).
+// Warp (quarter q, group g) owns the 32 pixels of its TMEM lane quarter in the chunks whose running index has parity g:
+// it reads 64 accumulator columns in two halves (the second half is in flight while the first is processed), applies
+// scale / shift (+ its 32 rows of the residual chunk) (+ ReLU), writes its 4 KB slab of the staging buffer and stores it
+// with its OWN TMA store.  Nothing in the chunk loop synchronises warps with each other, so their dependency chains
+// drift apart and overlap (the lock-step organisations leave the SM idle whenever all 8 warps wait on the same LDS /
+// fence / barrier).  A staging buffer returns to the residual producer after 4 arrivals (one per quarter).
+template <int BN, int NBUF, bool SS>
+__device__ __forceinline__ void conv_epilogue_half_warp(const ConvPersParams& p, float (&v)[32], int col0, int half,
+                                                        uint32_t buf_addr, uint32_t ss_addr, int ch, uint32_t row_off,
+                                                        uint32_t sw) {
+  if (SS) {
+    const uint32_t sa = ss_addr + static_cast<uint32_t>(ch * 64 + half * 32) * 4u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = lds128f(sa + q * 16), h = lds128f(sa + BN * 4 + q * 16);
+      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
+    }
+  } else {
+    const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
+    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
+      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
+      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
+      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
+      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+    const uint32_t sp = buf_addr + row_off + ((chunk ^ sw) << 4);
+    if (p.has_res) {
+      const uint4 r = lds128(sp);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_h2(rr[e]);
+        v[j * 8 + e * 2] += f.x;
+        v[j * 8 + e * 2 + 1] += f.y;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
+    }
+    uint4 o;
+    o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
+    o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
+    o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
+    o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
+    sts128(sp, o);
+  }
+}
+
+template <int BN, int NBUF, bool SS>
+__device__ __forceinline__ void conv_epilogue_tile_warp(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
+                                                        uint32_t stg_addr, uint32_t ss_addr, uint64_t* res_full,
+                                                        uint64_t* res_empty, uint64_t* acc_empty_a, uint32_t& cc,
+                                                        uint32_t row_off, uint32_t sw, int quarter, int g, int lane,
+                                                        const CUtensorMap& tmO) {
+  static_assert(NBUF % 2 == 0, "staging buffers are split between the two warp groups");
+  constexpr int CHUNKS = BN / 64;
+  constexpr int STG_BYTES = 128 * 128;
+  constexpr int NG = NBUF / 2;                              // staging buffers per group
+  if (SS) {                                                 // BN scale | shift of this tile's channels -> shared memory
+    const int j = static_cast<int>(threadIdx.x) - 128;
+    if (j < BN) {
+      sts32f(ss_addr + j * 4, __ldg(p.scale + c.n_tile * BN + j));
+      sts32f(ss_addr + (BN + j) * 4, __ldg(p.shift + c.n_tile * BN + j));
+    }
+    named_bar_sync(6, 256);                                 // (once per tile; the chunk loop below has no CTA-wide barrier)
+  }
+  int my_last = -1;
+#pragma unroll
+  for (int ch = 0; ch < CHUNKS; ++ch)
+    if (static_cast<int>((cc + ch) & 1u) == g) my_last = ch;
+  if (my_last < 0) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty_a);
+  }
+#pragma unroll 1
+  for (int ch = 0; ch < CHUNKS; ++ch) {
+    const uint32_t ccc = cc + ch;
+    if (static_cast<int>(ccc & 1u) != g) continue;
+    const int b = ccc % NBUF;
+    const uint32_t buf_addr = stg_addr + b * STG_BYTES;
+    if (p.has_res) {
+      mbar_wait(&res_full[b], (ccc / NBUF) & 1);            // residual chunk has landed in the buffer
+    } else {
+      if (lane == 0) bulk_wait_read<NG - 1>();               // this warp's store NG of its chunks ago has left its slab
+      __syncwarp();
+    }
+    const int col0 = c.n_tile * BN + ch * 64;
+    float va[32], vb[32];
+    tmem_ld32(taddr + ch * 64, va);
+    tmem_ld_wait();
+    tmem_ld32(taddr + ch * 64 + 32, vb);                    // second half in flight while the first is processed
+    conv_epilogue_half_warp<BN, NBUF, SS>(p, va, col0, 0, buf_addr, ss_addr, ch, row_off, sw);
+    tmem_ld_wait();
+    if (ch == my_last) {                                    // last TMEM read of this warp for this tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_a);
+    }
+    conv_epilogue_half_warp<BN, NBUF, SS>(p, vb, col0, 1, buf_addr, ss_addr, ch, row_off, sw);
+    fence_proxy_async_smem();                               // this warp's smem writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d_addr(&tmO, buf_addr + quarter * 4096, col0, c.m_tile * 128 + quarter * 32);
+      bulk_commit();
+      if (p.has_res) {
+        if (p.epi_mode & 2) {
+          bulk_wait_read<0>();                              // this very store has left the slab
+          mbar_arrive(&res_empty[b]);
+        } else {
+          bulk_wait_read<1>();                              // this warp's previous store (chunk ccc - 2) has left its slab
+          if (ccc >= 2u) mbar_arrive(&res_empty[(ccc - 2u) % NBUF]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  cc += CHUNKS;
 }
 
 // Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
@@ -348,7 +530,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&res_full[b], 1);
-      mbar_init(&res_empty[b], 1);
+      mbar_init(&res_empty[b], (EPI == PERS_EPI_CONV && (p.epi_mode & 4) && !p.a_spatial && NBUF >= 4) ? 4 : 1);   // one arrival per quarter warp
     }
     fence_mbar_init();
   }
@@ -366,17 +548,22 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t g = 0;  // ring slot counter, runs across tiles
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
-        if (EPI == PERS_EPI_CONV && p.l2_prefetch && p.taps == 1 && p.k_split == 0 && t + static_cast<int>(gridDim.x) < p.total_tiles) {
-          const TileCoord cn = decode_tile(p, t + gridDim.x);
-          if (cn.m_tile != c.m_tile) {                          // (n-tile-fastest order: same pixels, next channel slice)
-            for (int it = 0; it < k_iters; ++it) {
-              if (p.a_spatial) tma_prefetch_4d(&tmA, it * 64, cn.wo0 * p.stride - p.pad, cn.ho0 * p.stride - p.pad, cn.n0);
-              else tma_prefetch_2d(&tmA, it * 64, cn.m_tile * 128);
-            }
-          }
-        }
         for (int it = 0; it < k_iters; ++it, ++g) {
           const int s = g % STAGES;
+          if (EPI == PERS_EPI_CONV && p.l2_prefetch > 0 && p.taps == 1 && p.k_split == 0) {
+            // constant look-ahead: the activation box this CTA will load l2_prefetch ring slots from now is requested into
+            // L2 (one request per slot, interleaved with the loads - a burst per tile would queue in front of them)
+            const uint32_t j = g + static_cast<uint32_t>(p.l2_prefetch);
+            const int tj = blockIdx.x + static_cast<int>(j / k_iters) * static_cast<int>(gridDim.x);
+            if (tj < p.total_tiles) {
+              const TileCoord cn = decode_tile(p, tj);
+              if (p.n_tiles == 1 || cn.n_tile == 0) {           // (the CTAs of the other channel slices share these boxes)
+                const int itj = static_cast<int>(j % k_iters);
+                if (p.a_spatial) tma_prefetch_4d(&tmA, itj * 64, cn.wo0 * p.stride - p.pad, cn.ho0 * p.stride - p.pad, cn.n0);
+                else tma_prefetch_2d(&tmA, itj * 64, cn.m_tile * 128);
+              }
+            }
+          }
           mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -439,15 +626,18 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t cc = 0;  // staging chunk counter, runs across tiles
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord c = decode_tile(p, t);
-        if (p.l2_prefetch && t + static_cast<int>(gridDim.x) < p.total_tiles) {
-          const TileCoord cn = decode_tile(p, t + gridDim.x);
-          for (int ch = 0; ch < CHUNKS; ++ch) {
-            if (p.a_spatial) tma_prefetch_4d(&tmR, cn.n_tile * BN + ch * 64, cn.wo0, cn.ho0, cn.n0);
-            else tma_prefetch_2d(&tmR, cn.n_tile * BN + ch * 64, cn.m_tile * 128);
-          }
-        }
         for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
           const int b = cc % NBUF;
+          if (p.l2_prefetch > 0) {                            // residual chunk NBUF + 4 chunks from now -> L2
+            const uint32_t j = cc + NBUF + 4;
+            const int tj = blockIdx.x + static_cast<int>(j / CHUNKS) * static_cast<int>(gridDim.x);
+            if (tj < p.total_tiles) {
+              const TileCoord cn = decode_tile(p, tj);
+              const int chj = static_cast<int>(j % CHUNKS);
+              if (p.a_spatial) tma_prefetch_4d(&tmR, cn.n_tile * BN + chj * 64, cn.wo0, cn.ho0, cn.n0);
+              else tma_prefetch_2d(&tmR, cn.n_tile * BN + chj * 64, cn.m_tile * 128);
+            }
+          }
           mbar_wait(&res_empty[b], ((cc / NBUF) & 1) ^ 1);
           mbar_expect_tx(&res_full[b], L::STG_BYTES);
           if (p.a_spatial)
@@ -463,6 +653,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
     const int hsel = (warp - 4) >> 2;                  // conv epilogue: group of 4 warps (takes every other chunk)
     const int row = quarter * 32 + lane;
+    const bool warp_auto = (EPI == PERS_EPI_CONV) && (p.epi_mode & 4) && !p.a_spatial && (NBUF % 2 == 0) && (NBUF >= 4);
     const bool two_groups = (EPI == PERS_EPI_CONV) && (p.epi_mode & 1);
     const bool leader = two_groups ? (threadIdx.x == 128u + 128u * hsel) : (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
@@ -475,12 +666,17 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       if (EPI == PERS_EPI_CONV) {
-        if (two_groups)
+        if (warp_auto)
+          conv_epilogue_tile_warp<BN, (NBUF % 2 == 0 && NBUF > 0) ? NBUF : 2, L::SS>(
+              p, c, taddr, smem_u32(stg), smem_u32(smem + L::SS_OFF) + (i & 1) * 2 * BN * 4, res_full, res_empty, &acc_empty[a], cc,
+              row_off, sw, quarter, hsel, lane, tmO);
+        else if (two_groups)
           conv_epilogue_tile<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off, sw,
                                                     hsel, lane, leader, tmO);
         else
-          conv_epilogue_tile_1g<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off,
-                                                       sw, hsel, lane, leader, tmO);
+          conv_epilogue_tile_1g<BN, NBUF, EPI_THREADS, L::SS>(p, c, taddr, smem_u32(stg), smem_u32(smem + L::SS_OFF) + (i & 1) * 2 * BN * 4,
+                                                              res_full, res_empty, &acc_empty[a], cc, row_off, sw, hsel, lane,
+                                                              leader, tmO);
       } else {
         // ---------------------------------------------------------- similarity epilogues: row = query
         const int64_t qi = static_cast<int64_t>(c.m_tile) * 128 + row;
@@ -578,7 +774,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if (EPI == PERS_EPI_CONV && leader) bulk_wait<0>();     // all output bytes written before the CTA retires
+    if (EPI == PERS_EPI_CONV && (leader || (warp_auto && lane == 0))) bulk_wait<0>();   // all output bytes written before the CTA retires
   }
 
   tc_fence_before();

@@ -316,6 +316,19 @@ int dirb200_set_global_option(const char* key, double value) {
   return 0;
 }
 
+int dirb200_get_global_option(const char* key, double* value) {
+  DIRB_REQUIRE(key && value, DIRB200_EINVAL, "null argument");
+  const std::string k(key);
+  if (k == "halo") *value = get_conv_halo();
+  else if (k == "pdl") *value = g_use_pdl;
+  else if (k == "res_variant") *value = get_res_variant();
+  else if (k == "head_fused") *value = get_head_fused();
+  else if (k == "l2_prefetch") *value = get_l2_prefetch();
+  else if (k == "epi_mode") *value = get_epi_mode();
+  else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown global option '%s'", key);
+  return 0;
+}
+
 int dirb200_net_set_option(dirb200_net* n, const char* key, double value) {
   DIRB_REQUIRE(n && key, DIRB200_EINVAL, "null argument");
   const std::string k(key);

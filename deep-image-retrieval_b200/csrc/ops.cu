@@ -367,6 +367,7 @@ int head_fc_l2(const float* g, int B, int C, const float* fc_w, const float* fc_
 
 static int g_head_fused = 1;   // tuning knob (option "head_fused"): 0 = one kernel per phase
 void set_head_fused(int on) { g_head_fused = on; }
+int get_head_fused() { return g_head_fused; }
 
 // `bar`: two zero-initialised device words owned by the caller for the fused kernel's grid barrier (they return to a
 // reusable state after every launch); nullptr = use the tail of `ws` and clear it on the stream first.

@@ -37,6 +37,7 @@ SIGNATURES = {
     "dirb200_last_error": (C.c_char_p, []),
     "dirb200_device_check": (i32, [i32]),
     "dirb200_set_global_option": (i32, [C.c_char_p, f64]),
+    "dirb200_get_global_option": (i32, [C.c_char_p, C.POINTER(f64)]),
     "dirb200_net_create": (i32, [C.c_char_p, i32, C.POINTER(p)]),
     "dirb200_net_set_option": (i32, [p, C.c_char_p, f64]),
     "dirb200_net_set_tensor": (i32, [p, C.c_char_p, p, C.POINTER(i64), i32]),

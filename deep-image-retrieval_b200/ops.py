@@ -36,6 +36,12 @@ def set_global_option(key, value):
     lib.call("dirb200_set_global_option", key.encode(), float(value))
 
 
+def get_global_option(key):
+    v = C.c_double()
+    lib.call("dirb200_get_global_option", key.encode(), C.byref(v))
+    return v.value
+
+
 def nchw_to_nhwc8(x):
     _chk(x, torch.float32, "x")
     b, c, h, w = x.shape

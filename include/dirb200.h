@@ -53,9 +53,11 @@ int dirb200_device_check(int device);
  * once per tile (conv_halo.cuh) or tap by tap; "pdl" 1 (default) = programmatic dependent launch between consecutive
  * kernels; "res_variant" tile-variant selector of the residual 1x1 convolutions; "l2_prefetch" 1 = the 1x1
  * convolutions request the next tile's activation / residual boxes into L2 ahead of time; "head_fused" 1 (default) =
- * pooling + FC + L2 of the plain head as ONE persistent kernel, 0 = one kernel per phase (bit-identical results).
+ * pooling + FC + L2 of the plain head as ONE persistent kernel, 0 = one kernel per phase (bit-identical results);
+ * "epi_mode" epilogue organisation of the convolution kernels (bit 0: two warp groups, bit 1: early buffer release).
  * dirb200_net_set_option forwards these keys here. */
 int dirb200_set_global_option(const char* key, double value);
+int dirb200_get_global_option(const char* key, double* value);
 /* arch: "resnet50_rmac" | "resnet101_rmac" | "resnet152_rmac" (Bottleneck trunks, rmac_resnet.py:78-88). */
 int dirb200_net_create(const char* arch, int device, dirb200_net** out);
 /* Options.

@@ -80,6 +80,29 @@ def test_conv_bn_act(case, impl):
     assert err <= tol, (err, tol)
 
 
+@pytest.mark.parametrize("knobs", [dict(epi_mode=0), dict(epi_mode=1), dict(epi_mode=2), dict(epi_mode=3),
+                                   dict(epi_mode=3, l2_prefetch=1), dict(epi_mode=2, res_variant=1), dict(epi_mode=3, res_variant=2),
+                                   dict(epi_mode=3, res_variant=3, l2_prefetch=8), dict(epi_mode=0, res_variant=3),
+                                   dict(epi_mode=4), dict(epi_mode=6), dict(epi_mode=4, res_variant=1), dict(epi_mode=6, res_variant=2)],
+                         ids=lambda k: ",".join("%s=%d" % kv for kv in k.items()))
+def test_conv_epilogue_and_tile_variants(knobs):
+    """Every epilogue organisation (one / two warp groups, late / early release of the residual staging buffers), residual
+    tile variant and the next-tile L2 prefetch compute the same convolution: the residual and many-tile cases of
+    CONV_CASES vs the oracle, under each knob setting (process-wide selectors, restored afterwards)."""
+    ops = _ops()
+    cases = [c for c in CONV_CASES if c[8] or c[0] * c[1] * c[2] >= 128 * 148] + [(16, 64, 64, 256, 1024, 1, 1, 0, True, True)]
+    saved = {k: ops.get_global_option(k) for k in ("epi_mode", "res_variant", "l2_prefetch")}
+    try:
+        for k, v in knobs.items():
+            ops.set_global_option(k, v)
+        for case in cases:
+            err, tol = _conv_case(ops, *case, impl=0)
+            assert err <= tol, (case, err, tol)
+    finally:
+        for k, v in saved.items():
+            ops.set_global_option(k, v)
+
+
 def test_stem_and_maxpool():
     ops = _ops()
     x = synth.make_images(2, 64, 96, seed=3)
@@ -162,6 +185,7 @@ def test_head_single_kernel_is_bit_identical_to_the_phase_kernels(shape, kw):
     fc_b = None if without_fc else torch.from_numpy((0.01 * r.standard_normal(2048)).astype(np.float32)).to(DEV)
     args = dict(pooling=kw["pooling"], p=kw.get("p", 3.0), eps=1e-6, norm_features=kw.get("norm_features", False),
                 fc_w=fc_w, fc_b=fc_b, want_f16=True)
+    saved = ops.get_global_option("head_fused")
     try:
         ops.set_global_option("head_fused", 0)
         ref32, ref16 = ops.head_pool_fc_l2(feat, **args)
@@ -171,7 +195,7 @@ def test_head_single_kernel_is_bit_identical_to_the_phase_kernels(shape, kw):
             torch.cuda.synchronize()
             assert torch.equal(out32, ref32) and torch.equal(out16, ref16)
     finally:
-        ops.set_global_option("head_fused", 1)
+        ops.set_global_option("head_fused", saved)
     assert torch.isfinite(ref32).all() and abs(float(ref32[0].norm()) - 1.0) < 1e-5
 
 

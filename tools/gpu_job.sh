@@ -65,7 +65,7 @@ PY
       timeout 900 $TR bench.py --gpus $n $bargs > gpurun_out/bench_${n}gpu.log 2> gpurun_out/bench_${n}gpu.err; rc=$?; echo "== bench x$n rc=$rc"; tail -c 3000 gpurun_out/bench_${n}gpu.log; tail -3 gpurun_out/bench_${n}gpu.err; [ $rc -ne 0 ] && rc_all=$rc ;;
     py)
       script=$1; shift
-      timeout 900 python $script > gpurun_out/$(basename $script .py).log 2>&1; rc=$?; echo "== py $script rc=$rc"; tail -40 gpurun_out/$(basename $script .py).log; [ $rc -ne 0 ] && rc_all=$rc ;;
+      name=$(basename ${script%% *} .py); timeout 900 python $script > gpurun_out/$name.log 2>&1; rc=$?; echo "== py $script rc=$rc"; tail -40 gpurun_out/$name.log; [ $rc -ne 0 ] && rc_all=$rc ;;
     *) echo "unknown task $task"; rc_all=2 ;;
   esac
 done
