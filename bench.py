@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-search", action="store_true", help="c2: skip the 1M-row search measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="c2: skip the small-batch latency table")
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: exchange thresholds / lists with NCCL collectives instead of peer memory")
     ap.add_argument("--fuse-c23", type=int, default=-1, help="override the library default of option fuse_c23 (A/B runs)")
     ap.add_argument("--opt", action="append", default=[], help="library option KEY=VALUE for the network handle (A/B runs)")
     ap.add_argument("--chunk", type=int, default=0)
@@ -103,7 +104,7 @@ class ClockSampler(threading.Thread):
                     mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
                     mask = self._reasons_mask()
                     self.rows.append([mhz, self.max_mhz] + [bool(mask & b) for b in self.BITS])
-                    time.sleep(0.004)
+                    time.sleep(0.02)      # (NVML queries contend with kernel launches: 4 ms polling slowed 1 ms search steps)
                     continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -456,6 +457,9 @@ def bench_search(args, ctx, n_rows, n_q, aqe=False, whiten=False, steps=None):
     gq = torch.Generator(device="cuda").manual_seed(7)
     q = ops.l2_normalize(torch.randn((n_q, D), generator=gq, device="cuda", dtype=torch.float32))
     index = ShardedIndex(db, row_offset=s0, db16_local=db16)
+    peer = world > 1 and not args.no_peer
+    if peer:
+        index.enable_peer_exchange(max_q=n_q, max_k=K)
     if whiten:
         pca = synth.make_pca(D, seed=11)
         import numpy as np
@@ -517,7 +521,9 @@ def bench_search(args, ctx, n_rows, n_q, aqe=False, whiten=False, steps=None):
            "config": {"workload": "%d queries x %d x %d fp16 database, k=%d, exact fp64 re-scoring%s%s" %
                                   (n_q, n_rows, D, K, ", whitening p=0.25 of the queries" if whiten else "",
                                    ", alpha-QE k=2 alpha=0.5 (two searches)" if aqe else ""),
-                      "sharding": "rows / %d ranks; per search one MIN all-reduce of %d B + one all-gather of %d B per rank%s" %
+                      "sharding": ("rows / %d ranks; per search %d B of thresholds and %d B of lists per rank are stored into every peer's "
+                                   "exchange window over NVLink by the search kernels themselves (MIN + gather fused, no NCCL call)%s"
+                                   if peer else "rows / %d ranks; per search one MIN all-reduce of %d B + one all-gather of %d B per rank%s") %
                                   (world, 4 * n_q, 16 * n_q * K, "; alpha-QE adds one SUM all-reduce of %d B" % (4 * n_q * D) if aqe else "")},
            "e2e": {"value": n_q / s_e2e, "unit": "queries/s", "h2d_bytes_per_step": n_q * D * 4, "d2h_bytes_per_step": n_q * K * 16},
            "roofline": roof, "phases_ms": {k: round(v, 4) for k, v in prof.items()}, "stats": st,

@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include <limits.h>
+#include <string.h>
 
 #include <algorithm>
 #include <string>
@@ -261,6 +262,85 @@ __global__ void fill_empty_result_kernel(double* __restrict__ sc, int64_t* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Peer exchange of the sharded search (dirb200_index_search_sharded): the two collectives of the protocol - MIN of the
+// per-shard selection thresholds, gather of the per-shard lists - are done by the producing kernels themselves with
+// stores into the peers' memory over NVLink (P2P mappings, CUDA IPC between the one-process-per-GPU ranks), and the
+// consuming kernels wait on flags in their OWN memory.  Every rank owns one exchange buffer of identical layout:
+//   [0]   epoch (u32; the current search, bumped by the last block of the merge)      [16..] block-completion counters
+//   [64]  flag_sel[2][8]   [128] flag_list[2][8]      written by rank g into slot g of EVERY rank (release, system scope)
+//   [256] sel[2][G][max_q] fp32 | score[2][G][max_q*max_k] fp64 | idx[2][G][max_q*max_k] int64
+// Slots are double-buffered by epoch parity: rank r overwrites parity p two searches later, after it has seen every peer's
+// lists of the search in between - which a peer publishes only after its own merge of the earlier search has read them.
+constexpr int X_MAXW = 8;
+constexpr int X_OFF_EPOCH = 0, X_OFF_CNT = 16, X_OFF_FSEL = 64, X_OFF_FLIST = 128, X_OFF_SEL = 256;
+struct PeerX {
+  int world, rank, max_q, max_k;      // world == 0: no exchange (plain single-shard kernels)
+  uint8_t* peer[X_MAXW];              // every rank's exchange buffer as mapped in THIS process (peer[rank] = own)
+};
+__host__ __device__ inline size_t x_sel_bytes(int world, int max_q) { return (static_cast<size_t>(2) * world * max_q * 4 + 255) / 256 * 256; }
+__host__ __device__ inline size_t x_list_elems(int max_q, int max_k) { return static_cast<size_t>(max_q) * max_k; }
+__host__ __device__ inline size_t x_off_score(int world, int max_q) { return X_OFF_SEL + x_sel_bytes(world, max_q); }
+__host__ __device__ inline size_t x_off_idx(int world, int max_q, int max_k) {
+  return x_off_score(world, max_q) + static_cast<size_t>(2) * world * x_list_elems(max_q, max_k) * 8;
+}
+__host__ __device__ inline size_t x_total_bytes(int world, int max_q, int max_k) {
+  return x_off_idx(world, max_q, max_k) + static_cast<size_t>(2) * world * x_list_elems(max_q, max_k) * 8;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t x_epoch(const PeerX& x) {
+  return *reinterpret_cast<const volatile uint32_t*>(x.peer[x.rank] + X_OFF_EPOCH);
+}
+// One thread: wait until every rank has published epoch e in this rank's flag row.  Bounded (~10 s): a peer that never
+// arrives becomes error bit 4 of the status block instead of a hung GPU.
+__device__ __forceinline__ void x_wait_flags(const PeerX& x, int flag_off, uint32_t e, unsigned long long* status) {
+  const uint32_t* f = reinterpret_cast<const uint32_t*>(x.peer[x.rank] + flag_off) + (e & 1u) * X_MAXW;
+  for (int g = 0; g < x.world; ++g) {
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(f + g) - e) < 0) {
+      __nanosleep(100);
+      if (++spins > (1u << 26)) {
+        if (status) atomicOr(status + ST_ERR, 4ull);
+        break;
+      }
+    }
+  }
+}
+// End of a producing kernel: the LAST block to get here publishes epoch e in slot `rank` of every rank's flag row.
+__device__ __forceinline__ void x_signal_when_all_blocks_done(const PeerX& x, int cnt_slot, int flag_off, uint32_t e) {
+  __threadfence_system();                                   // this thread's stores to the peers before its block's arrival
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(x.peer[x.rank] + X_OFF_CNT) + cnt_slot;
+    if (atomicAdd(cnt, 1u) == gridDim.x * gridDim.y - 1u) {
+      *cnt = 0u;
+      __threadfence_system();
+      for (int g = 0; g < x.world; ++g)
+        st_release_sys(reinterpret_cast<uint32_t*>(x.peer[g] + flag_off) + (e & 1u) * X_MAXW + x.rank, e);
+    }
+  }
+}
+
+// Phase 1 -> peers: this shard's selection thresholds into slot `rank` of every rank's sel table.
+__global__ void sel_push_kernel(PeerX x, const float* __restrict__ sel_local, int Q) {
+  const uint32_t e = x_epoch(x);
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) {
+    const float v = sel_local[q];
+    const size_t o = X_OFF_SEL + ((static_cast<size_t>(e & 1u) * x.world + x.rank) * x.max_q + q) * 4;
+    for (int g = 0; g < x.world; ++g) *reinterpret_cast<float*>(x.peer[g] + o) = v;
+  }
+  x_signal_when_all_blocks_done(x, 0, X_OFF_FSEL, e);
+}
+
 // Phase 2 of a search in ONE launch, one block per query:
 //   survivors = candidates with fp16-path score >= max(sel[q], kth_k[q]) - band   (compacted into shared memory)
 //   exact score of each survivor = fp64-accumulated dot product of the fp32 rows  (one warp per survivor)
@@ -272,17 +352,33 @@ __global__ void __launch_bounds__(FIN_THREADS) search_finish_kernel(
     const unsigned long long* __restrict__ cand, const int* __restrict__ cnt, int cap, const float* __restrict__ kth_k,
     const float* __restrict__ sel, float band, const float* __restrict__ q32, const float* __restrict__ db32, int D,
     int cap2, int64_t offset, int k, double* __restrict__ out_score, int64_t* __restrict__ out_idx,
-    unsigned long long* __restrict__ status) {
+    unsigned long long* __restrict__ status, const PeerX x) {
+  // x.world > 0 (sharded search over peer memory): the selection threshold is the MINIMUM over the shards of the values the
+  // peers stored into this rank's sel table (waits for their flags), and the ordered list goes to slot `rank` of EVERY
+  // rank's list table instead of out_score / out_idx - MIN all-reduce and all-gather fused into this kernel.
   extern __shared__ uint8_t sm[];
   __shared__ int s_n;
+  __shared__ float s_sel;
   double* sc = reinterpret_cast<double*>(sm);          // [cap2]
   int* ix = reinterpret_cast<int*>(sc + cap2);         // [cap2]
   const int q = blockIdx.x;
-  const int n = min(cnt[q], cap);
+  const int n = cnt ? min(cnt[q], cap) : 0;            // (empty shard: no candidate buffers at all)
   const unsigned long long* c = cand + static_cast<int64_t>(q) * cap;
-  if (threadIdx.x == 0) s_n = 0;
+  const uint32_t epoch = x.world > 0 ? x_epoch(x) : 0u;
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    if (x.world > 0) {
+      x_wait_flags(x, X_OFF_FSEL, epoch, status);
+      const float* tab = reinterpret_cast<const float*>(x.peer[x.rank] + X_OFF_SEL) + static_cast<size_t>(epoch & 1u) * x.world * x.max_q;
+      float m = INFINITY;
+      for (int g = 0; g < x.world; ++g) m = fminf(m, __ldcg(tab + static_cast<size_t>(g) * x.max_q + q));
+      s_sel = m;
+    } else {
+      s_sel = sel[q];
+    }
+  }
   __syncthreads();
-  const float t2 = fmaxf(sel[q], kth_k[q]) - band;
+  const float t2 = fmaxf(s_sel, kth_k ? kth_k[q] : INFINITY) - band;
   for (int i = threadIdx.x; i < n; i += FIN_THREADS) {
     const unsigned long long e = c[i];
     if (__uint_as_float(static_cast<uint32_t>(e >> 32)) >= t2) {
@@ -322,16 +418,31 @@ __global__ void __launch_bounds__(FIN_THREADS) search_finish_kernel(
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
-    const bool ok = i < ns;
-    out_score[static_cast<int64_t>(q) * k + i] = ok ? sc[i] : -INFINITY;
-    out_idx[static_cast<int64_t>(q) * k + i] = ok ? static_cast<int64_t>(ix[i]) + offset : -1;
+  if (x.world > 0) {
+    const size_t slot = (static_cast<size_t>(epoch & 1u) * x.world + x.rank) * x_list_elems(x.max_q, x.max_k) + static_cast<size_t>(q) * k;
+    const size_t o_sc = x_off_score(x.world, x.max_q) + slot * 8, o_ix = x_off_idx(x.world, x.max_q, x.max_k) + slot * 8;
+    for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
+      const bool ok = i < ns;
+      const double vs = ok ? sc[i] : -INFINITY;
+      const int64_t vi = ok ? static_cast<int64_t>(ix[i]) + offset : -1;
+      for (int g = 0; g < x.world; ++g) {
+        reinterpret_cast<double*>(x.peer[g] + o_sc)[i] = vs;
+        reinterpret_cast<int64_t*>(x.peer[g] + o_ix)[i] = vi;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
+      const bool ok = i < ns;
+      out_score[static_cast<int64_t>(q) * k + i] = ok ? sc[i] : -INFINITY;
+      out_idx[static_cast<int64_t>(q) * k + i] = ok ? static_cast<int64_t>(ix[i]) + offset : -1;
+    }
   }
   if (threadIdx.x == 0) {
     if (found > cap2) atomicOr(status + ST_ERR, 2ull);
     atomicAdd(status + ST_CAND, static_cast<unsigned long long>(n));
     atomicAdd(status + ST_SURV, static_cast<unsigned long long>(ns));
   }
+  if (x.world > 0) x_signal_when_all_blocks_done(x, 1, X_OFF_FLIST, epoch);
 }
 
 // Exact dense scores for small evaluation sets: grid (ceil(N/8), ceil(Q/4)), warp = one db row x 4 queries.
@@ -535,20 +646,32 @@ __global__ void __launch_bounds__(RCE_THREADS) rank_count_exact_kernel(
 // Merge G per-shard lists that are each already ordered (score desc, index asc; empty slots = index -1 at the tail):
 // the final position of an entry = its position in its own list + the number of entries of every other list that come
 // before it (binary search) - no sorting network, no barriers after the load.  One block per query.
-__global__ void __launch_bounds__(1024) merge_lists_kernel(const double* __restrict__ in_score, const int64_t* __restrict__ in_idx,
+// x.world > 0: the lists are the ones the peers stored into this rank's list table (waits for their flags); the last block
+// then opens the next epoch of the exchange.
+__global__ void __launch_bounds__(1024) merge_lists_kernel(const double* in_score, const int64_t* in_idx,
                                                           int G, int k, int64_t shard_stride, double* __restrict__ out_score,
-                                                          int64_t* __restrict__ out_idx) {
+                                                          int64_t* __restrict__ out_idx, const PeerX x,
+                                                          unsigned long long* status) {
   extern __shared__ uint8_t sm[];
   __shared__ int s_valid;
   const int q = blockIdx.x;
   const int n = G * k;
   double* sc = reinterpret_cast<double*>(sm);
   int64_t* ix = reinterpret_cast<int64_t*>(sc + n);
+  if (x.world > 0) {
+    const uint32_t epoch = x_epoch(x);
+    if (threadIdx.x == 0) x_wait_flags(x, X_OFF_FLIST, epoch, status);
+    const size_t base = static_cast<size_t>(epoch & 1u) * x.world * x_list_elems(x.max_q, x.max_k);
+    in_score = reinterpret_cast<const double*>(x.peer[x.rank] + x_off_score(x.world, x.max_q)) + base;
+    in_idx = reinterpret_cast<const int64_t*>(x.peer[x.rank] + x_off_idx(x.world, x.max_q, x.max_k)) + base;
+    shard_stride = static_cast<int64_t>(x_list_elems(x.max_q, x.max_k));
+  }
   if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();                                        // (peer mode: the flags were acquired by thread 0)
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int64_t src = static_cast<int64_t>(e / k) * shard_stride + static_cast<int64_t>(q) * k + e % k;
-    sc[e] = in_score[src];
-    ix[e] = in_idx[src];
+    sc[e] = __ldcg(in_score + src);
+    ix[e] = __ldcg(in_idx + src);
   }
   __syncthreads();
   int my_valid = 0;
@@ -581,6 +704,17 @@ __global__ void __launch_bounds__(1024) merge_lists_kernel(const double* __restr
   for (int r = s_valid + threadIdx.x; r < k; r += blockDim.x) {      // fewer than k rows in the whole database
     out_score[static_cast<int64_t>(q) * k + r] = -INFINITY;
     out_idx[static_cast<int64_t>(q) * k + r] = -1;
+  }
+  if (x.world > 0) {                                      // last block: this search is over, open the next epoch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int* cnt = reinterpret_cast<unsigned int*>(x.peer[x.rank] + X_OFF_CNT) + 2;
+      if (atomicAdd(cnt, 1u) == gridDim.x - 1u) {
+        *cnt = 0u;
+        uint32_t* ep = reinterpret_cast<uint32_t*>(x.peer[x.rank] + X_OFF_EPOCH);
+        *ep = *ep + 1u;
+      }
+    }
   }
 }
 
@@ -747,6 +881,8 @@ int dirb200_index_check(dirb200_index* h) {
   }
   DIRB_REQUIRE((err & 1ull) == 0, DIRB200_EOVERFLOW,
                "candidate buffer overflow not resolved after %d retry passes (raise option cand_cap)", h->retries);
+  DIRB_REQUIRE((err & 4ull) == 0, DIRB200_EOVERFLOW,
+               "sharded search: a peer rank did not publish its thresholds / lists in time (ranks out of step?)");
   DIRB_REQUIRE((err & 2ull) == 0, DIRB200_EOVERFLOW,
                "more than %d rows within 2*eps16=%g of the k-th score for some query (near-duplicate rows?)",
                h->status_cap2, h->status_band);
@@ -922,18 +1058,31 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
 // Phase 2: survivors (candidates within the band of max(sel, local k-th)), exact re-scoring, ordered output - one
 // launch (search_finish_kernel) + an asynchronous copy of the status block.  Unless option deferred_check is set the
 // call ends with dirb200_index_check (the only host synchronisation of a search).
-int dirb200_index_search_finish(dirb200_index* h, const float* q32, const float* sel_dev, double* scores_dev,
-                                int64_t* idx_dev, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DIRB_REQUIRE(h && q32 && sel_dev && scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
+// Asynchronous copy of the status block of the search in flight + the event dirb200_index_check waits for.
+static int post_status_copy(dirb200_index* h, cudaStream_t stream) {
+  if (!h->h_status) DIRB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_status), ST_WORDS * 8));
+  if (!h->status_ev) DIRB_CUDA(cudaEventCreateWithFlags(&h->status_ev, cudaEventDisableTiming));
+  DIRB_CUDA(cudaMemcpyAsync(h->h_status, h->pend.status, ST_WORDS * 8, cudaMemcpyDeviceToHost, stream));
+  DIRB_CUDA(cudaEventRecord(h->status_ev, stream));
+  h->status_pending = true;
+  return 0;
+}
+
+static int search_finish_impl(dirb200_index* h, const float* q32, const float* sel_dev, double* scores_dev, int64_t* idx_dev,
+                              cudaStream_t stream, const PeerX& px, unsigned long long* x_status) {
   auto& P = h->pend;
   DIRB_REQUIRE(P.active, DIRB200_ESTATE, "dirb200_index_search_finish without a matching _begin");
   DIRB_CUDA(cudaSetDevice(h->device));
   const int Q = P.Q, k = P.k, cap2 = P.cap2;
   P.active = false;
   if (h->N == 0) {
-    const int64_t n = static_cast<int64_t>(Q) * k;
-    fill_empty_result_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(scores_dev, idx_dev, n);
+    if (px.world > 0) {   // an empty shard still publishes its (empty) lists: the peers wait for every rank's flag
+      search_finish_kernel<<<Q, FIN_THREADS, static_cast<size_t>(cap2) * 12, stream>>>(nullptr, nullptr, 0, nullptr, sel_dev, 0.f, q32, nullptr,
+                                                                                     h->dim, cap2, h->offset, k, nullptr, nullptr, x_status, px);
+    } else {
+      const int64_t n = static_cast<int64_t>(Q) * k;
+      fill_empty_result_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(scores_dev, idx_dev, n);
+    }
     count_launch();
     DIRB_CUDA(cudaGetLastError());
     h->stats[0] = h->stats[1] = h->stats[2] = h->stats[3] = 0;
@@ -942,21 +1091,24 @@ int dirb200_index_search_finish(dirb200_index* h, const float* q32, const float*
   }
   const size_t smem = static_cast<size_t>(cap2) * 12;
   search_finish_kernel<<<Q, FIN_THREADS, smem, stream>>>(P.cand, P.cnt, P.cap, P.kth_k, sel_dev, P.band, q32, h->db32, h->dim,
-                                                         cap2, h->offset, k, scores_dev, idx_dev, P.status);
+                                                         cap2, h->offset, k, scores_dev, idx_dev, P.status, px);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
   mark_phase(h, stream);  // 7: survivors + exact re-scoring + sort
-  if (!h->h_status) DIRB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->h_status), ST_WORDS * 8));
-  if (!h->status_ev) DIRB_CUDA(cudaEventCreateWithFlags(&h->status_ev, cudaEventDisableTiming));
-  DIRB_CUDA(cudaMemcpyAsync(h->h_status, P.status, ST_WORDS * 8, cudaMemcpyDeviceToHost, stream));
-  DIRB_CUDA(cudaEventRecord(h->status_ev, stream));
-  h->status_pending = true;
   h->status_cap2 = cap2;
   h->status_band = P.band;
   h->stats[0] = P.S;
   h->stats[4] = launches_total() - P.launches0;
+  if (px.world > 0) return 0;               // sharded search over peer memory: the merge (phase 3) can still raise error bits
+  DIRB_TRY(post_status_copy(h, stream));
   if (!h->deferred) return dirb200_index_check(h);
   return 0;
+}
+
+int dirb200_index_search_finish(dirb200_index* h, const float* q32, const float* sel_dev, double* scores_dev,
+                                int64_t* idx_dev, void* stream_) {
+  DIRB_REQUIRE(h && q32 && sel_dev && scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
+  return search_finish_impl(h, q32, sel_dev, scores_dev, idx_dev, static_cast<cudaStream_t>(stream_), PeerX{}, nullptr);
 }
 
 // Single-shard search = phase 1 with k_shard = k followed directly by phase 2.
@@ -1110,9 +1262,156 @@ int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, 
   const int n = G * k;
   const int threads = std::min(1024, (n + 31) / 32 * 32);
   merge_lists_kernel<<<Q, threads, static_cast<size_t>(n) * 16, stream>>>(scores_dev, idx_dev, G, k, shard_stride, out_scores_dev,
-                                                                        out_idx_dev);
+                                                                        out_idx_dev, PeerX{}, nullptr);
   count_launch();
   DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange of the sharded search (device side: PeerX, sel_push_kernel, search_finish_kernel, merge_lists_kernel)
+struct dirb200_exchange {
+  int device = 0, world = 1, rank = 0, max_q = 0, max_k = 0;
+  uint8_t* base = nullptr;           // this rank's window (cudaMalloc: exportable through CUDA IPC)
+  size_t bytes = 0;
+  uint8_t* peer[X_MAXW] = {};        // every rank's window as mapped in this process
+  bool ipc_opened[X_MAXW] = {};
+  bool open = false;
+  float* sel_local = nullptr;        // [max_q] this shard's selection thresholds before they are pushed
+  unsigned long long* status = nullptr;   // status words for kernels of an empty shard (no index workspace)
+};
+
+static PeerX peer_view(const dirb200_exchange* x) {
+  PeerX v{};
+  v.world = x->world; v.rank = x->rank; v.max_q = x->max_q; v.max_k = x->max_k;
+  for (int g = 0; g < x->world; ++g) v.peer[g] = x->peer[g];
+  return v;
+}
+
+int dirb200_exchange_create(int device, int world, int rank, int max_q, int max_k, dirb200_exchange** out) {
+  DIRB_REQUIRE(out, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(world >= 1 && world <= X_MAXW && rank >= 0 && rank < world, DIRB200_ENOTSUP,
+               "peer exchange supports 1..%d ranks of one box (got world=%d rank=%d)", X_MAXW, world, rank);
+  DIRB_REQUIRE(max_q >= 1 && max_k >= 1 && max_k <= 1024 && static_cast<int64_t>(world) * max_k <= 4096, DIRB200_ENOTSUP,
+               "need max_q >= 1, 1 <= max_k <= 1024 and world * max_k <= 4096");
+  DIRB_TRY(dirb200_device_check(device));
+  DIRB_CUDA(cudaSetDevice(device));
+  auto* x = new dirb200_exchange();
+  x->device = device; x->world = world; x->rank = rank; x->max_q = max_q; x->max_k = max_k;
+  x->bytes = x_total_bytes(world, max_q, max_k);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&x->base), x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->sel_local), static_cast<size_t>(max_q) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->status), ST_WORDS * 8);
+  if (e == cudaSuccess) e = cudaMemset(x->status, 0, ST_WORDS * 8);
+  if (e == cudaSuccess) {
+    const uint32_t one = 1;          // epochs start at 1: the zero-initialised flags read as "not yet published"
+    e = cudaMemcpy(x->base + X_OFF_EPOCH, &one, 4, cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    set_error("exchange window of %zu bytes: %s", x->bytes, cudaGetErrorString(e));
+    dirb200_exchange_destroy(x);
+    return static_cast<int>(e);
+  }
+  x->peer[rank] = x->base;
+  *out = x;
+  return 0;
+}
+
+int dirb200_exchange_ipc_handle(dirb200_exchange* x, void* handle64_out) {
+  DIRB_REQUIRE(x && handle64_out, DIRB200_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  DIRB_CUDA(cudaSetDevice(x->device));
+  cudaIpcMemHandle_t hd;
+  DIRB_CUDA(cudaIpcGetMemHandle(&hd, x->base));
+  memcpy(handle64_out, &hd, 64);
+  return 0;
+}
+
+int dirb200_exchange_open(dirb200_exchange* x, const void* handles) {
+  DIRB_REQUIRE(x && handles, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(!x->open, DIRB200_ESTATE, "exchange already opened");
+  DIRB_CUDA(cudaSetDevice(x->device));
+  for (int g = 0; g < x->world; ++g) {
+    if (g == x->rank) continue;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const uint8_t*>(handles) + static_cast<size_t>(g) * 64, 64);
+    void* ptr = nullptr;
+    DIRB_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    x->peer[g] = static_cast<uint8_t*>(ptr);
+    x->ipc_opened[g] = true;
+  }
+  x->open = true;
+  return 0;
+}
+
+int dirb200_exchange_open_local(dirb200_exchange* x, dirb200_exchange* const* all) {
+  DIRB_REQUIRE(x && all, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(!x->open, DIRB200_ESTATE, "exchange already opened");
+  for (int g = 0; g < x->world; ++g) {
+    DIRB_REQUIRE(all[g] && all[g]->world == x->world && all[g]->rank == g && all[g]->max_q == x->max_q && all[g]->max_k == x->max_k,
+                 DIRB200_EINVAL, "exchange %d of the group does not match (world / rank / sizes)", g);
+    if (all[g]->device != x->device) {
+      int can = 0;
+      DIRB_CUDA(cudaDeviceCanAccessPeer(&can, x->device, all[g]->device));
+      DIRB_REQUIRE(can, DIRB200_ENOTSUP, "device %d cannot access device %d", x->device, all[g]->device);
+      DIRB_CUDA(cudaSetDevice(x->device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[g]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) DIRB_CUDA(e);
+      cudaGetLastError();
+    }
+    x->peer[g] = all[g]->base;
+  }
+  x->open = true;
+  return 0;
+}
+
+int dirb200_exchange_destroy(dirb200_exchange* x) {
+  if (!x) return 0;
+  cudaSetDevice(x->device);
+  for (int g = 0; g < x->world; ++g)
+    if (x->ipc_opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
+  if (x->base) cudaFree(x->base);
+  if (x->sel_local) cudaFree(x->sel_local);
+  if (x->status) cudaFree(x->status);
+  delete x;
+  return 0;
+}
+
+int dirb200_index_search_sharded_phase(dirb200_index* h, dirb200_exchange* x, int phase, const float* q32, int Q, int k, int k_shard,
+                                       double* scores_dev, int64_t* idx_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_REQUIRE(h && x && q32, DIRB200_EINVAL, "null argument");
+  DIRB_REQUIRE(x->open, DIRB200_ESTATE, "exchange not opened (dirb200_exchange_open / _open_local)");
+  DIRB_REQUIRE(x->device == h->device, DIRB200_EINVAL, "index and exchange live on different devices");
+  DIRB_REQUIRE(Q >= 1 && Q <= x->max_q && k >= 1 && k <= x->max_k, DIRB200_ENOTSUP,
+               "exchange window holds %d queries x %d results (got Q=%d k=%d)", x->max_q, x->max_k, Q, k);
+  const PeerX px = peer_view(x);
+  if (phase == 1) {          // local tensor-core passes -> selection thresholds -> every peer's window
+    DIRB_TRY(dirb200_index_search_begin(h, q32, Q, k, k_shard, x->sel_local, stream_));
+    sel_push_kernel<<<static_cast<unsigned>(ceil_div(Q, 256)), 256, 0, stream>>>(px, x->sel_local, Q);
+    count_launch();
+    DIRB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (phase == 2)            // MIN over the shards + survivors + exact re-scoring -> ordered list into every peer's window
+    return search_finish_impl(h, q32, x->sel_local, nullptr, nullptr, stream, px, x->status);
+  DIRB_REQUIRE(phase == 3 && scores_dev && idx_dev, DIRB200_EINVAL, "phase is 1, 2 or 3 (3 needs the output buffers)");
+  const int n = x->world * k;
+  const int threads = std::min(1024, (n + 31) / 32 * 32);
+  merge_lists_kernel<<<Q, threads, static_cast<size_t>(n) * 16, stream>>>(nullptr, nullptr, x->world, k, 0, scores_dev, idx_dev, px,
+                                                                        h->pend.status ? h->pend.status : x->status);
+  count_launch();
+  DIRB_CUDA(cudaGetLastError());
+  if (h->pend.status) DIRB_TRY(post_status_copy(h, stream));   // (an empty shard has no status block of its own)
+  return 0;
+}
+
+int dirb200_index_search_sharded(dirb200_index* h, dirb200_exchange* x, const float* q32, int Q, int k, int k_shard,
+                                 double* scores_dev, int64_t* idx_dev, void* stream_) {
+  DIRB_REQUIRE(scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
+  for (int phase = 1; phase <= 3; ++phase)
+    DIRB_TRY(dirb200_index_search_sharded_phase(h, x, phase, q32, Q, k, k_shard, scores_dev, idx_dev, stream_));
   return 0;
 }
 

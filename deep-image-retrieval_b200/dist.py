@@ -52,6 +52,7 @@ class ShardedIndex:
         self.row_offset = int(row_offset)
         self.local = ops.Index(db32_local, index_offset=row_offset, db16=db16_local)
         self.local.set_option("retries", 2)      # a rank cannot re-run alone (collectives): one more gated retry pass up front
+        self.xchg = None                         # peer-memory exchange window (enable_peer_exchange)
         # row counts of all shards (one small all-gather at construction, not on the search path): the selection depth
         # of the two-phase search depends on them, see shard_quota
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -62,6 +63,27 @@ class ShardedIndex:
             self.shard_sizes = [int(v) for v in sizes.tolist()]
         else:
             self.shard_sizes = [int(self.local.n)]
+
+    def enable_peer_exchange(self, max_q: int = 1024, max_k: int = 128):
+        """Switch search() to the peer-memory protocol (dirb200_index_search_sharded): the MIN of the selection thresholds
+        and the gather of the per-shard lists are done by the search kernels themselves with stores into the other ranks'
+        exchange windows over NVLink - no NCCL call on the search path.  One process per GPU of ONE box (CUDA IPC); the
+        only collective is the one-off all-gather of the 64-byte IPC handles here.  Collective call."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        dev = self.local.db32.device
+        x = self.ops.Exchange(dev.index or 0, world, rank, max_q, max_k)
+        if world > 1:
+            mine = torch.frombuffer(bytearray(x.ipc_handle()), dtype=torch.uint8).to(dev)
+            allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine, group=self.group)
+            blob = bytes(allh.cpu().numpy().tobytes())
+            x.open([blob[64 * g: 64 * (g + 1)] for g in range(world)])
+            dist.barrier(group=self.group)          # every window is mapped everywhere before the first search writes to it
+        else:
+            self.ops.Exchange.open_local([x])
+        self.xchg = x
+        return self
 
     @classmethod
     def from_store(cls, store, device, group=None, chunk_rows: int = 65536):
@@ -93,6 +115,12 @@ class ShardedIndex:
             return self.local.search(q32, k)                 # the shard's ordered list IS the result: no merge pass
         self.local.set_option("deferred_check", 1)
         k_shard = shard_quota(k, self.shard_sizes)
+        x = self.xchg
+        if x is not None and q32.shape[0] <= x.max_q and k <= x.max_k:
+            out = self.local.search_sharded(x, q32, k, k_shard)   # thresholds + lists travel through peer memory
+            if check:
+                self.local.check()
+            return out
         sel = self.local.search_begin(q32, k, k_shard)
         dist.all_reduce(sel, op=dist.ReduceOp.MIN, group=self.group)
         packed = torch.empty((2, q32.shape[0], k), dtype=torch.int64, device=q32.device)

@@ -80,6 +80,13 @@ SIGNATURES = {
     "dirb200_index_rank_count": (i32, [p, p, i32, p, p, p, p, p, i32, p, p]),
     "dirb200_index_destroy": (i32, [p]),
     "dirb200_topk_merge": (i32, [p, p, i32, i32, i32, i64, p, p, p]),
+    "dirb200_exchange_create": (i32, [i32, i32, i32, i32, i32, C.POINTER(p)]),
+    "dirb200_exchange_ipc_handle": (i32, [p, p]),
+    "dirb200_exchange_open": (i32, [p, p]),
+    "dirb200_exchange_open_local": (i32, [p, C.POINTER(p)]),
+    "dirb200_exchange_destroy": (i32, [p]),
+    "dirb200_index_search_sharded": (i32, [p, p, p, i32, i32, i32, p, p, p]),
+    "dirb200_index_search_sharded_phase": (i32, [p, p, i32, p, i32, i32, i32, p, p, p]),
     "dirb200_scores_exact": (i32, [p, i32, p, i64, i32, p, p]),
     "dirb200_aqe_expand": (i32, [p, i32, i32, p, p, p, i32, f64, i32, i64, i64, p, p]),
 }

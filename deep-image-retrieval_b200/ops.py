@@ -256,6 +256,44 @@ def aqe_expand(q, db32, nn_idx, nn_scores, alpha, partial=False, row_offset=0, n
     return out
 
 
+class Exchange:
+    """This rank's window of the peer-memory exchange of a sharded search (include/dirb200.h: dirb200_exchange_*)."""
+
+    def __init__(self, device_index: int, world: int, rank: int, max_q: int, max_k: int):
+        self.world, self.rank, self.max_q, self.max_k = int(world), int(rank), int(max_q), int(max_k)
+        self._h = C.c_void_p()
+        lib.call("dirb200_exchange_create", int(device_index), self.world, self.rank, self.max_q, self.max_k, C.byref(self._h))
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        lib.call("dirb200_exchange_ipc_handle", self._h, buf)
+        return buf.raw
+
+    def open(self, handles) -> None:
+        """handles: the 64-byte IPC handles of all ranks in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.world
+        lib.call("dirb200_exchange_open", self._h, C.c_char_p(blob))
+
+    @staticmethod
+    def open_local(group) -> None:
+        """Same-process group: `group` = the exchange objects of all ranks, in rank order."""
+        arr = (C.c_void_p * len(group))(*[x._h for x in group])
+        for x in group:
+            lib.call("dirb200_exchange_open_local", x._h, arr)
+
+    def close(self):
+        if self._h:
+            lib.raw("dirb200_exchange_destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Index:
     """One row shard of a descriptor database on one GPU (dirb200_index)."""
 
@@ -330,6 +368,25 @@ class Index:
         lib.call("dirb200_index_search_finish", self._h, _ptr(q32), _ptr(_chk(sel, torch.float32, "sel")), _ptr(scores),
                  _ptr(idx), _stream())
         return scores, idx
+
+    def search_sharded(self, exchange: "Exchange", q32: torch.Tensor, k: int, k_shard: int, phase: int = 0):
+        """Collective exact top-k over all shards through the peer-memory exchange (no library collective): every rank
+        calls it with the same (Q, k, k_shard).  phase 0 = the whole search; 1 / 2 / 3 = one phase (several shards
+        driven shard by shard from one process).  -> (scores fp64, idx int64) (Q,k) after phase 0 / 3, else None.
+        Never synchronises: call check() (or the next search) to collect the status."""
+        _chk(q32, torch.float32, "q32")
+        nq = q32.shape[0]
+        scores = idx = None
+        if phase in (0, 3):
+            scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
+            idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
+        if phase == 0:
+            lib.call("dirb200_index_search_sharded", self._h, exchange._h, _ptr(q32), nq, int(k), int(k_shard), _ptr(scores),
+                     _ptr(idx), _stream())
+        else:
+            lib.call("dirb200_index_search_sharded_phase", self._h, exchange._h, int(phase), _ptr(q32), nq, int(k), int(k_shard),
+                     _ptr(scores), _ptr(idx), _stream())
+        return (scores, idx) if scores is not None else None
 
     def target_scores(self, q32, t_q, t_rows):
         """Exact scores <q32[t_q[t]], db[t_rows[t]]> (fp64) of the target rows this shard owns, 0 for the others.

@@ -36,6 +36,7 @@ extern "C" {
 
 typedef struct dirb200_net dirb200_net;     /* one ResNet-GeM network on one GPU            */
 typedef struct dirb200_index dirb200_index; /* one row-shard of a descriptor database       */
+typedef struct dirb200_exchange dirb200_exchange; /* this rank's window of the peer-memory exchange of a sharded search */
 
 int dirb200_version(void);
 const char* dirb200_last_error(void);
@@ -256,6 +257,30 @@ int dirb200_index_rank_count(dirb200_index* idx, const float* q32_dev, int Q, co
  * shard_stride = 2*Q*k with idx_dev = scores_dev + Q*k. */
 int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, int Q, int k, int64_t shard_stride,
                        double* out_scores_dev, int64_t* out_idx_dev, void* stream);
+/* Sharded search over PEER MEMORY (one process per GPU of one NVLink / NVSwitch box; the reference's analogue of a
+ * multi-GPU database is nn.DataParallel, utils/common.py:155, and scores = matmul(q, db) over the whole database,
+ * common.py:30-38 + datasets/generic.py:207).  Every rank creates an exchange window (device buffer for up to max_q
+ * queries x max_k results from `world` <= 8 ranks), hands its 64-byte CUDA IPC handle to the others (any transport:
+ * torch.distributed, MPI, a file), and opens theirs.  dirb200_index_search_sharded then runs the whole two-phase
+ * protocol on the caller's stream without any library collective: the selection thresholds and the per-shard lists are
+ * written by the producing kernels straight into every peer's window (stores over NVLink), the consuming kernels wait
+ * on flags in their own window - MIN all-reduce and all-gather fused into the search kernels.  It is a collective
+ * call: every rank calls it the same number of times with the same Q, k, k_shard (k_shard: see _search_begin).
+ * Results: global exact top-k on every rank.  Never synchronises; collect the status with dirb200_index_check
+ * (DIRB200_EOVERFLOW also when a peer did not arrive within ~10 s).
+ *   _open        handles = world x 64 bytes in rank order (entry `rank` is ignored)
+ *   _open_local  same-process variant: all = the `world` exchange objects of this process (several shards driven by
+ *                one process, tests); phases 1-3 of the search can then be issued shard by shard on one stream with
+ *                dirb200_index_search_sharded_phase (phase 1 for every shard, then phase 2, then phase 3). */
+int dirb200_exchange_create(int device, int world, int rank, int max_q, int max_k, dirb200_exchange** out);
+int dirb200_exchange_ipc_handle(dirb200_exchange* x, void* handle64_out);
+int dirb200_exchange_open(dirb200_exchange* x, const void* handles);
+int dirb200_exchange_open_local(dirb200_exchange* x, dirb200_exchange* const* all);
+int dirb200_exchange_destroy(dirb200_exchange* x);
+int dirb200_index_search_sharded(dirb200_index* idx, dirb200_exchange* x, const float* q32_dev, int Q, int k, int k_shard,
+                                 double* scores_dev, int64_t* idx_dev, void* stream);
+int dirb200_index_search_sharded_phase(dirb200_index* idx, dirb200_exchange* x, int phase, const float* q32_dev, int Q, int k,
+                                       int k_shard, double* scores_dev, int64_t* idx_dev, void* stream);
 /* Full exact score matrix (fp64 accumulate, fp32 out): the literal common.matmul for small evaluation sets. */
 int dirb200_scores_exact(const float* q_dev, int Q, const float* db_dev, int64_t N, int D, float* out_dev,
                          void* stream);

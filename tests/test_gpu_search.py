@@ -219,6 +219,23 @@ def test_config4_geometry_sharded_protocol_single_gpu():
         sh.search_finish(out, K, sel, out=packed[j])
     ms3, mi3 = ops.topk_merge_packed(packed, K)
     assert torch.equal(mi3, i3) and torch.equal(ms3, s3)
+    # the same protocol through the peer-memory exchange (dirb200_index_search_sharded_phase): thresholds and lists are
+    # stored by the kernels into all 8 windows, the MIN and the gather happen inside search_finish / merge_lists; every
+    # "rank" ends up with the global result.  Two searches: the double-buffered slots and the epoch counter advance.
+    xs = [ops.Exchange(0, G, r, Q, K) for r in range(G)]
+    ops.Exchange.open_local(xs)
+    for qq, (s_want, i_want) in ((q, (s_ref, i_ref)), (out, (s3, i3)), (q, (s_ref, i_ref))):
+        for sh, x in zip(shards, xs):
+            sh.search_sharded(x, qq, K, c, phase=1)
+        for sh, x in zip(shards, xs):
+            sh.search_sharded(x, qq, K, c, phase=2)
+        res = [sh.search_sharded(x, qq, K, c, phase=3) for sh, x in zip(shards, xs)]
+        for sh in shards:
+            sh.check()
+        for ps, pi in res:
+            assert torch.equal(pi, i_want) and torch.equal(ps, s_want)
+    for x in xs:
+        x.close()
     # sampled oracle check (fp64 scores of 8 queries against all rows, chunked)
     pick = [0, 1, 137, 500, 501, 777, 998, 999]
     qs = q[pick].cpu().numpy().astype(np.float64)
@@ -241,6 +258,49 @@ def test_config4_geometry_sharded_protocol_single_gpu():
             qe[r] += db[int(best_i[r, j])].cpu().numpy().astype(np.float64) * best_s[r, j] ** 0.5
     qe /= np.linalg.norm(qe, axis=1, keepdims=True)
     assert rel_l2(out[pick].cpu().numpy(), qe) < 1e-5
+
+
+@pytest.mark.parametrize("sizes", [(3000, 3000), (5000, 0, 700), (40, 9000, 2500, 1)], ids=lambda z: "-".join(map(str, z)))
+def test_peer_exchange_uneven_and_empty_shards(sizes):
+    """Sharded search over the peer-memory exchange with uneven, tiny and EMPTY shards (an empty shard still publishes its
+    thresholds and lists - the peers wait for every rank's flag), k larger than some shards, against the CPU oracle; the
+    whole-search entry point on a world of one."""
+    ops = _ops()
+    from dirb200.dist import shard_quota
+    n, k, nq = sum(sizes), 50, 37
+    db, q, _ = synth.make_descriptor_db(n, nq, dim=256, n_pos=4)
+    rs, ri = O.topk(q, db, k)
+    dbt, qt = torch.from_numpy(db).to(DEV), torch.from_numpy(q).to(DEV)
+    bounds = np.concatenate([[0], np.cumsum(sizes)])
+    shards = [ops.Index(dbt[a:b].contiguous(), index_offset=int(a)) for a, b in zip(bounds[:-1], bounds[1:])]
+    for sh in shards:
+        sh.set_option("deferred_check", 1)
+        sh.set_option("sample_rows", 512)
+    c = shard_quota(k, sizes)
+    G = len(sizes)
+    xs = [ops.Exchange(0, G, r, 64, 64) for r in range(G)]
+    ops.Exchange.open_local(xs)
+    for _ in range(3):
+        for ph in (1, 2):
+            for sh, x in zip(shards, xs):
+                sh.search_sharded(x, qt, k, c, phase=ph)
+        res = [sh.search_sharded(x, qt, k, c, phase=3) for sh, x in zip(shards, xs)]
+        for sh in shards:
+            sh.check()
+        for ps, pi in res:
+            assert np.array_equal(pi.cpu().numpy(), ri)
+            assert np.abs(ps.cpu().numpy() - rs).max() < 1e-12
+    # world of one: the whole search in one call == the plain search
+    one = ops.Index(dbt)
+    x1 = ops.Exchange(0, 1, 0, 64, 64)
+    ops.Exchange.open_local([x1])
+    one.set_option("deferred_check", 1)
+    for _ in range(2):
+        ps, pi = one.search_sharded(x1, qt, k, k)
+        one.check()
+        assert np.array_equal(pi.cpu().numpy(), ri) and np.abs(ps.cpu().numpy() - rs).max() < 1e-12
+    with pytest.raises(Exception):
+        one.search_sharded(x1, qt, 65, 65)                  # larger than the window
 
 
 def test_deferred_check_and_unresolved_overflow():

@@ -53,6 +53,14 @@ if os.environ.get("DIST_CHECK_STORE"):
     index2 = ShardedIndex.from_store(st, "cuda:%d" % local)
     s2, i2 = index2.search(qd, 100)
     ok = ok and bool(torch.equal(i2, i) and torch.equal(s2, s))
+# The same searches through the peer-memory exchange (no NCCL on the search path): thresholds and lists are stored by the
+# search kernels into every rank's window; every rank must end up with exactly the NCCL-path result, search after search.
+index.enable_peer_exchange(max_q=128, max_k=128)
+for _ in range(4):
+    sp, ip = index.search(qd, 100)
+    ok = ok and bool(torch.equal(ip, i) and torch.equal(sp, s))
+outp = index.expand_queries(qd, 2, 0.5)
+ok = ok and bool(torch.equal(outp, out))
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

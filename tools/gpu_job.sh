@@ -62,6 +62,7 @@ PY
       n=$1; shift; bargs=${1:-}; shift
       TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533"
       timeout 600 $TR tools/dist_check.py > gpurun_out/dist_check_$n.log 2>&1; rc=$?; echo "== dist_check x$n rc=$rc"; tail -3 gpurun_out/dist_check_$n.log; [ $rc -ne 0 ] && rc_all=$rc
+      timeout 300 $TR tools/dist_profile.py > gpurun_out/dist_profile_$n.log 2>&1; echo "== dist_profile x$n rc=$?"; tail -2 gpurun_out/dist_profile_$n.log
       timeout 900 $TR bench.py --gpus $n $bargs > gpurun_out/bench_${n}gpu.log 2> gpurun_out/bench_${n}gpu.err; rc=$?; echo "== bench x$n rc=$rc"; tail -c 3000 gpurun_out/bench_${n}gpu.log; tail -3 gpurun_out/bench_${n}gpu.err; [ $rc -ne 0 ] && rc_all=$rc ;;
     py)
       script=$1; shift
