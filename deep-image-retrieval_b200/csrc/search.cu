@@ -142,14 +142,21 @@ __device__ float block_kth_largest(Acc acc, int n, int k, uint32_t* hist /*[256]
   return key2f(prefix);
 }
 
-// thr[q] = (k-th largest of dense[q][0..S)) - band
+// thr[q] = (k-th largest of dense[q][0..S)) - band; k2 > 0: also thr2[q] = (k2-th largest) - band (the seed bound a shard
+// contributes to the MIN over the shards, see dirb200_index_search_sharded).
 __global__ void __launch_bounds__(SEL_THREADS) kth_dense_kernel(const float* __restrict__ dense, int64_t ld, int S,
-                                                                int k, float band, float* __restrict__ thr) {
+                                                                int k, float band, float* __restrict__ thr, int k2,
+                                                                float* __restrict__ thr2) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t bc[2];
   const int q = blockIdx.x;
   const float t = block_kth_largest(DenseAcc{dense + q * ld}, S, k, hist, bc);
   if (threadIdx.x == 0) thr[q] = t - band;
+  if (k2 > 0) {
+    __syncthreads();
+    const float t2 = (k2 == k) ? t : block_kth_largest(DenseAcc{dense + q * ld}, S, k2, hist, bc);
+    if (threadIdx.x == 0) thr2[q] = t2 - band;
+  }
 }
 
 // N <= S: candidates straight from the dense scores.
@@ -199,6 +206,7 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned lo
   if (gate_in != nullptr && q == 0 && threadIdx.x == 0) atomicAdd(status + ST_RETRIES, 1ull);
   const int total = cnt[q];
   const int n = min(total, cap);
+  const float thr_in = thr[q];                 // what the filter pass used: (a lower bound on the global k-th best) - band
   const unsigned long long* c = cand + static_cast<int64_t>(q) * cap;
   const int kk = (n_rows < static_cast<int64_t>(k)) ? static_cast<int>(n_rows) : k;
   const float t = block_kth_largest(CandAcc{c}, n, kk, hist, bc);
@@ -222,6 +230,10 @@ __global__ void __launch_bounds__(SEL_THREADS) cand_kth_kernel(const unsigned lo
     __syncthreads();
     ts = block_kth_largest(CandAcc{c}, n, k_shard, hist, bc);
   }
+  // Fewer than k_shard rows above a filter threshold that came from the other shards: this shard's k_shard-th best lies
+  // below that bound, which is itself a valid lower bound on the global k-th best - report the bound instead of -inf
+  // (the MIN over the shards must stay selective).  Shards with fewer than k_shard ROWS report their worst row.
+  if (ts == -INFINITY && n_rows >= static_cast<int64_t>(k_shard) && thr_in != -INFINITY) ts = thr_in + band;
   if (threadIdx.x == 0) {
     kth_k[q] = t;
     sel[q] = ts;
@@ -268,17 +280,21 @@ __global__ void fill_empty_result_kernel(double* __restrict__ sc, int64_t* __res
 // stores into the peers' memory over NVLink (P2P mappings, CUDA IPC between the one-process-per-GPU ranks), and the
 // consuming kernels wait on flags in their OWN memory.  Every rank owns one exchange buffer of identical layout:
 //   [0]   epoch (u32; the current search, bumped by the last block of the merge)      [16..] block-completion counters
-//   [64]  flag_sel[2][8]   [128] flag_list[2][8]      written by rank g into slot g of EVERY rank (release, system scope)
-//   [256] sel[2][G][max_q] fp32 | score[2][G][max_q*max_k] fp64 | idx[2][G][max_q*max_k] int64
+//   [64]  flag_sel[2][8]   [128] flag_list[2][8]   [192] flag_seed[2][8]
+//                                                    written by rank g into slot g of EVERY rank (release, system scope)
+//   [256] sel[2][G][max_q], seed[2][G][max_q] fp32 | score[2][G][max_q*max_k] fp64 | idx[2][G][max_q*max_k] int64
 // Slots are double-buffered by epoch parity: rank r overwrites parity p two searches later, after it has seen every peer's
 // lists of the search in between - which a peer publishes only after its own merge of the earlier search has read them.
 constexpr int X_MAXW = 8;
-constexpr int X_OFF_EPOCH = 0, X_OFF_CNT = 16, X_OFF_FSEL = 64, X_OFF_FLIST = 128, X_OFF_SEL = 256;
+constexpr int X_OFF_EPOCH = 0, X_OFF_CNT = 16, X_OFF_FSEL = 64, X_OFF_FLIST = 128, X_OFF_FSEED = 192, X_OFF_SEL = 256;
+constexpr int X_TAB_SEL = 0, X_TAB_SEED = 1;              // float tables [2][G][max_q]: selection thresholds, seed bounds
 struct PeerX {
   int world, rank, max_q, max_k;      // world == 0: no exchange (plain single-shard kernels)
   uint8_t* peer[X_MAXW];              // every rank's exchange buffer as mapped in THIS process (peer[rank] = own)
 };
-__host__ __device__ inline size_t x_sel_bytes(int world, int max_q) { return (static_cast<size_t>(2) * world * max_q * 4 + 255) / 256 * 256; }
+__host__ __device__ inline size_t x_tab_bytes(int world, int max_q) { return (static_cast<size_t>(2) * world * max_q * 4 + 255) / 256 * 256; }
+__host__ __device__ inline size_t x_sel_bytes(int world, int max_q) { return 2 * x_tab_bytes(world, max_q); }
+__host__ __device__ inline size_t x_off_tab(int tab, int world, int max_q) { return X_OFF_SEL + tab * x_tab_bytes(world, max_q); }
 __host__ __device__ inline size_t x_list_elems(int max_q, int max_k) { return static_cast<size_t>(max_q) * max_k; }
 __host__ __device__ inline size_t x_off_score(int world, int max_q) { return X_OFF_SEL + x_sel_bytes(world, max_q); }
 __host__ __device__ inline size_t x_off_idx(int world, int max_q, int max_k) {
@@ -329,16 +345,37 @@ __device__ __forceinline__ void x_signal_when_all_blocks_done(const PeerX& x, in
   }
 }
 
-// Phase 1 -> peers: this shard's selection thresholds into slot `rank` of every rank's sel table.
-__global__ void sel_push_kernel(PeerX x, const float* __restrict__ sel_local, int Q) {
+// This shard's per-query values (seed bounds / selection thresholds) into slot `rank` of every rank's float table.
+__global__ void tab_push_kernel(PeerX x, const float* __restrict__ local, int Q, int tab, int flag_off, int cnt_slot) {
   const uint32_t e = x_epoch(x);
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < Q) {
-    const float v = sel_local[q];
-    const size_t o = X_OFF_SEL + ((static_cast<size_t>(e & 1u) * x.world + x.rank) * x.max_q + q) * 4;
+    const float v = local[q];
+    const size_t o = x_off_tab(tab, x.world, x.max_q) + ((static_cast<size_t>(e & 1u) * x.world + x.rank) * x.max_q + q) * 4;
     for (int g = 0; g < x.world; ++g) *reinterpret_cast<float*>(x.peer[g] + o) = v;
   }
-  x_signal_when_all_blocks_done(x, 0, X_OFF_FSEL, e);
+  x_signal_when_all_blocks_done(x, cnt_slot, flag_off, e);
+}
+
+// MIN over the shards of one float table, per query (waits for every rank's flag).
+__device__ __forceinline__ float x_tab_min(const PeerX& x, int tab, uint32_t epoch, int q) {
+  const float* t = reinterpret_cast<const float*>(x.peer[x.rank] + x_off_tab(tab, x.world, x.max_q)) +
+                   static_cast<size_t>(epoch & 1u) * x.world * x.max_q;
+  float m = INFINITY;
+  for (int g = 0; g < x.world; ++g) m = fminf(m, __ldcg(t + static_cast<size_t>(g) * x.max_q + q));
+  return m;
+}
+
+// Filter threshold of the sharded search: thr[q] = max(local k-th seed bound, MIN over the shards of their c-th seed
+// bounds).  Both are lower bounds on the global k-th best score (the second by the shard-quota argument: every shard
+// certifies c rows at or above its own value, G * c >= k), and the second is ~10x more selective on a G = 8 split:
+// the local one keeps ~k / S of the rows as candidates, the global one ~c / S.
+__global__ void thr_min_kernel(PeerX x, float* __restrict__ thr, int Q, unsigned long long* status) {
+  const uint32_t e = x_epoch(x);
+  if (threadIdx.x == 0) x_wait_flags(x, X_OFF_FSEED, e, status);
+  __syncthreads();
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) thr[q] = fmaxf(thr[q], x_tab_min(x, X_TAB_SEED, e, q));
 }
 
 // Phase 2 of a search in ONE launch, one block per query:
@@ -369,10 +406,7 @@ __global__ void __launch_bounds__(FIN_THREADS) search_finish_kernel(
     s_n = 0;
     if (x.world > 0) {
       x_wait_flags(x, X_OFF_FSEL, epoch, status);
-      const float* tab = reinterpret_cast<const float*>(x.peer[x.rank] + X_OFF_SEL) + static_cast<size_t>(epoch & 1u) * x.world * x.max_q;
-      float m = INFINITY;
-      for (int g = 0; g < x.world; ++g) m = fminf(m, __ldcg(tab + static_cast<size_t>(g) * x.max_q + q));
-      s_sel = m;
+      s_sel = x_tab_min(x, X_TAB_SEL, epoch, q);
     } else {
       s_sel = sel[q];
     }
@@ -772,6 +806,15 @@ struct dirb200_index {
     unsigned long long* cand = nullptr;
     unsigned long long* status = nullptr;
     float* kth_k = nullptr;
+    // between the seed half and the filter half of phase 1 (the sharded search exchanges seed bounds in between)
+    float* thr = nullptr;
+    float* dense = nullptr;
+    float* sel_dev = nullptr;
+    __half* q16 = nullptr;
+    int* gates = nullptr;
+    int64_t S_ld = 0;
+    bool small = false;
+    int ks = 0;
   } pend;
   TmapCache tmaps;
   int profile = 0;                 // option "profile": time the phases of a search with CUDA events
@@ -930,9 +973,12 @@ static void mark_phase(dirb200_index* h, cudaStream_t stream) {
 // scores.  sel_dev[Q] receives the local k_shard-th best fp16-path score per query; with several shards the caller
 // MIN-reduces it over the shards before phase 2 (k_shard = ceil(k / shards)); with one shard k_shard = k.
 // Nothing here waits for the GPU: everything is enqueued on `stream`.
-int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k, int k_shard, float* sel_dev,
-                               void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// Split in two halves: search_begin_seed (queries -> fp16, seed pass, seed bounds) and search_begin_filter (filter pass,
+// candidate selection, gated retries).  seed2 != nullptr: the seed half also writes the k_shard-th seed bound of every
+// query there - what a shard contributes to the MIN over the shards that tightens the filter threshold of the sharded
+// search (thr_min_kernel, issued between the halves by dirb200_index_search_sharded_phase).
+static int search_begin_seed(dirb200_index* h, const float* q32, int Q, int k, int k_shard, float* sel_dev, cudaStream_t stream,
+                             float* seed2) {
   DIRB_REQUIRE(h && q32 && sel_dev, DIRB200_EINVAL, "null argument");
   DIRB_REQUIRE(h->has_db, DIRB200_ESTATE, "index has no database attached");
   DIRB_REQUIRE(Q > 0 && k > 0 && k <= 1024, DIRB200_ENOTSUP, "need 0 < Q and 0 < k <= 1024 (got Q=%d k=%d)", Q, k);
@@ -948,9 +994,14 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
   P.k = k;
   P.launches0 = launches_total();
   P.cap2 = (k > 256) ? 2048 : 1024;
+  P.sel_dev = sel_dev;
   if (N == 0) {   // empty shard: nothing can be selected; +inf never lowers the MIN over the shards
     fill_f32_kernel<<<static_cast<unsigned>(ceil_div(Q, 256)), 256, 0, stream>>>(sel_dev, Q, INFINITY);
     count_launch();
+    if (seed2) {
+      fill_f32_kernel<<<static_cast<unsigned>(ceil_div(Q, 256)), 256, 0, stream>>>(seed2, Q, INFINITY);
+      count_launch();
+    }
     DIRB_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1022,13 +1073,41 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
     mark_phase(h, stream);  // 2: seed GEMM
     const int n_vals = use_gmax ? static_cast<int>(ceil_div(S, 32)) : static_cast<int>(S);
     const int kk = static_cast<int>(std::min<int64_t>(k, n_vals));
-    kth_dense_kernel<<<Q, SEL_THREADS, 0, stream>>>(dense, S_ld, n_vals, kk, band, thr);
+    const int kk2 = seed2 ? static_cast<int>(std::min<int64_t>(k_shard, n_vals)) : 0;
+    kth_dense_kernel<<<Q, SEL_THREADS, 0, stream>>>(dense, S_ld, n_vals, kk, band, thr, kk2, seed2);
     count_launch();
     mark_phase(h, stream);  // 3: k-th of the seed scores
   }
+  P.thr = thr;
+  P.dense = dense;
+  P.q16 = q16;
+  P.gates = gates;
+  P.S_ld = S_ld;
+  P.small = small;
+  P.ks = std::min<int>(k_shard, static_cast<int>(std::min<int64_t>(k, N)));
+  DIRB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int search_begin_filter(dirb200_index* h, cudaStream_t stream) {
+  auto& P = h->pend;
+  DIRB_REQUIRE(P.active, DIRB200_ESTATE, "filter half of a search without its seed half");
+  const int64_t N = h->N;
+  if (N == 0) return 0;
+  DIRB_CUDA(cudaSetDevice(h->device));
+  const int Q = P.Q, k = P.k, D = h->dim, cap = P.cap, ks = P.ks;
+  const bool small = P.small;
+  const int64_t S_ld = P.S_ld;
+  const float band = P.band;
+  float* thr = P.thr;
+  float* dense = P.dense;
+  float* sel_dev = P.sel_dev;
+  __half* q16 = P.q16;
+  int* gates = P.gates;
+  int* cnt = P.cnt;
+  unsigned long long* cand = P.cand;
   // ---- 3./4. candidates + local k-th / k_shard-th candidate scores; pass r > 0 is armed by gate[r-1], which the
   //            selection of pass r-1 raises when some query overflowed its candidate list
-  const int ks = std::min<int>(k_shard, static_cast<int>(std::min<int64_t>(k, N)));
   for (int r = 0; r <= h->retries; ++r) {
     const int* gate_in = r > 0 ? gates + (r - 1) : nullptr;
     if (small) {
@@ -1053,6 +1132,13 @@ int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k,
   mark_phase(h, stream);  // 6: gated retry passes (empty launches unless a list overflowed)
   DIRB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int dirb200_index_search_begin(dirb200_index* h, const float* q32, int Q, int k, int k_shard, float* sel_dev,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DIRB_TRY(search_begin_seed(h, q32, Q, k, k_shard, sel_dev, stream, nullptr));
+  return search_begin_filter(h, stream);
 }
 
 // Phase 2: survivors (candidates within the band of max(sel, local k-th)), exact re-scoring, ordered output - one
@@ -1278,6 +1364,7 @@ struct dirb200_exchange {
   bool ipc_opened[X_MAXW] = {};
   bool open = false;
   float* sel_local = nullptr;        // [max_q] this shard's selection thresholds before they are pushed
+  float* seed_local = nullptr;       // [max_q] this shard's k_shard-th seed bounds before they are pushed
   unsigned long long* status = nullptr;   // status words for kernels of an empty shard (no index workspace)
 };
 
@@ -1302,6 +1389,7 @@ int dirb200_exchange_create(int device, int world, int rank, int max_q, int max_
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&x->base), x->bytes);
   if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->bytes);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->sel_local), static_cast<size_t>(max_q) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->seed_local), static_cast<size_t>(max_q) * 4);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->status), ST_WORDS * 8);
   if (e == cudaSuccess) e = cudaMemset(x->status, 0, ST_WORDS * 8);
   if (e == cudaSuccess) {
@@ -1373,6 +1461,7 @@ int dirb200_exchange_destroy(dirb200_exchange* x) {
     if (x->ipc_opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
   if (x->base) cudaFree(x->base);
   if (x->sel_local) cudaFree(x->sel_local);
+  if (x->seed_local) cudaFree(x->seed_local);
   if (x->status) cudaFree(x->status);
   delete x;
   return 0;
@@ -1387,16 +1476,30 @@ int dirb200_index_search_sharded_phase(dirb200_index* h, dirb200_exchange* x, in
   DIRB_REQUIRE(Q >= 1 && Q <= x->max_q && k >= 1 && k <= x->max_k, DIRB200_ENOTSUP,
                "exchange window holds %d queries x %d results (got Q=%d k=%d)", x->max_q, x->max_k, Q, k);
   const PeerX px = peer_view(x);
-  if (phase == 1) {          // local tensor-core passes -> selection thresholds -> every peer's window
-    DIRB_TRY(dirb200_index_search_begin(h, q32, Q, k, k_shard, x->sel_local, stream_));
-    sel_push_kernel<<<static_cast<unsigned>(ceil_div(Q, 256)), 256, 0, stream>>>(px, x->sel_local, Q);
+  const unsigned tb = static_cast<unsigned>(ceil_div(Q, 256));
+  if (phase == 1) {          // queries -> fp16, seed pass; this shard's k_shard-th seed bound -> every peer's window
+    DIRB_REQUIRE(k_shard >= 1 && k_shard <= k, DIRB200_EINVAL, "k_shard must be in [1, k]");
+    DIRB_TRY(search_begin_seed(h, q32, Q, k, k_shard, x->sel_local, stream, x->seed_local));
+    tab_push_kernel<<<tb, 256, 0, stream>>>(px, x->seed_local, Q, X_TAB_SEED, X_OFF_FSEED, 3);
     count_launch();
     DIRB_CUDA(cudaGetLastError());
     return 0;
   }
-  if (phase == 2)            // MIN over the shards + survivors + exact re-scoring -> ordered list into every peer's window
+  if (phase == 2) {          // filter threshold = max(local bound, MIN of the shards' seed bounds); filter pass + selection;
+                             // this shard's selection thresholds -> every peer's window
+    if (h->N > 0) {
+      thr_min_kernel<<<tb, 256, 0, stream>>>(px, h->pend.thr, Q, h->pend.status);
+      count_launch();
+    }
+    DIRB_TRY(search_begin_filter(h, stream));
+    tab_push_kernel<<<tb, 256, 0, stream>>>(px, x->sel_local, Q, X_TAB_SEL, X_OFF_FSEL, 0);
+    count_launch();
+    DIRB_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (phase == 3)            // MIN over the shards + survivors + exact re-scoring -> ordered list into every peer's window
     return search_finish_impl(h, q32, x->sel_local, nullptr, nullptr, stream, px, x->status);
-  DIRB_REQUIRE(phase == 3 && scores_dev && idx_dev, DIRB200_EINVAL, "phase is 1, 2 or 3 (3 needs the output buffers)");
+  DIRB_REQUIRE(phase == 4 && scores_dev && idx_dev, DIRB200_EINVAL, "phase is 1 .. 4 (4 needs the output buffers)");
   const int n = x->world * k;
   const int threads = std::min(1024, (n + 31) / 32 * 32);
   merge_lists_kernel<<<Q, threads, static_cast<size_t>(n) * 16, stream>>>(nullptr, nullptr, x->world, k, 0, scores_dev, idx_dev, px,
@@ -1410,7 +1513,7 @@ int dirb200_index_search_sharded_phase(dirb200_index* h, dirb200_exchange* x, in
 int dirb200_index_search_sharded(dirb200_index* h, dirb200_exchange* x, const float* q32, int Q, int k, int k_shard,
                                  double* scores_dev, int64_t* idx_dev, void* stream_) {
   DIRB_REQUIRE(scores_dev && idx_dev, DIRB200_EINVAL, "null argument");
-  for (int phase = 1; phase <= 3; ++phase)
+  for (int phase = 1; phase <= 4; ++phase)
     DIRB_TRY(dirb200_index_search_sharded_phase(h, x, phase, q32, Q, k, k_shard, scores_dev, idx_dev, stream_));
   return 0;
 }

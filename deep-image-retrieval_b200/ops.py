@@ -371,13 +371,14 @@ class Index:
 
     def search_sharded(self, exchange: "Exchange", q32: torch.Tensor, k: int, k_shard: int, phase: int = 0):
         """Collective exact top-k over all shards through the peer-memory exchange (no library collective): every rank
-        calls it with the same (Q, k, k_shard).  phase 0 = the whole search; 1 / 2 / 3 = one phase (several shards
-        driven shard by shard from one process).  -> (scores fp64, idx int64) (Q,k) after phase 0 / 3, else None.
+        calls it with the same (Q, k, k_shard).  phase 0 = the whole search; 1 .. 4 = one phase (seed bounds, filter +
+        selection, re-scoring, merge: several shards driven shard by shard from one process).
+        -> (scores fp64, idx int64) (Q,k) after phase 0 / 4, else None.
         Never synchronises: call check() (or the next search) to collect the status."""
         _chk(q32, torch.float32, "q32")
         nq = q32.shape[0]
         scores = idx = None
-        if phase in (0, 3):
+        if phase in (0, 4):
             scores = torch.empty((nq, k), dtype=torch.float64, device=q32.device)
             idx = torch.empty((nq, k), dtype=torch.int64, device=q32.device)
         if phase == 0:

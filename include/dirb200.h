@@ -262,16 +262,19 @@ int dirb200_topk_merge(const double* scores_dev, const int64_t* idx_dev, int G, 
  * common.py:30-38 + datasets/generic.py:207).  Every rank creates an exchange window (device buffer for up to max_q
  * queries x max_k results from `world` <= 8 ranks), hands its 64-byte CUDA IPC handle to the others (any transport:
  * torch.distributed, MPI, a file), and opens theirs.  dirb200_index_search_sharded then runs the whole two-phase
- * protocol on the caller's stream without any library collective: the selection thresholds and the per-shard lists are
- * written by the producing kernels straight into every peer's window (stores over NVLink), the consuming kernels wait
- * on flags in their own window - MIN all-reduce and all-gather fused into the search kernels.  It is a collective
+ * protocol on the caller's stream without any library collective: seed bounds, selection thresholds and the per-shard
+ * lists are written by the producing kernels straight into every peer's window (stores over NVLink), the consuming
+ * kernels wait on flags in their own window - two MIN all-reduces and the all-gather fused into the search kernels.  The
+ * first MIN (every shard's k_shard-th seed bound) tightens the filter threshold of all shards before their filter pass:
+ * ~k_shard / k of the candidates a stand-alone shard search captures.  It is a collective
  * call: every rank calls it the same number of times with the same Q, k, k_shard (k_shard: see _search_begin).
  * Results: global exact top-k on every rank.  Never synchronises; collect the status with dirb200_index_check
  * (DIRB200_EOVERFLOW also when a peer did not arrive within ~10 s).
  *   _open        handles = world x 64 bytes in rank order (entry `rank` is ignored)
  *   _open_local  same-process variant: all = the `world` exchange objects of this process (several shards driven by
- *                one process, tests); phases 1-3 of the search can then be issued shard by shard on one stream with
- *                dirb200_index_search_sharded_phase (phase 1 for every shard, then phase 2, then phase 3). */
+ *                one process, tests); the four phases of the search (1 seed pass + seed bounds, 2 filter pass + selection
+ *                thresholds, 3 exact re-scoring + lists, 4 merge) can then be issued shard by shard on one stream with
+ *                dirb200_index_search_sharded_phase: phase p for every shard before phase p + 1 of any. */
 int dirb200_exchange_create(int device, int world, int rank, int max_q, int max_k, dirb200_exchange** out);
 int dirb200_exchange_ipc_handle(dirb200_exchange* x, void* handle64_out);
 int dirb200_exchange_open(dirb200_exchange* x, const void* handles);

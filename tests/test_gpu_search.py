@@ -201,6 +201,7 @@ def test_config4_geometry_sharded_protocol_single_gpu():
         sh.check()
     assert torch.equal(mi, i_ref) and torch.equal(ms, s_ref)
     surv = sum(sh.stats()["survivors"] for sh in shards)
+    cand_nccl = sum(sh.stats()["candidates"] for sh in shards)
     assert surv < 3 * Q * K, surv                                          # ~1.4 k rows per query over ALL shards
     assert all(sh.stats()["retries"] == 0 for sh in shards)
     # alpha-QE from per-shard partial sums (what the all-reduce adds up) == unsharded expansion
@@ -225,15 +226,17 @@ def test_config4_geometry_sharded_protocol_single_gpu():
     xs = [ops.Exchange(0, G, r, Q, K) for r in range(G)]
     ops.Exchange.open_local(xs)
     for qq, (s_want, i_want) in ((q, (s_ref, i_ref)), (out, (s3, i3)), (q, (s_ref, i_ref))):
-        for sh, x in zip(shards, xs):
-            sh.search_sharded(x, qq, K, c, phase=1)
-        for sh, x in zip(shards, xs):
-            sh.search_sharded(x, qq, K, c, phase=2)
-        res = [sh.search_sharded(x, qq, K, c, phase=3) for sh, x in zip(shards, xs)]
+        for ph in (1, 2, 3):
+            for sh, x in zip(shards, xs):
+                sh.search_sharded(x, qq, K, c, phase=ph)
+        res = [sh.search_sharded(x, qq, K, c, phase=4) for sh, x in zip(shards, xs)]
         for sh in shards:
             sh.check()
         for ps, pi in res:
             assert torch.equal(pi, i_want) and torch.equal(ps, s_want)
+        # the filter threshold of the peer path is the MIN of the shards' 13th seed bounds, not the local 100th: an
+        # order of magnitude fewer candidates than the all-reduce path captured above
+        assert sum(sh.stats()["candidates"] for sh in shards) < 0.3 * cand_nccl
     for x in xs:
         x.close()
     # sampled oracle check (fp64 scores of 8 queries against all rows, chunked)
@@ -281,10 +284,10 @@ def test_peer_exchange_uneven_and_empty_shards(sizes):
     xs = [ops.Exchange(0, G, r, 64, 64) for r in range(G)]
     ops.Exchange.open_local(xs)
     for _ in range(3):
-        for ph in (1, 2):
+        for ph in (1, 2, 3):
             for sh, x in zip(shards, xs):
                 sh.search_sharded(x, qt, k, c, phase=ph)
-        res = [sh.search_sharded(x, qt, k, c, phase=3) for sh, x in zip(shards, xs)]
+        res = [sh.search_sharded(x, qt, k, c, phase=4) for sh, x in zip(shards, xs)]
         for sh in shards:
             sh.check()
         for ps, pi in res:
