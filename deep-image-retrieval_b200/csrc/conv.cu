@@ -137,9 +137,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
     p.tw = 128; p.th = 1; p.nb = 1; p.tiles_w = 1; p.tiles_h = 1;
     m_tiles = ceil_div(M, 128);
     DIRB_TRY(encode_tmap_2d(&tmA, in, s.Cin, M, (uint64_t)s.Cin * 2, 64, 128));
-    // warp-autonomous epilogue (epi_mode bit 2, kernels with a residual ring): every warp stores its own 32-row slab
-    const bool warp_store = (g_epi_mode & 4) && NB >= 4;
-    DIRB_TRY(encode_tmap_2d(&tmO, out, s.Cout, M, (uint64_t)s.Cout * 2, 64, warp_store ? 32 : 128));
+    DIRB_TRY(encode_tmap_2d(&tmO, out, s.Cout, M, (uint64_t)s.Cout * 2, 64, 128));
     if (res) DIRB_TRY(encode_tmap_2d(&tmR, res, s.Cout, M, (uint64_t)s.Cout * 2, 64, 128));
   } else {
     p.a_spatial = 1;

@@ -58,9 +58,12 @@ struct ConvPersParams {
   int l2_prefetch;
   // Epilogue organisation of the convolution kernels (A/B knobs, option "epi_mode"): bit 0 = 1: two independent groups of
   // 4 warps (two chunks in flight), 0: all 8 warps on one chunk; bit 1 = 1: a staging buffer goes back to the residual
-  // producer as soon as its own TMA store has finished reading it (earliest possible), 0: one store later; bit 2 = 1 (flat
-  // 1x1 convolutions only, whose output map has 32-row boxes): warp-autonomous epilogue - every warp stores its own
-  // 32-pixel slab, no CTA-wide barrier per chunk (conv_epilogue_tile_warp).
+  // producer as soon as its own TMA store has finished reading it (earliest possible), 0: one store later.
+  // Measured on ResNet-101 64 x 1024^2 (profiles/r2_conv_sweep.txt): 0 is the fastest; 1 starves the residual ring (two
+  // buffers per group), 2 puts the store's read-completion wait on the leader's critical path, 3 equals 0.  A third
+  // organisation (every warp storing its own 32-pixel slab, no CTA-wide barrier per chunk) also measured equal to 0 and
+  // was removed again: once the long-latency links are out of the chain (see conv_epilogue_tile_1g) the 1x1 convolutions
+  // with a residual run at ~4.9 TB/s in situ whatever the organisation.
   int epi_mode;
   // Device-side launch predicate (retry passes of the search): when non-null the whole grid returns at once unless
   // *gate != 0.  The value was written by the previous kernel of the stream, so it is read after pdl_wait().
@@ -347,138 +350,6 @@ __device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, c
   }
 }
 
-// Warp-autonomous organisation (flat 1x1 convolutions: output rows = pixels, the output tensor map has 64 x 32 boxes).
-// Warp (quarter q, group g) owns the 32 pixels of its TMEM lane quarter in the chunks whose running index has parity g:
-// it reads 64 accumulator columns in two halves (the second half is in flight while the first is processed), applies
-// scale / shift (+ its 32 rows of the residual chunk) (+ ReLU), writes its 4 KB slab of the staging buffer and stores it
-// with its OWN TMA store.  Nothing in the chunk loop synchronises warps with each other, so their dependency chains
-// drift apart and overlap (the lock-step organisations leave the SM idle whenever all 8 warps wait on the same LDS /
-// fence / barrier).  A staging buffer returns to the residual producer after 4 arrivals (one per quarter).
-template <int BN, int NBUF, bool SS>
-__device__ __forceinline__ void conv_epilogue_half_warp(const ConvPersParams& p, float (&v)[32], int col0, int half,
-                                                        uint32_t buf_addr, uint32_t ss_addr, int ch, uint32_t row_off,
-                                                        uint32_t sw) {
-  if (SS) {
-    const uint32_t sa = ss_addr + static_cast<uint32_t>(ch * 64 + half * 32) * 4u;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 s = lds128f(sa + q * 16), h = lds128f(sa + BN * 4 + q * 16);
-      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
-      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
-      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
-      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
-    }
-  } else {
-    const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
-    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
-      v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
-      v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
-      v[4 * q + 2] = fmaf(v[4 * q + 2], s.z, h.z);
-      v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
-    const uint32_t sp = buf_addr + row_off + ((chunk ^ sw) << 4);
-    if (p.has_res) {
-      const uint4 r = lds128(sp);
-      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_h2(rr[e]);
-        v[j * 8 + e * 2] += f.x;
-        v[j * 8 + e * 2 + 1] += f.y;
-      }
-    }
-    if (p.relu) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[j * 8 + e] = fmaxf(v[j * 8 + e], 0.0f);
-    }
-    uint4 o;
-    o.x = pack_h2(v[j * 8 + 0], v[j * 8 + 1]);
-    o.y = pack_h2(v[j * 8 + 2], v[j * 8 + 3]);
-    o.z = pack_h2(v[j * 8 + 4], v[j * 8 + 5]);
-    o.w = pack_h2(v[j * 8 + 6], v[j * 8 + 7]);
-    sts128(sp, o);
-  }
-}
-
-template <int BN, int NBUF, bool SS>
-__device__ __forceinline__ void conv_epilogue_tile_warp(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
-                                                        uint32_t stg_addr, uint32_t ss_addr, uint64_t* res_full,
-                                                        uint64_t* res_empty, uint64_t* acc_empty_a, uint32_t& cc,
-                                                        uint32_t row_off, uint32_t sw, int quarter, int g, int lane,
-                                                        const CUtensorMap& tmO) {
-  static_assert(NBUF % 2 == 0, "staging buffers are split between the two warp groups");
-  constexpr int CHUNKS = BN / 64;
-  constexpr int STG_BYTES = 128 * 128;
-  constexpr int NG = NBUF / 2;                              // staging buffers per group
-  if (SS) {                                                 // BN scale | shift of this tile's channels -> shared memory
-    const int j = static_cast<int>(threadIdx.x) - 128;
-    if (j < BN) {
-      sts32f(ss_addr + j * 4, __ldg(p.scale + c.n_tile * BN + j));
-      sts32f(ss_addr + (BN + j) * 4, __ldg(p.shift + c.n_tile * BN + j));
-    }
-    named_bar_sync(6, 256);                                 // (once per tile; the chunk loop below has no CTA-wide barrier)
-  }
-  int my_last = -1;
-#pragma unroll
-  for (int ch = 0; ch < CHUNKS; ++ch)
-    if (static_cast<int>((cc + ch) & 1u) == g) my_last = ch;
-  if (my_last < 0) {
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty_a);
-  }
-#pragma unroll 1
-  for (int ch = 0; ch < CHUNKS; ++ch) {
-    const uint32_t ccc = cc + ch;
-    if (static_cast<int>(ccc & 1u) != g) continue;
-    const int b = ccc % NBUF;
-    const uint32_t buf_addr = stg_addr + b * STG_BYTES;
-    if (p.has_res) {
-      mbar_wait(&res_full[b], (ccc / NBUF) & 1);            // residual chunk has landed in the buffer
-    } else {
-      if (lane == 0) bulk_wait_read<NG - 1>();               // this warp's store NG of its chunks ago has left its slab
-      __syncwarp();
-    }
-    const int col0 = c.n_tile * BN + ch * 64;
-    float va[32], vb[32];
-    tmem_ld32(taddr + ch * 64, va);
-    tmem_ld_wait();
-    tmem_ld32(taddr + ch * 64 + 32, vb);                    // second half in flight while the first is processed
-    conv_epilogue_half_warp<BN, NBUF, SS>(p, va, col0, 0, buf_addr, ss_addr, ch, row_off, sw);
-    tmem_ld_wait();
-    if (ch == my_last) {                                    // last TMEM read of this warp for this tile
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty_a);
-    }
-    conv_epilogue_half_warp<BN, NBUF, SS>(p, vb, col0, 1, buf_addr, ss_addr, ch, row_off, sw);
-    fence_proxy_async_smem();                               // this warp's smem writes -> visible to the TMA engine
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d_addr(&tmO, buf_addr + quarter * 4096, col0, c.m_tile * 128 + quarter * 32);
-      bulk_commit();
-      if (p.has_res) {
-        if (p.epi_mode & 2) {
-          bulk_wait_read<0>();                              // this very store has left the slab
-          mbar_arrive(&res_empty[b]);
-        } else {
-          bulk_wait_read<1>();                              // this warp's previous store (chunk ccc - 2) has left its slab
-          if (ccc >= 2u) mbar_arrive(&res_empty[(ccc - 2u) % NBUF]);
-        }
-      }
-    }
-    __syncwarp();
-  }
-  cc += CHUNKS;
-}
-
 // Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
 // convolutions), 4 for the light similarity epilogues.
 template <int EPI>
@@ -530,7 +401,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&res_full[b], 1);
-      mbar_init(&res_empty[b], (EPI == PERS_EPI_CONV && (p.epi_mode & 4) && !p.a_spatial && NBUF >= 4) ? 4 : 1);   // one arrival per quarter warp
+      mbar_init(&res_empty[b], 1);
     }
     fence_mbar_init();
   }
@@ -653,7 +524,6 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
     const int hsel = (warp - 4) >> 2;                  // conv epilogue: group of 4 warps (takes every other chunk)
     const int row = quarter * 32 + lane;
-    const bool warp_auto = (EPI == PERS_EPI_CONV) && (p.epi_mode & 4) && !p.a_spatial && (NBUF % 2 == 0) && (NBUF >= 4);
     const bool two_groups = (EPI == PERS_EPI_CONV) && (p.epi_mode & 1);
     const bool leader = two_groups ? (threadIdx.x == 128u + 128u * hsel) : (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
@@ -666,11 +536,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       if (EPI == PERS_EPI_CONV) {
-        if (warp_auto)
-          conv_epilogue_tile_warp<BN, (NBUF % 2 == 0 && NBUF > 0) ? NBUF : 2, L::SS>(
-              p, c, taddr, smem_u32(stg), smem_u32(smem + L::SS_OFF) + (i & 1) * 2 * BN * 4, res_full, res_empty, &acc_empty[a], cc,
-              row_off, sw, quarter, hsel, lane, tmO);
-        else if (two_groups)
+        if (two_groups)
           conv_epilogue_tile<BN, NBUF, EPI_THREADS>(p, c, taddr, stg, res_full, res_empty, &acc_empty[a], cc, row_off, sw,
                                                     hsel, lane, leader, tmO);
         else
@@ -774,7 +640,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if (EPI == PERS_EPI_CONV && (leader || (warp_auto && lane == 0))) bulk_wait<0>();   // all output bytes written before the CTA retires
+    if (EPI == PERS_EPI_CONV && leader) bulk_wait<0>();     // all output bytes written before the CTA retires
   }
 
   tc_fence_before();

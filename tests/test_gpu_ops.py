@@ -82,8 +82,7 @@ def test_conv_bn_act(case, impl):
 
 @pytest.mark.parametrize("knobs", [dict(epi_mode=0), dict(epi_mode=1), dict(epi_mode=2), dict(epi_mode=3),
                                    dict(epi_mode=3, l2_prefetch=1), dict(epi_mode=2, res_variant=1), dict(epi_mode=3, res_variant=2),
-                                   dict(epi_mode=3, res_variant=3, l2_prefetch=8), dict(epi_mode=0, res_variant=3),
-                                   dict(epi_mode=4), dict(epi_mode=6), dict(epi_mode=4, res_variant=1), dict(epi_mode=6, res_variant=2)],
+                                   dict(epi_mode=3, res_variant=3, l2_prefetch=8), dict(epi_mode=0, res_variant=3)],
                          ids=lambda k: ",".join("%s=%d" % kv for kv in k.items()))
 def test_conv_epilogue_and_tile_variants(knobs):
     """Every epilogue organisation (one / two warp groups, late / early release of the residual staging buffers), residual
