@@ -315,6 +315,67 @@ def test_sharded_index_learns_all_shard_sizes_gloo_world3(tmp_path):
     assert all(open(tmp_path / ("ok%d" % r)).read() == "1" for r in range(3))
 
 
+def _peer_handles_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    import dirb200  # noqa: F401
+    from dirb200 import dist as ddist
+    from dirb200 import ops
+
+    class _NoGpuIndex:
+        def __init__(self, db32, index_offset=0, db16=None):
+            self.db32, self.n, self.dim = db32, db32.shape[0], db32.shape[1]
+            self.calls = []
+
+        def set_option(self, key, value):
+            pass
+
+        def search_sharded(self, x, q32, k, k_shard, phase=0):
+            self.calls.append((x.rank, q32.shape[0], k, k_shard))
+            return "peer"
+
+        def check(self):
+            self.calls.append("check")
+
+    class _NoGpuExchange:                                  # the real one allocates a device window and opens CUDA IPC handles
+        def __init__(self, device_index, world, rank, max_q, max_k):
+            self.world, self.rank, self.max_q, self.max_k, self.opened = world, rank, max_q, max_k, None
+
+        def ipc_handle(self):
+            return bytes([self.rank + 1]) * 64
+
+        def open(self, handles):
+            self.opened = [bytes(h) for h in handles]
+    ops.Index, ops.Exchange = _NoGpuIndex, _NoGpuExchange
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = ddist.ShardedIndex(torch.zeros((10 + rank, 64)), row_offset=0).enable_peer_exchange(max_q=16, max_k=8)
+    x = sh.xchg
+    ok = x.rank == rank and x.world == world and x.opened == [bytes([g + 1]) * 64 for g in range(world)]
+    # searches that fit the window go through the exchange (with the shard quota), larger ones through the collectives
+    out = sh.search(torch.zeros((5, 64)), 8)
+    ok = ok and out == "peer" and sh.local.calls == [(rank, 5, 8, ddist.shard_quota(8, sh.shard_sizes)), "check"]
+    with open(os.path.join(tmp, "ok%d" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_handles_travel_in_rank_order_gloo_world3(tmp_path):
+    """ShardedIndex.enable_peer_exchange: every rank creates its window, the 64-byte IPC handles are all-gathered and each
+    rank opens them in rank order; search() then routes through dirb200_index_search_sharded with k_shard = shard_quota.
+    Plumbing under gloo with stand-ins for the GPU objects (the device side is covered by the -m gpu tests and
+    tools/dist_check.py under NCCL)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_peer_handles_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    assert all(open(tmp_path / ("ok%d" % r)).read() == "1" for r in range(3))
+
+
 class _FakeNet:
     """Stands in for the GPU network in host-plumbing tests: descriptor = per-channel mean / std of the image."""
     iscuda = False
