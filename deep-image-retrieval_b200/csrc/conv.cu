@@ -108,11 +108,14 @@ int num_sms() {
 static int g_l2_prefetch = 0;    // tuning knob (option "l2_prefetch"): next-tile L2 prefetch in the 1x1 convolutions
 void set_l2_prefetch(int v) { g_l2_prefetch = v; }
 int get_l2_prefetch() { return g_l2_prefetch; }
+static int g_epi_warps = 16;     // tuning knob (option "epi_warps"): 8 or 16 epilogue warps in the epilogue-bound 1x1 convolutions
+void set_epi_warps(int v) { g_epi_warps = (v == 16) ? 16 : 8; }
+int get_epi_warps() { return g_epi_warps; }
 static int g_epi_mode = 0;       // tuning knob (option "epi_mode"): epilogue organisation, see ConvPersParams::epi_mode
 void set_epi_mode(int v) { g_epi_mode = v; }
 int get_epi_mode() { return g_epi_mode; }
 
-template <int BN, int STAGES, int NB>
+template <int BN, int STAGES, int NB, int EW = 0>
 static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, const float* scale, const float* shift,
                         const __half* res, int relu, __half* out, cudaStream_t stream) {
   const int Ho = s.Ho(), Wo = s.Wo();
@@ -156,12 +159,12 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
   const int64_t total = m_tiles * p.n_tiles;
   DIRB_REQUIRE(total > 0 && total < (int64_t(1) << 31), DIRB200_ENOTSUP, "tile count %lld out of range", (long long)total);
   p.total_tiles = static_cast<int>(total);
-  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, NB>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
+  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, NB, EW>(tmA, tmB, tmR, tmO, p, num_sms(), stream);
 }
 
 // conv3 (1x1) of block 0 fused with the projection shortcut: out = relu([t2 | x_strided] . [W3*s3 | Wd*sd]^T + shift).
 // t2: (B,Ho,Wo,Cmid); x: (B,Hx,Wx,Cx) read with spatial stride `xstride`; wcat: [Cout][Cmid + Cx] fp16.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW = 0>
 static int conv_fused_ds_bn(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
                             const __half* x, const __half* wcat, int Cout, const float* scale, const float* shift,
                             __half* out, cudaStream_t stream) {
@@ -189,13 +192,16 @@ static int conv_fused_ds_bn(int B, int Ho, int Wo, int Cmid, const __half* t2, i
   DIRB_TRY(encode_tmap_nhwc(&tmX, x, B, Hx, Wx, Cx, p.tw, p.th, p.nb, xstride));
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, Cout, p.tw, p.th, p.nb, 1));
   DIRB_TRY(encode_tmap_2d(&tmB, wcat, Cmid + Cx, Cout, (uint64_t)(Cmid + Cx) * 2, 64, BN));
-  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, 2>(tmA, tmB, tmX, tmO, p, num_sms(), stream);
+  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, 2, EW>(tmA, tmB, tmX, tmO, p, num_sms(), stream);
 }
 
 int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
                   const __half* x, const __half* wcat, int Cout, const float* scale, const float* shift, __half* out,
                   cudaStream_t stream) {
   DIRB_REQUIRE(Cmid % 64 == 0 && Cx % 64 == 0 && Cout % 256 == 0, DIRB200_ENOTSUP, "fused shortcut needs 64-multiples");
+  // short K (layer1: 128, layer2: 384): the tile time is the epilogue's dependency chain -> 16 epilogue warps
+  if (g_epi_warps == 16 && Cmid + Cx <= 384)
+    return conv_fused_ds_bn<256, 4, 16>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
   return conv_fused_ds_bn<256, 4>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
 }
 
@@ -312,14 +318,17 @@ int conv_tc(const ConvShape& s, const __half* in, const __half* w, const float* 
       if (g_res_variant == 1) return conv_pers_bn<256, 2, 6>(s, in, w, scale, shift, res, relu, out, stream);
       if (g_res_variant == 2) return conv_pers_bn<128, 4, 6>(s, in, w, scale, shift, res, relu, out, stream);
       if (g_res_variant == 3) return conv_pers_bn<256, 2, 8>(s, in, w, scale, shift, res, relu, out, stream);
+      if (g_epi_warps == 16) return conv_pers_bn<256, 3, 4, 16>(s, in, w, scale, shift, res, relu, out, stream);
       return conv_pers_bn<256, 3, 4>(s, in, w, scale, shift, res, relu, out, stream);
     }
     return conv_pers_bn<256, 4, 2>(s, in, w, scale, shift, res, relu, out, stream);
   }
   if (bn == 128) {
+    if (res && g_epi_warps == 16) return conv_pers_bn<128, 5, 4, 16>(s, in, w, scale, shift, res, relu, out, stream);
     if (res) return conv_pers_bn<128, 5, 4>(s, in, w, scale, shift, res, relu, out, stream);
     return conv_pers_bn<128, 6, 2>(s, in, w, scale, shift, res, relu, out, stream);
   }
+  if (res && g_epi_warps == 16) return conv_pers_bn<64, 6, 4, 16>(s, in, w, scale, shift, res, relu, out, stream);
   return conv_pers_bn<64, 6, 4>(s, in, w, scale, shift, res, relu, out, stream);
 }
 

@@ -37,6 +37,8 @@ void set_conv_halo(int on);
 void set_res_variant(int v);
 void set_l2_prefetch(int v);
 void set_epi_mode(int v);
+void set_epi_warps(int v);
+int get_epi_warps();
 int get_l2_prefetch();
 int get_epi_mode();
 int get_conv_halo();

@@ -237,16 +237,18 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvPersParams& p, cons
 //   * staging-buffer accesses are explicit ld.shared / st.shared (see ptx.cuh: lds128).
 // The staging buffer of chunk cc - 1 goes back to the residual producer after the store of chunk cc (epi_mode bit 1: the
 // buffer of chunk cc itself, after its own store has been read).
-template <int BN, int NBUF, int EPI_THREADS, bool SS>
-__device__ __forceinline__ void conv_epilogue_chunk_1g(const ConvPersParams& p, const TileCoord& c, float (&v)[32], int ch,
+// CPT = channels per thread and chunk: 32 with 8 epilogue warps (two per TMEM lane quarter), 16 with 16 warps (four per
+// quarter); `slice` = which CPT-channel slice of the 64-channel chunk this warp owns.
+template <int BN, int NBUF, int EPI_THREADS, bool SS, int CPT>
+__device__ __forceinline__ void conv_epilogue_chunk_1g(const ConvPersParams& p, const TileCoord& c, float (&v)[CPT], int ch,
                                                        uint32_t buf_addr, int b, uint32_t cc, uint32_t ss_addr,
-                                                       uint64_t* res_empty, uint32_t row_off, uint32_t sw, int half,
+                                                       uint64_t* res_empty, uint32_t row_off, uint32_t sw, int slice,
                                                        bool leader, const CUtensorMap& tmO) {
   const int col0 = c.n_tile * BN + ch * 64;
   if (SS) {
-    const uint32_t sa = ss_addr + static_cast<uint32_t>(ch * 64 + half * 32) * 4u;
+    const uint32_t sa = ss_addr + static_cast<uint32_t>(ch * 64 + slice * CPT) * 4u;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < CPT / 4; ++q) {
       const float4 s = lds128f(sa + q * 16), h = lds128f(sa + BN * 4 + q * 16);
       v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
       v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
@@ -254,10 +256,10 @@ __device__ __forceinline__ void conv_epilogue_chunk_1g(const ConvPersParams& p, 
       v[4 * q + 3] = fmaf(v[4 * q + 3], s.w, h.w);
     }
   } else {
-    const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + half * 32);
-    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + half * 32);
+    const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0 + slice * CPT);
+    const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0 + slice * CPT);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < CPT / 4; ++q) {
       const float4 s = __ldg(sc4 + q), h = __ldg(sh4 + q);
       v[4 * q + 0] = fmaf(v[4 * q + 0], s.x, h.x);
       v[4 * q + 1] = fmaf(v[4 * q + 1], s.y, h.y);
@@ -266,8 +268,8 @@ __device__ __forceinline__ void conv_epilogue_chunk_1g(const ConvPersParams& p, 
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {                          // 4 x 16-byte chunks (8 channels each) of this half
-    const uint32_t chunk = static_cast<uint32_t>(half * 4 + j);
+  for (int j = 0; j < CPT / 8; ++j) {                    // 16-byte pieces (8 channels each) of this slice
+    const uint32_t chunk = static_cast<uint32_t>(slice * (CPT / 8) + j);
     const uint32_t sp = buf_addr + row_off + ((chunk ^ sw) << 4);
     if (p.has_res) {
       const uint4 r = lds128(sp);
@@ -312,11 +314,11 @@ template <int BN, int NBUF, int EPI_THREADS, bool SS>
 __device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, const TileCoord& c, uint32_t taddr,
                                                       uint32_t stg_addr, uint32_t ss_addr, uint64_t* res_full,
                                                       uint64_t* res_empty, uint64_t* acc_empty_a, uint32_t& cc,
-                                                      uint32_t row_off, uint32_t sw, int hsel, int lane, bool leader,
+                                                      uint32_t row_off, uint32_t sw, int slice, int lane, bool leader,
                                                       const CUtensorMap& tmO) {
   constexpr int CHUNKS = BN / 64;
   constexpr int STG_BYTES = 128 * 128;
-  const int half = hsel;
+  constexpr int CPT = EPI_THREADS >= 512 ? 16 : 32;      // 32 channels per thread and chunk with 8 warps, 16 with 16
   if (SS) {                                              // BN scale | shift of this tile's channels -> shared memory
     const int j = static_cast<int>(threadIdx.x) - 128;
     if (j < BN) {
@@ -325,8 +327,8 @@ __device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, c
     }
     named_bar_sync(6, EPI_THREADS);
   }
-  float va[32], vb[32];
-  tmem_ld32(taddr + half * 32, va);
+  float va[CPT], vb[CPT];
+  tmem_ld_cols<CPT>(taddr + slice * CPT, va);
 #pragma unroll
   for (int ch = 0; ch < CHUNKS; ++ch, ++cc) {
     const int b = cc % NBUF;
@@ -339,27 +341,30 @@ __device__ __forceinline__ void conv_epilogue_tile_1g(const ConvPersParams& p, c
     }
     tmem_ld_wait();                                        // this chunk's accumulator columns are in registers
     if (ch + 1 < CHUNKS) {
-      tmem_ld32(taddr + (ch + 1) * 64 + half * 32, (ch & 1) ? va : vb);
+      tmem_ld_cols<CPT>(taddr + (ch + 1) * 64 + slice * CPT, (ch & 1) ? va : vb);
     } else {                                               // last TMEM read of this tile: release the accumulator
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty_a);
     }
-    conv_epilogue_chunk_1g<BN, NBUF, EPI_THREADS, SS>(p, c, (ch & 1) ? vb : va, ch, buf_addr, b, cc, ss_addr, res_empty,
-                                                      row_off, sw, half, leader, tmO);
+    conv_epilogue_chunk_1g<BN, NBUF, EPI_THREADS, SS, CPT>(p, c, (ch & 1) ? vb : va, ch, buf_addr, b, cc, ss_addr, res_empty,
+                                                           row_off, sw, slice, leader, tmO);
   }
 }
 
 // Epilogue warps: 8 for the convolution epilogue (its per-chunk critical path bounds the memory-bound 1x1
 // convolutions), 4 for the light similarity epilogues.
-template <int EPI>
+template <int EPI, int EW = 0>
 struct PersThreads {
-  static constexpr int EPI_WARPS = (EPI == 0) ? 8 : 4;
+  static constexpr int EPI_WARPS = EW > 0 ? EW : ((EPI == 0) ? 8 : 4);
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
 };
 
-template <int BN, int STAGES, int EPI, int NB = 4>
-__global__ void __launch_bounds__(PersThreads<EPI>::THREADS, 1)
+// EW = 0: default number of epilogue warps (8 for the convolution epilogue, 4 otherwise); EW = 16 (convolution epilogue
+// only): four warps per TMEM lane quarter, each taking 16 of the 64 channels of a chunk - for the convolutions whose
+// tile time is the epilogue's dependency chain (1x1 with a residual, short K).
+template <int BN, int STAGES, int EPI, int NB = 4, int EW = 0>
+__global__ void __launch_bounds__(PersThreads<EPI, EW>::THREADS, 1)
 conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                  const ConvPersParams p) {
@@ -397,7 +402,7 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], PersThreads<EPI>::EPI_WARPS);      // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], PersThreads<EPI, EW>::EPI_WARPS);  // one arrival per epilogue warp
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&res_full[b], 1);
@@ -520,11 +525,11 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // -------------------------------------------------------------- epilogue
-    constexpr int EPI_THREADS = 32 * PersThreads<EPI>::EPI_WARPS;
+    constexpr int EPI_THREADS = 32 * PersThreads<EPI, EW>::EPI_WARPS;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
-    const int hsel = (warp - 4) >> 2;                  // conv epilogue: group of 4 warps (takes every other chunk)
+    const int hsel = (warp - 4) >> 2;                  // conv epilogue: which channel slice of a chunk (one-group) / which group
     const int row = quarter * 32 + lane;
-    const bool two_groups = (EPI == PERS_EPI_CONV) && (p.epi_mode & 1);
+    const bool two_groups = (EPI == PERS_EPI_CONV) && (p.epi_mode & 1) && PersThreads<EPI, EW>::EPI_WARPS == 8;
     const bool leader = two_groups ? (threadIdx.x == 128u + 128u * hsel) : (threadIdx.x == 128);
     const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
@@ -651,17 +656,17 @@ conv_pers_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int STAGES, int EPI, int NB = 4>
+template <int BN, int STAGES, int EPI, int NB = 4, int EW = 0>
 int conv_pers_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const CUtensorMap& tmO,
                      const ConvPersParams& p, int num_sms, cudaStream_t stream) {
   using L = ConvPersSmem<BN, STAGES, EPI, NB>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  auto kern = conv_pers_kernel<BN, STAGES, EPI, NB>;
+  auto kern = conv_pers_kernel<BN, STAGES, EPI, NB, EW>;
   static std::atomic<uint64_t> attr_done{0};
   if (first_launch_on_device(attr_done))
     DIRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  DIRB_CUDA(launch_pdl(kern, dim3(grid), dim3(PersThreads<EPI>::THREADS), L::TOTAL, stream, tmA, tmB, tmR, tmO, p));
+  DIRB_CUDA(launch_pdl(kern, dim3(grid), dim3(PersThreads<EPI, EW>::THREADS), L::TOTAL, stream, tmA, tmB, tmR, tmO, p));
   count_launch();
   return 0;
 }

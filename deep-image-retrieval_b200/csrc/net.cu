@@ -300,7 +300,7 @@ int dirb200_net_create(const char* arch, int device, dirb200_net** out) {
 }
 
 static bool is_global_option(const std::string& k) {
-  return k == "halo" || k == "pdl" || k == "res_variant" || k == "head_fused" || k == "l2_prefetch" || k == "epi_mode";
+  return k == "halo" || k == "pdl" || k == "res_variant" || k == "head_fused" || k == "l2_prefetch" || k == "epi_mode" || k == "epi_warps";
 }
 
 int dirb200_set_global_option(const char* key, double value) {
@@ -312,6 +312,7 @@ int dirb200_set_global_option(const char* key, double value) {
   else if (k == "head_fused") set_head_fused(static_cast<int>(value));
   else if (k == "l2_prefetch") set_l2_prefetch(static_cast<int>(value));
   else if (k == "epi_mode") set_epi_mode(static_cast<int>(value));
+  else if (k == "epi_warps") set_epi_warps(static_cast<int>(value));
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown global option '%s'", key);
   return 0;
 }
@@ -325,6 +326,7 @@ int dirb200_get_global_option(const char* key, double* value) {
   else if (k == "head_fused") *value = get_head_fused();
   else if (k == "l2_prefetch") *value = get_l2_prefetch();
   else if (k == "epi_mode") *value = get_epi_mode();
+  else if (k == "epi_warps") *value = get_epi_warps();
   else DIRB_REQUIRE(false, DIRB200_EKEY, "unknown global option '%s'", key);
   return 0;
 }

@@ -55,7 +55,8 @@ int dirb200_device_check(int device);
  * kernels; "res_variant" tile-variant selector of the residual 1x1 convolutions; "l2_prefetch" 1 = the 1x1
  * convolutions request the next tile's activation / residual boxes into L2 ahead of time; "head_fused" 1 (default) =
  * pooling + FC + L2 of the plain head as ONE persistent kernel, 0 = one kernel per phase (bit-identical results);
- * "epi_mode" epilogue organisation of the convolution kernels (bit 0: two warp groups, bit 1: early buffer release).
+ * "epi_mode" epilogue organisation of the convolution kernels (bit 0: two warp groups, bit 1: early buffer release);
+ * "epi_warps" 16 (default) / 8 epilogue warps in the 1x1 convolutions whose tile time is the epilogue (residual, short K).
  * dirb200_net_set_option forwards these keys here. */
 int dirb200_set_global_option(const char* key, double value);
 int dirb200_get_global_option(const char* key, double* value);

@@ -82,7 +82,8 @@ def test_conv_bn_act(case, impl):
 
 @pytest.mark.parametrize("knobs", [dict(epi_mode=0), dict(epi_mode=1), dict(epi_mode=2), dict(epi_mode=3),
                                    dict(epi_mode=3, l2_prefetch=1), dict(epi_mode=2, res_variant=1), dict(epi_mode=3, res_variant=2),
-                                   dict(epi_mode=3, res_variant=3, l2_prefetch=8), dict(epi_mode=0, res_variant=3)],
+                                   dict(epi_mode=3, res_variant=3, l2_prefetch=8), dict(epi_mode=0, res_variant=3),
+                                   dict(epi_warps=8), dict(epi_warps=16), dict(epi_warps=16, epi_mode=2), dict(epi_warps=8, epi_mode=1)],
                          ids=lambda k: ",".join("%s=%d" % kv for kv in k.items()))
 def test_conv_epilogue_and_tile_variants(knobs):
     """Every epilogue organisation (one / two warp groups, late / early release of the residual staging buffers), residual
@@ -90,7 +91,7 @@ def test_conv_epilogue_and_tile_variants(knobs):
     CONV_CASES vs the oracle, under each knob setting (process-wide selectors, restored afterwards)."""
     ops = _ops()
     cases = [c for c in CONV_CASES if c[8] or c[0] * c[1] * c[2] >= 128 * 148] + [(16, 64, 64, 256, 1024, 1, 1, 0, True, True)]
-    saved = {k: ops.get_global_option(k) for k in ("epi_mode", "res_variant", "l2_prefetch")}
+    saved = {k: ops.get_global_option(k) for k in ("epi_mode", "res_variant", "l2_prefetch", "epi_warps")}
     try:
         for k, v in knobs.items():
             ops.set_global_option(k, v)

@@ -39,6 +39,10 @@ while [ $# -gt 0 ]; do
         python tools/search_profile.py c3 > gpurun_out/traffic_s3.log 2>&1; echo "== traffic c3 rc=$?"
       timeout 300 ncu --metrics $M --clock-control none -k regex:"conv_pers" -s 6 -c 4 --csv --log-file gpurun_out/traffic_search_1000q_125k.csv \
         python tools/search_profile.py one > gpurun_out/traffic_s8.log 2>&1; echo "== traffic shard rc=$?" ;;
+    launchlist)
+      # ncu launch list of one default bench run (per-launch times are cold-cache and serialised: shares only)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 460 --csv --log-file gpurun_out/r2_b64_launches.csv \
+        python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-search --no-latency > gpurun_out/launchlist.log 2>&1; echo "== launchlist rc=$?" ;;
     benchall)
       # one JSON line per BASELINE configuration (1 GPU), kept for profiles/
       for cfg in c2 c3 c4 c5; do

@@ -5,7 +5,7 @@
 # Not part of the default test run: budget ~5-10 GPU-minutes per tool.
 TOOL=${1:-memcheck}
 mkdir -p gpurun_out
-SEL='test_conv_bn_act or test_stem or test_head or test_pool_scales or test_topk_small_db or test_topk_filtered or test_topk_ties or test_aqe or test_resize'
+SEL=${SANITIZE_SEL:-'test_conv_bn_act or test_stem or test_head or test_pool_scales or test_topk_small_db or test_topk_filtered or test_topk_ties or test_aqe or test_resize or test_peer_exchange or test_conv_epilogue'}
 timeout 420 /usr/local/cuda/bin/compute-sanitizer --tool "$TOOL" --error-exitcode 86 --target-processes all \
   python -m pytest tests/test_gpu_ops.py tests/test_gpu_search.py -m gpu -q -x -p no:cacheprovider -k "$SEL" \
   > "gpurun_out/sanitize_${TOOL}.log" 2>&1

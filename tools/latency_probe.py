@@ -2,7 +2,11 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import synthdata as synth
-from dirb200 import nets
+from dirb200 import nets, ops
+for kv in sys.argv[1:]:
+    k, v = kv.split("=")
+    ops.set_global_option(k, float(v))
+    print("option", k, v)
 net = nets.create_model("resnet101_rmac"); net.load_state_dict(synth.make_state_dict("resnet101_rmac", seed=0))
 for (b, h, w) in ((1, 1024, 768), (1, 1024, 1024), (1, 512, 384), (4, 1024, 768), (8, 1024, 1024), (1, 224, 224), (16, 224, 224)):
     x = torch.randn((b, 3, h, w), device="cuda")
