@@ -579,6 +579,26 @@ def main():
             line["roofline"]["search"] = {"metric": s["metric"], "value": s["value"], "unit": s["unit"], "ms_per_step": s["ms_per_step"],
                                           "e2e": s["e2e"]["value"], "bound": s["roofline"]["bound"], "achieved": s["roofline"]["achieved"],
                                           "peak": s["roofline"]["peak"], "frac": s["roofline"]["frac"], "traffic": s["roofline"]["traffic"]}
+            # The other two retrieval configurations of BASELINE.json, short forms of --config c5 / c3 on the same line:
+            # alpha-QE (k=2, alpha=0.5: search + expand + search) on the 1M database, and 70 queries x 100k rows per GPU
+            # with PCA-whitening p=0.25 (the HBM-bound search: the roofline is the filter pass against the copy peak).
+            index.disable_peer_exchange()
+            del s, db, index
+            torch.cuda.empty_cache()
+            sa, db, index = bench_search(args, ctx, args.search_n, args.search_q, aqe=True, steps=max(10, args.steps // 2))
+            line["roofline"]["search_aqe_c5"] = {"metric": "1M-DB alpha-QE queries/sec", "value": sa["value"], "unit": sa["unit"],
+                                                 "ms_per_step": sa["ms_per_step"], "e2e": sa["e2e"]["value"], "config": sa["config"]}
+            index.disable_peer_exchange()
+            del sa, db, index
+            torch.cuda.empty_cache()
+            s3, db, index = bench_search(args, ctx, C3_N * world, C3_Q, whiten=True, steps=max(20, args.steps))
+            line["roofline"]["search_c3"] = {"metric": "queries/sec, 70 x 100k per GPU + whitening", "value": s3["value"], "unit": s3["unit"],
+                                             "ms_per_step": s3["ms_per_step"], "e2e": s3["e2e"]["value"], "bound": s3["roofline"]["bound"],
+                                             "achieved": s3["roofline"]["achieved"], "peak": s3["roofline"]["peak"], "unit_roofline": s3["roofline"]["unit"],
+                                             "frac": s3["roofline"]["frac"], "traffic": s3["roofline"]["traffic"],
+                                             "algorithmic_bytes_per_launch": s3["roofline"]["algorithmic_bytes_per_launch"],
+                                             "launch_ms": s3["roofline"]["launch_ms"], "config": s3["config"]}
+            index.disable_peer_exchange()
     elif args.config in ("c3", "c4"):
         sampler = ClockSampler(ctx.local)
         sampler.start()
@@ -660,6 +680,8 @@ def main():
                                                "" if n == full_n else ", scaled to %d rows" % full_n)}
     if rank == 0:
         print(json.dumps(line))
+    if "index" in locals():
+        locals()["index"].disable_peer_exchange()      # unmap the peers' windows before any rank frees its own
     if ctx.dist is not None:
         ctx.dist.destroy_process_group()
 

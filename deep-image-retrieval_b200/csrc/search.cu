@@ -1454,6 +1454,23 @@ int dirb200_exchange_open_local(dirb200_exchange* x, dirb200_exchange* const* al
   return 0;
 }
 
+// Unmap the other ranks' windows (CUDA IPC).  An exporting process must not free its window while an importer still has
+// it mapped: ranks call this, synchronise among themselves (a barrier), and only then destroy their own window.
+int dirb200_exchange_close_peers(dirb200_exchange* x) {
+  DIRB_REQUIRE(x, DIRB200_EINVAL, "null argument");
+  DIRB_CUDA(cudaSetDevice(x->device));
+  DIRB_CUDA(cudaDeviceSynchronize());                       // no kernel of this rank may still be writing to a peer
+  for (int g = 0; g < x->world; ++g) {
+    if (x->ipc_opened[g] && x->peer[g]) {
+      DIRB_CUDA(cudaIpcCloseMemHandle(x->peer[g]));
+      x->ipc_opened[g] = false;
+    }
+    if (g != x->rank) x->peer[g] = nullptr;
+  }
+  x->open = false;
+  return 0;
+}
+
 int dirb200_exchange_destroy(dirb200_exchange* x) {
   if (!x) return 0;
   cudaSetDevice(x->device);

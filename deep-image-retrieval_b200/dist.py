@@ -85,6 +85,18 @@ class ShardedIndex:
         self.xchg = x
         return self
 
+    def disable_peer_exchange(self):
+        """Tear the exchange down in the order CUDA IPC requires: every rank unmaps the peers' windows, barrier, every rank
+        frees its own window.  Collective call; search() goes back to the torch.distributed collectives."""
+        x, self.xchg = self.xchg, None
+        if x is None:
+            return self
+        x.close_peers()
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.barrier(group=self.group)
+        x.close()
+        return self
+
     @classmethod
     def from_store(cls, store, device, group=None, chunk_rows: int = 65536):
         """Load this rank's row range of an on-disk descriptor store (store.py) and index it.  The split is

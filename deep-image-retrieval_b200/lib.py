@@ -84,6 +84,7 @@ SIGNATURES = {
     "dirb200_exchange_ipc_handle": (i32, [p, p]),
     "dirb200_exchange_open": (i32, [p, p]),
     "dirb200_exchange_open_local": (i32, [p, C.POINTER(p)]),
+    "dirb200_exchange_close_peers": (i32, [p]),
     "dirb200_exchange_destroy": (i32, [p]),
     "dirb200_index_search_sharded": (i32, [p, p, p, i32, i32, i32, p, p, p]),
     "dirb200_index_search_sharded_phase": (i32, [p, p, i32, p, i32, i32, i32, p, p, p]),

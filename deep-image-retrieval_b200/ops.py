@@ -282,6 +282,11 @@ class Exchange:
         for x in group:
             lib.call("dirb200_exchange_open_local", x._h, arr)
 
+    def close_peers(self):
+        """Unmap the other ranks' windows (every rank, then a barrier, then close())."""
+        if self._h:
+            lib.call("dirb200_exchange_close_peers", self._h)
+
     def close(self):
         if self._h:
             lib.raw("dirb200_exchange_destroy")(self._h)

@@ -280,6 +280,7 @@ int dirb200_exchange_create(int device, int world, int rank, int max_q, int max_
 int dirb200_exchange_ipc_handle(dirb200_exchange* x, void* handle64_out);
 int dirb200_exchange_open(dirb200_exchange* x, const void* handles);
 int dirb200_exchange_open_local(dirb200_exchange* x, dirb200_exchange* const* all);
+int dirb200_exchange_close_peers(dirb200_exchange* x);   /* unmap the peers' windows; barrier among the ranks; then _destroy */
 int dirb200_exchange_destroy(dirb200_exchange* x);
 int dirb200_index_search_sharded(dirb200_index* idx, dirb200_exchange* x, const float* q32_dev, int Q, int k, int k_shard,
                                  double* scores_dev, int64_t* idx_dev, void* stream);

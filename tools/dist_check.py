@@ -65,5 +65,6 @@ flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("DIST-OK" if int(flag.item()) == 1 else "DIST-FAIL", "world", world)
+index.disable_peer_exchange()
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) == 1 else 1)

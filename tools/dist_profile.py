@@ -90,4 +90,5 @@ if rank == 0:
 if rank == 0:
     print("world %d rows/rank %d: " % (world, s1 - s0) + "  ".join("%s %.3f" % (n, v) for n, v in zip(names + ["sum"], t.tolist())) +
           " ms | sustained %.3f ms/search = %.0f q/s | stats %s" % (ms.item(), Q / ms.item() * 1e3, index.local.stats()), flush=True)
+index.disable_peer_exchange()
 dist.destroy_process_group()
