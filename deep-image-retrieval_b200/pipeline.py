@@ -55,6 +55,10 @@ def expand_descriptors(descs, db=None, alpha=0, k=0, q_block=4096, to_numpy=True
     assert k >= 0 and alpha >= 0, "k and alpha must be non-negative"
     if k == 0:
         return descs
+    if k + (db is None) > 1024:
+        # the reference expands with any k (a full argsort per query); the exact top-k search returns at most 1024 rows
+        raise ValueError("query expansion / database augmentation with more than %d neighbours is not supported "
+                         "(dirb200_index_search returns at most 1024 rows per query); got k=%d" % (1024 - (db is None), k))
     dim = np.shape(descs)[1]
     pad = (-dim) % 64                      # the tensor-core search wants D % 64 == 0; zero columns change no score
 
