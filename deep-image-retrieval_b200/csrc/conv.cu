@@ -164,7 +164,7 @@ static int conv_pers_bn(const ConvShape& s, const __half* in, const __half* w, c
 
 // conv3 (1x1) of block 0 fused with the projection shortcut: out = relu([t2 | x_strided] . [W3*s3 | Wd*sd]^T + shift).
 // t2: (B,Ho,Wo,Cmid); x: (B,Hx,Wx,Cx) read with spatial stride `xstride`; wcat: [Cout][Cmid + Cx] fp16.
-template <int BN, int STAGES, int EW = 0>
+template <int BN, int STAGES, int EW = 0, int NB = 2>
 static int conv_fused_ds_bn(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
                             const __half* x, const __half* wcat, int Cout, const float* scale, const float* shift,
                             __half* out, cudaStream_t stream) {
@@ -192,7 +192,7 @@ static int conv_fused_ds_bn(int B, int Ho, int Wo, int Cmid, const __half* t2, i
   DIRB_TRY(encode_tmap_nhwc(&tmX, x, B, Hx, Wx, Cx, p.tw, p.th, p.nb, xstride));
   DIRB_TRY(encode_tmap_nhwc(&tmO, out, B, Ho, Wo, Cout, p.tw, p.th, p.nb, 1));
   DIRB_TRY(encode_tmap_2d(&tmB, wcat, Cmid + Cx, Cout, (uint64_t)(Cmid + Cx) * 2, 64, BN));
-  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, 2, EW>(tmA, tmB, tmX, tmO, p, num_sms(), stream);
+  return conv_pers_launch<BN, STAGES, PERS_EPI_CONV, NB, EW>(tmA, tmB, tmX, tmO, p, num_sms(), stream);
 }
 
 int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int Wx, int Cx, int xstride,
@@ -200,6 +200,10 @@ int conv_fused_ds(int B, int Ho, int Wo, int Cmid, const __half* t2, int Hx, int
                   cudaStream_t stream) {
   DIRB_REQUIRE(Cmid % 64 == 0 && Cx % 64 == 0 && Cout % 256 == 0, DIRB200_ENOTSUP, "fused shortcut needs 64-multiples");
   // short K (layer1: 128, layer2: 384): the tile time is the epilogue's dependency chain -> 16 epilogue warps
+  // K = 128 (layer1): two ring slots are a whole tile; the freed shared memory buys 4 staging buffers and the per-tile
+  // scale / shift staging (ncu: without it the epilogue's FFMAs wait on 16 LDG.128 per chunk, profiles/r2_conv_sweep.txt)
+  if (g_epi_warps == 16 && Cmid + Cx <= 128)
+    return conv_fused_ds_bn<256, 2, 16, 4>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
   if (g_epi_warps == 16 && Cmid + Cx <= 384)
     return conv_fused_ds_bn<256, 4, 16>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
   return conv_fused_ds_bn<256, 4>(B, Ho, Wo, Cmid, t2, Hx, Wx, Cx, xstride, x, wcat, Cout, scale, shift, out, stream);
