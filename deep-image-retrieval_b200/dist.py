@@ -68,7 +68,9 @@ class ShardedIndex:
         """Switch search() to the peer-memory protocol (dirb200_index_search_sharded): the MIN of the selection thresholds
         and the gather of the per-shard lists are done by the search kernels themselves with stores into the other ranks'
         exchange windows over NVLink - no NCCL call on the search path.  One process per GPU of ONE box (CUDA IPC); the
-        only collective is the one-off all-gather of the 64-byte IPC handles here.  Collective call."""
+        only collective is the one-off all-gather of the 64-byte IPC handles here.  Collective call.  Searches with more
+        than max_q queries or k > max_k keep using the torch.distributed collectives (same results); call
+        disable_peer_exchange() (collective) before the ranks drop their indices."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         dev = self.local.db32.device
