@@ -1053,7 +1053,6 @@ static int search_begin_seed(dirb200_index* h, const float* q32, int Q, int k, i
   P.kth_k = reinterpret_cast<float*>(w + o_kthk);
   P.status = reinterpret_cast<unsigned long long*>(w + o_status);
   int* cnt = P.cnt;
-  unsigned long long* cand = P.cand;
 
   mark_phase(h, stream);  // 0
   // ---- 1. queries to fp16, counters / gates / status cleared
